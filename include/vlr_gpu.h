@@ -1,0 +1,235 @@
+/*
+ * vlr_gpu.h -- C ABI of libvlr_b200.so: the B200 (sm_100a) implementation of Varlociraptor
+ * 4.1.0's per-site likelihood hot path (pair-HMM realignment + AF-grid pileup likelihood with
+ * event integration).  This is the drop-in boundary: plain pointers and sizes, `int` status
+ * (0 = OK, <0 = error, message via vlr_last_error), no exceptions cross it, one opaque context
+ * per GPU (not thread-safe per context, independent across contexts).
+ *
+ * The reference has no FFI of its own; the seams these entry points sit behind are Rust traits
+ * (paths relative to the reference checkout):
+ *   - trait Realigner::calculate_prob_allele / prob_allele / allele_support
+ *       src/variants/evidence/realignment/mod.rs:164-335, 338-385, 387-389, 430-444
+ *   - bio::stats::pairhmm::PairHMM::prob_related      (call site realignment/mod.rs:439-443)
+ *   - EditDistanceCalculation::calc_best_hit          src/variants/evidence/realignment/edit_distance.rs:56-154
+ *   - Likelihood::compute of SampleLikelihoodModel / ContaminatedSampleLikelihoodModel
+ *       src/variants/model/likelihood.rs:118-152, 215-245
+ *   - GenericPosterior::compute + Model::compute      src/variants/model/modes/generic.rs:238-282,
+ *       src/calling/variants/calling.rs:568-602, 635-677
+ * INTEGRATION.md shows the Rust `extern "C"` block and the trait impls that bind them.
+ *
+ * All probabilities are natural-log doubles (bio::stats::LogProb) unless stated otherwise.
+ */
+#ifndef VLR_GPU_H
+#define VLR_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VLR_OK 0
+#define VLR_ERR_INVALID (-1)   /* bad argument */
+#define VLR_ERR_CUDA (-2)      /* CUDA runtime error (see vlr_last_error) */
+#define VLR_ERR_NOMEM (-3)
+#define VLR_ERR_UNSUPPORTED (-4)
+
+typedef struct vlr_ctx vlr_ctx;
+
+/* ---- context ------------------------------------------------------------------------ */
+int vlr_version(void);
+/* One context per GPU.  Fails with VLR_ERR_CUDA if `device` is not a CUDA device: there is no
+ * CPU fallback anywhere in this library. */
+int vlr_ctx_create(int device, vlr_ctx **out);
+void vlr_ctx_destroy(vlr_ctx *ctx);
+const char *vlr_last_error(const vlr_ctx *ctx);
+/* Bind the context to a caller-owned CUDA stream (cudaStream_t as void*); NULL = the context's
+ * own stream.  All *_dev entry points enqueue on it and do not synchronise. */
+int vlr_ctx_set_stream(vlr_ctx *ctx, void *cuda_stream);
+int vlr_ctx_synchronize(vlr_ctx *ctx);
+/* number of kernels launched through this context so far */
+int64_t vlr_ctx_launch_count(const vlr_ctx *ctx);
+
+/* ---- pair-HMM forward: replaces PairHMM::prob_related (realignment/mod.rs:439-443) ------
+ * Gap parameters: GapParams, realignment/pairhmm.rs:73-101 (ln probabilities). */
+typedef struct {
+    double prob_gap_x;        /* prob_insertion_artifact        (cli.rs:207-212 default 2.8e-6) */
+    double prob_gap_y;        /* prob_deletion_artifact         (cli.rs:213-218 default 5.1e-6) */
+    double prob_gap_x_extend; /* prob_insertion_extend_artifact (default 0 -> ln = -inf)        */
+    double prob_gap_y_extend; /* prob_deletion_extend_artifact  (default 0 -> ln = -inf)        */
+} vlr_gap_params;
+
+/* flags */
+#define VLR_HMM_SUM3_APPROX 1u /* bio's ln_sum3_exp_approx in the M-state sum (reference behaviour) */
+#define VLR_HMM_PATH_CLOSE 2u  /* close-gap constants paired as PathHMMRealigner (mod.rs:469-470)   */
+#define VLR_HMM_DEFAULT VLR_HMM_SUM3_APPROX
+
+/*
+ * Host-buffer entry point (H2D, kernels, D2H inside; synchronous).
+ *   haps:  n_haps haplotype windows, bytes of window h at hap_bytes[hap_off[h] .. hap_off[h+1])
+ *          (already spliced by the host: RefBaseEmission::ref_base(i), pairhmm.rs:213-237,
+ *          deletion.rs:300-312, insertion.rs:200-214; lower case is upper-cased on device)
+ *   reads: n_reads read windows; bases are decoded IUPAC upper-case (bam::record::Seq),
+ *          quals are raw PHRED bytes (ReadEmission::new, pairhmm.rs:160-180)
+ *   pairs: pair k aligns read pair_read[k] to haplotype pair_hap[k]; either may be NULL,
+ *          meaning the identity mapping k -> k
+ *   max_edit_dist: per pair band `hit.dist_upper_bound()` (edit_distance.rs:180-182);
+ *          NULL or a negative entry = unbanded
+ *   out_lnprob[k]: ln P(read | haplotype), capped at ln 1
+ */
+int vlr_pairhmm_batch(vlr_ctx *ctx, int64_t n_pairs,
+                      const uint8_t *hap_bytes, const int64_t *hap_off, int64_t n_haps,
+                      const uint8_t *read_bases, const uint8_t *read_quals,
+                      const int64_t *read_off, int64_t n_reads,
+                      const int32_t *pair_hap, const int32_t *pair_read,
+                      const int32_t *max_edit_dist,
+                      const vlr_gap_params *gap, uint32_t flags, double *out_lnprob);
+
+/*
+ * Device-resident entry point: every pointer is a device pointer, work is enqueued on the
+ * context's stream, nothing is copied or synchronised.  Layout requirement: hap_off[h] must be
+ * a multiple of 16 (TMA bulk-copy granularity) and the hap buffer must extend 512 bytes past
+ * hap_off[n_haps].  `workspace` must hold vlr_pairhmm_workspace_bytes(n_pairs) bytes.
+ */
+size_t vlr_pairhmm_workspace_bytes(int64_t n_pairs, int64_t max_len_x, int64_t max_len_y);
+int vlr_pairhmm_batch_dev(vlr_ctx *ctx, int64_t n_pairs,
+                          const uint8_t *d_hap_bytes, const int64_t *d_hap_off, int64_t n_haps,
+                          const uint8_t *d_read_bases, const uint8_t *d_read_quals,
+                          const int64_t *d_read_off, int64_t n_reads,
+                          const int32_t *d_pair_hap, const int32_t *d_pair_read,
+                          const int32_t *d_max_edit_dist,
+                          const vlr_gap_params *gap, uint32_t flags,
+                          void *d_workspace, size_t workspace_bytes, double *d_out_lnprob);
+
+/* fp64 DFMA peak of the device (register-resident FMA chains), in TFLOP/s; the roofline
+ * denominator for the pair-HMM and likelihood kernels. */
+int vlr_measure_fp64_peak(vlr_ctx *ctx, double *out_tflops);
+
+/* ---- Myers best hit: replaces EditDistanceCalculation::calc_best_hit
+ *      (edit_distance.rs:56-154); same haps/reads/pairs layout as above (host buffers) ------ */
+int vlr_besthit_batch(vlr_ctx *ctx, int64_t n_pairs,
+                      const uint8_t *hap_bytes, const int64_t *hap_off, int64_t n_haps,
+                      const uint8_t *read_bases, const int64_t *read_off, int64_t n_reads,
+                      const int32_t *pair_hap, const int32_t *pair_read,
+                      int32_t *out_dist, int32_t *out_start, int32_t *out_end,
+                      int32_t *out_n_best);
+
+/* ---- pileup likelihood + posterior: replaces Likelihood::compute (likelihood.rs:118-152,
+ *      215-245) and GenericPosterior/Model::compute (generic.rs:124-365, calling.rs:568-677) --
+ * Observation columns, struct of arrays over all rows of the batch (Observation,
+ * observation.rs:172-215).  Pileup of (site s, sample m) = rows obs_off[s*n_samples+m] ..
+ * obs_off[s*n_samples+m+1]. */
+typedef struct {
+    const double *prob_mapping;        /* Observation::prob_mapping()    */
+    const double *prob_mismapping;     /* Observation::prob_mismapping() */
+    const double *prob_alt;
+    const double *prob_ref;
+    const double *prob_missed_allele;
+    const double *prob_sample_alt;
+    const double *prob_double_overlap;
+    const double *prob_single_overlap;
+    const double *prob_hit_base;
+    const uint16_t *cat;               /* packed categoricals, VLR_CAT_* */
+} vlr_obs_columns;
+
+/* cat bit layout: strand (observation.rs:40-45), read orientation (bio-types
+ * SequenceReadPairOrientation), read_position (118-121), softclipped, indel_operations
+ * (130-134), paired */
+#define VLR_CAT_STRAND(c) ((c) & 3u)           /* 0 Forward 1 Reverse 2 Both 3 None */
+#define VLR_CAT_ORIENT(c) (((c) >> 2) & 15u)   /* 0 F1R2 1 F2R1 2..7 other 8 None   */
+#define VLR_CAT_READPOS(c) (((c) >> 6) & 1u)   /* 0 Major 1 Some                    */
+#define VLR_CAT_SOFTCLIP(c) (((c) >> 7) & 1u)
+#define VLR_CAT_INDEL(c) (((c) >> 8) & 3u)     /* 0 Major 1 Other 2 None            */
+#define VLR_CAT_PAIRED(c) (((c) >> 10) & 1u)
+
+/* Biases (bias/mod.rs:86-99) */
+typedef struct {
+    int32_t strand;        /* 0 None 1 Forward 2 Reverse */
+    int32_t orientation;   /* 0 None 1 F1R2 2 F2R1 */
+    int32_t read_position; /* 0 None 1 Some */
+    int32_t softclip;      /* 0 None 1 Some */
+    int32_t divindel;      /* 0 None 1 Some */
+    int32_t _pad;
+    double min_other_rate; /* DivIndelBias::Some::min_other_rate (cli.rs:420-430) */
+} vlr_biases;
+
+/* Likelihood work item: one (site, sample, AF[, secondary AF], bias config) evaluation =
+ * one Likelihood::compute cache key (likelihood.rs:128, 221). */
+typedef struct {
+    int32_t site;
+    int32_t sample;
+    int32_t bias;          /* index into biases[] */
+    int32_t contaminated;  /* 0: SampleLikelihoodModel; 1: ContaminatedSampleLikelihoodModel */
+    double af;             /* primary allele frequency (linear) */
+    double af_secondary;   /* contaminating sample's allele frequency */
+    double purity;         /* 1 - contamination.fraction (generic.rs:303-305) */
+    double other_rate;     /* learned DivIndelBias other_rate for this site (divindel_bias.rs:98-132) */
+} vlr_lh_item;
+
+int vlr_likelihood_batch(vlr_ctx *ctx, int64_t n_sites, int32_t n_samples,
+                         const vlr_obs_columns *obs, const int64_t *obs_off,
+                         const vlr_biases *biases, int32_t n_biases,
+                         const vlr_lh_item *items, int64_t n_items, double *out_ln_lh);
+
+/* Flattened scenario for the posterior (grammar::VAFTree, vaftree.rs:10-96; model::Event,
+ * model/mod.rs:28-44).  Variant nodes are resolved by the host into SKIP/FALSE. */
+#define VLR_NODE_SET 0
+#define VLR_NODE_RANGE 1
+#define VLR_NODE_FALSE 2
+#define VLR_NODE_SKIP 3
+typedef struct {
+    int32_t kind;
+    int32_t sample;
+    int32_t child_off;  /* into children[] */
+    int32_t n_children;
+    int32_t vaf_off;    /* into vafs[]: SET: n_vafs ascending values; RANGE: start,end,left_excl,right_excl */
+    int32_t n_vafs;
+} vlr_node;
+typedef struct {
+    int32_t root_off;   /* into roots[] */
+    int32_t n_roots;
+    int32_t bias_off;   /* into biases[] */
+    int32_t n_biases;
+} vlr_event;
+typedef struct {
+    int32_t n_samples;          /* <= 8 */
+    int32_t n_events;
+    int32_t n_nodes;
+    int32_t n_biases;
+    const int32_t *resolution;  /* per sample (grammar/mod.rs:425-427) */
+    const int32_t *contaminated;
+    const int32_t *by;
+    const double *purity;
+    const vlr_node *nodes;
+    const int32_t *children;
+    const double *vafs;
+    const int32_t *roots;
+    const vlr_event *events;
+    const vlr_biases *biases;
+} vlr_model;
+
+/*
+ * Whole part 2 for a batch of sites: bias learning + gating (bias/mod.rs:30-83, 192-223),
+ * AF-grid likelihoods, VAF-tree integration (Simpson, generic.rs:196-208), marginal, MAP.
+ * Prior: flat (ln 1) when prior_ln == NULL.
+ *   out_event_ln[s*n_events + e]  unnormalised ln posterior of event e (Posterior::compute)
+ *   out_marginal[s]               ln marginal (Model::compute)
+ *   out_map_af[s*n_samples + m]   MAP allele frequency (calling.rs:635-677)
+ *   out_map_bias[s*n_samples + m] bias index of an artifact MAP, else -1
+ */
+int vlr_posterior_batch(vlr_ctx *ctx, int64_t n_sites, const vlr_model *model,
+                        const vlr_obs_columns *obs, const int64_t *obs_off,
+                        double *out_event_ln, double *out_marginal, double *out_map_af,
+                        int32_t *out_map_bias);
+
+/* device-resident variant (obs columns / obs_off / outputs are device pointers) */
+int vlr_posterior_batch_dev(vlr_ctx *ctx, int64_t n_sites, const vlr_model *model,
+                            const vlr_obs_columns *d_obs, const int64_t *d_obs_off,
+                            double *d_out_event_ln, double *d_out_marginal, double *d_out_map_af,
+                            int32_t *d_out_map_bias);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,119 @@
+"""Host-side handle on one GPU context (vlr_ctx) with numpy / device-pointer entry points.
+
+Mirrors the reference seams:
+  * ``Context.pairhmm_batch``  <-> PairHMM::prob_related at realignment/mod.rs:439-443
+  * ``Context.likelihood_batch`` / ``posterior_batch`` <-> Likelihood::compute / Model::compute
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import GapParams as _GapParams
+from ._ffi import VlrError
+
+
+class GapParams:
+    """GapParams of realignment/pairhmm.rs:73-79, built from linear artifact rates like
+    cli.rs:672-677 does (``LogProb::from(Prob(rate))``)."""
+
+    def __init__(self, prob_insertion_artifact=2.8e-6, prob_deletion_artifact=5.1e-6,
+                 prob_insertion_extend_artifact=0.0, prob_deletion_extend_artifact=0.0):
+        def ln(p):
+            return math.log(p) if p > 0.0 else -math.inf
+        self.c = _GapParams(ln(prob_insertion_artifact), ln(prob_deletion_artifact),
+                            ln(prob_insertion_extend_artifact), ln(prob_deletion_extend_artifact))
+
+    def as_ln_array(self):
+        return np.array([self.c.prob_gap_x, self.c.prob_gap_y, self.c.prob_gap_x_extend,
+                         self.c.prob_gap_y_extend], dtype=np.float64)
+
+
+def _ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def _arr(a, dt):
+    return None if a is None else np.ascontiguousarray(a, dtype=dt)
+
+
+class Context:
+    def __init__(self, device=0):
+        self.lib = _ffi.load()
+        h = C.c_void_p()
+        rc = self.lib.vlr_ctx_create(int(device), C.byref(h))
+        if rc != _ffi.VLR_OK:
+            raise VlrError(rc, "vlr_ctx_create(device=%d) failed: no CUDA device? "
+                               "(there is no CPU fallback)" % device)
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.vlr_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != _ffi.VLR_OK:
+            raise VlrError(rc, self.lib.vlr_last_error(self.h).decode())
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self.lib.vlr_ctx_set_stream(self.h, C.c_void_p(cuda_stream_ptr or 0)))
+
+    def synchronize(self):
+        self._check(self.lib.vlr_ctx_synchronize(self.h))
+
+    def launch_count(self):
+        return int(self.lib.vlr_ctx_launch_count(self.h))
+
+    def measure_fp64_peak(self):
+        v = C.c_double()
+        self._check(self.lib.vlr_measure_fp64_peak(self.h, C.byref(v)))
+        return v.value
+
+    # ---------------------------------------------------------------- pair-HMM
+    def pairhmm_batch(self, hap_bytes, hap_off, read_bases, read_quals, read_off, gap,
+                      pair_hap=None, pair_read=None, max_edit_dist=None, flags=_ffi.HMM_DEFAULT,
+                      out=None):
+        """ln P(read | haplotype) for every pair (host buffers; copies inside)."""
+        hap_bytes = _arr(hap_bytes, np.uint8)
+        hap_off = _arr(hap_off, np.int64)
+        read_bases = _arr(read_bases, np.uint8)
+        read_quals = _arr(read_quals, np.uint8)
+        read_off = _arr(read_off, np.int64)
+        pair_hap = _arr(pair_hap, np.int32)
+        pair_read = _arr(pair_read, np.int32)
+        max_edit_dist = _arr(max_edit_dist, np.int32)
+        n_haps, n_reads = len(hap_off) - 1, len(read_off) - 1
+        if pair_hap is not None:
+            n_pairs = len(pair_hap)
+        elif pair_read is not None:
+            n_pairs = len(pair_read)
+        else:
+            n_pairs = min(n_haps, n_reads)
+        if out is None:
+            out = np.empty(n_pairs, dtype=np.float64)
+        self._check(self.lib.vlr_pairhmm_batch(
+            self.h, n_pairs, _ptr(hap_bytes), _ptr(hap_off), n_haps, _ptr(read_bases),
+            _ptr(read_quals), _ptr(read_off), n_reads, _ptr(pair_hap), _ptr(pair_read),
+            _ptr(max_edit_dist), C.byref(gap.c), int(flags), _ptr(out)))
+        return out
+
+    def pairhmm_workspace_bytes(self, n_pairs, max_len_x=0, max_len_y=0):
+        return int(self.lib.vlr_pairhmm_workspace_bytes(n_pairs, max_len_x, max_len_y))
+
+    def pairhmm_batch_dev(self, n_pairs, d_hap, d_hap_off, n_haps, d_rb, d_rq, d_read_off, n_reads,
+                          d_pair_hap, d_pair_read, d_med, gap, flags, d_ws, ws_bytes, d_out):
+        """All arguments are raw device pointers (ints); enqueues on the bound stream."""
+        vp = C.c_void_p
+        self._check(self.lib.vlr_pairhmm_batch_dev(
+            self.h, n_pairs, vp(d_hap), vp(d_hap_off), n_haps, vp(d_rb), vp(d_rq), vp(d_read_off),
+            n_reads, vp(d_pair_hap or 0), vp(d_pair_read or 0), vp(d_med or 0), C.byref(gap.c),
+            int(flags), vp(d_ws), ws_bytes, vp(d_out)))

@@ -1,0 +1,58 @@
+// common.cuh -- shared declarations of libvlr_b200 (sm_100a only; no CPU fallback).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/vlr_gpu.h"
+
+struct vlr_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;  // stream all work is enqueued on
+    std::string err;
+    int64_t launches = 0;
+    int sm_count = 0;
+    // device LUT: per base quality {eps, 1-eps, eps*0.3333} (linear) followed by the ln versions
+    double *d_qlut = nullptr;
+    // grow-only device / pinned scratch owned by the context (host-buffer entry points)
+    struct Buf {
+        void *p = nullptr;
+        size_t cap = 0;
+    };
+    std::vector<Buf> dev_bufs;   // indexed by slot
+    std::vector<Buf> pin_bufs;
+};
+
+namespace vlr {
+
+int set_err(vlr_ctx *ctx, int code, const char *fmt, ...);
+// returns device scratch of at least `bytes` in slot `slot` (grow-only), nullptr on failure
+void *dev_scratch(vlr_ctx *ctx, int slot, size_t bytes);
+void *pin_scratch(vlr_ctx *ctx, int slot, size_t bytes);
+
+#define VLR_CUDA(ctx, call)                                                                  \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess)                                                              \
+            return vlr::set_err((ctx), VLR_ERR_CUDA, "%s failed: %s (%s:%d)", #call,         \
+                                cudaGetErrorString(e__), __FILE__, __LINE__);                \
+    } while (0)
+
+#define VLR_LAUNCH_CHECK(ctx)                                                                \
+    do {                                                                                     \
+        cudaError_t e__ = cudaGetLastError();                                                \
+        if (e__ != cudaSuccess)                                                              \
+            return vlr::set_err((ctx), VLR_ERR_CUDA, "kernel launch failed: %s (%s:%d)",     \
+                                cudaGetErrorString(e__), __FILE__, __LINE__);                \
+        (ctx)->launches++;                                                                   \
+    } while (0)
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// qlut layout: [256][4] doubles: eps, 1-eps, eps*0.3333, ln(1-eps)
+constexpr int kQlutStride = 4;
+
+}  // namespace vlr

@@ -1,0 +1,123 @@
+// ctx.cu -- context management of libvlr_b200 (C ABI: include/vlr_gpu.h).
+#include <math.h>
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace vlr {
+
+int set_err(vlr_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+static void *grow(std::vector<vlr_ctx::Buf> &bufs, int slot, size_t bytes, bool pinned) {
+    if ((int)bufs.size() <= slot) bufs.resize(slot + 1);
+    auto &b = bufs[slot];
+    if (b.cap >= bytes && b.p) return b.p;
+    if (b.p) {
+        if (pinned) cudaFreeHost(b.p); else cudaFree(b.p);
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t cap = align_up(bytes + bytes / 4 + 4096, 4096);
+    cudaError_t e = pinned ? cudaMallocHost(&b.p, cap) : cudaMalloc(&b.p, cap);
+    if (e != cudaSuccess) {
+        b.p = nullptr;
+        return nullptr;
+    }
+    b.cap = cap;
+    return b.p;
+}
+
+void *dev_scratch(vlr_ctx *ctx, int slot, size_t bytes) {
+    // a grow may free memory still in use by enqueued work: drain first
+    if ((int)ctx->dev_bufs.size() <= slot || ctx->dev_bufs[slot].cap < bytes)
+        cudaStreamSynchronize(ctx->stream);
+    return grow(ctx->dev_bufs, slot, bytes, false);
+}
+void *pin_scratch(vlr_ctx *ctx, int slot, size_t bytes) {
+    if ((int)ctx->pin_bufs.size() <= slot || ctx->pin_bufs[slot].cap < bytes)
+        cudaStreamSynchronize(ctx->stream);
+    return grow(ctx->pin_bufs, slot, bytes, true);
+}
+
+}  // namespace vlr
+
+extern "C" {
+
+int vlr_version(void) { return 100; }
+
+int vlr_ctx_create(int device, vlr_ctx **out) {
+    if (!out) return VLR_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || device < 0 || device >= n) return VLR_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return VLR_ERR_CUDA;
+    vlr_ctx *ctx = new vlr_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return VLR_ERR_CUDA; }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return VLR_ERR_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    // base-quality LUT, computed the way the reference does (bases.rs:23-48):
+    // ln eps = q * (-ln10/10); ln(1-eps) = ln_one_minus_exp(ln eps); mismatch = ln eps + ln .3333
+    std::vector<double> lut(256 * vlr::kQlutStride);
+    const double f = -0.23025850929940456;
+    for (int q = 0; q < 256; ++q) {
+        double ln_eps = (double)q * f;
+        double ln_call = ln_eps < -0.693 ? log1p(-exp(ln_eps)) : log(-expm1(ln_eps));
+        lut[q * 4 + 0] = exp(ln_eps);
+        lut[q * 4 + 1] = exp(ln_call);
+        lut[q * 4 + 2] = exp(ln_eps + log(0.3333));
+        lut[q * 4 + 3] = ln_call;
+    }
+    if (cudaMalloc(&ctx->d_qlut, lut.size() * sizeof(double)) != cudaSuccess ||
+        cudaMemcpy(ctx->d_qlut, lut.data(), lut.size() * sizeof(double), cudaMemcpyHostToDevice) !=
+            cudaSuccess) {
+        vlr_ctx_destroy(ctx);
+        return VLR_ERR_CUDA;
+    }
+    *out = ctx;
+    return VLR_OK;
+}
+
+void vlr_ctx_destroy(vlr_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto &b : ctx->dev_bufs) if (b.p) cudaFree(b.p);
+    for (auto &b : ctx->pin_bufs) if (b.p) cudaFreeHost(b.p);
+    if (ctx->d_qlut) cudaFree(ctx->d_qlut);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char *vlr_last_error(const vlr_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int vlr_ctx_set_stream(vlr_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return VLR_ERR_INVALID;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return VLR_OK;
+}
+
+int vlr_ctx_synchronize(vlr_ctx *ctx) {
+    if (!ctx) return VLR_ERR_INVALID;
+    VLR_CUDA(ctx, cudaSetDevice(ctx->device));
+    VLR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VLR_OK;
+}
+
+int64_t vlr_ctx_launch_count(const vlr_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,127 @@
+"""Synthetic workloads of SURVEY.md section 8(d) (fixed PCG64 seeds; shapes of BASELINE.json configs).
+
+Pure numpy input generation shared by tests/ and bench.py; nothing here computes a likelihood.
+"""
+import numpy as np
+
+SEED_C2 = 20261019
+SEED_C3 = 20261020
+SEED_C4 = 20261021
+SEED_C5 = 20261022
+
+_ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+
+def _quals(rng, shape, mean=32.0, sd=5.0, lo=2, hi=41):
+    return np.clip(np.rint(rng.normal(mean, sd, size=shape)), lo, hi).astype(np.uint8)
+
+
+def make_pairhmm_workload(n_sites, reads_per_site, seed=SEED_C3, read_len=150, hap_len=300,
+                          max_indel=30, indel_err=1e-4, qual_mean=32.0, qual_sd=5.0, qual_lo=2,
+                          qual_hi=41, sub_scale=1.0):
+    """Config C3 part 1: per site a ref and an alt haplotype window (alt = ref with one indel of
+    length U[1,max_indel] at the centre), reads of `read_len` sampled 50/50 from ref or alt at a
+    uniform offset with substitution errors at the base-quality rate and rare indel errors.
+    Every read is paired with both haplotypes of its site (2 pairs per read).
+
+    Returns dict(hap_bytes, hap_off, read_bases, read_quals, read_off, pair_hap, pair_read,
+    cells) in the CSR layout of include/vlr_gpu.h.
+    """
+    rng = np.random.Generator(np.random.PCG64(seed))
+    pad = max_indel + 8
+    contig_len = hap_len + 2 * pad
+    contigs = _ACGT[rng.integers(0, 4, size=(n_sites, contig_len))]
+    centre = pad + hap_len // 2
+    ind_len = rng.integers(1, max_indel + 1, size=n_sites)
+    is_ins = rng.random(n_sites) < 0.5
+    ins_seq = _ACGT[rng.integers(0, 4, size=(n_sites, max_indel))]
+    haps = np.empty((n_sites, 2, hap_len), dtype=np.uint8)
+    haps[:, 0, :] = contigs[:, pad:pad + hap_len]
+    half = hap_len // 2
+    for s in range(n_sites):
+        L = int(ind_len[s])
+        c = contigs[s]
+        if is_ins[s]:
+            alt = np.concatenate([c[pad:centre], ins_seq[s, :L], c[centre:centre + (hap_len - half - L)]])
+        else:
+            alt = np.concatenate([c[pad:centre], c[centre + L:centre + L + (hap_len - half)]])
+        haps[s, 1, :] = alt[:hap_len]
+    n_reads = n_sites * reads_per_site
+    site_of = np.repeat(np.arange(n_sites), reads_per_site)
+    from_alt = rng.random(n_reads) < 0.5
+    offs = rng.integers(0, hap_len - read_len + 1, size=n_reads)
+    idx = offs[:, None] + np.arange(read_len)[None, :]
+    reads = haps[site_of, from_alt.astype(np.int64)][np.arange(n_reads)[:, None], idx]
+    quals = _quals(rng, (n_reads, read_len), qual_mean, qual_sd, qual_lo, qual_hi)
+    eps = np.power(10.0, -quals.astype(np.float64) / 10.0) * sub_scale
+    sub = rng.random((n_reads, read_len)) < eps
+    shift = rng.integers(1, 4, size=(n_reads, read_len))
+    code = np.zeros(256, dtype=np.int64)
+    code[_ACGT] = np.arange(4)
+    reads = np.where(sub, _ACGT[(code[reads] + shift) % 4], reads).astype(np.uint8)
+    # rare indel errors: delete or duplicate one base, keep the length by shifting in a random base
+    n_err = rng.binomial(n_reads * read_len, indel_err)
+    for _ in range(int(n_err)):
+        r = int(rng.integers(0, n_reads))
+        p = int(rng.integers(1, read_len - 1))
+        if rng.random() < 0.5:
+            reads[r, p:-1] = reads[r, p + 1:]
+            reads[r, -1] = _ACGT[rng.integers(0, 4)]
+        else:
+            reads[r, p + 1:] = reads[r, p:-1].copy()
+    hap_bytes = haps.reshape(-1)
+    hap_off = np.arange(0, (2 * n_sites + 1) * hap_len, hap_len, dtype=np.int64)
+    read_off = np.arange(0, (n_reads + 1) * read_len, read_len, dtype=np.int64)
+    pair_read = np.repeat(np.arange(n_reads, dtype=np.int32), 2)
+    pair_hap = (2 * site_of[:, None] + np.arange(2)[None, :]).reshape(-1).astype(np.int32)
+    return dict(hap_bytes=np.ascontiguousarray(hap_bytes), hap_off=hap_off,
+                read_bases=np.ascontiguousarray(reads.reshape(-1)),
+                read_quals=np.ascontiguousarray(quals.reshape(-1)), read_off=read_off,
+                pair_hap=pair_hap, pair_read=pair_read, from_alt=from_alt, site_of=site_of,
+                cells=int(len(pair_hap)) * read_len * hap_len)
+
+
+def make_ragged_pairs(n_pairs, seed, min_ly=1, max_ly=256, min_lx=1, max_lx=700, lower_frac=0.05,
+                      related_frac=0.7, qual_lo=0, qual_hi=60):
+    """Ragged (read, haplotype) pairs for edge-case parity: random lengths, some reads derived from
+    their haplotype with edits, lower-case and N bases, quality 0 .. 60."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    haps, reads, quals = [], [], []
+    alphabet = np.frombuffer(b"ACGTN", dtype=np.uint8)
+    for _ in range(n_pairs):
+        lx = int(rng.integers(min_lx, max_lx + 1))
+        ly = int(rng.integers(min_ly, max_ly + 1))
+        hap = alphabet[rng.choice(5, size=lx, p=[0.245, 0.245, 0.245, 0.245, 0.02])]
+        if rng.random() < related_frac and lx >= 2:
+            start = int(rng.integers(0, max(1, lx - 1)))
+            seg = hap[start:start + ly]
+            read = list(seg)
+            # a few edits
+            for _e in range(int(rng.integers(0, 6))):
+                if not read:
+                    break
+                p = int(rng.integers(0, len(read)))
+                k = rng.random()
+                if k < 0.5:
+                    read[p] = int(alphabet[rng.integers(0, 4)])
+                elif k < 0.75:
+                    del read[p]
+                else:
+                    read.insert(p, int(alphabet[rng.integers(0, 4)]))
+            while len(read) < ly:
+                read.append(int(alphabet[rng.integers(0, 4)]))
+            read = np.array(read[:ly], dtype=np.uint8)
+        else:
+            read = alphabet[rng.integers(0, 4, size=ly)]
+        if rng.random() < lower_frac:
+            hap = np.where(hap < 96, hap + 32, hap).astype(np.uint8)  # lower-case haplotype
+        q = rng.integers(qual_lo, qual_hi + 1, size=ly).astype(np.uint8)
+        haps.append(hap)
+        reads.append(read)
+        quals.append(q)
+    hap_off = np.zeros(n_pairs + 1, dtype=np.int64)
+    hap_off[1:] = np.cumsum([len(h) for h in haps])
+    read_off = np.zeros(n_pairs + 1, dtype=np.int64)
+    read_off[1:] = np.cumsum([len(r) for r in reads])
+    return dict(hap_bytes=np.concatenate(haps), hap_off=hap_off, read_bases=np.concatenate(reads),
+                read_quals=np.concatenate(quals), read_off=read_off)

@@ -1,0 +1,116 @@
+"""GPU parity of K1 (pair-HMM forward) against the CPU oracle, through the C ABI
+(vlr_pairhmm_batch).  Tolerance: |delta| <= 1e-6 in natural-log space (BASELINE.json north_star).
+"""
+import numpy as np
+import pytest
+
+import libprosic_b200 as P
+from libprosic_b200 import synth
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-6
+
+
+def _gap_sets():
+    return [P.GapParams(),  # CLI defaults 2.8e-6 / 5.1e-6 / 0 / 0 (cli.rs:207-230)
+            P.GapParams(0.02, 0.03, 0.3, 0.3),   # C4-style raised rates, symmetric extension
+            P.GapParams(1e-3, 2e-3, 0.1, 0.1)]
+
+
+def _compare(got, want, tol=TOL):
+    got, want = np.asarray(got), np.asarray(want)
+    both_inf = np.isneginf(got) & np.isneginf(want)
+    diff = np.abs(np.where(both_inf, 0.0, got - want))
+    assert not np.isnan(got).any(), "NaN from the GPU path"
+    assert np.nanmax(diff) <= tol, "max |delta| = %g at %d (got %r want %r)" % (
+        np.nanmax(diff), int(np.nanargmax(diff)), got[np.nanargmax(diff)], want[np.nanargmax(diff)])
+
+
+@pytest.mark.parametrize("flags", [P.HMM_DEFAULT, 0])
+def test_c3_shape_unbanded(ctx, oracle, flags):
+    w = synth.make_pairhmm_workload(n_sites=6, reads_per_site=16, seed=synth.SEED_C3)
+    gap = P.GapParams()
+    got = ctx.pairhmm_batch(w["hap_bytes"], w["hap_off"], w["read_bases"], w["read_quals"],
+                            w["read_off"], gap, w["pair_hap"], w["pair_read"], flags=flags)
+    want = np.array([oracle.pairhmm_prob_related(
+        w["hap_bytes"][w["hap_off"][h]:w["hap_off"][h + 1]],
+        w["read_bases"][w["read_off"][r]:w["read_off"][r + 1]],
+        w["read_quals"][w["read_off"][r]:w["read_off"][r + 1]], gap.as_ln_array(), -1, flags)
+        for h, r in zip(w["pair_hap"], w["pair_read"])])
+    _compare(got, want)
+
+
+@pytest.mark.parametrize("gi", [0, 1, 2])
+def test_ragged_unbanded(ctx, oracle, gi):
+    gap = _gap_sets()[gi]
+    w = synth.make_ragged_pairs(300, seed=100 + gi, max_ly=256, max_lx=600)
+    got = ctx.pairhmm_batch(w["hap_bytes"], w["hap_off"], w["read_bases"], w["read_quals"],
+                            w["read_off"], gap)
+    want = oracle.pairhmm_batch(w["hap_bytes"], w["hap_off"], w["read_bases"], w["read_quals"],
+                                w["read_off"], gap.as_ln_array())
+    _compare(got, want)
+
+
+@pytest.mark.parametrize("gi", [0, 1])
+def test_ragged_banded(ctx, oracle, gi):
+    """Band k = dist + 2 as the reference runs it (edit_distance.rs:180-182)."""
+    gap = _gap_sets()[gi]
+    w = synth.make_ragged_pairs(300, seed=200 + gi, max_ly=128, max_lx=330)
+    n = len(w["hap_off"]) - 1
+    med = np.empty(n, dtype=np.int32)
+    for k in range(n):
+        hit = oracle.best_hit(w["hap_bytes"][w["hap_off"][k]:w["hap_off"][k + 1]],
+                              w["read_bases"][w["read_off"][k]:w["read_off"][k + 1]])
+        med[k] = hit["dist"] + 2
+    med[::17] = -1  # a few unbanded pairs inside a banded batch
+    got = ctx.pairhmm_batch(w["hap_bytes"], w["hap_off"], w["read_bases"], w["read_quals"],
+                            w["read_off"], gap, max_edit_dist=med)
+    want = oracle.pairhmm_batch(w["hap_bytes"], w["hap_off"], w["read_bases"], w["read_quals"],
+                                w["read_off"], gap.as_ln_array(), med)
+    _compare(got, want)
+
+
+def test_underflow_goes_through_log_space_pass(ctx, oracle):
+    """Unrelated read/haplotype with Q60 bases: P ~ 1e-900, outside scaled fp64 range."""
+    rng = np.random.default_rng(5)
+    n = 8
+    hap = np.frombuffer(b"A" * 300, dtype=np.uint8)
+    haps = np.tile(hap, n)
+    reads = np.tile(np.frombuffer(b"C" * 150, dtype=np.uint8), n)
+    quals = np.full(n * 150, 60, dtype=np.uint8)
+    quals[:150] = rng.integers(50, 61, 150)
+    hap_off = np.arange(0, (n + 1) * 300, 300, dtype=np.int64)
+    read_off = np.arange(0, (n + 1) * 150, 150, dtype=np.int64)
+    gap = P.GapParams()
+    got = ctx.pairhmm_batch(haps, hap_off, reads, quals, read_off, gap)
+    want = oracle.pairhmm_batch(haps, hap_off, reads, quals, read_off, gap.as_ln_array())
+    assert (want < -1500).all()
+    _compare(got, want, tol=1e-6 * 10)  # |ln p| ~ 2000: allow relative 5e-9
+
+
+def test_edge_cases(ctx, oracle):
+    gap = P.GapParams()
+    # single-base read, single-base haplotype, Q0 base (ln(1-eps) = -inf), read longer than hap
+    cases = [(b"A", b"A", [30]), (b"A", b"C", [30]), (b"ACGT", b"G", [0]), (b"AC", b"ACGTACGT", [20] * 8),
+             (b"acgtacgtac", b"ACGTACGTAC", [40] * 10), (b"NNNN", b"NN", [10, 10])]
+    haps = np.frombuffer(b"".join(c[0] for c in cases), dtype=np.uint8)
+    reads = np.frombuffer(b"".join(c[1] for c in cases), dtype=np.uint8)
+    quals = np.array(sum((c[2] for c in cases), []), dtype=np.uint8)
+    hap_off = np.concatenate([[0], np.cumsum([len(c[0]) for c in cases])]).astype(np.int64)
+    read_off = np.concatenate([[0], np.cumsum([len(c[1]) for c in cases])]).astype(np.int64)
+    got = ctx.pairhmm_batch(haps, hap_off, reads, quals, read_off, gap)
+    want = oracle.pairhmm_batch(haps, hap_off, reads, quals, read_off, gap.as_ln_array())
+    _compare(got, want)
+
+
+def test_errors_are_loud(ctx):
+    gap = P.GapParams()
+    hap = np.frombuffer(b"ACGT" * 100, dtype=np.uint8)
+    read = np.frombuffer(b"A" * 300, dtype=np.uint8)
+    with pytest.raises(P.VlrError):
+        ctx.pairhmm_batch(hap, np.array([0, 400]), read, np.full(300, 30, np.uint8),
+                          np.array([0, 300]), gap)  # 300 rows > 256: unsupported for now
+    with pytest.raises(P.VlrError):
+        ctx.pairhmm_batch(hap, np.array([0, 400]), read[:10], np.full(10, 30, np.uint8),
+                          np.array([0, 10]), gap, pair_hap=np.array([3], np.int32),
+                          pair_read=np.array([0], np.int32))
