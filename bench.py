@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the per-site likelihood hot path on B200.
+
+Metric (BASELINE.json): pair-HMM GCUPS and candidate sites/sec.  The JSON line's `value` is the
+pair-HMM throughput in GCUPS on the config-3 shape (150 bp reads x 2 haplotype windows of 300 bp,
+unbanded, Sum_pairs len_x*len_y / time); the part-2 throughput (AF-grid
+likelihood + event integration, sites/s) rides in the same line under "sites_per_sec".
+
+    python bench.py --gpus N --steps K --warmup W            # our arm
+    python bench.py --impl reference --gpus N --steps K ...   # CPU arm: the oracle port on all host cores
+
+A "step" is one pass of the hot path over one synthetic batch (inputs larger than L2, so no flush
+is needed between steps).  Timing: CUDA events on the launching stream, barrier + synchronize on
+both sides, max over ranks.  One process per GPU (torchrun); ranks own disjoint shards (region
+sharding, no collective on the data path) -> scaling "weak".
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOPS_PER_CELL = 14.0  # algorithmic fp64 flops per pair-HMM cell update
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sites", type=int, default=7168, help="candidate sites per step and GPU")
+    ap.add_argument("--reads-per-site", type=int, default=140)
+    ap.add_argument("--exact-sum", action="store_true",
+                    help="time the exact M-state sum instead of bio's ln_sum3_exp_approx")
+    ap.add_argument("--cpu-sample-pairs", type=int, default=0, help="0 = auto (about 15 s)")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi sampler running during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names)
+                   if any(len(r) >= 7 and r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def gen_workload(args, rank):
+    from libprosic_b200 import synth
+    return synth.make_pairhmm_workload(args.sites, args.reads_per_site, seed=synth.SEED_C3 + rank)
+
+
+def cpu_sample(w, n_pairs, threads, flags):
+    """Time the oracle port on the first n_pairs pairs of the workload; returns (GCUPS, seconds)."""
+    import oracle as O
+    from concurrent.futures import ThreadPoolExecutor
+    from libprosic_b200 import GapParams
+    O.lib()
+    gap = GapParams().as_ln_array()
+    hb, ho, rb, rq, ro = (w["hap_bytes"], w["hap_off"], w["read_bases"], w["read_quals"],
+                          w["read_off"])
+    ph, pr = w["pair_hap"][:n_pairs], w["pair_read"][:n_pairs]
+
+    def run(k):
+        h, r = int(ph[k]), int(pr[k])
+        return O.pairhmm_prob_related(hb[ho[h]:ho[h + 1]], rb[ro[r]:ro[r + 1]], rq[ro[r]:ro[r + 1]],
+                                      gap, -1, flags)
+
+    t0 = time.perf_counter()
+    if threads <= 1:
+        for k in range(n_pairs):
+            run(k)
+    else:
+        with ThreadPoolExecutor(max_workers=threads) as ex:  # ctypes releases the GIL
+            list(ex.map(run, range(n_pairs), chunksize=8))
+    dt = time.perf_counter() - t0
+    cells = sum(int(ho[int(h) + 1] - ho[int(h)]) * int(ro[int(r) + 1] - ro[int(r)])
+                for h, r in zip(ph, pr))
+    return cells / dt / 1e9, dt, cells
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle restatement (the Rust reference cannot be built in this image) on all
+    host cores, bounded sample per step."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    flags = 0 if args.exact_sum else 1
+    small = argparse.Namespace(**vars(args))
+    small.sites, small.reads_per_site = 8, 140
+    w = gen_workload(small, 0)
+    # calibrate the per-step sample to ~3 s on all cores
+    g, dt, _ = cpu_sample(w, 64, cores, flags)
+    per_step = int(max(64, min(len(w["pair_hap"]), 64 * 3.0 / max(dt, 1e-3))))
+    for _ in range(max(args.warmup, 0) and 1):
+        cpu_sample(w, per_step, cores, flags)
+    tot_cells, tot_t = 0, 0.0
+    for _ in range(args.steps):
+        g, dt, cells = cpu_sample(w, per_step, cores, flags)
+        tot_cells += cells
+        tot_t += dt
+    val = tot_cells / tot_t / 1e9
+    line = {"impl": "reference", "metric": "pairhmm_gcups", "value": val, "unit": "GCUPS",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C3 pair-HMM: 150bp reads x 2 x 300bp haplotype windows, unbanded",
+                       "sample_pairs_per_step": per_step,
+                       "m_state_sum": "exact" if args.exact_sum else "ln_sum3_exp_approx"},
+            "cpu_baseline": {"value": val, "unit": "GCUPS", "cores": cores, "kind": "port",
+                             "sample": "%d pairs (150x300 cells each) per step on %d threads; oracle "
+                                       "restatement, not the Rust binary" % (per_step, cores)},
+            "e2e": {"value": val, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    import torch
+    import torch.distributed as dist
+    import libprosic_b200 as P
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = P.Context(local_rank)
+    # a real (non-default) stream: the context enqueues on it and the CUDA events are recorded on it
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    gap = P.GapParams()
+    flags = 0 if args.exact_sum else P.HMM_DEFAULT
+
+    # ---- synthetic shard of this rank (config C3 shape), pinned on the host for the e2e path
+    w = gen_workload(args, rank)
+    n_pairs = len(w["pair_hap"])
+    n_haps, n_reads = len(w["hap_off"]) - 1, len(w["read_off"]) - 1
+    cells = w["cells"]
+    host = {k: torch.from_numpy(w[k]).pin_memory() for k in
+            ("hap_bytes", "hap_off", "read_bases", "read_quals", "read_off", "pair_hap", "pair_read")}
+    h_out = torch.empty(n_pairs, dtype=torch.float64).pin_memory()
+    # device-resident copies for the kernel-only number
+    d = {k: v.to(dev) for k, v in host.items()}
+    d_hap = torch.zeros(d["hap_bytes"].numel() + 64, dtype=torch.uint8, device=dev)
+    d_hap[:d["hap_bytes"].numel()] = d["hap_bytes"]
+    ws_bytes = ctx.pairhmm_workspace_bytes(n_pairs)
+    d_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(n_pairs, dtype=torch.float64, device=dev)
+
+    def step_dev(fl=None):
+        ctx.pairhmm_batch_dev(n_pairs, d_hap.data_ptr(), d["hap_off"].data_ptr(), n_haps,
+                              d["read_bases"].data_ptr(), d["read_quals"].data_ptr(),
+                              d["read_off"].data_ptr(), n_reads, d["pair_hap"].data_ptr(),
+                              d["pair_read"].data_ptr(), 0, gap, flags if fl is None else fl,
+                              d_ws.data_ptr(), ws_bytes, d_out.data_ptr())
+
+    def step_e2e():
+        ctx.pairhmm_batch(host["hap_bytes"].numpy(), host["hap_off"].numpy(),
+                          host["read_bases"].numpy(), host["read_quals"].numpy(),
+                          host["read_off"].numpy(), gap, host["pair_hap"].numpy(),
+                          host["pair_read"].numpy(), flags=flags, out=h_out.numpy())
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        e1.synchronize()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launch_count()
+    ms = timed(step_dev, args.steps)
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    # the other M-state-sum mode, for the record (same inputs, same timing discipline)
+    other = P.HMM_DEFAULT if args.exact_sum else 0
+    for _ in range(2):
+        step_dev(other)
+    ms_other = timed(lambda: step_dev(other), args.steps)
+    step_dev()  # leave the headline mode's results in d_out for the parity spot check
+
+    # ---- end-to-end through the host-buffer C-ABI call (H2D + kernels + D2H inside the timed region)
+    step_e2e()
+    t0 = time.perf_counter()
+    ms_e2e_ev = timed(step_e2e, args.steps)
+    wall_e2e = (time.perf_counter() - t0) * 1e3
+    ms_e2e = max(ms_e2e_ev, 0.0)
+    if world > 1:
+        t = torch.tensor([wall_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall_e2e = float(t.item())
+    # the host call is synchronous: its cost is wall time, CUDA events on the stream agree to the ms
+    ms_e2e = max(ms_e2e, wall_e2e) if ms_e2e < 0.5 * wall_e2e else ms_e2e
+
+    # ---- parity spot check against the oracle on a few pairs (outside the timed regions)
+    parity = None
+    if rank == 0:
+        import oracle as O
+        got = d_out[:64].cpu().numpy()
+        want = np.array([O.pairhmm_prob_related(
+            w["hap_bytes"][w["hap_off"][h]:w["hap_off"][h + 1]],
+            w["read_bases"][w["read_off"][r]:w["read_off"][r + 1]],
+            w["read_quals"][w["read_off"][r]:w["read_off"][r + 1]], gap.as_ln_array(), -1, flags)
+            for h, r in zip(w["pair_hap"][:64], w["pair_read"][:64])])
+        parity = float(np.max(np.abs(got - want)))
+        same_e2e = bool(np.array_equal(h_out.numpy(), d_out.cpu().numpy()))
+
+    total_cells = cells * world
+    gcups = total_cells * args.steps / (ms * 1e-3) / 1e9
+    gcups_e2e = total_cells * args.steps / (ms_e2e * 1e-3) / 1e9
+    if rank == 0:
+        peak_tf = ctx.measure_fp64_peak()
+        ach_tf = cells * args.steps * FLOPS_PER_CELL / (ms * 1e-3) / 1e12  # this rank's GPU
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        in_bytes = sum(int(host[k].numel() * host[k].element_size()) for k in host)
+        cores = os.cpu_count() or 1
+        # bounded CPU sample of the same workload, one thread (the reference is single-threaded)
+        n_cpu = args.cpu_sample_pairs or 256
+        g1, dt1, _ = cpu_sample(w, n_cpu, 1, flags)
+        line = {
+            "metric": "pairhmm_gcups", "value": gcups, "unit": "GCUPS", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "C3 pair-HMM: 150bp reads x 2 x 300bp haplotype windows, unbanded",
+                       "sites_per_gpu": args.sites, "reads_per_site": args.reads_per_site,
+                       "pairs_per_gpu": n_pairs, "cells_per_step_per_gpu": cells,
+                       "m_state_sum": "exact" if args.exact_sum else "ln_sum3_exp_approx (reference)",
+                       "gap_params": "cli defaults 2.8e-6/5.1e-6/0/0", "parallelism": "region-sharded x%d" % world,
+                       "l2": "inputs %.0f MB per step > 126 MB L2, no flush" % (in_bytes / 1e6)},
+            "e2e": {"value": gcups_e2e, "unit": "GCUPS", "h2d_bytes_per_step": in_bytes,
+                    "d2h_bytes_per_step": n_pairs * 8, "ms_per_step": ms_e2e / args.steps,
+                    "identical_to_device_path": same_e2e},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": ach_tf / peak_tf if peak_tf else None, "traffic": None,
+                         "peak_source": "vlr_measure_fp64_peak (DFMA chains, measured live); "
+                                        "MEASURED_PEAKS.json has no fp64 entry",
+                         "flops_per_cell": FLOPS_PER_CELL,
+                         "hbm": {"achieved": in_bytes * args.steps / (ms * 1e-3) / 1e9,
+                                 "peak": hbm_peak, "unit": "GB/s"}},
+            "cpu_baseline": {"value": g1, "unit": "GCUPS", "cores": 1, "kind": "port",
+                             "sample": "%d pairs of this workload, 1 thread of %d host cores, %.1f s; "
+                                       "oracle restatement (C), not the Rust binary" % (n_cpu, cores, dt1)},
+            "other_mode": {"m_state_sum": "ln_sum3_exp_approx" if args.exact_sum else "exact",
+                           "value": total_cells * args.steps / (ms_other * 1e-3) / 1e9, "unit": "GCUPS"},
+            "parity_max_abs_ln": parity,
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

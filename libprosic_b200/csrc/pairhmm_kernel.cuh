@@ -1,0 +1,480 @@
+// pairhmm_kernel.cuh -- K1: anti-diagonal wavefront pair-HMM forward kernel for sm_100a.
+//
+// Replaces bio::stats::pairhmm::PairHMM::prob_related as called from
+// PairHMMRealigner::calculate_prob_allele (reference src/variants/evidence/realignment/mod.rs:430-444)
+// with the emission model of realignment/pairhmm.rs:123-211 and the semiglobal start/end rules of
+// pairhmm.rs:103-121.  Recurrence (x = haplotype column i, y = read row j):
+//   M[i][j] = e_xy(i,j) * sum3( t_mm*M[i-1][j-1], t_xm*X[i-1][j-1], t_ym*Y[i-1][j-1] )
+//   X[i][j] =             t_gy*M[i-1][j] + t_gye*X[i-1][j]            (hap-only state, emit 1)
+//   Y[i][j] = eps_j *   ( t_gx*M[i][j-1] + t_gxe*Y[i][j-1] )          (read-only state)
+//   M[i][0] = 1 for every column (free start), result = sum_i (M+X+Y)[i][len_y] (free end), capped at 1.
+//
+// Mapping: one warp per (read, haplotype) pair.  Lane l owns R consecutive read rows
+// [l*R, l*R+R); at step t it computes column i = t - l for its rows, so the warp sweeps
+// anti-diagonals.  The bottom row of lane l-1 travels to lane l by __shfl_up_sync (M, X, Y, and the
+// band's min-edit-distance); the haplotype window is staged into a per-warp shared-memory ring by
+// 1-D TMA bulk copies (cp.async.bulk + mbarrier), read bases/qualities become per-row register
+// constants from a 256-entry LUT.  Arithmetic is fp64 in SCALED LINEAR space (start mass 2^960,
+// no per-cell transcendental, one log per pair); pairs whose result leaves the representable
+// range are re-run by the same kernel instantiated with log-space arithmetic (still on the GPU).
+#pragma once
+#include <math.h>
+
+#include "common.cuh"
+
+namespace vlr {
+
+constexpr int kWarps = 4;          // warps per CTA; each warp owns one pair at a time
+constexpr int kChunk = 256;        // haplotype bytes per TMA bulk copy
+constexpr int kRing = 2 * kChunk;  // per-warp ring buffer (two chunks)
+constexpr int kMedMax = 1 << 20;   // "usize::MAX" of the band bookkeeping
+constexpr int kNumClasses = 8;     // R = 1,2,3,4,5,6,8 and "too long"
+
+// 2^960 and its log; linear-space values are scaled by this (see header comment)
+#define VLR_SCALE 9.7453140114e288
+__device__ __constant__ double c_scale_ln = 665.4212933375474;  // 960 * ln 2
+
+struct HmmConsts {  // linear or ln, depending on the arithmetic policy
+    double t_mm, t_xm, t_ym, t_gy, t_gye, t_gx, t_gxe;
+};
+
+struct HmmArgs {
+    const uint8_t *hap;
+    const int64_t *hap_off;
+    const uint8_t *rbase;
+    const uint8_t *rqual;
+    const int64_t *read_off;
+    const int32_t *pair_hap;
+    const int32_t *pair_read;
+    const int32_t *med;
+    const int32_t *list;      // pair ids handled by this launch (device)
+    const int32_t *list_off;  // device offset into `list` (nullable)
+    const int32_t *count;  // number of entries of `list` (device)
+    int32_t *cursor;       // dynamic work counter (device, zero at launch)
+    int32_t *fb_list;      // pairs that need the log-space pass
+    int32_t *fb_count;
+    double *out;
+    const double *qlut;
+    HmmConsts lin, ln;
+};
+
+// ---------------------------------------------------------------- PTX helpers (TMA + mbarrier)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes,
+                                            uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "VLR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra VLR_DONE;\n"
+        "bra VLR_WAIT;\n"
+        "VLR_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// ---------------------------------------------------------------- arithmetic policies
+__device__ __forceinline__ double ln_add_exp_d(double a, double b) {
+    double p0 = fmax(a, b), p1 = fmin(a, b);
+    if (p0 == -INFINITY) return -INFINITY;
+    if (p1 == -INFINITY) return p0;
+    return p0 + log1p(exp(p1 - p0));
+}
+
+// EXT = false is the specialisation for gap-extension probabilities of exactly 0 (the CLI
+// default, cli.rs:219-230): then t_xm = t_ym = 1, t_gye = t_gxe = 0 and three products vanish.
+struct Lin {  // scaled linear space
+    static constexpr bool kLog = false;
+    __device__ static double zero() { return 0.0; }
+    __device__ static double one() { return VLR_SCALE; }
+    __device__ static double mul(double a, double b) { return a * b; }
+    __device__ static double add(double a, double b) { return a + b; }
+    // a*b + c*d   (EXT = false: c*d == 0)
+    template <bool EXT>
+    __device__ static double dot2(double a, double b, double c, double d) {
+        return EXT ? fma(a, b, c * d) : a * b;
+    }
+    // sum over the three predecessors of the M state
+    template <bool APPROX, bool EXT>
+    __device__ static double sum3(const HmmConsts &k, double dM, double dX, double dY) {
+        if (APPROX) {
+            // bio pairhmm ln_sum3_exp_approx: return the maximum alone if the second largest term is
+            // more than e^-10 below it, else the exact sum.  "second < max*e^-10" <=> exactly one of
+            // the three terms reaches max*e^-10.
+            const double a = k.t_mm * dM;
+            const double b = EXT ? k.t_xm * dX : dX;
+            const double c = EXT ? k.t_ym * dY : dY;
+            const double hi = a > b ? a : b;
+            const double mx = hi > c ? hi : c;
+            const double thr = mx * 4.5399929762484854e-05;  // e^-10
+            const bool pa = a >= thr, pb = b >= thr, pc = c >= thr;
+            const bool two = (pa && pb) || (pc && (pa || pb));
+            return two ? (a + b + c) : mx;
+        }
+        if (EXT) return fma(k.t_ym, dY, fma(k.t_xm, dX, k.t_mm * dM));
+        return fma(k.t_mm, dM, dX + dY);
+    }
+};
+
+struct Log {  // natural-log space, the literal arithmetic of the reference
+    static constexpr bool kLog = true;
+    __device__ static double zero() { return -INFINITY; }
+    __device__ static double one() { return 0.0; }
+    __device__ static double mul(double a, double b) { return a + b; }
+    __device__ static double add(double a, double b) { return ln_add_exp_d(a, b); }
+    template <bool EXT>
+    __device__ static double dot2(double a, double b, double c, double d) {
+        return ln_add_exp_d(a + b, c + d);
+    }
+    template <bool APPROX, bool EXT>
+    __device__ static double sum3(const HmmConsts &k, double dM, double dX, double dY) {
+        double p0 = k.t_mm + dM, p1 = k.t_xm + dX, p2 = k.t_ym + dY, t;
+        if (p1 < p2) { t = p1; p1 = p2; p2 = t; }
+        if (p1 > p0) { t = p1; p1 = p0; p0 = t; }
+        if (p2 > p0) { t = p2; p2 = p0; p0 = t; }
+        const double second = fmax(p1, p2);
+        if (APPROX && (p0 - second > 10.0)) return p0;
+        if (p0 == -INFINITY) return -INFINITY;
+        double s = 0.0;
+        if (p1 != -INFINITY) s += exp(p1 - p0);
+        if (p2 != -INFINITY) s += exp(p2 - p0);
+        return p0 + log1p(s);
+    }
+};
+
+// ---------------------------------------------------------------- the kernel
+template <int R>
+struct Occ {
+    static constexpr int kMinBlocks = R <= 3 ? 5 : (R <= 4 ? 4 : (R <= 6 ? 3 : 2));
+};
+
+// Per-pair state that lives in registers across the sweep.
+template <int R>
+struct PairState {
+    double pm[R], pmm[R], cyo[R], cye[R];  // per-row emission / Y-transition constants
+    int rb[R];                             // read base per row (-1 = padding row)
+    double M[R], X[R], Y[R];               // previous column of my rows
+    int med[R];                            // band bookkeeping (min edit distance)
+    double bM, bX, bY, dM, dX, dY;         // bottom row of last column; diagonal inputs of row 0
+    int bMed, dMed;
+    double acc;
+};
+
+// Ring of haplotype bytes: two 256-byte slots filled by TMA; `pos` is the ring position
+// (column + misalignment shift).
+struct HapRing {
+    uint8_t *ring;
+    uint64_t *bar;
+    const uint8_t *hsrc;  // 16-byte aligned source
+    int lxs;              // window length + shift
+    int n_chunks;
+    uint32_t parity0, parity1;
+};
+
+// One anti-diagonal step (lane `lane` computes column t - lane).  LR >= 0: compile-time index of
+// the last read row inside lane `last_lane` (free-end accumulation); LR < 0: run-time `last_r`.
+template <int R, int LR, bool BANDED, bool APPROX, bool EXT, typename A>
+__device__ __forceinline__ void hmm_step(PairState<R> &s, const HmmConsts &c, const uint8_t *ring,
+                                         int t, int lane, int shift, int band, int last_r) {
+    const int i = t - lane;
+    int xb = ring[(i + shift) & (kRing - 1)];
+    if ((unsigned)(xb - 'a') < 26u) xb -= 32;  // to_ascii_uppercase (pairhmm.rs:190)
+
+    // receive the bottom row of the lane above (its column i)
+    double uM = __shfl_up_sync(0xffffffffu, s.bM, 1);
+    double uX = __shfl_up_sync(0xffffffffu, s.bX, 1);
+    double uY = __shfl_up_sync(0xffffffffu, s.bY, 1);
+    int uMed = kMedMax;
+    if (BANDED) uMed = __shfl_up_sync(0xffffffffu, s.bMed, 1);
+    if (lane == 0) {  // row 0 boundary: fm[curr][0] = 0, fx = fy = 0, med[curr][0] = MAX
+        uM = A::zero(); uX = A::zero(); uY = A::zero();
+        uMed = kMedMax;
+    }
+    double diagM = s.dM, diagX = s.dX, diagY = s.dY, upM = uM, upY = uY;
+    int diagMed = s.dMed, upMed = uMed;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const bool match = xb == s.rb[r];
+        const double e = match ? s.pm[r] : s.pmm[r];
+        double nM = A::mul(e, A::template sum3<APPROX, EXT>(c, diagM, diagX, diagY));
+        double nX = A::template dot2<EXT>(c.t_gy, s.M[r], c.t_gye, s.X[r]);
+        double nY = A::template dot2<EXT>(s.cyo[r], upM, s.cye[r], upY);
+        if (BANDED) {
+            // PairHMM band: skip the cell if all three predecessors exceed max_edit_dist
+            const int leftMed = s.med[r];
+            const bool skip = min(diagMed, min(upMed, leftMed)) > band;
+            int nMed = min(min(diagMed + (match ? 0 : 1), leftMed + 1), upMed + 1);
+            nMed = min(nMed, kMedMax);
+            if (skip) {
+                nM = A::zero(); nX = A::zero(); nY = A::zero();
+                nMed = kMedMax;
+            }
+            diagMed = leftMed;
+            s.med[r] = nMed;
+            upMed = nMed;
+        }
+        diagM = s.M[r]; diagX = s.X[r]; diagY = s.Y[r];
+        s.M[r] = nM; s.X[r] = nX; s.Y[r] = nY;
+        upM = nM; upY = nY;
+    }
+    // next column's diagonal inputs of my row 0 are this column's "up" values
+    s.dM = lane == 0 ? A::one() : uM;
+    s.dX = uX;
+    s.dY = uY;
+    s.bM = s.M[R - 1]; s.bX = s.X[R - 1]; s.bY = s.Y[R - 1];
+    if (BANDED) { s.dMed = lane == 0 ? 0 : uMed; s.bMed = s.med[R - 1]; }
+
+    // free end: add the last read row of this column (prob_cols).  Only the accumulator of lane
+    // `last_lane` is used; its column is always inside [0, len_x) or still all-zero (i < 0).
+    if (LR >= 0) {
+        s.acc = A::add(s.acc, A::add(A::add(s.M[LR >= 0 ? LR : 0], s.X[LR >= 0 ? LR : 0]),
+                                     s.Y[LR >= 0 ? LR : 0]));
+    } else {
+        double tsum = A::zero();
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (r == last_r) tsum = A::add(A::add(s.M[r], s.X[r]), s.Y[r]);
+        s.acc = A::add(s.acc, tsum);
+    }
+}
+
+// Sweep all columns of one pair.  Ring maintenance happens only at segment boundaries
+// (ring position == 0 or 32 mod 256), the inner loop is branch-free.
+template <int R, int LR, bool BANDED, bool APPROX, bool EXT, typename A>
+__device__ __forceinline__ void hmm_sweep(PairState<R> &s, const HmmConsts &c, HapRing &h, int T,
+                                          int lane, int shift, int band, int last_r) {
+    int t = 0;
+    while (t < T) {
+        const int ts = t + shift;
+        const int ph = ts & (kChunk - 1);
+        if (ph == 32) {  // every lane has left the previous chunk: refill its slot
+            const int cnext = (ts >> 8) + 1;
+            if (cnext < h.n_chunks && lane == 0) {
+                const int off = cnext * kChunk;
+                const uint32_t bytes = (uint32_t)min(kChunk, ((h.lxs - off) + 15) & ~15);
+                uint64_t *b = &h.bar[cnext & 1];
+                mbar_expect_tx(b, bytes);
+                tma_load_1d(h.ring + (cnext & 1) * kChunk, h.hsrc + off, bytes, b);
+            }
+        } else if (ph == 0 && t > 0) {  // lane 0 enters a new chunk: it must have landed
+            const int cidx = ts >> 8;
+            if (cidx < h.n_chunks) {
+                if (cidx & 1) { mbar_wait(&h.bar[1], h.parity1); h.parity1 ^= 1; }
+                else { mbar_wait(&h.bar[0], h.parity0); h.parity0 ^= 1; }
+            }
+        }
+        const int next_ts = ph < 32 ? (ts & ~(kChunk - 1)) + 32 : (ts & ~(kChunk - 1)) + kChunk;
+        const int t_end = min(T, next_ts - shift);
+#pragma unroll 2
+        for (; t < t_end; ++t)
+            hmm_step<R, LR, BANDED, APPROX, EXT, A>(s, c, h.ring, t, lane, shift, band, last_r);
+    }
+}
+
+template <int R, int LR, bool BANDED, bool APPROX, bool EXT, typename A>
+struct SweepDispatch {
+    __device__ __forceinline__ static void run(PairState<R> &s, const HmmConsts &c, HapRing &h,
+                                               int T, int lane, int shift, int band, int last_r) {
+        if (last_r == LR)
+            hmm_sweep<R, LR, BANDED, APPROX, EXT, A>(s, c, h, T, lane, shift, band, last_r);
+        else
+            SweepDispatch<R, LR - 1, BANDED, APPROX, EXT, A>::run(s, c, h, T, lane, shift, band,
+                                                                  last_r);
+    }
+};
+template <int R, bool BANDED, bool APPROX, bool EXT, typename A>
+struct SweepDispatch<R, -1, BANDED, APPROX, EXT, A> {
+    __device__ __forceinline__ static void run(PairState<R> &s, const HmmConsts &c, HapRing &h,
+                                               int T, int lane, int shift, int band, int last_r) {
+        hmm_sweep<R, -1, BANDED, APPROX, EXT, A>(s, c, h, T, lane, shift, band, last_r);
+    }
+};
+
+template <int R, bool BANDED, bool APPROX, bool EXT, typename A>
+__global__ void __launch_bounds__(kWarps * 32, Occ<R>::kMinBlocks) pairhmm_kernel(HmmArgs g) {
+    __shared__ __align__(128) uint8_t s_hap[kWarps][kRing];
+    __shared__ __align__(8) uint64_t s_bar[kWarps][2];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    HapRing h;
+    h.ring = s_hap[warp];
+    h.bar = s_bar[warp];
+    if (lane == 0) {
+        mbar_init(&h.bar[0], 1);
+        mbar_init(&h.bar[1], 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    h.parity0 = 0;
+    h.parity1 = 0;
+
+    const HmmConsts c = A::kLog ? g.ln : g.lin;
+    const int n = *g.count;
+    const int32_t *list = g.list ? g.list + (g.list_off ? *g.list_off : 0) : nullptr;
+
+    for (;;) {
+        int p = 0;
+        if (lane == 0) p = atomicAdd(g.cursor, 1);
+        p = __shfl_sync(0xffffffffu, p, 0);
+        if (p >= n) break;
+        const int pair = list ? list[p] : p;
+        const int64_t hidx = g.pair_hap ? (int64_t)g.pair_hap[pair] : (int64_t)pair;
+        const int64_t rd = g.pair_read ? (int64_t)g.pair_read[pair] : (int64_t)pair;
+        const int64_t ho = g.hap_off[hidx];
+        const int lx = (int)(g.hap_off[hidx + 1] - ho);
+        const int64_t ro = g.read_off[rd];
+        const int ly = (int)(g.read_off[rd + 1] - ro);
+        int band = kMedMax;
+        if (BANDED) {
+            const int k = g.med[pair];
+            band = k < 0 ? kMedMax : k;
+        }
+        if (lx <= 0 || ly <= 0) {
+            // len_x == 0: ln_sum_exp of no columns = ln 0; len_y == 0 cannot occur in the reference
+            if (lane == 0) g.out[pair] = -INFINITY;
+            continue;
+        }
+
+        // ---- stage the first haplotype chunk (TMA) while the row constants are loaded.
+        // Bulk copies need 16-byte aligned sources: copy from the aligned-down address and shift
+        // the ring index by the misalignment.
+        const int shift = (int)((uintptr_t)(g.hap + ho) & 15);
+        h.hsrc = g.hap + ho - shift;
+        h.lxs = lx + shift;
+        h.n_chunks = (h.lxs + kChunk - 1) / kChunk;
+        __syncwarp();  // every lane is done with the ring contents of the previous pair
+        if (lane == 0) {
+            const uint32_t bytes = (uint32_t)min(kChunk, (h.lxs + 15) & ~15);
+            mbar_expect_tx(&h.bar[0], bytes);
+            tma_load_1d(h.ring, h.hsrc, bytes, &h.bar[0]);
+        }
+
+        // ---- per-row constants (ReadEmission, pairhmm.rs:160-200)
+        PairState<R> s;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int j = lane * R + r;
+            if (j < ly) {
+                const int q = g.rqual[ro + j];
+                s.rb[r] = g.rbase[ro + j];
+                if (A::kLog) {
+                    const double ln_eps = (double)q * -0.23025850929940456;
+                    s.pm[r] = g.qlut[q * kQlutStride + 3];
+                    s.pmm[r] = ln_eps + -1.098712293668443;  // ln(0.3333), pairhmm.rs:21-23
+                    s.cyo[r] = ln_eps + c.t_gx;
+                    s.cye[r] = ln_eps + c.t_gxe;
+                } else {
+                    const double eps = g.qlut[q * kQlutStride + 0];
+                    s.pm[r] = g.qlut[q * kQlutStride + 1];
+                    s.pmm[r] = g.qlut[q * kQlutStride + 2];
+                    s.cyo[r] = eps * c.t_gx;
+                    s.cye[r] = eps * c.t_gxe;
+                }
+            } else {  // padding row below the read: stays at zero mass
+                s.rb[r] = -1;
+                s.pm[r] = s.pmm[r] = s.cyo[r] = s.cye[r] = A::zero();
+            }
+            s.M[r] = s.X[r] = s.Y[r] = A::zero();
+            s.med[r] = kMedMax;
+        }
+        const int last_lane = (ly - 1) / R;
+        const int last_r = (ly - 1) - last_lane * R;
+        s.bM = s.bX = s.bY = A::zero();
+        s.dM = lane == 0 ? A::one() : A::zero();
+        s.dX = s.dY = A::zero();
+        s.bMed = kMedMax;
+        s.dMed = lane == 0 ? 0 : kMedMax;
+        s.acc = A::zero();
+
+        mbar_wait(&h.bar[0], h.parity0);
+        h.parity0 ^= 1;
+
+        const int T = lx + last_lane;
+        // the log-space instantiation keeps one loop body (run-time last row); the linear one is
+        // specialised on the last-row index so that the free-end sum costs three adds per step
+        SweepDispatch<R, A::kLog ? -1 : R - 1, BANDED, APPROX, EXT, A>::run(s, c, h, T, lane, shift,
+                                                                            band, last_r);
+
+        // ---- result lives in lane last_lane
+        const double acc = __shfl_sync(0xffffffffu, s.acc, last_lane);
+        if (lane == 0) {
+            double res;
+            if (A::kLog) {
+                res = acc;
+            } else {
+                // representable? (2^-940 of scaled mass; also catches inf/nan)
+                if (!(acc >= 4.3e-283 && acc < 1.0e307)) {
+                    const int slot = atomicAdd(g.fb_count, 1);
+                    g.fb_list[slot] = pair;
+                    res = NAN;
+                } else {
+                    res = log(acc) - c_scale_ln;
+                }
+            }
+            if (res > 0.0) res = 0.0;  // "sum of paths can exceed 1" cap
+            g.out[pair] = res;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- launch table (pairhmm_inst_*.cu)
+// cls: 0..6 -> R = 1,2,3,4,5,6,8
+template <bool BANDED, bool APPROX>
+cudaError_t launch_pairhmm_lin(int cls, bool ext, const HmmArgs &a, int sm_count, cudaStream_t st);
+template <bool BANDED, bool APPROX>
+cudaError_t launch_pairhmm_log(const HmmArgs &a, int sm_count, cudaStream_t st);
+
+#define VLR_PAIRHMM_INSTANTIATE(BANDED, APPROX)                                                   \
+    template <int R, bool EXT>                                                                    \
+    static cudaError_t launch_r(const HmmArgs &a, int sm_count, cudaStream_t st) {                \
+        pairhmm_kernel<R, BANDED, APPROX, EXT, Lin>                                               \
+            <<<sm_count * Occ<R>::kMinBlocks, kWarps * 32, 0, st>>>(a);                           \
+        return cudaGetLastError();                                                                \
+    }                                                                                             \
+    template <>                                                                                   \
+    cudaError_t launch_pairhmm_lin<BANDED, APPROX>(int cls, bool ext, const HmmArgs &a,           \
+                                                   int sm_count, cudaStream_t st) {               \
+        switch (cls) {                                                                            \
+        case 0: return ext ? launch_r<1, true>(a, sm_count, st) : launch_r<1, false>(a, sm_count, st); \
+        case 1: return ext ? launch_r<2, true>(a, sm_count, st) : launch_r<2, false>(a, sm_count, st); \
+        case 2: return ext ? launch_r<3, true>(a, sm_count, st) : launch_r<3, false>(a, sm_count, st); \
+        case 3: return ext ? launch_r<4, true>(a, sm_count, st) : launch_r<4, false>(a, sm_count, st); \
+        case 4: return ext ? launch_r<5, true>(a, sm_count, st) : launch_r<5, false>(a, sm_count, st); \
+        case 5: return ext ? launch_r<6, true>(a, sm_count, st) : launch_r<6, false>(a, sm_count, st); \
+        case 6: return ext ? launch_r<8, true>(a, sm_count, st) : launch_r<8, false>(a, sm_count, st); \
+        default: return cudaErrorInvalidValue;                                                    \
+        }                                                                                         \
+    }                                                                                             \
+    template <>                                                                                   \
+    cudaError_t launch_pairhmm_log<BANDED, APPROX>(const HmmArgs &a, int sm_count,                \
+                                                   cudaStream_t st) {                             \
+        pairhmm_kernel<8, BANDED, APPROX, true, Log>                                              \
+            <<<sm_count * Occ<8>::kMinBlocks, kWarps * 32, 0, st>>>(a);                           \
+        return cudaGetLastError();                                                                \
+    }
+
+}  // namespace vlr
