@@ -117,3 +117,106 @@ class Context:
             self.h, n_pairs, vp(d_hap), vp(d_hap_off), n_haps, vp(d_rb), vp(d_rq), vp(d_read_off),
             n_reads, vp(d_pair_hap or 0), vp(d_pair_read or 0), vp(d_med or 0), C.byref(gap.c),
             int(flags), vp(d_ws), ws_bytes, vp(d_out)))
+
+    # ---------------------------------------------------------------- likelihood + posterior
+    @staticmethod
+    def _obs_columns(cols, cat, keep):
+        from ._ffi import ObsColumns
+        names = ("prob_mapping", "prob_mismapping", "prob_alt", "prob_ref", "prob_missed_allele",
+                 "prob_sample_alt", "prob_double_overlap", "prob_single_overlap", "prob_hit_base")
+        arrs = [np.ascontiguousarray(cols[n], dtype=np.float64) for n in names]
+        catc = np.ascontiguousarray(cat, dtype=np.uint16)
+        keep.extend(arrs + [catc])
+        return ObsColumns(*[a.ctypes.data for a in arrs], catc.ctypes.data)
+
+    @staticmethod
+    def build_model(scn, keep):
+        """dict scenario (libprosic_b200.scenario) -> ctypes vlr_model."""
+        from ._ffi import Biases, Event, Model, Node
+        nodes = (Node * max(1, len(scn["nodes"])))()
+        children, vafs = [], []
+        for k, nd in enumerate(scn["nodes"]):
+            nodes[k] = Node(nd["kind"], nd.get("sample", 0), len(children), len(nd["children"]),
+                            len(vafs), len(nd["vafs"]))
+            children.extend(nd["children"])
+            vafs.extend(nd["vafs"])
+        roots, flat = [], []
+        events = (Event * len(scn["events"]))()
+        for k, ev in enumerate(scn["events"]):
+            events[k] = Event(len(roots), len(ev["roots"]), len(flat), len(ev["biases"]))
+            roots.extend(ev["roots"])
+            flat.extend(ev["biases"])
+        biases = (Biases * max(1, len(flat)))()
+        for k, bi in enumerate(flat):
+            b = scn["biases"][bi]
+            biases[k] = Biases(b["strand"], b["orientation"], b["read_position"], b["softclip"],
+                               b["divindel"], 0, b["min_other_rate"])
+        res = np.asarray(scn["resolution"], np.int32)
+        cont = np.asarray(scn["contaminated"], np.int32)
+        by = np.asarray(scn["by"], np.int32)
+        pur = np.asarray(scn["purity"], np.float64)
+        ch = np.asarray(children if children else [0], np.int32)
+        vf = np.asarray(vafs if vafs else [0.0], np.float64)
+        rt = np.asarray(roots, np.int32)
+        keep.extend([nodes, events, biases, res, cont, by, pur, ch, vf, rt])
+        return Model(scn["n_samples"], len(scn["events"]), len(scn["nodes"]), len(flat),
+                     res.ctypes.data, cont.ctypes.data, by.ctypes.data, pur.ctypes.data,
+                     C.addressof(nodes), ch.ctypes.data, vf.ctypes.data, rt.ctypes.data,
+                     C.addressof(events), C.addressof(biases))
+
+    def posterior_batch(self, scn, cols, cat, obs_off):
+        """Model::compute for every site: returns dict(event_ln[n_sites, n_events], marginal,
+        map_af[n_sites, n_samples], map_bias)."""
+        keep = []
+        model = self.build_model(scn, keep)
+        oc = self._obs_columns(cols, cat, keep)
+        obs_off = np.ascontiguousarray(obs_off, dtype=np.int64)
+        ns, ne = scn["n_samples"], len(scn["events"])
+        n_sites = (len(obs_off) - 1) // ns
+        ev = np.empty((n_sites, ne), np.float64)
+        marg = np.empty(n_sites, np.float64)
+        maf = np.empty((n_sites, ns), np.float64)
+        mb = np.empty((n_sites, ns), np.int32)
+        self._check(self.lib.vlr_posterior_batch(self.h, n_sites, C.byref(model), C.byref(oc),
+                                                 _ptr(obs_off), _ptr(ev), _ptr(marg), _ptr(maf),
+                                                 _ptr(mb)))
+        return dict(event_ln=ev, marginal=marg, map_af=maf, map_bias=mb)
+
+    def posterior_batch_dev(self, scn, n_sites, d_cols, d_cat, d_obs_off, d_ev, d_marg, d_maf, d_mb,
+                            _cache={}):
+        """Device-pointer variant (ints).  d_cols: dict name -> device pointer."""
+        from ._ffi import ObsColumns
+        key = id(scn)
+        if key not in _cache:
+            keep = []
+            _cache[key] = (self.build_model(scn, keep), keep)
+        model = _cache[key][0]
+        names = ("prob_mapping", "prob_mismapping", "prob_alt", "prob_ref", "prob_missed_allele",
+                 "prob_sample_alt", "prob_double_overlap", "prob_single_overlap", "prob_hit_base")
+        oc = ObsColumns(*[d_cols[n] for n in names], d_cat)
+        vp = C.c_void_p
+        self._check(self.lib.vlr_posterior_batch_dev(self.h, n_sites, C.byref(model), C.byref(oc),
+                                                     vp(d_obs_off), vp(d_ev), vp(d_marg), vp(d_maf),
+                                                     vp(d_mb)))
+
+    def likelihood_batch(self, n_sites, n_samples, cols, cat, obs_off, biases, items):
+        """Likelihood::compute per work item.  biases: list of scenario bias dicts; items: list of
+        dict(site, sample, bias, contaminated, af, af_secondary, purity, other_rate)."""
+        from ._ffi import Biases, LhItem
+        keep = []
+        oc = self._obs_columns(cols, cat, keep)
+        obs_off = np.ascontiguousarray(obs_off, dtype=np.int64)
+        barr = (Biases * len(biases))()
+        for k, b in enumerate(biases):
+            barr[k] = Biases(b["strand"], b["orientation"], b["read_position"], b["softclip"],
+                             b["divindel"], 0, b["min_other_rate"])
+        iarr = (LhItem * max(1, len(items)))()
+        for k, it in enumerate(items):
+            iarr[k] = LhItem(it["site"], it["sample"], it["bias"], int(it.get("contaminated", 0)),
+                             it["af"], it.get("af_secondary", 0.0), it.get("purity", 1.0),
+                             it.get("other_rate", 0.0))
+        out = np.empty(len(items), np.float64)
+        self._check(self.lib.vlr_likelihood_batch(self.h, n_sites, n_samples, C.byref(oc),
+                                                  _ptr(obs_off), C.addressof(barr), len(biases),
+                                                  C.addressof(iarr), len(items), _ptr(out)))
+        return out

@@ -1,0 +1,1147 @@
+// posterior.cu -- K3/K4: AF-grid pileup likelihood and fused event integration for sm_100a.
+//
+// Replaces, per candidate site,
+//   * SampleLikelihoodModel / ContaminatedSampleLikelihoodModel::compute
+//       (reference src/variants/model/likelihood.rs:118-152, 215-245; likelihood_mapping 191-213)
+//   * Biases::{prob, prob_any, is_possible, is_informative, is_likely, learn_parameters}
+//       (src/variants/model/bias/*.rs)
+//   * GenericPosterior::{grid_points, density, compute} (src/variants/model/modes/generic.rs:109-282)
+//   * bio Model::compute (marginal) and the MAP selection of calling.rs:635-677.
+//
+// Arithmetic.  For observation i, bias configuration B and effective alt-sampling probability z
+//   T_i = pm_i * ( z * beta_iB * A_i + (1 - z) * R_i * betabar_i ) + pmm_i * mu_i * betabar_i
+// with A,R,mu = exp(prob_alt, prob_ref, prob_missed_allele), z = s_i(af) for a plain sample and
+// z = rho*s_i(af_primary) + (1-rho)*s_i(af_secondary) for a contaminated one (likelihood_mapping
+// is affine in s), s_i(af) = af * exp(prob_sample_alt_i) (exactly 1 for af == 1, quirk Q4).
+// The pileup likelihood is sum_i ln T_i = sum_i m_i + ln prod_i T'_i with per-observation scaling
+// m_i = max(prob_alt, prob_ref, prob_missed): the kernel multiplies mantissas and adds exponents
+// (no per-evaluation log), and takes ONE log per (allele-frequency key, bias configuration).
+// Evaluations whose T' leaves the normal fp64 range are recomputed in log space (same formulas as
+// the reference), still on the GPU.
+//
+// Mapping.  A team of TEAM warps owns one site at a time.  Observations sit one per lane
+// (strided) in registers; for every likelihood key the lanes evaluate their observations and the
+// warp reduces mantissa product / exponent sum by shuffles (segmented reduction over the
+// observation columns, struct-of-arrays in HBM).  The likelihood table of the site is then
+// integrated: every (event, bias configuration, tree path, grid combination) is one term
+// W * exp(joint) of a log-sum-exp, where W carries the Simpson weights (generic.rs:196-208) -- the
+// nested ln_sum_exp / ln_simpsons_integrate_exp of the reference are distributive sums.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace vlr {
+
+constexpr int kMaxSamples = 8;
+constexpr int kMaxSpectra = 48;
+constexpr int kMaxValues = 384;   // distinct allele-frequency values per site (all samples)
+constexpr int kMaxCfg = 32;       // distinct bias configurations
+constexpr int kMaxEvents = 64;
+constexpr int kMaxObsPerLane = 8; // <= 256 observations per (site, sample)
+constexpr int kTeamThreadsMax = 128;
+
+struct DevSpectrum {
+    int32_t sample, kind, vaf_off, n_vafs;
+};
+struct DevPath {
+    int32_t event;
+    int32_t spec[kMaxSamples];
+};
+struct DevEventBias {  // one (event, bias configuration) entry
+    int32_t event, cfg;
+};
+struct DevEvent {
+    int32_t is_artifact;
+    int32_t path_off, n_paths;
+    int32_t eb_off, n_eb;
+    double bias_prior;  // ln .5 (+ ln 1/|biases| for artifact events), generic.rs:251-255
+};
+
+struct DevModel {
+    int32_t n_samples, n_events, n_spectra, n_paths, n_cfg, n_eb;
+    int32_t resolution[kMaxSamples], contaminated[kMaxSamples], by[kMaxSamples];
+    double purity[kMaxSamples];
+    const DevSpectrum *spectra;
+    const DevPath *paths;
+    const DevEvent *events;
+    const DevEventBias *eb;
+    const vlr_biases *cfg;
+    const double *vafs;
+};
+
+struct PostArgs {
+    DevModel m;
+    vlr_obs_columns obs;
+    const int64_t *obs_off;
+    int64_t n_sites;
+    int32_t *cursor;
+    double *table;          // per-team scratch: likelihood tables
+    int64_t table_stride;   // doubles per team
+    double *out_event_ln, *out_marginal, *out_map_af;
+    int32_t *out_map_bias;
+    int32_t *status;        // [0] = number of sites that overflowed a kernel limit
+};
+
+__device__ __forceinline__ double ln_one_minus_exp_d(double p) {
+    return p < -0.693 ? log1p(-exp(p)) : log(-expm1(p));
+}
+__device__ __forceinline__ double ln_add_exp2(double a, double b) {
+    double p0 = fmax(a, b), p1 = fmin(a, b);
+    if (p0 == -INFINITY) return -INFINITY;
+    if (p1 == -INFINITY) return p0;
+    return p0 + log1p(exp(p1 - p0));
+}
+
+// ---- bias terms (bias/*.rs).  Returns the linear probability; NaN where the reference panics.
+__device__ __forceinline__ double bias_lin(const vlr_biases &b, double other_rate, unsigned cat,
+                                           double strand_none, double hb) {
+    const unsigned st = VLR_CAT_STRAND(cat), orr = VLR_CAT_ORIENT(cat);
+    double v;
+    if (b.strand == 1) v = st == 0 ? 1.0 : (st == 3 ? NAN : 0.0);          // strand_bias.rs:21-33
+    else if (b.strand == 2) v = st == 1 ? 1.0 : (st == 3 ? NAN : 0.0);
+    else v = strand_none;  // e^double_overlap | .5 * e^single_overlap
+    double o = 0.5;                                                          // read_orientation_bias.rs:22-36
+    if (b.orientation == 1) o = orr == 0 ? 1.0 : (orr == 1 ? 0.0 : 0.5);
+    else if (b.orientation == 2) o = orr == 1 ? 1.0 : (orr == 0 ? 0.0 : 0.5);
+    v *= o;
+    v *= b.read_position == 0 ? hb : (VLR_CAT_READPOS(cat) == 0 ? 1.0 : 0.0);  // read_position_bias.rs:19-29
+    if (b.softclip) v *= VLR_CAT_SOFTCLIP(cat) ? 1.0 : 0.0;                    // softclip_bias.rs:19-29
+    const bool other = VLR_CAT_INDEL(cat) == 1;                                // divindel_bias.rs:37-59
+    if (b.divindel == 0) v *= other ? 0.0 : 1.0;
+    else v *= other_rate == 0.0 ? 0.0 : (other ? other_rate : 1.0 - other_rate);
+    return v;
+}
+__device__ __forceinline__ double bias_ln(const vlr_biases &b, double other_rate, unsigned cat,
+                                          double ln_dov, double ln_sov, double ln_hb) {
+    const double LN05 = -0.6931471805599453;
+    const unsigned st = VLR_CAT_STRAND(cat), orr = VLR_CAT_ORIENT(cat);
+    double v;
+    if (b.strand == 1) v = st == 0 ? 0.0 : (st == 3 ? NAN : -INFINITY);
+    else if (b.strand == 2) v = st == 1 ? 0.0 : (st == 3 ? NAN : -INFINITY);
+    else v = st == 2 ? ln_dov : LN05 + ln_sov;
+    double o = LN05;
+    if (b.orientation == 1) o = orr == 0 ? 0.0 : (orr == 1 ? -INFINITY : LN05);
+    else if (b.orientation == 2) o = orr == 1 ? 0.0 : (orr == 0 ? -INFINITY : LN05);
+    v += o;
+    v += b.read_position == 0 ? ln_hb : (VLR_CAT_READPOS(cat) == 0 ? 0.0 : -INFINITY);
+    v += b.softclip ? (VLR_CAT_SOFTCLIP(cat) ? 0.0 : -INFINITY) : 0.0;
+    const bool other = VLR_CAT_INDEL(cat) == 1;
+    if (b.divindel == 0) v += other ? -INFINITY : 0.0;
+    else v += other_rate == 0.0 ? -INFINITY : (other ? log(other_rate) : log(1.0 - other_rate));
+    return v;
+}
+
+// likelihood_mapping in log space (likelihood.rs:191-213), used by the out-of-range path
+__device__ double lh_mapping_ln(double af, double psa_obs, double pb, double pab, double pa,
+                                double pr) {
+    const double ln_af = log(af);
+    double psa;
+    if (ln_af != 0.0) {
+        psa = ln_af + psa_obs;
+        if (psa > 0.0) psa = psa <= 1e-3 ? 0.0 : NAN;  // cap_numerical_overshoot
+    } else {
+        psa = ln_af;
+    }
+    const double psr = ln_one_minus_exp_d(psa);
+    const double t0 = psa + pb + pa, t1 = psr + pr + pab;
+    // ln_sum_exp of two terms
+    const double mx = fmax(t0, t1), mn = fmin(t0, t1);
+    if (isnan(t0) || isnan(t1)) return NAN;
+    if (mx == -INFINITY) return -INFINITY;
+    if (mn == -INFINITY) return mx;
+    return mx + log1p(exp(mn - mx));
+}
+
+// exact ln T of one observation in log space (likelihood.rs:75-116, 165-187)
+__device__ double ln_T_exact(const vlr_obs_columns &o, int64_t row, const vlr_biases &b,
+                             double other_rate, double af_p, double af_s, bool contaminated,
+                             double purity) {
+    const unsigned cat = o.cat[row];
+    const double ln_hb = o.prob_hit_base[row];
+    const double pb = bias_ln(b, other_rate, cat, o.prob_double_overlap[row],
+                              o.prob_single_overlap[row], ln_hb);
+    const double pab = -0.6931471805599453 + -0.6931471805599453 + ln_hb + 0.0 + 0.0;
+    const double pa = o.prob_alt[row], pr = o.prob_ref[row], psa = o.prob_sample_alt[row];
+    double mapped;
+    if (contaminated) {
+        const double lp = log(purity);
+        const double li = ln_one_minus_exp_d(lp);
+        const double a = lp + lh_mapping_ln(af_p, psa, pb, pab, pa, pr);
+        const double c = li + lh_mapping_ln(af_s, psa, pb, pab, pa, pr);
+        mapped = (isnan(a) || isnan(c)) ? NAN : ln_add_exp2(c, a);
+    } else {
+        mapped = lh_mapping_ln(af_p, psa, pb, pab, pa, pr);
+    }
+    const double t0 = o.prob_mapping[row] + mapped;
+    const double t1 = o.prob_mismapping[row] + o.prob_missed_allele[row] + pab;
+    if (isnan(t0) || isnan(t1)) return NAN;
+    return ln_add_exp2(t0, t1);
+}
+
+// Bias::is_strong_obs (bias/mod.rs:79-83)
+__device__ __forceinline__ bool strong_obs(double prob_mapping, double pa, double pr) {
+    return prob_mapping >= -0.05129329438755058 && exp(pa - pr) > 20.0;
+}
+
+// VAFRange::observable_{min,max} (grammar/formula.rs:1029-1071)
+__device__ double observable_max_d(double end, bool rex, int n_obs) {
+    if (n_obs < 10) return end;
+    double c = (double)n_obs * end;
+    if (rex && fmod(c, 1.0) == 0.0) c -= 1.0;
+    return floor(c) / (double)n_obs;
+}
+__device__ double observable_min_d(double start, double end, bool lex, bool rex, int n_obs) {
+    if (n_obs < 10) return start;
+    const double c = (double)n_obs * start;
+    if (lex && fmod(c, 1.0) == 0.0) {
+        const double adj_end = observable_max_d(end, rex, n_obs);
+        for (int k = 0; k < 2; ++k) {
+            const double adj = ceil(c + (k == 0 ? 1.0 : 0.0)) / (double)n_obs;
+            if (adj <= 1.0 && adj <= adj_end) return adj;
+        }
+    }
+    return ceil(c) / (double)n_obs;
+}
+
+// evidence "variants" of the gating counters
+enum { EV_SF = 0, EV_SR, EV_OF1R2, EV_OF2R1, EV_RP, EV_SC, EV_DI, EV_N };
+// possibility flags of the unbiased components
+enum { PS_STRAND_NONE = 0, PS_RP_NONE, PS_DI_NONE, PS_ANYOBS, PS_N };
+
+struct TeamShared {
+    int n_obs[kMaxSamples];
+    int grid[kMaxSamples];
+    int strong_all[kMaxSamples];
+    int strong_ev[kMaxSamples][EV_N];
+    int any_ev[EV_N];
+    int any_ps[PS_N];
+    int n_uncertain, n_total, strong_other_total, strong_all_total;
+    int spec_off[kMaxSpectra + 1];       // into val[]
+    int sample_voff[kMaxSamples + 1];    // value ranges are grouped by sample: val index base
+    int sample_nv[kMaxSamples];
+    int64_t tab_off[kMaxSamples];        // offset of sample's table (doubles), per cfg stride below
+    int64_t tab_cfg_stride[kMaxSamples];
+    double val[kMaxValues];
+    double lnw[kMaxValues];
+    double sum_m[kMaxSamples];
+    double other_rate[kMaxCfg];
+    int allowed[kMaxCfg];
+    double ev_ln[kMaxEvents];
+    // reduction scratch
+    double red_mx[4], red_sum[4];
+    double best_j[4][2];
+    int best_id[4][2][3];  // eb index, path, combo
+    int overflow;
+};
+
+
+// decode the allele-frequency vector of (path, combo) -- LAST sample is the fastest digit
+__device__ void decode_afs(const DevModel &m, const TeamShared &S, const DevPath &path, int64_t combo,
+                           double *afs) {
+    for (int smp = m.n_samples - 1; smp >= 0; --smp) {
+        const DevSpectrum spc = m.spectra[path.spec[smp]];
+        const int cnt = spc.kind == VLR_NODE_RANGE ? S.grid[smp] : spc.n_vafs;
+        const int d = (int)(combo % cnt);
+        combo /= cnt;
+        afs[smp] = S.val[S.spec_off[path.spec[smp]] + d];
+    }
+}
+// MAP tie-break: larger joint first; then the earlier (event, bias) entry; then the
+// lexicographically smaller allele-frequency vector (the reference's order among exact ties is
+// unspecified: HashMap iteration, SURVEY quirk Q14 -- the oracle uses this same rule)
+__device__ bool map_better(const DevModel &m, const TeamShared &S, double j, int eb, int p, int combo,
+                           bool have, double bj, int beb, int bp, int bcombo) {
+    if (!have) return true;
+    if (j != bj) return j > bj;
+    if (eb != beb) return eb < beb;
+    if (p == bp && combo == bcombo) return false;
+    double a[kMaxSamples], b[kMaxSamples];
+    decode_afs(m, S, m.paths[m.events[m.eb[eb].event].path_off + p], combo, a);
+    decode_afs(m, S, m.paths[m.events[m.eb[beb].event].path_off + bp], bcombo, b);
+    for (int smp = 0; smp < m.n_samples; ++smp)
+        if (a[smp] != b[smp]) return a[smp] < b[smp];
+    return false;
+}
+
+template <int TEAM>
+__device__ __forceinline__ void team_sync() {
+    if (TEAM == 1) __syncwarp();
+    else __syncthreads();
+}
+
+__device__ __forceinline__ double warp_prod(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v *= __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// s_i(af): effective probability to sample the alt allele (likelihood.rs:25-38)
+__device__ __forceinline__ double s_eff(double af, double sigma) {
+    if (af == 1.0) return 1.0;
+    double s = af * sigma;
+    if (s > 1.0) s = s <= 1.0010005001667084 ? 1.0 : NAN;  // e^(1e-3) overshoot cap
+    return s;
+}
+
+template <int TEAM>
+__global__ void __launch_bounds__(kTeamThreadsMax, 3) posterior_kernel(PostArgs g) {
+    constexpr int kTeamsPerCta = kTeamThreadsMax / (32 * TEAM);
+    __shared__ TeamShared s_team[kTeamsPerCta];
+    const int lane = threadIdx.x & 31;
+    const int warp_in_cta = threadIdx.x >> 5;
+    const int team_in_cta = warp_in_cta / TEAM;
+    const int wt = warp_in_cta % TEAM;           // warp index within the team
+    const int tt = wt * 32 + lane;               // thread index within the team
+    constexpr int TT = TEAM * 32;
+    TeamShared &S = s_team[team_in_cta];
+    const int team_global = blockIdx.x * kTeamsPerCta + team_in_cta;
+    double *table = g.table + (int64_t)team_global * g.table_stride;
+    const DevModel &m = g.m;
+    const int NS = m.n_samples;
+
+    for (;;) {
+        // ---- next site (dynamic)
+        __shared__ int64_t s_site[kTeamsPerCta];
+        team_sync<TEAM>();
+        if (tt == 0) s_site[team_in_cta] = (int64_t)atomicAdd(g.cursor, 1);
+        team_sync<TEAM>();
+        const int64_t site = s_site[team_in_cta];
+        if (site >= g.n_sites) break;
+
+        // ---- 0. reset counters
+        for (int k = tt; k < (int)(sizeof(TeamShared) / 4); k += TT) {
+            // only the integer counter block at the front needs zeroing; cheap to clear it all
+            if (k < (int)(offsetof(TeamShared, spec_off) / 4)) ((int *)&S)[k] = 0;
+        }
+        if (tt == 0) S.overflow = 0;
+        team_sync<TEAM>();
+
+        // ---- 1. per-sample counters for grid sizes, bias learning and gating
+        for (int smp = wt; smp < NS; smp += TEAM) {
+            const int64_t o0 = g.obs_off[site * NS + smp], o1 = g.obs_off[site * NS + smp + 1];
+            const int n = (int)(o1 - o0);
+            int c_strong = 0, c_ev[EV_N], a_ev[EV_N], a_ps[PS_N], c_unc = 0, c_so = 0;
+            double sm = 0.0;
+#pragma unroll
+            for (int v = 0; v < EV_N; ++v) { c_ev[v] = 0; a_ev[v] = 0; }
+#pragma unroll
+            for (int v = 0; v < PS_N; ++v) a_ps[v] = 0;
+            for (int i = lane; i < n; i += 32) {
+                const int64_t row = o0 + i;
+                const unsigned cat = g.obs.cat[row];
+                const double pa = g.obs.prob_alt[row], pr = g.obs.prob_ref[row];
+                const bool strong = strong_obs(g.obs.prob_mapping[row], pa, pr);
+                const unsigned st = VLR_CAT_STRAND(cat), orr = VLR_CAT_ORIENT(cat);
+                // "bias evidence" = prob(obs) != ln 0 for the biased variant of each component
+                const bool ev[EV_N] = {st == 0, st == 1, orr != 1, orr != 0,
+                                       VLR_CAT_READPOS(cat) == 0, VLR_CAT_SOFTCLIP(cat) != 0,
+                                       VLR_CAT_INDEL(cat) == 1};
+#pragma unroll
+                for (int v = 0; v < EV_N; ++v) { a_ev[v] |= ev[v]; c_ev[v] += (strong && ev[v]); }
+                c_strong += strong;
+                c_so += strong && ev[EV_DI];
+                c_unc += orr > 1;
+                // unbiased components: StrandBias::None prob = double_overlap | ln.5+single_overlap
+                const double sn = st == 2 ? g.obs.prob_double_overlap[row]
+                                          : -0.6931471805599453 + g.obs.prob_single_overlap[row];
+                a_ps[PS_STRAND_NONE] |= sn != -INFINITY;
+                a_ps[PS_RP_NONE] |= g.obs.prob_hit_base[row] != -INFINITY;
+                a_ps[PS_DI_NONE] |= VLR_CAT_INDEL(cat) != 1;
+                a_ps[PS_ANYOBS] = 1;
+                const double mi = fmax(fmax(pa, pr), g.obs.prob_missed_allele[row]);
+                sm += mi;
+            }
+            c_strong = __reduce_add_sync(0xffffffffu, c_strong);
+            c_unc = __reduce_add_sync(0xffffffffu, c_unc);
+            c_so = __reduce_add_sync(0xffffffffu, c_so);
+            sm = warp_sum(sm);
+#pragma unroll
+            for (int v = 0; v < EV_N; ++v) {
+                c_ev[v] = __reduce_add_sync(0xffffffffu, c_ev[v]);
+                a_ev[v] = __reduce_or_sync(0xffffffffu, a_ev[v]);
+            }
+#pragma unroll
+            for (int v = 0; v < PS_N; ++v) a_ps[v] = __reduce_or_sync(0xffffffffu, a_ps[v]);
+            if (lane == 0) {
+                S.n_obs[smp] = n;
+                S.strong_all[smp] = c_strong;
+                S.sum_m[smp] = sm;
+                for (int v = 0; v < EV_N; ++v) {
+                    S.strong_ev[smp][v] = c_ev[v];
+                    if (a_ev[v]) atomicOr(&S.any_ev[v], 1);
+                }
+                for (int v = 0; v < PS_N; ++v) if (a_ps[v]) atomicOr(&S.any_ps[v], 1);
+                atomicAdd(&S.n_uncertain, c_unc);
+                atomicAdd(&S.n_total, n);
+                atomicAdd(&S.strong_other_total, c_so);
+                atomicAdd(&S.strong_all_total, c_strong);
+                int gp = max(n + 1, 5);                      // generic.rs:109-122
+                gp = min(gp, m.resolution[smp]);
+                if ((gp & 1) == 0) gp += 1;
+                S.grid[smp] = gp;
+                if (n > 32 * kMaxObsPerLane) S.overflow = 1;
+            }
+        }
+        team_sync<TEAM>();
+
+        // ---- 2. allele-frequency values of every spectrum (grouped by sample) + Simpson ln-weights
+        if (tt == 0) {
+            int off = 0;
+            for (int smp = 0; smp < NS; ++smp) {
+                S.sample_voff[smp] = off;
+                for (int sp = 0; sp < m.n_spectra; ++sp) {
+                    if (m.spectra[sp].sample != smp) continue;
+                    S.spec_off[sp] = off;
+                    off += m.spectra[sp].kind == VLR_NODE_RANGE ? S.grid[smp] : m.spectra[sp].n_vafs;
+                }
+                S.sample_nv[smp] = off - S.sample_voff[smp];
+            }
+            S.sample_voff[NS] = off;
+            if (off > kMaxValues) S.overflow = 1;
+            // table layout: per sample, per cfg, per key
+            int64_t toff = 0;
+            for (int smp = 0; smp < NS; ++smp) {
+                const int64_t keys = m.contaminated[smp]
+                                         ? (int64_t)S.sample_nv[smp] * S.sample_nv[m.by[smp]]
+                                         : (int64_t)S.sample_nv[smp];
+                S.tab_off[smp] = toff;
+                S.tab_cfg_stride[smp] = keys;
+                toff += keys * m.n_cfg;
+            }
+            if (toff > g.table_stride) S.overflow = 1;
+        }
+        team_sync<TEAM>();
+        if (S.overflow) {
+            if (tt == 0) {
+                atomicAdd(g.status, 1);
+                for (int e = 0; e < m.n_events; ++e) g.out_event_ln[site * m.n_events + e] = NAN;
+                g.out_marginal[site] = NAN;
+                for (int smp = 0; smp < NS; ++smp) {
+                    g.out_map_af[site * NS + smp] = NAN;
+                    g.out_map_bias[site * NS + smp] = -1;
+                }
+            }
+            continue;
+        }
+        for (int sp = wt; sp < m.n_spectra; sp += TEAM) {
+            const DevSpectrum spc = m.spectra[sp];
+            const int base = S.spec_off[sp];
+            if (spc.kind == VLR_NODE_RANGE) {
+                const double *r = m.vafs + spc.vaf_off;
+                const int nobs = S.n_obs[spc.sample], n = S.grid[spc.sample];
+                const double a = observable_min_d(r[0], r[1], r[2] != 0.0, r[3] != 0.0, nobs);
+                const double b = observable_max_d(r[1], r[3] != 0.0, nobs);
+                const double step = (b - a) / (double)(n - 1);  // itertools_num::linspace
+                const double lnc = log(b - a) - log((double)(n - 1)) - log(3.0);
+                for (int i = lane; i < n; i += 32) {
+                    // no FMA contraction: the grid point must be bit-identical to linspace's a + step*i
+                    double x = __dadd_rn(a, __dmul_rn(step, (double)i)), w = 0.0;
+                    if (i == 0) x = a;
+                    else if (i == n - 1) x = b;
+                    else w = log((double)(2 + (i & 1) * 2));  // weights 4,2,4,... (Appendix A.1)
+                    S.val[base + i] = x;
+                    S.lnw[base + i] = w + lnc;
+                }
+            } else {
+                for (int i = lane; i < spc.n_vafs; i += 32) {
+                    S.val[base + i] = m.vafs[spc.vaf_off + i];
+                    S.lnw[base + i] = 0.0;
+                }
+            }
+        }
+        // ---- 3. bias learning + gating (one thread per configuration)
+        for (int c = tt; c < m.n_cfg; c += TT) {
+            const vlr_biases b = m.cfg[c];
+            // DivIndelBias::learn_parameters (divindel_bias.rs:98-132)
+            double orate = 0.0;
+            if (b.divindel) {
+                const double r = S.strong_all_total > 0
+                                     ? (double)S.strong_other_total / (double)S.strong_all_total : 0.0;
+                orate = fmax(r, b.min_other_rate);
+            }
+            S.other_rate[c] = orate;
+            bool ok = true;
+            // is_possible (bias/mod.rs:30-36, divindel_bias.rs:77-84)
+            ok &= b.strand == 0 ? S.any_ps[PS_STRAND_NONE] : S.any_ev[b.strand == 1 ? EV_SF : EV_SR];
+            ok &= b.orientation == 0 ? S.any_ps[PS_ANYOBS]
+                                     : S.any_ev[b.orientation == 1 ? EV_OF1R2 : EV_OF2R1];
+            ok &= b.read_position == 0 ? S.any_ps[PS_RP_NONE] : S.any_ev[EV_RP];
+            ok &= b.softclip == 0 ? S.any_ps[PS_ANYOBS] : S.any_ev[EV_SC];
+            ok &= b.divindel == 0 ? S.any_ps[PS_DI_NONE] : S.any_ev[EV_DI];
+            // is_informative (read_orientation_bias.rs:42-68, softclip_bias.rs:35-43, divindel_bias.rs:65-75)
+            if (b.orientation) ok &= (double)S.n_uncertain < (double)S.n_total / 2.0;
+            if (b.softclip) ok &= S.any_ev[EV_SC];
+            if (b.divindel) ok &= S.any_ev[EV_DI];
+            // is_likely (bias/mod.rs:46-67): any sample with < 10 strong obs or enough evidence
+            const int comp_ev[5] = {b.strand == 0 ? -1 : (b.strand == 1 ? EV_SF : EV_SR),
+                                    b.orientation == 0 ? -1 : (b.orientation == 1 ? EV_OF1R2 : EV_OF2R1),
+                                    b.read_position == 0 ? -1 : EV_RP, b.softclip == 0 ? -1 : EV_SC,
+                                    b.divindel == 0 ? -1 : EV_DI};
+            for (int k = 0; k < 5; ++k) {
+                if (comp_ev[k] < 0) continue;
+                bool likely = false;
+                for (int smp = 0; smp < NS; ++smp) {
+                    const int sa = S.strong_all[smp];
+                    if (sa >= 10) {
+                        const double ratio = (double)S.strong_ev[smp][comp_ev[k]] / (double)sa;
+                        const double need = k == 4 ? 0.66666 * orate : 0.66666;
+                        if (ratio >= need) { likely = true; break; }
+                    } else { likely = true; break; }
+                }
+                ok &= likely;
+            }
+            S.allowed[c] = ok;
+        }
+        team_sync<TEAM>();
+
+        // ---- 4. likelihood tables: sample by sample, bias configuration by configuration
+        for (int smp = 0; smp < NS; ++smp) {
+            const int64_t o0 = g.obs_off[site * NS + smp];
+            const int n = S.n_obs[smp];
+            const bool cont = m.contaminated[smp] != 0;
+            const double rho = m.purity[smp];
+            const int nv = S.sample_nv[smp], v0 = S.sample_voff[smp];
+            const int byv0 = cont ? S.sample_voff[m.by[smp]] : 0;
+            const int bynv = cont ? S.sample_nv[m.by[smp]] : 1;
+            const int64_t nkeys = (int64_t)nv * bynv;
+            // per-lane observation constants (scaled linear space)
+            double cA[kMaxObsPerLane], cR[kMaxObsPerLane], kk[kMaxObsPerLane], sg[kMaxObsPerLane];
+            double sN[kMaxObsPerLane], hb[kMaxObsPerLane];
+            unsigned cat[kMaxObsPerLane];
+            const int rp = (n + 31) / 32;
+#pragma unroll
+            for (int r = 0; r < kMaxObsPerLane; ++r) {
+                const int i = r * 32 + lane;
+                if (r < rp && i < n) {
+                    const int64_t row = o0 + i;
+                    const double pa = g.obs.prob_alt[row], pr = g.obs.prob_ref[row],
+                                 pmiss = g.obs.prob_missed_allele[row];
+                    const double mi = fmax(fmax(pa, pr), pmiss);
+                    const double pm = exp(g.obs.prob_mapping[row]), pmm = exp(g.obs.prob_mismapping[row]);
+                    hb[r] = exp(g.obs.prob_hit_base[row]);
+                    const double bbar = 0.25 * hb[r];
+                    if (mi == -INFINITY) {
+                        cA[r] = cR[r] = kk[r] = 0.0;  // T == 0: resolved by the exact path (-inf)
+                    } else {
+                        cA[r] = pm * exp(pa - mi);
+                        cR[r] = pm * exp(pr - mi) * bbar;
+                        kk[r] = pmm * exp(pmiss - mi) * bbar;
+                    }
+                    sg[r] = exp(g.obs.prob_sample_alt[row]);
+                    cat[r] = g.obs.cat[row];
+                    sN[r] = VLR_CAT_STRAND(cat[r]) == 2 ? exp(g.obs.prob_double_overlap[row])
+                                                        : 0.5 * exp(g.obs.prob_single_overlap[row]);
+                } else {
+                    cA[r] = cR[r] = 0.0; kk[r] = 1.0; sg[r] = 1.0;  // neutral factor T = 1
+                    sN[r] = hb[r] = 1.0; cat[r] = 0;
+                }
+            }
+            for (int c = 0; c < m.n_cfg; ++c) {
+                if (!S.allowed[c]) continue;  // gated out: never requested (generic.rs:258-262)
+                const vlr_biases b = m.cfg[c];
+                const double orate = S.other_rate[c];
+                double bcA[kMaxObsPerLane];
+#pragma unroll
+                for (int r = 0; r < kMaxObsPerLane; ++r) {
+                    const int i = r * 32 + lane;
+                    bcA[r] = (r < rp && i < n)
+                                 ? bias_lin(b, orate, cat[r], sN[r], hb[r]) * cA[r] : 0.0;
+                }
+                double *tab = table + S.tab_off[smp] + (int64_t)c * S.tab_cfg_stride[smp];
+                for (int64_t key = wt; key < nkeys; key += TEAM) {
+                    const int vi = (int)(key / bynv), vb = (int)(key - (int64_t)vi * bynv);
+                    const double af_p = S.val[v0 + vi];
+                    const double af_s = cont ? S.val[byv0 + vb] : 0.0;
+                    double mant = 1.0, lnslow = 0.0;
+                    int ex = 0;
+                    bool slow_any = false;
+#pragma unroll
+                    for (int r = 0; r < kMaxObsPerLane; ++r) {
+                        if (r < rp) {
+                            double z = s_eff(af_p, sg[r]);
+                            double zr = 1.0 - z;
+                            if (cont) {
+                                const double z2 = s_eff(af_s, sg[r]);
+                                zr = rho * zr + (1.0 - rho) * (1.0 - z2);
+                                z = rho * z + (1.0 - rho) * z2;
+                            }
+                            const double T = fma(zr, cR[r], fma(z, bcA[r], kk[r]));
+                            const int hi = __double2hiint(T);
+                            const int e = (hi >> 20) & 0x7ff;  // sign is 0 for every valid T
+                            if (hi > 0 && e > 23 && e < 2000) {
+                                ex += e - 1023;
+                                mant *= __hiloint2double((hi & 0x000fffff) | 0x3ff00000,
+                                                         __double2loint(T));
+                            } else if (r * 32 + lane < n) {
+                                // zero / subnormal / NaN: recompute this observation in log space
+                                const int64_t row = o0 + r * 32 + lane;
+                                const double mi = fmax(fmax(g.obs.prob_alt[row], g.obs.prob_ref[row]),
+                                                       g.obs.prob_missed_allele[row]);
+                                const double lt = ln_T_exact(g.obs, row, b, orate, af_p, af_s, cont, rho);
+                                // sum_m already contains m_i: subtract it again here
+                                lnslow += (mi == -INFINITY) ? lt : lt - mi;
+                                slow_any = true;
+                            }
+                        }
+                    }
+                    mant = warp_prod(mant);
+                    ex = __reduce_add_sync(0xffffffffu, ex);
+                    double L = S.sum_m[smp] + (double)ex * 0.6931471805599453 + log(mant);
+                    if (__any_sync(0xffffffffu, slow_any)) {
+                        lnslow = warp_sum(lnslow);
+                        L = (S.sum_m[smp] == -INFINITY) ? lnslow + ((double)ex * 0.6931471805599453 + log(mant))
+                                                       : L + lnslow;
+                    }
+                    if (n == 0) L = 0.0;  // empty pileup: fold identity ln 1 (likelihood.rs:135,227)
+                    if (lane == 0) __stcg(&tab[key], L);
+                }
+            }
+        }
+        team_sync<TEAM>();
+
+        // ---- 5. integrate: per event a log-sum-exp over (bias cfg, path, grid combination)
+        double bestJ[2] = {-INFINITY, -INFINITY};  // [0] any, [1] non-artifact
+        int bestId[2][3] = {{0x7fffffff, 0, 0}, {0x7fffffff, 0, 0}};
+        bool have[2] = {false, false};
+        for (int e = 0; e < m.n_events; ++e) {
+            const DevEvent ev = m.events[e];
+            double mx = -INFINITY, sum = 0.0;
+            for (int q = 0; q < ev.n_eb; ++q) {
+                const int ebi = ev.eb_off + q;
+                const int c = m.eb[ebi].cfg;
+                if (!S.allowed[c]) continue;
+                const bool art = m.cfg[c].strand | m.cfg[c].orientation | m.cfg[c].read_position |
+                                 m.cfg[c].softclip | m.cfg[c].divindel;
+                for (int p = 0; p < ev.n_paths; ++p) {
+                    const DevPath &path = m.paths[ev.path_off + p];
+                    int cnt[kMaxSamples], base[kMaxSamples];
+                    int64_t total = 1;
+                    for (int smp = 0; smp < NS; ++smp) {
+                        const int sp = path.spec[smp];
+                        const DevSpectrum spc = m.spectra[sp];
+                        cnt[smp] = spc.kind == VLR_NODE_RANGE ? S.grid[smp] : spc.n_vafs;
+                        base[smp] = S.spec_off[sp] - S.sample_voff[smp];  // value index within sample
+                        total *= cnt[smp];
+                    }
+                    for (int64_t combo = tt; combo < total; combo += TT) {
+                        int64_t rem = combo;
+                        int vidx[kMaxSamples];
+                        double lw = 0.0;
+                        // mixed radix, LAST sample fastest
+                        for (int smp = NS - 1; smp >= 0; --smp) {
+                            const int d = (int)(rem % cnt[smp]);
+                            rem /= cnt[smp];
+                            vidx[smp] = base[smp] + d;
+                            lw += S.lnw[S.sample_voff[smp] + vidx[smp]];
+                        }
+                        double J = 0.0;  // flat prior (ln 1)
+                        for (int smp = 0; smp < NS; ++smp) {
+                            const int64_t key = m.contaminated[smp]
+                                                    ? (int64_t)vidx[smp] * S.sample_nv[m.by[smp]] + vidx[m.by[smp]]
+                                                    : (int64_t)vidx[smp];
+                            J += __ldcg(&table[S.tab_off[smp] + (int64_t)c * S.tab_cfg_stride[smp] + key]);
+                        }
+                        // joint_probs bookkeeping for the MAP (ties: lowest (eb, path, combo))
+                        for (int w = 0; w < 2; ++w) {
+                            if (w == 1 && art) continue;
+                            const bool better = map_better(m, S, J, ebi, p, (int)combo, have[w], bestJ[w],
+                                                           bestId[w][0], bestId[w][1], bestId[w][2]);
+                            if (better && !isnan(J)) {
+                                have[w] = true; bestJ[w] = J;
+                                bestId[w][0] = ebi; bestId[w][1] = p; bestId[w][2] = (int)combo;
+                            }
+                        }
+                        const double t = J + lw;
+                        if (isnan(t)) { sum = NAN; }
+                        else if (t > mx) { sum = sum * exp(mx - t) + 1.0; mx = t; }
+                        else if (t != -INFINITY) sum += exp(t - mx);
+                    }
+                }
+            }
+            // reduce (mx, sum) over the team
+            for (int o = 16; o > 0; o >>= 1) {
+                const double omx = __shfl_xor_sync(0xffffffffu, mx, o);
+                const double osum = __shfl_xor_sync(0xffffffffu, sum, o);
+                const double nm = fmax(mx, omx);
+                sum = (nm == -INFINITY) ? 0.0
+                                        : sum * (mx == -INFINITY ? 0.0 : exp(mx - nm)) +
+                                              osum * (omx == -INFINITY ? 0.0 : exp(omx - nm));
+                mx = nm;
+            }
+            if (TEAM > 1) {
+                if (lane == 0) { S.red_mx[wt] = mx; S.red_sum[wt] = sum; }
+                team_sync<TEAM>();
+                if (tt == 0) {
+                    double M = -INFINITY, Ssum = 0.0;
+                    for (int w = 0; w < TEAM; ++w) M = fmax(M, S.red_mx[w]);
+                    for (int w = 0; w < TEAM; ++w)
+                        if (S.red_mx[w] != -INFINITY) Ssum += S.red_sum[w] * exp(S.red_mx[w] - M);
+                    S.red_mx[0] = M; S.red_sum[0] = Ssum;
+                }
+                team_sync<TEAM>();
+                mx = S.red_mx[0]; sum = S.red_sum[0];
+                team_sync<TEAM>();
+            }
+            if (tt == 0) S.ev_ln[e] = (mx == -INFINITY) ? -INFINITY : ev.bias_prior + mx + log(sum);
+        }
+        // ---- MAP reduction (ties -> lowest id)
+        for (int w = 0; w < 2; ++w) {
+            double j = have[w] ? bestJ[w] : -INFINITY;
+            int i0 = have[w] ? bestId[w][0] : 0x7fffffff, i1 = bestId[w][1], i2 = bestId[w][2];
+            int hv = have[w];
+            for (int o = 16; o > 0; o >>= 1) {
+                const double oj = __shfl_xor_sync(0xffffffffu, j, o);
+                const int o0 = __shfl_xor_sync(0xffffffffu, i0, o), o1 = __shfl_xor_sync(0xffffffffu, i1, o),
+                          o2 = __shfl_xor_sync(0xffffffffu, i2, o), oh = __shfl_xor_sync(0xffffffffu, hv, o);
+                const bool take = oh && map_better(m, S, oj, o0, o1, o2, hv != 0, j, i0, i1, i2);
+                if (take) { j = oj; i0 = o0; i1 = o1; i2 = o2; hv = 1; }
+            }
+            if (lane == 0) {
+                S.best_j[wt][w] = hv ? j : -INFINITY;
+                S.best_id[wt][w][0] = hv ? i0 : 0x7fffffff;
+                S.best_id[wt][w][1] = i1; S.best_id[wt][w][2] = i2;
+            }
+        }
+        team_sync<TEAM>();
+
+        // ---- 6. outputs (one thread): marginal, is_artifact, MAP allele frequencies
+        if (tt == 0) {
+            const int NE = m.n_events;
+            double M = -INFINITY;
+            bool nan_any = false;
+            for (int e = 0; e < NE; ++e) { nan_any |= isnan(S.ev_ln[e]); M = fmax(M, S.ev_ln[e]); }
+            double marg;
+            if (nan_any) marg = NAN;
+            else if (M == -INFINITY) marg = -INFINITY;
+            else {
+                // LogProb::ln_sum_exp: pmax + ln_1p(sum of the others)
+                int imax = 0;
+                for (int e = 1; e < NE; ++e) if (S.ev_ln[e] > S.ev_ln[imax]) imax = e;
+                double acc = 0.0;
+                for (int e = 0; e < NE; ++e)
+                    if (e != imax && S.ev_ln[e] != -INFINITY) acc += exp(S.ev_ln[e] - S.ev_ln[imax]);
+                marg = S.ev_ln[imax] + log1p(acc);
+            }
+            for (int e = 0; e < NE; ++e) g.out_event_ln[site * NE + e] = S.ev_ln[e];
+            g.out_marginal[site] = marg;
+            // artifact event = ln_sum_exp of artifact posteriors (calling.rs:581-598)
+            double am = -INFINITY;
+            for (int e = 0; e < NE; ++e) if (m.events[e].is_artifact) am = fmax(am, S.ev_ln[e] - marg);
+            double prob_art = -INFINITY;
+            if (am != -INFINITY && !isnan(am)) {
+                double acc = 0.0;
+                for (int e = 0; e < NE; ++e)
+                    if (m.events[e].is_artifact && S.ev_ln[e] - marg != -INFINITY)
+                        acc += exp(S.ev_ln[e] - marg - am);
+                prob_art = am + log(acc);
+            } else if (isnan(am)) prob_art = NAN;
+            bool is_artifact = true;
+            for (int e = 0; e < NE; ++e)
+                if (!m.events[e].is_artifact && !((S.ev_ln[e] - marg) < prob_art)) is_artifact = false;
+            const int w = is_artifact ? 0 : 1;
+            double j = -INFINITY; int i0 = 0x7fffffff, i1 = 0, i2 = 0;
+            for (int k = 0; k < TEAM; ++k) {
+                const double oj = S.best_j[k][w];
+                const int o0 = S.best_id[k][w][0], o1 = S.best_id[k][w][1], o2 = S.best_id[k][w][2];
+                if (o0 == 0x7fffffff) continue;
+                const bool take = map_better(m, S, oj, o0, o1, o2, i0 != 0x7fffffff, j, i0, i1, i2);
+                if (take) { j = oj; i0 = o0; i1 = o1; i2 = o2; }
+            }
+            if (i0 == 0x7fffffff) {
+                for (int smp = 0; smp < NS; ++smp) {
+                    g.out_map_af[site * NS + smp] = NAN;
+                    g.out_map_bias[site * NS + smp] = -1;
+                }
+            } else {
+                const int c = m.eb[i0].cfg;
+                const bool art = m.cfg[c].strand | m.cfg[c].orientation | m.cfg[c].read_position |
+                                 m.cfg[c].softclip | m.cfg[c].divindel;
+                const DevPath &path = m.paths[m.events[m.eb[i0].event].path_off + i1];
+                int64_t rem = i2;
+                for (int smp = NS - 1; smp >= 0; --smp) {
+                    const DevSpectrum spc = m.spectra[path.spec[smp]];
+                    const int cnt = spc.kind == VLR_NODE_RANGE ? S.grid[smp] : spc.n_vafs;
+                    const int d = (int)(rem % cnt);
+                    rem /= cnt;
+                    // artifact MAP: allele frequency forced to 0 (calling.rs:659-663)
+                    g.out_map_af[site * NS + smp] = art ? 0.0 : S.val[S.spec_off[path.spec[smp]] + d];
+                    g.out_map_bias[site * NS + smp] = art ? c : -1;
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- host: model flattening
+struct HostModel {
+    std::vector<DevSpectrum> spectra;
+    std::vector<DevPath> paths;
+    std::vector<DevEvent> events;
+    std::vector<DevEventBias> eb;
+    std::vector<vlr_biases> cfg;
+    std::vector<double> vafs;
+    int max_paths_combos_hint = 0;
+};
+
+static bool same_cfg(const vlr_biases &a, const vlr_biases &b) {
+    return a.strand == b.strand && a.orientation == b.orientation &&
+           a.read_position == b.read_position && a.softclip == b.softclip &&
+           a.divindel == b.divindel && a.min_other_rate == b.min_other_rate;
+}
+
+static int flatten_model(vlr_ctx *ctx, const vlr_model *mdl, HostModel &H) {
+    const int NS = mdl->n_samples;
+    if (NS < 1 || NS > kMaxSamples) return set_err(ctx, VLR_ERR_UNSUPPORTED, "n_samples must be 1..8");
+    if (mdl->n_events < 1 || mdl->n_events > kMaxEvents)
+        return set_err(ctx, VLR_ERR_UNSUPPORTED, "n_events must be 1..%d", kMaxEvents);
+    // copy vafs referenced by nodes lazily: keep the caller's array layout
+    int max_vaf = 0;
+    for (int k = 0; k < mdl->n_nodes; ++k) {
+        const vlr_node &nd = mdl->nodes[k];
+        if (nd.kind == VLR_NODE_SET) max_vaf = std::max(max_vaf, nd.vaf_off + nd.n_vafs);
+        if (nd.kind == VLR_NODE_RANGE) max_vaf = std::max(max_vaf, nd.vaf_off + 4);
+    }
+    H.vafs.assign(mdl->vafs, mdl->vafs + max_vaf);
+    auto spectrum_of = [&](const vlr_node &nd) -> int {
+        for (size_t s = 0; s < H.spectra.size(); ++s) {
+            const DevSpectrum &sp = H.spectra[s];
+            if (sp.sample != nd.sample || sp.kind != nd.kind) continue;
+            const int n = nd.kind == VLR_NODE_RANGE ? 4 : nd.n_vafs;
+            if (nd.kind == VLR_NODE_SET && sp.n_vafs != nd.n_vafs) continue;
+            bool eq = true;
+            for (int i = 0; i < n && eq; ++i) eq = H.vafs[sp.vaf_off + i] == H.vafs[nd.vaf_off + i];
+            if (eq) return (int)s;
+        }
+        H.spectra.push_back(DevSpectrum{nd.sample, nd.kind, nd.vaf_off, nd.kind == VLR_NODE_RANGE ? 4 : nd.n_vafs});
+        return (int)H.spectra.size() - 1;
+    };
+    for (int e = 0; e < mdl->n_events; ++e) {
+        const vlr_event &ev = mdl->events[e];
+        DevEvent de;
+        de.path_off = (int)H.paths.size();
+        de.eb_off = (int)H.eb.size();
+        bool art = false;
+        for (int k = 0; k < ev.n_biases; ++k) {
+            const vlr_biases &b = mdl->biases[ev.bias_off + k];
+            art |= b.strand || b.orientation || b.read_position || b.softclip || b.divindel;
+            int id = -1;
+            for (size_t c = 0; c < H.cfg.size(); ++c) if (same_cfg(H.cfg[c], b)) { id = (int)c; break; }
+            if (id < 0) { H.cfg.push_back(b); id = (int)H.cfg.size() - 1; }
+            H.eb.push_back(DevEventBias{e, id});
+        }
+        de.n_eb = ev.n_biases;
+        de.is_artifact = art;
+        de.bias_prior = art ? log(0.5) + log(1.0 / (double)ev.n_biases) : log(0.5);
+        // depth-first path extraction (generic.rs:124-235): SET/RANGE bind a sample, SKIP passes,
+        // FALSE kills the branch, >1 children fan out, no children = leaf
+        struct Frame { int node; DevPath p; };
+        std::vector<Frame> stack;
+        for (int r = ev.n_roots - 1; r >= 0; --r) {
+            Frame f;
+            f.node = mdl->roots[ev.root_off + r];
+            f.p.event = e;
+            for (int s = 0; s < kMaxSamples; ++s) f.p.spec[s] = -1;
+            stack.push_back(f);
+        }
+        // (stack order reversed above so that paths come out in root order)
+        std::vector<DevPath> out;
+        while (!stack.empty()) {
+            Frame f = stack.back();
+            stack.pop_back();
+            if (f.node < 0 || f.node >= mdl->n_nodes) return set_err(ctx, VLR_ERR_INVALID, "bad node index");
+            const vlr_node &nd = mdl->nodes[f.node];
+            if (nd.kind == VLR_NODE_FALSE) continue;
+            if (nd.kind == VLR_NODE_SET || nd.kind == VLR_NODE_RANGE) {
+                if (nd.sample < 0 || nd.sample >= NS) return set_err(ctx, VLR_ERR_INVALID, "bad sample index");
+                if (nd.kind == VLR_NODE_SET && nd.n_vafs < 1) return set_err(ctx, VLR_ERR_INVALID, "empty VAF set");
+                f.p.spec[nd.sample] = spectrum_of(nd);
+            } else if (nd.kind != VLR_NODE_SKIP) {
+                return set_err(ctx, VLR_ERR_INVALID, "bad node kind");
+            }
+            if (nd.n_children == 0) {
+                for (int s = 0; s < NS; ++s)
+                    if (f.p.spec[s] < 0)
+                        return set_err(ctx, VLR_ERR_UNSUPPORTED, "event %d: a tree path does not bind sample %d", e, s);
+                out.push_back(f.p);
+            } else {
+                for (int c = nd.n_children - 1; c >= 0; --c) {
+                    Frame g2 = f;
+                    g2.node = mdl->children[nd.child_off + c];
+                    stack.push_back(g2);
+                }
+            }
+        }
+        de.n_paths = (int)out.size();
+        H.paths.insert(H.paths.end(), out.begin(), out.end());
+        H.events.push_back(de);
+    }
+    if ((int)H.spectra.size() > kMaxSpectra) return set_err(ctx, VLR_ERR_UNSUPPORTED, "too many distinct VAF spectra");
+    if ((int)H.cfg.size() > kMaxCfg) return set_err(ctx, VLR_ERR_UNSUPPORTED, "too many bias configurations");
+    return VLR_OK;
+}
+
+// upper bound of the likelihood-table size (doubles) for one site
+static int64_t table_bound(const vlr_model *mdl, const HostModel &H) {
+    int64_t nv[kMaxSamples] = {0};
+    for (const DevSpectrum &sp : H.spectra) {
+        int64_t c = sp.kind == VLR_NODE_RANGE ? (int64_t)mdl->resolution[sp.sample] + 1 : sp.n_vafs;
+        if (sp.kind == VLR_NODE_RANGE && c < 5) c = 5;
+        nv[sp.sample] += c;
+    }
+    int64_t tot = 0;
+    for (int s = 0; s < mdl->n_samples; ++s) {
+        int64_t keys = mdl->contaminated[s] ? nv[s] * nv[mdl->by[s]] : nv[s];
+        tot += keys * (int64_t)H.cfg.size();
+    }
+    return tot;
+}
+
+}  // namespace vlr
+
+using namespace vlr;
+
+extern "C" {
+
+int vlr_posterior_batch_dev(vlr_ctx *ctx, int64_t n_sites, const vlr_model *model,
+                            const vlr_obs_columns *d_obs, const int64_t *d_obs_off,
+                            double *d_out_event_ln, double *d_out_marginal, double *d_out_map_af,
+                            int32_t *d_out_map_bias) {
+    if (!ctx) return VLR_ERR_INVALID;
+    if (!model || !d_obs || !d_obs_off || !d_out_event_ln || !d_out_marginal || !d_out_map_af ||
+        !d_out_map_bias || n_sites < 0 || n_sites > 0x7fffffff)
+        return set_err(ctx, VLR_ERR_INVALID, "bad argument");
+    if (n_sites == 0) return VLR_OK;
+    VLR_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    HostModel H;
+    int rc = flatten_model(ctx, model, H);
+    if (rc != VLR_OK) return rc;
+    for (int s = 0; s < model->n_samples; ++s)
+        if (model->contaminated[s] && (model->by[s] < 0 || model->by[s] >= model->n_samples || model->by[s] == s))
+            return set_err(ctx, VLR_ERR_INVALID, "bad contamination source for sample %d", s);
+    const int64_t tbound = table_bound(model, H);
+    // team size: whole CTA for big tables (tumor/normal-like), one warp per site for small ones
+    const bool big = tbound > 1024;
+    const int teams_per_cta = big ? 1 : 4;
+    const int grid = ctx->sm_count * 3;
+    const int64_t n_teams = (int64_t)grid * teams_per_cta;
+    if (tbound > ((int64_t)1 << 24))
+        return set_err(ctx, VLR_ERR_UNSUPPORTED, "likelihood table of %lld entries per site is too large", (long long)tbound);
+    enum { S_MODEL = 16, S_TABLE, S_CNT };
+    // model blob
+    const size_t b_spec = H.spectra.size() * sizeof(DevSpectrum), b_path = H.paths.size() * sizeof(DevPath),
+                 b_ev = H.events.size() * sizeof(DevEvent), b_eb = H.eb.size() * sizeof(DevEventBias),
+                 b_cfg = H.cfg.size() * sizeof(vlr_biases), b_vaf = H.vafs.size() * sizeof(double);
+    size_t off[7];
+    off[0] = 0;
+    off[1] = align_up(off[0] + b_spec, 16);
+    off[2] = align_up(off[1] + b_path, 16);
+    off[3] = align_up(off[2] + b_ev, 16);
+    off[4] = align_up(off[3] + b_eb, 16);
+    off[5] = align_up(off[4] + b_cfg, 16);
+    off[6] = align_up(off[5] + b_vaf, 16);
+    uint8_t *h_blob = (uint8_t *)pin_scratch(ctx, 4, off[6] + 16);
+    uint8_t *d_blob = (uint8_t *)dev_scratch(ctx, S_MODEL, off[6] + 16);
+    double *d_table = (double *)dev_scratch(ctx, S_TABLE, (size_t)(n_teams * tbound + 8) * sizeof(double));
+    int32_t *d_cnt = (int32_t *)dev_scratch(ctx, S_CNT, 256);
+    if (!h_blob || !d_blob || !d_table || !d_cnt) return set_err(ctx, VLR_ERR_NOMEM, "scratch allocation failed");
+    // the pinned blob may still be in flight from a previous call on this stream
+    VLR_CUDA(ctx, cudaStreamSynchronize(st));
+    memcpy(h_blob + off[0], H.spectra.data(), b_spec);
+    memcpy(h_blob + off[1], H.paths.data(), b_path);
+    memcpy(h_blob + off[2], H.events.data(), b_ev);
+    memcpy(h_blob + off[3], H.eb.data(), b_eb);
+    memcpy(h_blob + off[4], H.cfg.data(), b_cfg);
+    memcpy(h_blob + off[5], H.vafs.data(), b_vaf);
+    VLR_CUDA(ctx, cudaMemcpyAsync(d_blob, h_blob, off[6], cudaMemcpyHostToDevice, st));
+    VLR_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, 256, st));
+    PostArgs a;
+    memset(&a, 0, sizeof(a));
+    a.m.n_samples = model->n_samples;
+    a.m.n_events = model->n_events;
+    a.m.n_spectra = (int)H.spectra.size();
+    a.m.n_paths = (int)H.paths.size();
+    a.m.n_cfg = (int)H.cfg.size();
+    a.m.n_eb = (int)H.eb.size();
+    for (int s = 0; s < model->n_samples; ++s) {
+        a.m.resolution[s] = model->resolution[s];
+        a.m.contaminated[s] = model->contaminated[s];
+        a.m.by[s] = model->by[s];
+        a.m.purity[s] = model->purity[s];
+        if (model->resolution[s] < 1) return set_err(ctx, VLR_ERR_INVALID, "resolution must be >= 1");
+    }
+    a.m.spectra = (const DevSpectrum *)(d_blob + off[0]);
+    a.m.paths = (const DevPath *)(d_blob + off[1]);
+    a.m.events = (const DevEvent *)(d_blob + off[2]);
+    a.m.eb = (const DevEventBias *)(d_blob + off[3]);
+    a.m.cfg = (const vlr_biases *)(d_blob + off[4]);
+    a.m.vafs = (const double *)(d_blob + off[5]);
+    a.obs = *d_obs;
+    a.obs_off = d_obs_off;
+    a.n_sites = n_sites;
+    a.cursor = d_cnt;
+    a.status = d_cnt + 1;
+    a.table = d_table;
+    a.table_stride = tbound;
+    a.out_event_ln = d_out_event_ln;
+    a.out_marginal = d_out_marginal;
+    a.out_map_af = d_out_map_af;
+    a.out_map_bias = d_out_map_bias;
+    if (big) posterior_kernel<4><<<grid, kTeamThreadsMax, 0, st>>>(a);
+    else posterior_kernel<1><<<grid, kTeamThreadsMax, 0, st>>>(a);
+    VLR_LAUNCH_CHECK(ctx);
+    return VLR_OK;
+}
+
+int vlr_posterior_batch(vlr_ctx *ctx, int64_t n_sites, const vlr_model *model,
+                        const vlr_obs_columns *obs, const int64_t *obs_off, double *out_event_ln,
+                        double *out_marginal, double *out_map_af, int32_t *out_map_bias) {
+    if (!ctx) return VLR_ERR_INVALID;
+    if (!model || !obs || !obs_off || !out_event_ln || !out_marginal || !out_map_af || !out_map_bias ||
+        n_sites < 0)
+        return set_err(ctx, VLR_ERR_INVALID, "bad argument");
+    if (n_sites == 0) return VLR_OK;
+    VLR_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int NS = model->n_samples, NE = model->n_events;
+    if (NS < 1 || NS > kMaxSamples) return set_err(ctx, VLR_ERR_UNSUPPORTED, "n_samples must be 1..8");
+    const int64_t n_off = n_sites * NS + 1;
+    const int64_t r0 = obs_off[0], r1 = obs_off[n_off - 1];
+    const int64_t n_rows = r1 - r0;
+    for (int64_t k = 0; k + 1 < n_off; ++k) {
+        const int64_t l = obs_off[k + 1] - obs_off[k];
+        if (l < 0) return set_err(ctx, VLR_ERR_INVALID, "obs_off not monotone");
+        if (l > 32 * kMaxObsPerLane)
+            return set_err(ctx, VLR_ERR_UNSUPPORTED, "pileup of %lld observations exceeds %d", (long long)l, 32 * kMaxObsPerLane);
+    }
+    enum { S_COL0 = 20, S_CAT = 29, S_OFF, S_EV, S_MARG, S_AF, S_MB };
+    const double *cols[9] = {obs->prob_mapping, obs->prob_mismapping, obs->prob_alt, obs->prob_ref,
+                             obs->prob_missed_allele, obs->prob_sample_alt, obs->prob_double_overlap,
+                             obs->prob_single_overlap, obs->prob_hit_base};
+    double *d_cols[9];
+    for (int c = 0; c < 9; ++c) {
+        if (!cols[c] && n_rows > 0) return set_err(ctx, VLR_ERR_INVALID, "null observation column");
+        d_cols[c] = (double *)dev_scratch(ctx, S_COL0 + c, (size_t)(n_rows + 1) * 8);
+        if (!d_cols[c]) return set_err(ctx, VLR_ERR_NOMEM, "scratch allocation failed");
+        if (n_rows > 0)
+            VLR_CUDA(ctx, cudaMemcpyAsync(d_cols[c], cols[c] + r0, (size_t)n_rows * 8, cudaMemcpyHostToDevice, st));
+    }
+    uint16_t *d_cat = (uint16_t *)dev_scratch(ctx, S_CAT, (size_t)(n_rows + 1) * 2);
+    int64_t *d_off = (int64_t *)dev_scratch(ctx, S_OFF, (size_t)n_off * 8);
+    double *d_ev = (double *)dev_scratch(ctx, S_EV, (size_t)n_sites * NE * 8);
+    double *d_marg = (double *)dev_scratch(ctx, S_MARG, (size_t)n_sites * 8);
+    double *d_af = (double *)dev_scratch(ctx, S_AF, (size_t)n_sites * NS * 8);
+    int32_t *d_mb = (int32_t *)dev_scratch(ctx, S_MB, (size_t)n_sites * NS * 4);
+    if (!d_cat || !d_off || !d_ev || !d_marg || !d_af || !d_mb)
+        return set_err(ctx, VLR_ERR_NOMEM, "scratch allocation failed");
+    if (n_rows > 0)
+        VLR_CUDA(ctx, cudaMemcpyAsync(d_cat, obs->cat + r0, (size_t)n_rows * 2, cudaMemcpyHostToDevice, st));
+    VLR_CUDA(ctx, cudaMemcpyAsync(d_off, obs_off, (size_t)n_off * 8, cudaMemcpyHostToDevice, st));
+    vlr_obs_columns dc;
+    dc.prob_mapping = d_cols[0] - r0; dc.prob_mismapping = d_cols[1] - r0; dc.prob_alt = d_cols[2] - r0;
+    dc.prob_ref = d_cols[3] - r0; dc.prob_missed_allele = d_cols[4] - r0; dc.prob_sample_alt = d_cols[5] - r0;
+    dc.prob_double_overlap = d_cols[6] - r0; dc.prob_single_overlap = d_cols[7] - r0;
+    dc.prob_hit_base = d_cols[8] - r0; dc.cat = d_cat - r0;
+    int rc = vlr_posterior_batch_dev(ctx, n_sites, model, &dc, d_off, d_ev, d_marg, d_af, d_mb);
+    if (rc != VLR_OK) return rc;
+    VLR_CUDA(ctx, cudaMemcpyAsync(out_event_ln, d_ev, (size_t)n_sites * NE * 8, cudaMemcpyDeviceToHost, st));
+    VLR_CUDA(ctx, cudaMemcpyAsync(out_marginal, d_marg, (size_t)n_sites * 8, cudaMemcpyDeviceToHost, st));
+    VLR_CUDA(ctx, cudaMemcpyAsync(out_map_af, d_af, (size_t)n_sites * NS * 8, cudaMemcpyDeviceToHost, st));
+    VLR_CUDA(ctx, cudaMemcpyAsync(out_map_bias, d_mb, (size_t)n_sites * NS * 4, cudaMemcpyDeviceToHost, st));
+    VLR_CUDA(ctx, cudaStreamSynchronize(st));
+    return VLR_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------- Likelihood::compute work items
+// One warp per (site, sample, AF[, secondary AF], bias configuration) item: the literal log-space
+// formulas of likelihood.rs (this entry point is the per-call seam; the batched table path above
+// is the fast one).
+namespace vlr {
+__global__ void likelihood_items_kernel(vlr_obs_columns obs, const int64_t *obs_off, int32_t n_samples,
+                                        const vlr_biases *biases, const vlr_lh_item *items,
+                                        int64_t n_items, double *out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t it = w; it < n_items; it += nw) {
+        const vlr_lh_item item = items[it];
+        const int64_t o0 = obs_off[(int64_t)item.site * n_samples + item.sample];
+        const int64_t o1 = obs_off[(int64_t)item.site * n_samples + item.sample + 1];
+        const vlr_biases b = biases[item.bias];
+        double acc = 0.0;
+        for (int64_t row = o0 + lane; row < o1; row += 32)
+            acc += ln_T_exact(obs, row, b, item.other_rate, item.af, item.af_secondary,
+                              item.contaminated != 0, item.purity);
+        acc = warp_sum(acc);
+        if (lane == 0) out[it] = acc;
+    }
+}
+}  // namespace vlr
+
+extern "C" int vlr_likelihood_batch(vlr_ctx *ctx, int64_t n_sites, int32_t n_samples,
+                                    const vlr_obs_columns *obs, const int64_t *obs_off,
+                                    const vlr_biases *biases, int32_t n_biases,
+                                    const vlr_lh_item *items, int64_t n_items, double *out_ln_lh) {
+    if (!ctx) return VLR_ERR_INVALID;
+    if (!obs || !obs_off || !biases || !items || !out_ln_lh || n_sites <= 0 || n_samples <= 0 ||
+        n_biases <= 0 || n_items < 0)
+        return set_err(ctx, VLR_ERR_INVALID, "bad argument");
+    if (n_items == 0) return VLR_OK;
+    VLR_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    for (int64_t k = 0; k < n_items; ++k) {
+        const vlr_lh_item &it = items[k];
+        if (it.site < 0 || it.site >= n_sites || it.sample < 0 || it.sample >= n_samples ||
+            it.bias < 0 || it.bias >= n_biases)
+            return set_err(ctx, VLR_ERR_INVALID, "item %lld out of range", (long long)k);
+        if (it.contaminated && !(it.purity > 0.0 && it.purity <= 1.0))
+            return set_err(ctx, VLR_ERR_INVALID, "item %lld: purity must be in (0,1]", (long long)k);
+    }
+    const int64_t n_off = n_sites * n_samples + 1;
+    const int64_t r0 = obs_off[0], n_rows = obs_off[n_off - 1] - r0;
+    enum { S_COL0 = 20, S_CAT = 29, S_OFF, S_B = 36, S_IT, S_O };
+    const double *cols[9] = {obs->prob_mapping, obs->prob_mismapping, obs->prob_alt, obs->prob_ref,
+                             obs->prob_missed_allele, obs->prob_sample_alt, obs->prob_double_overlap,
+                             obs->prob_single_overlap, obs->prob_hit_base};
+    double *d_cols[9];
+    for (int c = 0; c < 9; ++c) {
+        d_cols[c] = (double *)dev_scratch(ctx, S_COL0 + c, (size_t)(n_rows + 1) * 8);
+        if (!d_cols[c]) return set_err(ctx, VLR_ERR_NOMEM, "scratch allocation failed");
+        if (n_rows > 0)
+            VLR_CUDA(ctx, cudaMemcpyAsync(d_cols[c], cols[c] + r0, (size_t)n_rows * 8, cudaMemcpyHostToDevice, st));
+    }
+    uint16_t *d_cat = (uint16_t *)dev_scratch(ctx, S_CAT, (size_t)(n_rows + 1) * 2);
+    int64_t *d_off = (int64_t *)dev_scratch(ctx, S_OFF, (size_t)n_off * 8);
+    vlr_biases *d_b = (vlr_biases *)dev_scratch(ctx, S_B, (size_t)n_biases * sizeof(vlr_biases));
+    vlr_lh_item *d_it = (vlr_lh_item *)dev_scratch(ctx, S_IT, (size_t)n_items * sizeof(vlr_lh_item));
+    double *d_o = (double *)dev_scratch(ctx, S_O, (size_t)n_items * 8);
+    if (!d_cat || !d_off || !d_b || !d_it || !d_o) return set_err(ctx, VLR_ERR_NOMEM, "scratch allocation failed");
+    if (n_rows > 0)
+        VLR_CUDA(ctx, cudaMemcpyAsync(d_cat, obs->cat + r0, (size_t)n_rows * 2, cudaMemcpyHostToDevice, st));
+    VLR_CUDA(ctx, cudaMemcpyAsync(d_off, obs_off, (size_t)n_off * 8, cudaMemcpyHostToDevice, st));
+    VLR_CUDA(ctx, cudaMemcpyAsync(d_b, biases, (size_t)n_biases * sizeof(vlr_biases), cudaMemcpyHostToDevice, st));
+    VLR_CUDA(ctx, cudaMemcpyAsync(d_it, items, (size_t)n_items * sizeof(vlr_lh_item), cudaMemcpyHostToDevice, st));
+    vlr_obs_columns dc;
+    dc.prob_mapping = d_cols[0] - r0; dc.prob_mismapping = d_cols[1] - r0; dc.prob_alt = d_cols[2] - r0;
+    dc.prob_ref = d_cols[3] - r0; dc.prob_missed_allele = d_cols[4] - r0; dc.prob_sample_alt = d_cols[5] - r0;
+    dc.prob_double_overlap = d_cols[6] - r0; dc.prob_single_overlap = d_cols[7] - r0;
+    dc.prob_hit_base = d_cols[8] - r0; dc.cat = d_cat - r0;
+    const int64_t want = (n_items * 32 + 255) / 256;
+    const int grid = (int)std::min<int64_t>(want, (int64_t)ctx->sm_count * 16);
+    vlr::likelihood_items_kernel<<<grid, 256, 0, st>>>(dc, d_off, n_samples, d_b, d_it, n_items, d_o);
+    VLR_LAUNCH_CHECK(ctx);
+    VLR_CUDA(ctx, cudaMemcpyAsync(out_ln_lh, d_o, (size_t)n_items * 8, cudaMemcpyDeviceToHost, st));
+    VLR_CUDA(ctx, cudaStreamSynchronize(st));
+    return VLR_OK;
+}

@@ -125,3 +125,123 @@ def make_ragged_pairs(n_pairs, seed, min_ly=1, max_ly=256, min_lx=1, max_lx=700,
     read_off[1:] = np.cumsum([len(r) for r in reads])
     return dict(hap_bytes=np.concatenate(haps), hap_off=hap_off, read_bases=np.concatenate(reads),
                 read_quals=np.concatenate(quals), read_off=read_off)
+
+
+# ------------------------------------------------------------------------------------------------
+# pileups (part 2 inputs): Observation columns of include/vlr_gpu.h
+# ------------------------------------------------------------------------------------------------
+OBS_COLUMNS = ("prob_mapping", "prob_mismapping", "prob_alt", "prob_ref", "prob_missed_allele",
+               "prob_sample_alt", "prob_double_overlap", "prob_single_overlap", "prob_hit_base")
+
+
+def minilogprob(p):
+    """MiniLogProb wire quantisation (reference src/utils/mod.rs:381-407): f16 if p < -10 and
+    floor(f16(p)) == floor(p), else f32.  The likelihood model only ever sees these values."""
+    p = np.asarray(p, dtype=np.float64)
+    with np.errstate(over="ignore", invalid="ignore"):
+        h = p.astype(np.float16).astype(np.float64)
+        use16 = (p < -10.0) & (np.floor(h) == np.floor(p))
+        return np.where(use16, h, p.astype(np.float32).astype(np.float64))
+
+
+def _ln1mexp(p):
+    p = np.asarray(p, dtype=np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.where(p < -0.693, np.log1p(-np.exp(p)), np.log(-np.expm1(p)))
+
+
+def pack_cat(strand, orientation, read_position, softclipped, indel_ops, paired):
+    return (np.asarray(strand, np.uint16) | (np.asarray(orientation, np.uint16) << 2)
+            | (np.asarray(read_position, np.uint16) << 6)
+            | (np.asarray(softclipped, np.uint16) << 7) | (np.asarray(indel_ops, np.uint16) << 8)
+            | (np.asarray(paired, np.uint16) << 10)).astype(np.uint16)
+
+
+def make_pileups(n_sites, depths, seed=SEED_C2, kind="snv", af_sets=None, purity=None,
+                 quantise=True, ragged=False, artifact_frac=0.0):
+    """Synthetic pileups per SURVEY.md section 8(d), config C2 (kind="snv") / C3 part 2
+    (kind="indel", tumor/normal).
+
+    depths: observations per sample (list, one entry per sample, sample order of the scenario).
+    af_sets: per sample list of (af, probability) for the site's true allele frequency; default
+             {0: .9, .5: .07, 1: .03} (C2).  purity: per-sample mixing with sample 0's AF (tumor
+             contaminated by normal), or None.
+    ragged: depths vary per site (Poisson around the given depth, zero allowed).
+    Returns (cols dict, cat, obs_off[n_sites*n_samples+1], true_af[n_sites, n_samples]).
+    """
+    rng = np.random.Generator(np.random.PCG64(seed))
+    ns = len(depths)
+    if af_sets is None:
+        af_sets = [[(0.0, 0.90), (0.5, 0.07), (1.0, 0.03)]] * ns
+    true_af = np.empty((n_sites, ns))
+    for s in range(ns):
+        vals = np.array([a for a, _ in af_sets[s]])
+        pr = np.array([p for _, p in af_sets[s]])
+        true_af[:, s] = vals[rng.choice(len(vals), size=n_sites, p=pr / pr.sum())]
+    if ragged:
+        n_obs = np.stack([rng.poisson(d, size=n_sites) for d in depths], axis=1)
+        n_obs = np.minimum(n_obs, 250)
+        n_obs[rng.random(n_sites) < 0.03] = 0
+    else:
+        n_obs = np.tile(np.asarray(depths, dtype=np.int64), (n_sites, 1))
+    obs_off = np.zeros(n_sites * ns + 1, dtype=np.int64)
+    obs_off[1:] = np.cumsum(n_obs.reshape(-1))
+    n = int(obs_off[-1])
+    site_of = np.repeat(np.arange(n_sites * ns) // ns, n_obs.reshape(-1))
+    samp_of = np.repeat(np.arange(n_sites * ns) % ns, n_obs.reshape(-1))
+    eff_af = true_af[site_of, samp_of]
+    if purity is not None:
+        pur = np.asarray(purity)[samp_of]
+        eff_af = pur * eff_af + (1.0 - pur) * true_af[site_of, 0]
+    is_alt = rng.random(n) < eff_af
+    ln_conf = np.log(0.3333)
+    if kind == "snv":
+        q = np.clip(np.rint(rng.normal(32, 5, n)), 2, 41)
+        ln_eps = q * (-np.log(10.0) / 10.0)
+        sup, oth = _ln1mexp(ln_eps), ln_eps + ln_conf      # prob_read_base, bases.rs:13-21
+        indel = np.full(n, 2)                               # IndelOperations::None
+    else:
+        # realignment-like: normalised pair of allele probabilities, some uninformative reads
+        d = np.power(10.0, -rng.uniform(0.5, 30.0, n))
+        sup, oth = np.log1p(-d), np.log(d)
+        uninf = rng.random(n) < 0.08
+        sup = np.where(uninf, np.log(0.5), sup)
+        oth = np.where(uninf, np.log(0.5), oth)
+        indel = np.where(is_alt & ~uninf, np.where(rng.random(n) < 0.9, 0, 1), 2)
+    p_alt = np.where(is_alt, sup, oth)
+    p_ref = np.where(is_alt, oth, sup)
+    mapq = np.where(rng.random(n) < 0.92, 60.0, rng.integers(1, 60, n).astype(np.float64))
+    prob_mapping = np.log1p(-np.power(10.0, -mapq / 10.0))
+    strand = rng.integers(0, 2, n)
+    both = rng.random(n) < 0.05
+    strand = np.where(both, 2, strand)
+    orient = rng.integers(0, 2, n)
+    orient = np.where(rng.random(n) < 0.03, 8, orient)      # a few without orientation info
+    softclip = rng.random(n) < 0.02
+    readpos = rng.integers(0, 150, n)
+    major = np.zeros(n, dtype=bool)
+    # ReadPosition::Major = most common read position within the pileup (observation.rs:314-326)
+    if kind == "snv":
+        starts = obs_off[:-1]
+        for k in range(n_sites * ns):
+            lo, hi = int(starts[k]), int(obs_off[k + 1])
+            if hi > lo:
+                vals, cnt = np.unique(readpos[lo:hi], return_counts=True)
+                major[lo:hi] = readpos[lo:hi] == vals[np.argmax(cnt)]
+    if artifact_frac > 0:
+        # strand artifact: at some sites every alt-supporting read is on the forward strand
+        art_site = rng.random(n_sites) < artifact_frac
+        force = art_site[site_of] & is_alt
+        strand = np.where(force, 0, strand)
+    prob_double_overlap = np.where(strand == 2, 0.0, -np.inf)
+    with np.errstate(divide="ignore"):
+        missed = np.logaddexp(p_ref, p_alt) - np.log(2.0)
+    cols = dict(prob_mapping=prob_mapping, prob_alt=p_alt, prob_ref=p_ref, prob_missed_allele=missed,
+                prob_sample_alt=np.zeros(n) if kind == "snv" else np.log(rng.uniform(0.7, 1.0, n)),
+                prob_double_overlap=prob_double_overlap, prob_hit_base=np.full(n, -np.log(150.0)))
+    if quantise:
+        cols = {k: minilogprob(v) for k, v in cols.items()}
+    cols["prob_mismapping"] = _ln1mexp(cols["prob_mapping"])          # prob_mapping_mismapping()
+    cols["prob_single_overlap"] = _ln1mexp(cols["prob_double_overlap"])  # prob_overlap()
+    cat = pack_cat(strand, orient, np.where(major, 0, 1), softclip, indel, np.ones(n, dtype=int))
+    return cols, cat, obs_off, true_af

@@ -882,15 +882,28 @@ static double joint_prob(post_ctx_t *c) {
     }
     double j = prior + p;
     if (isnan(j)) c->nan_flag = 1;
-    /* joint_probs.insert(base_event, p): keep the running maxima (first max wins ties) */
+    /* joint_probs.insert(base_event, p): keep the running maxima.  The reference sorts a HashMap
+     * (order among exact ties unspecified, quirk Q14); the oracle and the GPU path share one
+     * explicit rule: larger joint, then earlier (event, bias) entry, then the lexicographically
+     * smaller allele-frequency vector. */
     int art = vlro_biases_is_artifact(b);
-    if (!c->have_any || j > c->best_any.p) {
-        c->have_any = 1; c->best_any.p = j; c->best_any.bias = c->cur_bias;
-        memcpy(c->best_any.af, c->cur_af, sizeof(double) * (size_t)m->n_samples);
-    }
-    if (!art && (!c->have_clean || j > c->best_clean.p)) {
-        c->have_clean = 1; c->best_clean.p = j; c->best_clean.bias = c->cur_bias;
-        memcpy(c->best_clean.af, c->cur_af, sizeof(double) * (size_t)m->n_samples);
+    joint_t *slots[2] = {&c->best_any, art ? NULL : &c->best_clean};
+    int *have[2] = {&c->have_any, &c->have_clean};
+    for (int w = 0; w < 2; ++w) {
+        joint_t *bst = slots[w];
+        if (!bst || isnan(j)) continue;
+        int better = 0;
+        if (!*have[w]) better = 1;
+        else if (j != bst->p) better = j > bst->p;
+        else if (c->cur_bias != bst->bias) better = c->cur_bias < bst->bias;
+        else {
+            for (int s = 0; s < m->n_samples; ++s)
+                if (c->cur_af[s] != bst->af[s]) { better = c->cur_af[s] < bst->af[s]; break; }
+        }
+        if (better) {
+            *have[w] = 1; bst->p = j; bst->bias = c->cur_bias;
+            memcpy(bst->af, c->cur_af, sizeof(double) * (size_t)m->n_samples);
+        }
     }
     return j;
 }

@@ -1,0 +1,192 @@
+"""GPU parity of K3/K4 (pileup likelihood on the AF grid + event integration) against the CPU
+oracle, through the C ABI (vlr_posterior_batch / vlr_likelihood_batch).
+Tolerances: |delta| <= 1e-6 in natural-log space for event posteriors and marginals; MAP allele
+frequencies and bias calls identical."""
+import math
+
+import numpy as np
+import pytest
+
+import libprosic_b200 as P
+from libprosic_b200 import scenario, synth
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-6
+
+
+def _oracle_spec(oracle, scn):
+    return oracle.ModelSpec(scn["n_samples"], scn["resolution"], scn["contaminated"], scn["by"],
+                            scn["purity"], scn["nodes"], scn["events"],
+                            [oracle.make_biases(**b) for b in scn["biases"]])
+
+
+def _oracle_run(oracle, scn, cols, cat, off, sites):
+    spec = _oracle_spec(oracle, scn)
+    ns = scn["n_samples"]
+    out = []
+    for s in sites:
+        pv = [oracle.PileupView(cols, cat, int(off[s * ns + k]), int(off[s * ns + k + 1]))
+              for k in range(ns)]
+        r = oracle.model_compute(spec, pv)
+        r["map_bias_cfg"] = np.array([spec.flat_bias_idx[b] if b >= 0 else -1 for b in r["map_bias"]])
+        out.append(r)
+    return out
+
+
+def _close(a, b, tol=TOL):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    same_inf = (np.isinf(a) & np.isinf(b) & (np.sign(a) == np.sign(b))) | (np.isnan(a) & np.isnan(b))
+    d = np.abs(np.where(same_inf, 0.0, a - b))
+    assert not np.isnan(d).any(), (a, b)
+    assert d.max(initial=0.0) <= tol, "max |delta| = %g (got %r want %r)" % (
+        d.max(), a.ravel()[d.argmax()], b.ravel()[d.argmax()])
+
+
+def _check(ctx, oracle, scn, cols, cat, off, sites=None):
+    ns = scn["n_samples"]
+    n_sites = (len(off) - 1) // ns
+    got = ctx.posterior_batch(scn, cols, cat, off)
+    sites = range(n_sites) if sites is None else sites
+    want = _oracle_run(oracle, scn, cols, cat, off, sites)
+    for s, w in zip(sites, want):
+        _close(got["event_ln"][s], w["event_ln"])
+        _close(got["marginal"][s], w["marginal"])
+        assert np.array_equal(got["map_af"][s], w["map_af"], equal_nan=True), (s, got["map_af"][s], w["map_af"])
+        assert np.array_equal(got["map_bias"][s], w["map_bias_cfg"]), (s, got["map_bias"][s], w["map_bias_cfg"])
+    return got, want
+
+
+@pytest.mark.parametrize("continuous", [False, True])
+def test_c2_single_sample(ctx, oracle, continuous):
+    scn = scenario.single_sample(continuous=continuous)
+    cols, cat, off, _ = synth.make_pileups(300, [30], seed=synth.SEED_C2, artifact_frac=0.1)
+    got, want = _check(ctx, oracle, scn, cols, cat, off)
+    # some sites must be called present, some absent, some artifact for the test to mean anything
+    post = got["event_ln"] - got["marginal"][:, None]
+    assert (post.argmax(1) == 0).sum() > 100 and (post.argmax(1) != 0).sum() > 10
+    assert (got["map_bias"] >= 0).any()
+
+
+def test_c2_ragged_depths_and_empty(ctx, oracle):
+    scn = scenario.single_sample(continuous=True)
+    cols, cat, off, _ = synth.make_pileups(200, [30], seed=7, ragged=True)
+    assert (np.diff(off) == 0).any()
+    _check(ctx, oracle, scn, cols, cat, off)
+
+
+def test_tumor_normal_indel(ctx, oracle):
+    scn = scenario.tumor_normal(purity=0.75, indel=True)
+    cols, cat, off, _ = synth.make_pileups(
+        24, [40, 100], seed=synth.SEED_C3, kind="indel",
+        af_sets=[[(0, .6), (.5, .3), (1, .1)], [(0, .4), (.3, .4), (.05, .2)]], purity=[1.0, 0.75])
+    _check(ctx, oracle, scn, cols, cat, off)
+
+
+def test_tumor_normal_snv_ragged(ctx, oracle):
+    scn = scenario.tumor_normal(purity=0.6, indel=False, tumor_resolution=31)
+    cols, cat, off, _ = synth.make_pileups(
+        24, [20, 45], seed=11, kind="snv", ragged=True, artifact_frac=0.2,
+        af_sets=[[(0, .6), (.5, .3), (1, .1)], [(0, .4), (.3, .4), (.05, .2)]], purity=[1.0, 0.6])
+    _check(ctx, oracle, scn, cols, cat, off)
+
+
+def test_trio_with_branching_tree(ctx, oracle):
+    scn = scenario.trio(with_biases=True)
+    cols, cat, off, _ = synth.make_pileups(60, [30, 30, 30], seed=synth.SEED_C5)
+    _check(ctx, oracle, scn, cols, cat, off)
+
+
+def test_unquantised_extreme_probabilities(ctx, oracle):
+    """Allele probabilities down to e^-2000 and MAPQ 255 (prob_mismapping = ln 0): the scaled
+    linear product leaves fp64 range and the log-space path must take over."""
+    scn = scenario.single_sample(continuous=False)
+    cols, cat, off, _ = synth.make_pileups(40, [12], seed=3, quantise=False)
+    n = len(cat)
+    rng = np.random.default_rng(0)
+    k = rng.random(n) < 0.5
+    cols["prob_ref"] = np.where(k & (cols["prob_alt"] > cols["prob_ref"]), -2000.0, cols["prob_ref"])
+    cols["prob_alt"] = np.where(k & (cols["prob_alt"] < cols["prob_ref"]), -1500.0, cols["prob_alt"])
+    cols["prob_mapping"] = np.where(rng.random(n) < 0.5, 0.0, cols["prob_mapping"])
+    cols["prob_mismapping"] = synth._ln1mexp(cols["prob_mapping"])
+    cols["prob_missed_allele"] = np.logaddexp(cols["prob_ref"], cols["prob_alt"]) - math.log(2.0)
+    _check(ctx, oracle, scn, cols, cat, off)
+
+
+def test_all_other_indel_ops_drops_unbiased_events(ctx, oracle):
+    """Quirk Q16: if every observation is IndelOperations::Other, DivIndelBias::None is impossible
+    and only artifact events survive."""
+    scn = scenario.single_sample(continuous=False, snv=False)
+    cols, cat, off, _ = synth.make_pileups(6, [25], seed=5, kind="indel", af_sets=[[(0.5, 1.0)]])
+    cat = (cat & ~np.uint16(3 << 8)) | np.uint16(1 << 8)
+    got, _ = _check(ctx, oracle, scn, cols, cat, off)
+    unbiased = [i for i, e in enumerate(scn["events"]) if e["biases"] == [0]]
+    assert np.isneginf(got["event_ln"][:, unbiased]).all()
+
+
+def test_likelihood_items_and_reference_identities(ctx, oracle):
+    """vlr_likelihood_batch vs the oracle, plus the reference's own identities
+    (likelihood.rs:267-386) evaluated on the GPU."""
+    cols, cat, off, _ = synth.make_pileups(20, [15, 25], seed=9, kind="indel",
+                                           af_sets=[[(0, .5), (.5, .5)], [(0.2, 1.0)]])
+    biases = [scenario.bias()] + scenario.artifact_biases(True, True, True, True, True)
+    rng = np.random.default_rng(1)
+    items = []
+    for _ in range(400):
+        items.append(dict(site=int(rng.integers(0, 20)), sample=int(rng.integers(0, 2)),
+                          bias=int(rng.integers(0, len(biases))), contaminated=int(rng.integers(0, 2)),
+                          af=float(rng.choice([0.0, 0.13, 0.5, 1.0, rng.random()])),
+                          af_secondary=float(rng.choice([0.0, 0.5, 1.0, rng.random()])),
+                          purity=float(rng.uniform(0.3, 1.0)), other_rate=float(rng.choice([0.0, 0.25, 0.6]))))
+    got = ctx.likelihood_batch(20, 2, cols, cat, off, biases, items)
+    for it, g in zip(items, got):
+        k = it["site"] * 2 + it["sample"]
+        pv = oracle.PileupView(cols, cat, int(off[k]), int(off[k + 1]))
+        b = oracle.make_biases(**biases[it["bias"]])
+        b.other_rate = it["other_rate"]
+        if it["contaminated"]:
+            w = oracle.likelihood_contaminated(pv, it["purity"], it["af"], b, it["af_secondary"], b)
+        else:
+            w = oracle.likelihood_single(pv, it["af"], b)
+        if math.isnan(w):
+            assert math.isnan(g)     # Strand::None x strand bias is unreachable!() in the reference
+        else:
+            _close(g, w)
+    # reference identities: 10 alt-zero reads at AF 0 -> sum of prob_any; AF .5 maximises 5+5 reads
+    ninf = -math.inf
+
+    def obs_rows(rows):
+        c = {n: [] for n in synth.OBS_COLUMNS}
+        for pm, pa, pr in rows:
+            c["prob_mapping"].append(pm); c["prob_mismapping"].append(float(synth._ln1mexp(pm)))
+            c["prob_alt"].append(pa); c["prob_ref"].append(pr)
+            c["prob_missed_allele"].append(float(np.logaddexp(pr, pa)) - math.log(2.0))
+            c["prob_sample_alt"].append(0.0); c["prob_double_overlap"].append(0.0)
+            c["prob_single_overlap"].append(ninf); c["prob_hit_base"].append(math.log(0.01))
+        n = len(rows)
+        return ({k: np.array(v) for k, v in c.items()},
+                synth.pack_cat([2] * n, [8] * n, [1] * n, [0] * n, [2] * n, [1] * n))
+    c1, k1 = obs_rows([(0.0, ninf, 0.0)] * 10)
+    none = [scenario.bias()]
+    any_sum = 10 * (math.log(0.5) + math.log(0.5) + math.log(0.01))
+    g = ctx.likelihood_batch(1, 1, c1, k1, [0, 10], none,
+                             [dict(site=0, sample=0, bias=0, af=0.0),
+                              dict(site=0, sample=0, bias=0, af=0.0, contaminated=1, af_secondary=0.0, purity=1.0)])
+    _close(g, [any_sum, any_sum], tol=1e-9)
+    c2, k2 = obs_rows([(0.0, 0.0, ninf)] * 5 + [(0.0, ninf, 0.0)] * 5)
+    afs = [0.5] + [a for a in np.linspace(0, 1, 10)]
+    g = ctx.likelihood_batch(1, 1, c2, k2, [0, 10], none,
+                             [dict(site=0, sample=0, bias=0, af=float(a), contaminated=1, af_secondary=0.0,
+                                   purity=1.0) for a in afs])
+    assert (g[0] > g[1:]).all()
+
+
+def test_posterior_errors_are_loud(ctx):
+    scn = scenario.single_sample()
+    cols, cat, off, _ = synth.make_pileups(2, [300], seed=1)
+    with pytest.raises(P.VlrError):
+        ctx.posterior_batch(scn, cols, cat, off)  # 300 observations > 256 per pileup
+    bad = scenario.single_sample()
+    bad["nodes"][0]["sample"] = 5
+    cols, cat, off, _ = synth.make_pileups(2, [10], seed=1)
+    with pytest.raises(P.VlrError):
+        ctx.posterior_batch(bad, cols, cat, off)
