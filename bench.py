@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--exact-sum", action="store_true",
                     help="time the exact M-state sum instead of bio's ln_sum3_exp_approx")
     ap.add_argument("--cpu-sample-pairs", type=int, default=0, help="0 = auto (about 15 s)")
+    ap.add_argument("--p2-sites", type=int, default=262144, help="C2 sites per step and GPU (part 2)")
+    ap.add_argument("--skip-part2", action="store_true")
     return ap.parse_args()
 
 
@@ -156,6 +158,131 @@ def run_reference(args, rank, world):
                                        "restatement, not the Rust binary" % (per_step, cores)},
             "e2e": {"value": val, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+FLOPS_PER_EVAL_SINGLE = 34.0  # 10 flops + 1 fp64 log counted as 24
+FLOPS_PER_EVAL_CONTAM = 42.0
+BYTES_PER_OBS = 74.0          # 9 fp64 columns + 2 bytes of categoricals as laid out in HBM
+
+
+def part2_workloads(args):
+    from libprosic_b200 import scenario
+    return {
+        "c2_continuous": dict(scn=scenario.single_sample(continuous=True), depths=[30], kind="snv",
+                              n_sites=args.p2_sites, af_sets=None, purity=None,
+                              desc="C2 scenario B: 1 sample x 30 obs, universe [0,1] on a 31-point "
+                                   "Simpson grid, SNV bias configs (1+7)", flops=FLOPS_PER_EVAL_SINGLE),
+        "c2_germline": dict(scn=scenario.single_sample(continuous=False), depths=[30], kind="snv",
+                            n_sites=args.p2_sites, af_sets=None, purity=None,
+                            desc="C2 scenario A: 1 sample x 30 obs, universe {0,.5,1}, SNV bias configs",
+                            flops=FLOPS_PER_EVAL_SINGLE),
+        "c3_tumor_normal": dict(scn=scenario.tumor_normal(purity=0.75, indel=True), depths=[40, 100],
+                                kind="indel", n_sites=max(1024, args.p2_sites // 64),
+                                af_sets=[[(0, .6), (.5, .3), (1, .1)], [(0, .4), (.3, .4), (.05, .2)]],
+                                purity=[1.0, 0.75],
+                                desc="C3 part 2: built-in tumor/normal scenario, 40x normal + 100x tumor, "
+                                     "purity .75, tumor grid 101 x normal grid 5, indel bias configs (1+3)",
+                                flops=FLOPS_PER_EVAL_CONTAM),
+    }
+
+
+def oracle_part2(wl, cols, cat, off, n_sample):
+    """Oracle (1 thread) on the first n_sample sites: sites/s and distinct evaluations per site."""
+    import oracle as O
+    scn = wl["scn"]
+    spec = O.ModelSpec(scn["n_samples"], scn["resolution"], scn["contaminated"], scn["by"],
+                       scn["purity"], scn["nodes"], scn["events"],
+                       [O.make_biases(**b) for b in scn["biases"]])
+    ns = scn["n_samples"]
+    res, evals = [], 0.0
+    t0 = time.perf_counter()
+    for s in range(n_sample):
+        pv = [O.PileupView(cols, cat, int(off[s * ns + k]), int(off[s * ns + k + 1])) for k in range(ns)]
+        r = O.model_compute(spec, pv)
+        res.append(r)
+    dt = time.perf_counter() - t0
+    return res, n_sample / dt, dt
+
+
+def bench_part2(args, ctx, torch, dist, dev, stream, rank, world, name, wl, timed):
+    """sites/s of AF-grid likelihood + event integration (K3/K4) on one synthetic shard per rank."""
+    from libprosic_b200 import synth
+    scn = wl["scn"]
+    ns, ne = scn["n_samples"], len(scn["events"])
+    cols, cat, off, _ = synth.make_pileups(wl["n_sites"], wl["depths"], seed=synth.SEED_C2 + 17 * rank,
+                                           kind=wl["kind"], af_sets=wl["af_sets"], purity=wl["purity"],
+                                           artifact_frac=0.05)
+    n_sites = wl["n_sites"]
+    names = synth.OBS_COLUMNS
+    h_cols = {n: torch.from_numpy(np.ascontiguousarray(cols[n])).pin_memory() for n in names}
+    h_cat = torch.from_numpy(cat.view(np.int16)).pin_memory()
+    h_off = torch.from_numpy(off).pin_memory()
+    d_cols = {n: h_cols[n].to(dev) for n in names}
+    d_cat, d_off = h_cat.to(dev), h_off.to(dev)
+    d_ev = torch.empty(n_sites * ne, dtype=torch.float64, device=dev)
+    d_marg = torch.empty(n_sites, dtype=torch.float64, device=dev)
+    d_af = torch.empty(n_sites * ns, dtype=torch.float64, device=dev)
+    d_mb = torch.empty(n_sites * ns, dtype=torch.int32, device=dev)
+    ptrs = {n: d_cols[n].data_ptr() for n in names}
+
+    def step_dev():
+        ctx.posterior_batch_dev(scn, n_sites, ptrs, d_cat.data_ptr(), d_off.data_ptr(),
+                                d_ev.data_ptr(), d_marg.data_ptr(), d_af.data_ptr(), d_mb.data_ptr())
+
+    np_cols = {n: h_cols[n].numpy() for n in names}
+    np_cat = h_cat.numpy().view(np.uint16)
+
+    def step_e2e():
+        return ctx.posterior_batch(scn, np_cols, np_cat, h_off.numpy())
+
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    l0 = ctx.launch_count()
+    ms = timed(step_dev, args.steps)
+    launches = ctx.launch_count() - l0
+    out_e2e = step_e2e()
+    t0 = time.perf_counter()
+    timed(step_e2e, args.steps)
+    ms_e2e = (time.perf_counter() - t0) * 1e3
+    if world > 1:
+        t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+    in_bytes = sum(int(v.numel() * v.element_size()) for v in h_cols.values()) + \
+        int(h_cat.numel() * 2 + h_off.numel() * 8)
+    out_bytes = n_sites * (ne * 8 + 8 + ns * 12)
+    res = {"workload": wl["desc"], "sites_per_gpu": n_sites, "value": n_sites * world * args.steps / (ms * 1e-3),
+           "unit": "sites/s", "ms_per_step": ms / args.steps, "gpu_launches": int(launches),
+           "e2e": {"value": n_sites * world * args.steps / (ms_e2e * 1e-3), "unit": "sites/s",
+                   "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
+                   "ms_per_step": ms_e2e / args.steps}}
+    if rank == 0:
+        n_cpu = 200 if ns == 1 else 24
+        ores, cpu_sps, cpu_dt = oracle_part2(wl, cols, cat, off, n_cpu)
+        ev = d_ev.cpu().numpy().reshape(n_sites, ne)[:n_cpu]
+        want = np.array([r["event_ln"] for r in ores])
+        fin = np.isfinite(ev) & np.isfinite(want)
+        res["parity_max_abs_ln"] = float(np.max(np.abs(ev[fin] - want[fin]))) if fin.any() else 0.0
+        res["parity_map_af_identical"] = bool(np.array_equal(
+            d_af.cpu().numpy().reshape(n_sites, ns)[:n_cpu], np.array([r["map_af"] for r in ores]),
+            equal_nan=True))
+        res["e2e"]["identical_to_device_path"] = bool(np.array_equal(
+            out_e2e["event_ln"], d_ev.cpu().numpy().reshape(n_sites, ne), equal_nan=True))
+        n_obs_site = float(np.sum(wl["depths"]))
+        # distinct likelihood evaluations per site (cache-miss semantics of likelihood.rs:128,221):
+        # oracle count of distinct keys x observations of the sample they run over
+        keys = float(np.mean([r["n_evals"] for r in ores]))
+        evals = keys * (wl["depths"][-1] if ns > 1 else wl["depths"][0])
+        sps_gpu = n_sites * args.steps / (ms * 1e-3)
+        res["evals_per_site"] = evals
+        res["roofline"] = {"bound": "fp64", "achieved": sps_gpu * evals * wl["flops"] / 1e12,
+                           "unit": "TFLOP/s", "flops_per_eval": wl["flops"],
+                           "note": "survey convention (a software fp64 log = 24 flops per evaluation); the "
+                                   "kernel takes one log per key instead of one per observation",
+                           "hbm": {"achieved": sps_gpu * n_obs_site * BYTES_PER_OBS / 1e9, "unit": "GB/s"}}
+        res["cpu_baseline"] = {"value": cpu_sps, "unit": "sites/s", "cores": 1, "kind": "port",
+                               "sample": "%d sites of this workload, 1 thread, %.1f s" % (n_cpu, cpu_dt)}
+    return res
 
 
 def main():
@@ -276,6 +403,13 @@ def main():
         parity = float(np.max(np.abs(got - want)))
         same_e2e = bool(np.array_equal(h_out.numpy(), d_out.cpu().numpy()))
 
+    part2 = {}
+    if not args.skip_part2:
+        del d, d_hap, d_ws, d_out
+        torch.cuda.empty_cache()
+        for name, wl in part2_workloads(args).items():
+            part2[name] = bench_part2(args, ctx, torch, dist, dev, stream, rank, world, name, wl, timed)
+
     total_cells = cells * world
     gcups = total_cells * args.steps / (ms * 1e-3) / 1e9
     gcups_e2e = total_cells * args.steps / (ms_e2e * 1e-3) / 1e9
@@ -321,8 +455,14 @@ def main():
             "other_mode": {"m_state_sum": "ln_sum3_exp_approx" if args.exact_sum else "exact",
                            "value": total_cells * args.steps / (ms_other * 1e-3) / 1e9, "unit": "GCUPS"},
             "parity_max_abs_ln": parity,
+            "sites_per_sec": part2,
             "clocks": clocks,
         }
+        for v in part2.values():
+            if "roofline" in v:
+                v["roofline"]["peak"] = peak_tf
+                v["roofline"]["frac"] = v["roofline"]["achieved"] / peak_tf if peak_tf else None
+                v["roofline"]["hbm"]["peak"] = hbm_peak
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -218,16 +218,11 @@ def make_pileups(n_sites, depths, seed=SEED_C2, kind="snv", af_sets=None, purity
     orient = rng.integers(0, 2, n)
     orient = np.where(rng.random(n) < 0.03, 8, orient)      # a few without orientation info
     softclip = rng.random(n) < 0.02
-    readpos = rng.integers(0, 150, n)
-    major = np.zeros(n, dtype=bool)
-    # ReadPosition::Major = most common read position within the pileup (observation.rs:314-326)
-    if kind == "snv":
-        starts = obs_off[:-1]
-        for k in range(n_sites * ns):
-            lo, hi = int(starts[k]), int(obs_off[k + 1])
-            if hi > lo:
-                vals, cnt = np.unique(readpos[lo:hi], return_counts=True)
-                major[lo:hi] = readpos[lo:hi] == vals[np.argmax(cnt)]
+    # ReadPosition::Major = the most common read position of the pileup (observation.rs:314-326);
+    # synthetic: every pileup has one over-represented position
+    major_pos = rng.integers(0, 150, n_sites * ns)[np.repeat(np.arange(n_sites * ns), n_obs.reshape(-1))]
+    readpos = np.where(rng.random(n) < 0.12, major_pos, rng.integers(0, 150, n))
+    major = (readpos == major_pos) & (kind == "snv")
     if artifact_frac > 0:
         # strand artifact: at some sites every alt-supporting read is on the forward strand
         art_site = rng.random(n_sites) < artifact_frac
