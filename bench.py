@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--cpu-sample-pairs", type=int, default=0, help="0 = auto (about 15 s)")
     ap.add_argument("--p2-sites", type=int, default=262144, help="C2 sites per step and GPU (part 2)")
     ap.add_argument("--skip-part2", action="store_true")
+    ap.add_argument("--part2-only", default="", help="run only this part-2 workload (profiling aid)")
     return ap.parse_args()
 
 
@@ -226,7 +227,7 @@ def bench_part2(args, ctx, torch, dist, dev, stream, rank, world, name, wl, time
     ptrs = {n: d_cols[n].data_ptr() for n in names}
 
     def step_dev():
-        ctx.posterior_batch_dev(scn, n_sites, ptrs, d_cat.data_ptr(), d_off.data_ptr(),
+        ctx.posterior_batch_dev(scn, n_sites, ptrs, d_cat.data_ptr(), d_off.data_ptr(), max(wl["depths"]),
                                 d_ev.data_ptr(), d_marg.data_ptr(), d_af.data_ptr(), d_mb.data_ptr())
 
     np_cols = {n: h_cols[n].numpy() for n in names}
@@ -408,6 +409,8 @@ def main():
         del d, d_hap, d_ws, d_out
         torch.cuda.empty_cache()
         for name, wl in part2_workloads(args).items():
+            if args.part2_only and name != args.part2_only:
+                continue
             part2[name] = bench_part2(args, ctx, torch, dist, dev, stream, rank, world, name, wl, timed)
 
     total_cells = cells * world

@@ -88,9 +88,10 @@ int vlr_pairhmm_batch(vlr_ctx *ctx, int64_t n_pairs,
 
 /*
  * Device-resident entry point: every pointer is a device pointer, work is enqueued on the
- * context's stream, nothing is copied or synchronised.  Layout requirement: hap_off[h] must be
- * a multiple of 16 (TMA bulk-copy granularity) and the hap buffer must extend 512 bytes past
- * hap_off[n_haps].  `workspace` must hold vlr_pairhmm_workspace_bytes(n_pairs) bytes.
+ * context's stream, nothing is copied or synchronised.  Any byte alignment of the windows is
+ * accepted (the kernel aligns its TMA bulk copies down to 16 bytes); the hap buffer must be
+ * readable for 32 bytes past hap_off[n_haps] and 16 bytes before hap_off[0].  `workspace` must
+ * hold vlr_pairhmm_workspace_bytes(n_pairs) bytes.  Read windows longer than 248 rows yield NaN.
  */
 size_t vlr_pairhmm_workspace_bytes(int64_t n_pairs, int64_t max_len_x, int64_t max_len_y);
 int vlr_pairhmm_batch_dev(vlr_ctx *ctx, int64_t n_pairs,
@@ -223,11 +224,13 @@ int vlr_posterior_batch(vlr_ctx *ctx, int64_t n_sites, const vlr_model *model,
                         double *out_event_ln, double *out_marginal, double *out_map_af,
                         int32_t *out_map_bias);
 
-/* device-resident variant (obs columns / obs_off / outputs are device pointers) */
+/* device-resident variant (obs columns / obs_off / outputs are device pointers; `model` stays a
+ * host struct).  max_obs_per_pileup: upper bound of observations per (site, sample), e.g.
+ * --max-depth (cli.rs:246-252); sites exceeding it get NaN outputs. */
 int vlr_posterior_batch_dev(vlr_ctx *ctx, int64_t n_sites, const vlr_model *model,
                             const vlr_obs_columns *d_obs, const int64_t *d_obs_off,
-                            double *d_out_event_ln, double *d_out_marginal, double *d_out_map_af,
-                            int32_t *d_out_map_bias);
+                            int32_t max_obs_per_pileup, double *d_out_event_ln,
+                            double *d_out_marginal, double *d_out_map_af, int32_t *d_out_map_bias);
 
 #ifdef __cplusplus
 }

@@ -111,7 +111,7 @@ def load():
     L.vlr_likelihood_batch.argtypes = [vp, i64, i32, C.POINTER(ObsColumns), vp, vp, i32, vp, i64, vp]
     L.vlr_posterior_batch.argtypes = [vp, i64, C.POINTER(Model), C.POINTER(ObsColumns), vp, vp, vp,
                                       vp, vp]
-    L.vlr_posterior_batch_dev.argtypes = [vp, i64, C.POINTER(Model), C.POINTER(ObsColumns), vp, vp,
-                                          vp, vp, vp]
+    L.vlr_posterior_batch_dev.argtypes = [vp, i64, C.POINTER(Model), C.POINTER(ObsColumns), vp, i32,
+                                          vp, vp, vp, vp]
     _lib = L
     return L

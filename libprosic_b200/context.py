@@ -182,8 +182,8 @@ class Context:
                                                  _ptr(mb)))
         return dict(event_ln=ev, marginal=marg, map_af=maf, map_bias=mb)
 
-    def posterior_batch_dev(self, scn, n_sites, d_cols, d_cat, d_obs_off, d_ev, d_marg, d_maf, d_mb,
-                            _cache={}):
+    def posterior_batch_dev(self, scn, n_sites, d_cols, d_cat, d_obs_off, max_obs, d_ev, d_marg, d_maf,
+                            d_mb, _cache={}):
         """Device-pointer variant (ints).  d_cols: dict name -> device pointer."""
         from ._ffi import ObsColumns
         key = id(scn)
@@ -196,8 +196,8 @@ class Context:
         oc = ObsColumns(*[d_cols[n] for n in names], d_cat)
         vp = C.c_void_p
         self._check(self.lib.vlr_posterior_batch_dev(self.h, n_sites, C.byref(model), C.byref(oc),
-                                                     vp(d_obs_off), vp(d_ev), vp(d_marg), vp(d_maf),
-                                                     vp(d_mb)))
+                                                     vp(d_obs_off), int(max_obs), vp(d_ev), vp(d_marg),
+                                                     vp(d_maf), vp(d_mb)))
 
     def likelihood_batch(self, n_sites, n_samples, cols, cat, obs_off, biases, items):
         """Likelihood::compute per work item.  biases: list of scenario bias dicts; items: list of

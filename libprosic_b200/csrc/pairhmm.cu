@@ -11,16 +11,16 @@ namespace vlr {
 
 // ---------------------------------------------------------------- classification of pairs by row count
 __host__ __device__ inline int class_of_len(int ly) {
-    if (ly <= 32) return 0;
-    if (ly <= 64) return 1;
-    if (ly <= 96) return 2;
-    if (ly <= 128) return 3;
-    if (ly <= 160) return 4;
-    if (ly <= 192) return 5;
-    if (ly <= 256) return 6;
+    // R rows per lane over 31 lanes (lane 31 stays a zero padding lane, see hmm_step)
+    if (ly <= 31) return 0;
+    if (ly <= 62) return 1;
+    if (ly <= 93) return 2;
+    if (ly <= 124) return 3;
+    if (ly <= 155) return 4;
+    if (ly <= 186) return 5;
+    if (ly <= 248) return 6;
     return 7;
 }
-static const int kClassR[kNumClasses] = {1, 2, 3, 4, 5, 6, 8, 0};
 
 // counters layout (int32): [0..7] class counts, [8..15] class offsets, [16..23] scatter cursors,
 // [24..31] work cursors (one per class launch), [32] fallback count, [33] fallback work cursor
@@ -243,8 +243,8 @@ int vlr_pairhmm_batch(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *hap_bytes,
         if (l < 0) return set_err(ctx, VLR_ERR_INVALID, "read_off not monotone");
         if (l > max_ly) max_ly = l;
     }
-    if (max_ly > 256)
-        return set_err(ctx, VLR_ERR_UNSUPPORTED, "read window of %lld rows exceeds 256",
+    if (max_ly > 248)
+        return set_err(ctx, VLR_ERR_UNSUPPORTED, "read window of %lld rows exceeds 248",
                        (long long)max_ly);
     if (pair_hap || pair_read)
         for (int64_t k = 0; k < n_pairs; ++k) {

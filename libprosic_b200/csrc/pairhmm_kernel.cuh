@@ -10,7 +10,8 @@
 //   M[i][0] = 1 for every column (free start), result = sum_i (M+X+Y)[i][len_y] (free end), capped at 1.
 //
 // Mapping: one warp per (read, haplotype) pair.  Lane l owns R consecutive read rows
-// [l*R, l*R+R); at step t it computes column i = t - l for its rows, so the warp sweeps
+// [l*R, l*R+R) with R = ceil(len_y / 31) (lane 31 is always padding); at step t it computes
+// column i = t - l for its rows, so the warp sweeps
 // anti-diagonals.  The bottom row of lane l-1 travels to lane l by __shfl_up_sync (M, X, Y, and the
 // band's min-edit-distance); the haplotype window is staged into a per-warp shared-memory ring by
 // 1-D TMA bulk copies (cp.async.bulk + mbarrier), read bases/qualities become per-row register
@@ -203,15 +204,17 @@ __device__ __forceinline__ void hmm_step(PairState<R> &s, const HmmConsts &c, co
     int xb = ring[(i + shift) & (kRing - 1)];
     if ((unsigned)(xb - 'a') < 26u) xb -= 32;  // to_ascii_uppercase (pairhmm.rs:190)
 
-    // receive the bottom row of the lane above (its column i)
-    double uM = __shfl_up_sync(0xffffffffu, s.bM, 1);
-    double uX = __shfl_up_sync(0xffffffffu, s.bX, 1);
-    double uY = __shfl_up_sync(0xffffffffu, s.bY, 1);
+    // receive the bottom row of the lane above (its column i).  The rotation makes lane 0 read
+    // lane 31, which is always a padding lane (R = ceil(len_y / 31)) whose state is identically
+    // zero: exactly the row-0 boundary fm[curr][0] = fx = fy = 0, with no select.
+    const int src = (lane + 31) & 31;
+    const double uM = __shfl_sync(0xffffffffu, s.bM, src);
+    const double uX = __shfl_sync(0xffffffffu, s.bX, src);
+    const double uY = __shfl_sync(0xffffffffu, s.bY, src);
     int uMed = kMedMax;
-    if (BANDED) uMed = __shfl_up_sync(0xffffffffu, s.bMed, 1);
-    if (lane == 0) {  // row 0 boundary: fm[curr][0] = 0, fx = fy = 0, med[curr][0] = MAX
-        uM = A::zero(); uX = A::zero(); uY = A::zero();
-        uMed = kMedMax;
+    if (BANDED) {
+        uMed = __shfl_sync(0xffffffffu, s.bMed, src);
+        if (lane == 0) uMed = kMedMax;  // med[curr][0] = MAX
     }
     double diagM = s.dM, diagX = s.dX, diagY = s.dY, upM = uM, upY = uY;
     int diagMed = s.dMed, upMed = uMed;

@@ -41,7 +41,6 @@ constexpr int kMaxSpectra = 48;
 constexpr int kMaxValues = 384;   // distinct allele-frequency values per site (all samples)
 constexpr int kMaxCfg = 32;       // distinct bias configurations
 constexpr int kMaxEvents = 64;
-constexpr int kMaxObsPerLane = 8; // <= 256 observations per (site, sample)
 constexpr int kTeamThreadsMax = 128;
 
 struct DevSpectrum {
@@ -84,16 +83,23 @@ struct PostArgs {
     double *out_event_ln, *out_marginal, *out_map_af;
     int32_t *out_map_bias;
     int32_t *status;        // [0] = number of sites that overflowed a kernel limit
+    int32_t obs_cap;        // observations per (site, sample) the shared staging can hold
 };
+__device__ __forceinline__ int m_ncfg_cap(const PostArgs &g) { return g.m.n_cfg; }
 
-__device__ __forceinline__ double ln_one_minus_exp_d(double p) {
+// Out-of-line transcendentals: one copy each instead of one per call site (the fully inlined kernel
+// was 343 KB of SASS and stalled on instruction fetch; ncu profile r1 `no_instruction`).
+__device__ __noinline__ double exp_ni(double x) { return exp(x); }
+__device__ __noinline__ double log_ni(double x) { return log(x); }
+__device__ __noinline__ double log1p_ni(double x) { return log1p(x); }
+__device__ __noinline__ double ln_one_minus_exp_d(double p) {
     return p < -0.693 ? log1p(-exp(p)) : log(-expm1(p));
 }
-__device__ __forceinline__ double ln_add_exp2(double a, double b) {
+__device__ __noinline__ double ln_add_exp2(double a, double b) {
     double p0 = fmax(a, b), p1 = fmin(a, b);
     if (p0 == -INFINITY) return -INFINITY;
     if (p1 == -INFINITY) return p0;
-    return p0 + log1p(exp(p1 - p0));
+    return p0 + log1p_ni(exp_ni(p1 - p0));
 }
 
 // ---- bias terms (bias/*.rs).  Returns the linear probability; NaN where the reference panics.
@@ -115,7 +121,7 @@ __device__ __forceinline__ double bias_lin(const vlr_biases &b, double other_rat
     else v *= other_rate == 0.0 ? 0.0 : (other ? other_rate : 1.0 - other_rate);
     return v;
 }
-__device__ __forceinline__ double bias_ln(const vlr_biases &b, double other_rate, unsigned cat,
+__device__ __noinline__ double bias_ln(const vlr_biases &b, double other_rate, unsigned cat,
                                           double ln_dov, double ln_sov, double ln_hb) {
     const double LN05 = -0.6931471805599453;
     const unsigned st = VLR_CAT_STRAND(cat), orr = VLR_CAT_ORIENT(cat);
@@ -131,14 +137,14 @@ __device__ __forceinline__ double bias_ln(const vlr_biases &b, double other_rate
     v += b.softclip ? (VLR_CAT_SOFTCLIP(cat) ? 0.0 : -INFINITY) : 0.0;
     const bool other = VLR_CAT_INDEL(cat) == 1;
     if (b.divindel == 0) v += other ? -INFINITY : 0.0;
-    else v += other_rate == 0.0 ? -INFINITY : (other ? log(other_rate) : log(1.0 - other_rate));
+    else v += other_rate == 0.0 ? -INFINITY : (other ? log_ni(other_rate) : log_ni(1.0 - other_rate));
     return v;
 }
 
 // likelihood_mapping in log space (likelihood.rs:191-213), used by the out-of-range path
-__device__ double lh_mapping_ln(double af, double psa_obs, double pb, double pab, double pa,
+__device__ __noinline__ double lh_mapping_ln(double af, double psa_obs, double pb, double pab, double pa,
                                 double pr) {
-    const double ln_af = log(af);
+    const double ln_af = log_ni(af);
     double psa;
     if (ln_af != 0.0) {
         psa = ln_af + psa_obs;
@@ -153,11 +159,11 @@ __device__ double lh_mapping_ln(double af, double psa_obs, double pb, double pab
     if (isnan(t0) || isnan(t1)) return NAN;
     if (mx == -INFINITY) return -INFINITY;
     if (mn == -INFINITY) return mx;
-    return mx + log1p(exp(mn - mx));
+    return mx + log1p_ni(exp_ni(mn - mx));
 }
 
 // exact ln T of one observation in log space (likelihood.rs:75-116, 165-187)
-__device__ double ln_T_exact(const vlr_obs_columns &o, int64_t row, const vlr_biases &b,
+__device__ __noinline__ double ln_T_exact(const vlr_obs_columns &o, int64_t row, const vlr_biases &b,
                              double other_rate, double af_p, double af_s, bool contaminated,
                              double purity) {
     const unsigned cat = o.cat[row];
@@ -168,7 +174,7 @@ __device__ double ln_T_exact(const vlr_obs_columns &o, int64_t row, const vlr_bi
     const double pa = o.prob_alt[row], pr = o.prob_ref[row], psa = o.prob_sample_alt[row];
     double mapped;
     if (contaminated) {
-        const double lp = log(purity);
+        const double lp = log_ni(purity);
         const double li = ln_one_minus_exp_d(lp);
         const double a = lp + lh_mapping_ln(af_p, psa, pb, pab, pa, pr);
         const double c = li + lh_mapping_ln(af_s, psa, pb, pab, pa, pr);
@@ -184,17 +190,17 @@ __device__ double ln_T_exact(const vlr_obs_columns &o, int64_t row, const vlr_bi
 
 // Bias::is_strong_obs (bias/mod.rs:79-83)
 __device__ __forceinline__ bool strong_obs(double prob_mapping, double pa, double pr) {
-    return prob_mapping >= -0.05129329438755058 && exp(pa - pr) > 20.0;
+    return prob_mapping >= -0.05129329438755058 && exp_ni(pa - pr) > 20.0;
 }
 
 // VAFRange::observable_{min,max} (grammar/formula.rs:1029-1071)
-__device__ double observable_max_d(double end, bool rex, int n_obs) {
+__device__ __noinline__ double observable_max_d(double end, bool rex, int n_obs) {
     if (n_obs < 10) return end;
     double c = (double)n_obs * end;
     if (rex && fmod(c, 1.0) == 0.0) c -= 1.0;
     return floor(c) / (double)n_obs;
 }
-__device__ double observable_min_d(double start, double end, bool lex, bool rex, int n_obs) {
+__device__ __noinline__ double observable_min_d(double start, double end, bool lex, bool rex, int n_obs) {
     if (n_obs < 10) return start;
     const double c = (double)n_obs * start;
     if (lex && fmod(c, 1.0) == 0.0) {
@@ -240,8 +246,9 @@ struct TeamShared {
 
 
 // decode the allele-frequency vector of (path, combo) -- LAST sample is the fastest digit
-__device__ void decode_afs(const DevModel &m, const TeamShared &S, const DevPath &path, int64_t combo,
+__device__ __noinline__ void decode_afs(const DevModel &m, const TeamShared &S, const DevPath &path, int64_t combo,
                            double *afs) {
+#pragma unroll 1
     for (int smp = m.n_samples - 1; smp >= 0; --smp) {
         const DevSpectrum spc = m.spectra[path.spec[smp]];
         const int cnt = spc.kind == VLR_NODE_RANGE ? S.grid[smp] : spc.n_vafs;
@@ -253,10 +260,9 @@ __device__ void decode_afs(const DevModel &m, const TeamShared &S, const DevPath
 // MAP tie-break: larger joint first; then the earlier (event, bias) entry; then the
 // lexicographically smaller allele-frequency vector (the reference's order among exact ties is
 // unspecified: HashMap iteration, SURVEY quirk Q14 -- the oracle uses this same rule)
-__device__ bool map_better(const DevModel &m, const TeamShared &S, double j, int eb, int p, int combo,
+__device__ __noinline__ bool map_tie_better(const DevModel &m, const TeamShared &S, double j, int eb, int p, int combo,
                            bool have, double bj, int beb, int bp, int bcombo) {
-    if (!have) return true;
-    if (j != bj) return j > bj;
+    (void)have; (void)j; (void)bj;
     if (eb != beb) return eb < beb;
     if (p == bp && combo == bcombo) return false;
     double a[kMaxSamples], b[kMaxSamples];
@@ -265,6 +271,13 @@ __device__ bool map_better(const DevModel &m, const TeamShared &S, double j, int
     for (int smp = 0; smp < m.n_samples; ++smp)
         if (a[smp] != b[smp]) return a[smp] < b[smp];
     return false;
+}
+
+__device__ __forceinline__ bool map_better(const DevModel &m, const TeamShared &S, double j, int eb, int p,
+                                           int combo, bool have, double bj, int beb, int bp, int bcombo) {
+    if (!have) return true;
+    if (j != bj) return j > bj;
+    return map_tie_better(m, S, j, eb, p, combo, have, bj, beb, bp, bcombo);  // exact tie: rare
 }
 
 template <int TEAM>
@@ -303,11 +316,18 @@ __global__ void __launch_bounds__(kTeamThreadsMax, 3) posterior_kernel(PostArgs 
     const int tt = wt * 32 + lane;               // thread index within the team
     constexpr int TT = TEAM * 32;
     TeamShared &S = s_team[team_in_cta];
+    // per-team staging of one sample's observations: OC = {cR, kk, sigma, m_i}, BC = beta*cA per cfg
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    const int obs_cap = g.obs_cap;
+    const size_t per_team = (size_t)obs_cap * sizeof(double4) + (size_t)obs_cap * m_ncfg_cap(g) * sizeof(double);
+    double4 *OC = (double4 *)(s_dyn + (size_t)team_in_cta * per_team);
+    double *BC = (double *)(OC + obs_cap);
     const int team_global = blockIdx.x * kTeamsPerCta + team_in_cta;
     double *table = g.table + (int64_t)team_global * g.table_stride;
     const DevModel &m = g.m;
     const int NS = m.n_samples;
 
+    #pragma unroll 1
     for (;;) {
         // ---- next site (dynamic)
         __shared__ int64_t s_site[kTeamsPerCta];
@@ -318,14 +338,13 @@ __global__ void __launch_bounds__(kTeamThreadsMax, 3) posterior_kernel(PostArgs 
         if (site >= g.n_sites) break;
 
         // ---- 0. reset counters
-        for (int k = tt; k < (int)(sizeof(TeamShared) / 4); k += TT) {
-            // only the integer counter block at the front needs zeroing; cheap to clear it all
-            if (k < (int)(offsetof(TeamShared, spec_off) / 4)) ((int *)&S)[k] = 0;
-        }
+        #pragma unroll 1
+        for (int k = tt; k < (int)(offsetof(TeamShared, spec_off) / 4); k += TT) ((int *)&S)[k] = 0;
         if (tt == 0) S.overflow = 0;
         team_sync<TEAM>();
 
         // ---- 1. per-sample counters for grid sizes, bias learning and gating
+        #pragma unroll 1
         for (int smp = wt; smp < NS; smp += TEAM) {
             const int64_t o0 = g.obs_off[site * NS + smp], o1 = g.obs_off[site * NS + smp + 1];
             const int n = (int)(o1 - o0);
@@ -335,6 +354,7 @@ __global__ void __launch_bounds__(kTeamThreadsMax, 3) posterior_kernel(PostArgs 
             for (int v = 0; v < EV_N; ++v) { c_ev[v] = 0; a_ev[v] = 0; }
 #pragma unroll
             for (int v = 0; v < PS_N; ++v) a_ps[v] = 0;
+            #pragma unroll 1
             for (int i = lane; i < n; i += 32) {
                 const int64_t row = o0 + i;
                 const unsigned cat = g.obs.cat[row];
@@ -388,7 +408,7 @@ __global__ void __launch_bounds__(kTeamThreadsMax, 3) posterior_kernel(PostArgs 
                 gp = min(gp, m.resolution[smp]);
                 if ((gp & 1) == 0) gp += 1;
                 S.grid[smp] = gp;
-                if (n > 32 * kMaxObsPerLane) S.overflow = 1;
+                if (n > g.obs_cap) S.overflow = 1;
             }
         }
         team_sync<TEAM>();
@@ -396,8 +416,10 @@ __global__ void __launch_bounds__(kTeamThreadsMax, 3) posterior_kernel(PostArgs 
         // ---- 2. allele-frequency values of every spectrum (grouped by sample) + Simpson ln-weights
         if (tt == 0) {
             int off = 0;
+            #pragma unroll 1
             for (int smp = 0; smp < NS; ++smp) {
                 S.sample_voff[smp] = off;
+                #pragma unroll 1
                 for (int sp = 0; sp < m.n_spectra; ++sp) {
                     if (m.spectra[sp].sample != smp) continue;
                     S.spec_off[sp] = off;
@@ -409,6 +431,7 @@ __global__ void __launch_bounds__(kTeamThreadsMax, 3) posterior_kernel(PostArgs 
             if (off > kMaxValues) S.overflow = 1;
             // table layout: per sample, per cfg, per key
             int64_t toff = 0;
+            #pragma unroll 1
             for (int smp = 0; smp < NS; ++smp) {
                 const int64_t keys = m.contaminated[smp]
                                          ? (int64_t)S.sample_nv[smp] * S.sample_nv[m.by[smp]]
@@ -423,8 +446,10 @@ __global__ void __launch_bounds__(kTeamThreadsMax, 3) posterior_kernel(PostArgs 
         if (S.overflow) {
             if (tt == 0) {
                 atomicAdd(g.status, 1);
+                #pragma unroll 1
                 for (int e = 0; e < m.n_events; ++e) g.out_event_ln[site * m.n_events + e] = NAN;
                 g.out_marginal[site] = NAN;
+                #pragma unroll 1
                 for (int smp = 0; smp < NS; ++smp) {
                     g.out_map_af[site * NS + smp] = NAN;
                     g.out_map_bias[site * NS + smp] = -1;
@@ -432,6 +457,7 @@ __global__ void __launch_bounds__(kTeamThreadsMax, 3) posterior_kernel(PostArgs 
             }
             continue;
         }
+        #pragma unroll 1
         for (int sp = wt; sp < m.n_spectra; sp += TEAM) {
             const DevSpectrum spc = m.spectra[sp];
             const int base = S.spec_off[sp];
@@ -441,17 +467,19 @@ __global__ void __launch_bounds__(kTeamThreadsMax, 3) posterior_kernel(PostArgs 
                 const double a = observable_min_d(r[0], r[1], r[2] != 0.0, r[3] != 0.0, nobs);
                 const double b = observable_max_d(r[1], r[3] != 0.0, nobs);
                 const double step = (b - a) / (double)(n - 1);  // itertools_num::linspace
-                const double lnc = log(b - a) - log((double)(n - 1)) - log(3.0);
+                const double lnc = log_ni(b - a) - log_ni((double)(n - 1)) - 1.0986122886681098;
+                #pragma unroll 1
                 for (int i = lane; i < n; i += 32) {
                     // no FMA contraction: the grid point must be bit-identical to linspace's a + step*i
                     double x = __dadd_rn(a, __dmul_rn(step, (double)i)), w = 0.0;
                     if (i == 0) x = a;
                     else if (i == n - 1) x = b;
-                    else w = log((double)(2 + (i & 1) * 2));  // weights 4,2,4,... (Appendix A.1)
+                    else w = (i & 1) ? 1.3862943611198906 : 0.6931471805599453;  // ln 4, ln 2 (Appendix A.1)
                     S.val[base + i] = x;
                     S.lnw[base + i] = w + lnc;
                 }
             } else {
+                #pragma unroll 1
                 for (int i = lane; i < spc.n_vafs; i += 32) {
                     S.val[base + i] = m.vafs[spc.vaf_off + i];
                     S.lnw[base + i] = 0.0;
@@ -459,6 +487,7 @@ __global__ void __launch_bounds__(kTeamThreadsMax, 3) posterior_kernel(PostArgs 
             }
         }
         // ---- 3. bias learning + gating (one thread per configuration)
+        #pragma unroll 1
         for (int c = tt; c < m.n_cfg; c += TT) {
             const vlr_biases b = m.cfg[c];
             // DivIndelBias::learn_parameters (divindel_bias.rs:98-132)
@@ -489,6 +518,7 @@ __global__ void __launch_bounds__(kTeamThreadsMax, 3) posterior_kernel(PostArgs 
             for (int k = 0; k < 5; ++k) {
                 if (comp_ev[k] < 0) continue;
                 bool likely = false;
+                #pragma unroll 1
                 for (int smp = 0; smp < NS; ++smp) {
                     const int sa = S.strong_all[smp];
                     if (sa >= 10) {
@@ -503,7 +533,11 @@ __global__ void __launch_bounds__(kTeamThreadsMax, 3) posterior_kernel(PostArgs 
         }
         team_sync<TEAM>();
 
-        // ---- 4. likelihood tables: sample by sample, bias configuration by configuration
+        // ---- 4. likelihood tables.  Per sample: the team stages the observation constants
+        // (scaled linear space) and the per-(observation, bias cfg) factor beta*cA in shared memory,
+        // then every thread owns (key, cfg) pairs and walks the observations: mantissa product +
+        // exponent sum per pair, ONE log per pair, no cross-lane traffic.
+        #pragma unroll 1
         for (int smp = 0; smp < NS; ++smp) {
             const int64_t o0 = g.obs_off[site * NS + smp];
             const int n = S.n_obs[smp];
@@ -512,98 +546,83 @@ __global__ void __launch_bounds__(kTeamThreadsMax, 3) posterior_kernel(PostArgs 
             const int nv = S.sample_nv[smp], v0 = S.sample_voff[smp];
             const int byv0 = cont ? S.sample_voff[m.by[smp]] : 0;
             const int bynv = cont ? S.sample_nv[m.by[smp]] : 1;
-            const int64_t nkeys = (int64_t)nv * bynv;
-            // per-lane observation constants (scaled linear space)
-            double cA[kMaxObsPerLane], cR[kMaxObsPerLane], kk[kMaxObsPerLane], sg[kMaxObsPerLane];
-            double sN[kMaxObsPerLane], hb[kMaxObsPerLane];
-            unsigned cat[kMaxObsPerLane];
-            const int rp = (n + 31) / 32;
-#pragma unroll
-            for (int r = 0; r < kMaxObsPerLane; ++r) {
-                const int i = r * 32 + lane;
-                if (r < rp && i < n) {
-                    const int64_t row = o0 + i;
-                    const double pa = g.obs.prob_alt[row], pr = g.obs.prob_ref[row],
-                                 pmiss = g.obs.prob_missed_allele[row];
-                    const double mi = fmax(fmax(pa, pr), pmiss);
-                    const double pm = exp(g.obs.prob_mapping[row]), pmm = exp(g.obs.prob_mismapping[row]);
-                    hb[r] = exp(g.obs.prob_hit_base[row]);
-                    const double bbar = 0.25 * hb[r];
-                    if (mi == -INFINITY) {
-                        cA[r] = cR[r] = kk[r] = 0.0;  // T == 0: resolved by the exact path (-inf)
-                    } else {
-                        cA[r] = pm * exp(pa - mi);
-                        cR[r] = pm * exp(pr - mi) * bbar;
-                        kk[r] = pmm * exp(pmiss - mi) * bbar;
-                    }
-                    sg[r] = exp(g.obs.prob_sample_alt[row]);
-                    cat[r] = g.obs.cat[row];
-                    sN[r] = VLR_CAT_STRAND(cat[r]) == 2 ? exp(g.obs.prob_double_overlap[row])
-                                                        : 0.5 * exp(g.obs.prob_single_overlap[row]);
-                } else {
-                    cA[r] = cR[r] = 0.0; kk[r] = 1.0; sg[r] = 1.0;  // neutral factor T = 1
-                    sN[r] = hb[r] = 1.0; cat[r] = 0;
+            const int nkeys = nv * bynv;
+            const int ncfg = m.n_cfg;
+            team_sync<TEAM>();  // previous sample's shared constants are no longer read
+            #pragma unroll 1
+            for (int i = tt; i < n; i += TT) {
+                const int64_t row = o0 + i;
+                const double pa = g.obs.prob_alt[row], pr = g.obs.prob_ref[row],
+                             pmiss = g.obs.prob_missed_allele[row];
+                const double mi = fmax(fmax(pa, pr), pmiss);
+                const double pm = exp_ni(g.obs.prob_mapping[row]), pmm = exp_ni(g.obs.prob_mismapping[row]);
+                const double hb = exp_ni(g.obs.prob_hit_base[row]);
+                const double bbar = 0.25 * hb;
+                double cA = 0.0, cR = 0.0, kk = 0.0;  // mi == -inf: T == 0, resolved by the exact path
+                if (mi != -INFINITY) {
+                    cA = pm * exp_ni(pa - mi);
+                    cR = pm * exp_ni(pr - mi) * bbar;
+                    kk = pmm * exp_ni(pmiss - mi) * bbar;
                 }
+                const unsigned cat = g.obs.cat[row];
+                const double sN = VLR_CAT_STRAND(cat) == 2 ? exp_ni(g.obs.prob_double_overlap[row])
+                                                           : 0.5 * exp_ni(g.obs.prob_single_overlap[row]);
+                OC[i] = make_double4(cR, kk, exp_ni(g.obs.prob_sample_alt[row]), mi);
+                #pragma unroll 1
+                for (int c = 0; c < ncfg; ++c)
+                    BC[i * ncfg + c] = S.allowed[c]
+                                           ? bias_lin(m.cfg[c], S.other_rate[c], cat, sN, hb) * cA : 0.0;
             }
-            for (int c = 0; c < m.n_cfg; ++c) {
+            team_sync<TEAM>();
+            const int npairs = nkeys * ncfg;
+            #pragma unroll 1
+            for (int q = tt; q < npairs; q += TT) {
+                const int c = q / nkeys, key = q - c * nkeys;
                 if (!S.allowed[c]) continue;  // gated out: never requested (generic.rs:258-262)
-                const vlr_biases b = m.cfg[c];
-                const double orate = S.other_rate[c];
-                double bcA[kMaxObsPerLane];
-#pragma unroll
-                for (int r = 0; r < kMaxObsPerLane; ++r) {
-                    const int i = r * 32 + lane;
-                    bcA[r] = (r < rp && i < n)
-                                 ? bias_lin(b, orate, cat[r], sN[r], hb[r]) * cA[r] : 0.0;
-                }
-                double *tab = table + S.tab_off[smp] + (int64_t)c * S.tab_cfg_stride[smp];
-                for (int64_t key = wt; key < nkeys; key += TEAM) {
-                    const int vi = (int)(key / bynv), vb = (int)(key - (int64_t)vi * bynv);
-                    const double af_p = S.val[v0 + vi];
-                    const double af_s = cont ? S.val[byv0 + vb] : 0.0;
-                    double mant = 1.0, lnslow = 0.0;
-                    int ex = 0;
-                    bool slow_any = false;
-#pragma unroll
-                    for (int r = 0; r < kMaxObsPerLane; ++r) {
-                        if (r < rp) {
-                            double z = s_eff(af_p, sg[r]);
-                            double zr = 1.0 - z;
-                            if (cont) {
-                                const double z2 = s_eff(af_s, sg[r]);
-                                zr = rho * zr + (1.0 - rho) * (1.0 - z2);
-                                z = rho * z + (1.0 - rho) * z2;
-                            }
-                            const double T = fma(zr, cR[r], fma(z, bcA[r], kk[r]));
-                            const int hi = __double2hiint(T);
-                            const int e = (hi >> 20) & 0x7ff;  // sign is 0 for every valid T
-                            if (hi > 0 && e > 23 && e < 2000) {
-                                ex += e - 1023;
-                                mant *= __hiloint2double((hi & 0x000fffff) | 0x3ff00000,
-                                                         __double2loint(T));
-                            } else if (r * 32 + lane < n) {
-                                // zero / subnormal / NaN: recompute this observation in log space
-                                const int64_t row = o0 + r * 32 + lane;
-                                const double mi = fmax(fmax(g.obs.prob_alt[row], g.obs.prob_ref[row]),
-                                                       g.obs.prob_missed_allele[row]);
-                                const double lt = ln_T_exact(g.obs, row, b, orate, af_p, af_s, cont, rho);
-                                // sum_m already contains m_i: subtract it again here
-                                lnslow += (mi == -INFINITY) ? lt : lt - mi;
-                                slow_any = true;
-                            }
-                        }
+                const int vi = key / bynv, vb = key - vi * bynv;
+                const double af_p = S.val[v0 + vi];
+                const double af_s = cont ? S.val[byv0 + vb] : 0.0;
+                double mant0 = 1.0, mant1 = 1.0, lnslow = 0.0;
+                int ex = 0;
+                bool slow_any = false;
+#pragma unroll 2
+                for (int i = 0; i < n; ++i) {
+                    const double4 oc = OC[i];            // cR, kk, sigma, m_i
+                    const double bcA = BC[i * ncfg + c];
+                    double z = s_eff(af_p, oc.z);
+                    double zr = 1.0 - z;
+                    if (cont) {
+                        const double z2 = s_eff(af_s, oc.z);
+                        zr = rho * zr + (1.0 - rho) * (1.0 - z2);
+                        z = rho * z + (1.0 - rho) * z2;
                     }
-                    mant = warp_prod(mant);
-                    ex = __reduce_add_sync(0xffffffffu, ex);
-                    double L = S.sum_m[smp] + (double)ex * 0.6931471805599453 + log(mant);
-                    if (__any_sync(0xffffffffu, slow_any)) {
-                        lnslow = warp_sum(lnslow);
-                        L = (S.sum_m[smp] == -INFINITY) ? lnslow + ((double)ex * 0.6931471805599453 + log(mant))
-                                                       : L + lnslow;
+                    const double T = fma(zr, oc.x, fma(z, bcA, oc.y));
+                    const int hi = __double2hiint(T);
+                    const int e = (hi >> 20) & 0x7ff;  // the sign bit is 0 for every valid T
+                    if (hi > 0 && e > 23 && e < 2000) {
+                        ex += e - 1023;
+                        const double mt = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(T));
+                        if (i & 1) mant1 *= mt; else mant0 *= mt;
+                    } else {
+                        // zero / subnormal / NaN: recompute this observation in log space
+                        const double lt = ln_T_exact(g.obs, o0 + i, m.cfg[c], S.other_rate[c], af_p, af_s,
+                                                     cont, rho);
+                        lnslow += (oc.w == -INFINITY) ? lt : lt - oc.w;  // sum_m already holds m_i
+                        slow_any = true;
                     }
-                    if (n == 0) L = 0.0;  // empty pileup: fold identity ln 1 (likelihood.rs:135,227)
-                    if (lane == 0) __stcg(&tab[key], L);
+                    if ((i & 127) == 127) {  // keep the mantissa products inside fp64 range
+                        const double mm = mant0 * mant1;
+                        const int h2 = __double2hiint(mm);
+                        ex += ((h2 >> 20) & 0x7ff) - 1023;
+                        mant0 = __hiloint2double((h2 & 0x000fffff) | 0x3ff00000, __double2loint(mm));
+                        mant1 = 1.0;
+                    }
                 }
+                const double lm = (double)ex * 0.6931471805599453 + log_ni(mant0 * mant1);
+                double L = S.sum_m[smp] + lm;
+                if (slow_any) L = (S.sum_m[smp] == -INFINITY) ? lnslow + lm : L + lnslow;
+                if (n == 0) L = 0.0;  // empty pileup: fold identity ln 1 (likelihood.rs:135,227)
+                __stcg(&table[S.tab_off[smp] + (int64_t)c * S.tab_cfg_stride[smp] + key], L);
             }
         }
         team_sync<TEAM>();
@@ -612,19 +631,23 @@ __global__ void __launch_bounds__(kTeamThreadsMax, 3) posterior_kernel(PostArgs 
         double bestJ[2] = {-INFINITY, -INFINITY};  // [0] any, [1] non-artifact
         int bestId[2][3] = {{0x7fffffff, 0, 0}, {0x7fffffff, 0, 0}};
         bool have[2] = {false, false};
+        #pragma unroll 1
         for (int e = 0; e < m.n_events; ++e) {
             const DevEvent ev = m.events[e];
             double mx = -INFINITY, sum = 0.0;
+            #pragma unroll 1
             for (int q = 0; q < ev.n_eb; ++q) {
                 const int ebi = ev.eb_off + q;
                 const int c = m.eb[ebi].cfg;
                 if (!S.allowed[c]) continue;
                 const bool art = m.cfg[c].strand | m.cfg[c].orientation | m.cfg[c].read_position |
                                  m.cfg[c].softclip | m.cfg[c].divindel;
+                #pragma unroll 1
                 for (int p = 0; p < ev.n_paths; ++p) {
                     const DevPath &path = m.paths[ev.path_off + p];
                     int cnt[kMaxSamples], base[kMaxSamples];
                     int64_t total = 1;
+                    #pragma unroll 1
                     for (int smp = 0; smp < NS; ++smp) {
                         const int sp = path.spec[smp];
                         const DevSpectrum spc = m.spectra[sp];
@@ -632,11 +655,13 @@ __global__ void __launch_bounds__(kTeamThreadsMax, 3) posterior_kernel(PostArgs 
                         base[smp] = S.spec_off[sp] - S.sample_voff[smp];  // value index within sample
                         total *= cnt[smp];
                     }
+                    #pragma unroll 1
                     for (int64_t combo = tt; combo < total; combo += TT) {
                         int64_t rem = combo;
                         int vidx[kMaxSamples];
                         double lw = 0.0;
                         // mixed radix, LAST sample fastest
+                        #pragma unroll 1
                         for (int smp = NS - 1; smp >= 0; --smp) {
                             const int d = (int)(rem % cnt[smp]);
                             rem /= cnt[smp];
@@ -644,6 +669,7 @@ __global__ void __launch_bounds__(kTeamThreadsMax, 3) posterior_kernel(PostArgs 
                             lw += S.lnw[S.sample_voff[smp] + vidx[smp]];
                         }
                         double J = 0.0;  // flat prior (ln 1)
+                        #pragma unroll 1
                         for (int smp = 0; smp < NS; ++smp) {
                             const int64_t key = m.contaminated[smp]
                                                     ? (int64_t)vidx[smp] * S.sample_nv[m.by[smp]] + vidx[m.by[smp]]
@@ -662,36 +688,30 @@ __global__ void __launch_bounds__(kTeamThreadsMax, 3) posterior_kernel(PostArgs 
                         }
                         const double t = J + lw;
                         if (isnan(t)) { sum = NAN; }
-                        else if (t > mx) { sum = sum * exp(mx - t) + 1.0; mx = t; }
-                        else if (t != -INFINITY) sum += exp(t - mx);
+                        else if (t > mx) { sum = sum * exp_ni(mx - t) + 1.0; mx = t; }
+                        else if (t != -INFINITY) sum += exp_ni(t - mx);
                     }
                 }
             }
-            // reduce (mx, sum) over the team
-            for (int o = 16; o > 0; o >>= 1) {
-                const double omx = __shfl_xor_sync(0xffffffffu, mx, o);
-                const double osum = __shfl_xor_sync(0xffffffffu, sum, o);
-                const double nm = fmax(mx, omx);
-                sum = (nm == -INFINITY) ? 0.0
-                                        : sum * (mx == -INFINITY ? 0.0 : exp(mx - nm)) +
-                                              osum * (omx == -INFINITY ? 0.0 : exp(omx - nm));
-                mx = nm;
-            }
+            // reduce (mx, sum) over the team: max first, then one rescale per lane, then a plain sum
+            double M = mx;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) M = fmax(M, __shfl_xor_sync(0xffffffffu, M, o));
             if (TEAM > 1) {
-                if (lane == 0) { S.red_mx[wt] = mx; S.red_sum[wt] = sum; }
+                if (lane == 0) S.red_mx[wt] = M;
                 team_sync<TEAM>();
-                if (tt == 0) {
-                    double M = -INFINITY, Ssum = 0.0;
-                    for (int w = 0; w < TEAM; ++w) M = fmax(M, S.red_mx[w]);
-                    for (int w = 0; w < TEAM; ++w)
-                        if (S.red_mx[w] != -INFINITY) Ssum += S.red_sum[w] * exp(S.red_mx[w] - M);
-                    S.red_mx[0] = M; S.red_sum[0] = Ssum;
-                }
+                M = fmax(fmax(S.red_mx[0], S.red_mx[1]), fmax(S.red_mx[2], S.red_mx[3]));
+            }
+            double part = (mx == -INFINITY) ? 0.0 : sum * exp_ni(mx - M);
+            part = warp_sum(part);
+            if (TEAM > 1) {
+                if (lane == 0) S.red_sum[wt] = part;
                 team_sync<TEAM>();
-                mx = S.red_mx[0]; sum = S.red_sum[0];
+                part = S.red_sum[0] + S.red_sum[1] + S.red_sum[2] + S.red_sum[3];
                 team_sync<TEAM>();
             }
-            if (tt == 0) S.ev_ln[e] = (mx == -INFINITY) ? -INFINITY : ev.bias_prior + mx + log(sum);
+            mx = M; sum = part;
+            if (tt == 0) S.ev_ln[e] = (mx == -INFINITY) ? -INFINITY : ev.bias_prior + mx + log_ni(sum);
         }
         // ---- MAP reduction (ties -> lowest id)
         for (int w = 0; w < 2; ++w) {
@@ -718,6 +738,7 @@ __global__ void __launch_bounds__(kTeamThreadsMax, 3) posterior_kernel(PostArgs 
             const int NE = m.n_events;
             double M = -INFINITY;
             bool nan_any = false;
+            #pragma unroll 1
             for (int e = 0; e < NE; ++e) { nan_any |= isnan(S.ev_ln[e]); M = fmax(M, S.ev_ln[e]); }
             double marg;
             if (nan_any) marg = NAN;
@@ -725,26 +746,32 @@ __global__ void __launch_bounds__(kTeamThreadsMax, 3) posterior_kernel(PostArgs 
             else {
                 // LogProb::ln_sum_exp: pmax + ln_1p(sum of the others)
                 int imax = 0;
+                #pragma unroll 1
                 for (int e = 1; e < NE; ++e) if (S.ev_ln[e] > S.ev_ln[imax]) imax = e;
                 double acc = 0.0;
+                #pragma unroll 1
                 for (int e = 0; e < NE; ++e)
-                    if (e != imax && S.ev_ln[e] != -INFINITY) acc += exp(S.ev_ln[e] - S.ev_ln[imax]);
-                marg = S.ev_ln[imax] + log1p(acc);
+                    if (e != imax && S.ev_ln[e] != -INFINITY) acc += exp_ni(S.ev_ln[e] - S.ev_ln[imax]);
+                marg = S.ev_ln[imax] + log1p_ni(acc);
             }
+            #pragma unroll 1
             for (int e = 0; e < NE; ++e) g.out_event_ln[site * NE + e] = S.ev_ln[e];
             g.out_marginal[site] = marg;
             // artifact event = ln_sum_exp of artifact posteriors (calling.rs:581-598)
             double am = -INFINITY;
+            #pragma unroll 1
             for (int e = 0; e < NE; ++e) if (m.events[e].is_artifact) am = fmax(am, S.ev_ln[e] - marg);
             double prob_art = -INFINITY;
             if (am != -INFINITY && !isnan(am)) {
                 double acc = 0.0;
+                #pragma unroll 1
                 for (int e = 0; e < NE; ++e)
                     if (m.events[e].is_artifact && S.ev_ln[e] - marg != -INFINITY)
-                        acc += exp(S.ev_ln[e] - marg - am);
-                prob_art = am + log(acc);
+                        acc += exp_ni(S.ev_ln[e] - marg - am);
+                prob_art = am + log_ni(acc);
             } else if (isnan(am)) prob_art = NAN;
             bool is_artifact = true;
+            #pragma unroll 1
             for (int e = 0; e < NE; ++e)
                 if (!m.events[e].is_artifact && !((S.ev_ln[e] - marg) < prob_art)) is_artifact = false;
             const int w = is_artifact ? 0 : 1;
@@ -757,6 +784,7 @@ __global__ void __launch_bounds__(kTeamThreadsMax, 3) posterior_kernel(PostArgs 
                 if (take) { j = oj; i0 = o0; i1 = o1; i2 = o2; }
             }
             if (i0 == 0x7fffffff) {
+                #pragma unroll 1
                 for (int smp = 0; smp < NS; ++smp) {
                     g.out_map_af[site * NS + smp] = NAN;
                     g.out_map_bias[site * NS + smp] = -1;
@@ -767,6 +795,7 @@ __global__ void __launch_bounds__(kTeamThreadsMax, 3) posterior_kernel(PostArgs 
                                  m.cfg[c].softclip | m.cfg[c].divindel;
                 const DevPath &path = m.paths[m.events[m.eb[i0].event].path_off + i1];
                 int64_t rem = i2;
+                #pragma unroll 1
                 for (int smp = NS - 1; smp >= 0; --smp) {
                     const DevSpectrum spc = m.spectra[path.spec[smp]];
                     const int cnt = spc.kind == VLR_NODE_RANGE ? S.grid[smp] : spc.n_vafs;
@@ -913,11 +942,11 @@ extern "C" {
 
 int vlr_posterior_batch_dev(vlr_ctx *ctx, int64_t n_sites, const vlr_model *model,
                             const vlr_obs_columns *d_obs, const int64_t *d_obs_off,
-                            double *d_out_event_ln, double *d_out_marginal, double *d_out_map_af,
-                            int32_t *d_out_map_bias) {
+                            int32_t max_obs_per_pileup, double *d_out_event_ln,
+                            double *d_out_marginal, double *d_out_map_af, int32_t *d_out_map_bias) {
     if (!ctx) return VLR_ERR_INVALID;
     if (!model || !d_obs || !d_obs_off || !d_out_event_ln || !d_out_marginal || !d_out_map_af ||
-        !d_out_map_bias || n_sites < 0 || n_sites > 0x7fffffff)
+        !d_out_map_bias || n_sites < 0 || n_sites > 0x7fffffff || max_obs_per_pileup < 0)
         return set_err(ctx, VLR_ERR_INVALID, "bad argument");
     if (n_sites == 0) return VLR_OK;
     VLR_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -930,9 +959,17 @@ int vlr_posterior_batch_dev(vlr_ctx *ctx, int64_t n_sites, const vlr_model *mode
             return set_err(ctx, VLR_ERR_INVALID, "bad contamination source for sample %d", s);
     const int64_t tbound = table_bound(model, H);
     // team size: whole CTA for big tables (tumor/normal-like), one warp per site for small ones
-    const bool big = tbound > 1024;
+    const int obs_cap = std::max(8, (max_obs_per_pileup + 7) & ~7);
+    const size_t team_smem = (size_t)obs_cap * sizeof(double4) + (size_t)obs_cap * H.cfg.size() * sizeof(double);
+    const bool big = tbound > 2048 || 4 * team_smem > 64 * 1024;
     const int teams_per_cta = big ? 1 : 4;
-    const int grid = ctx->sm_count * 3;
+    const size_t dyn_smem = (size_t)teams_per_cta *
+                            ((size_t)obs_cap * sizeof(double4) + (size_t)obs_cap * H.cfg.size() * sizeof(double));
+    if (dyn_smem > 160 * 1024)
+        return set_err(ctx, VLR_ERR_UNSUPPORTED,
+                       "%d observations x %d bias configurations do not fit the shared-memory staging",
+                       max_obs_per_pileup, (int)H.cfg.size());
+    const int grid = ctx->sm_count * (dyn_smem > 48 * 1024 ? 2 : 3);
     const int64_t n_teams = (int64_t)grid * teams_per_cta;
     if (tbound > ((int64_t)1 << 24))
         return set_err(ctx, VLR_ERR_UNSUPPORTED, "likelihood table of %lld entries per site is too large", (long long)tbound);
@@ -996,8 +1033,14 @@ int vlr_posterior_batch_dev(vlr_ctx *ctx, int64_t n_sites, const vlr_model *mode
     a.out_marginal = d_out_marginal;
     a.out_map_af = d_out_map_af;
     a.out_map_bias = d_out_map_bias;
-    if (big) posterior_kernel<4><<<grid, kTeamThreadsMax, 0, st>>>(a);
-    else posterior_kernel<1><<<grid, kTeamThreadsMax, 0, st>>>(a);
+    a.obs_cap = obs_cap;
+    if (big) {
+        VLR_CUDA(ctx, cudaFuncSetAttribute(posterior_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+        posterior_kernel<4><<<grid, kTeamThreadsMax, dyn_smem, st>>>(a);
+    } else {
+        VLR_CUDA(ctx, cudaFuncSetAttribute(posterior_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+        posterior_kernel<1><<<grid, kTeamThreadsMax, dyn_smem, st>>>(a);
+    }
     VLR_LAUNCH_CHECK(ctx);
     return VLR_OK;
 }
@@ -1017,12 +1060,13 @@ int vlr_posterior_batch(vlr_ctx *ctx, int64_t n_sites, const vlr_model *model,
     const int64_t n_off = n_sites * NS + 1;
     const int64_t r0 = obs_off[0], r1 = obs_off[n_off - 1];
     const int64_t n_rows = r1 - r0;
+    int64_t max_obs = 0;
     for (int64_t k = 0; k + 1 < n_off; ++k) {
         const int64_t l = obs_off[k + 1] - obs_off[k];
         if (l < 0) return set_err(ctx, VLR_ERR_INVALID, "obs_off not monotone");
-        if (l > 32 * kMaxObsPerLane)
-            return set_err(ctx, VLR_ERR_UNSUPPORTED, "pileup of %lld observations exceeds %d", (long long)l, 32 * kMaxObsPerLane);
+        if (l > max_obs) max_obs = l;
     }
+    if (max_obs > 4096) return set_err(ctx, VLR_ERR_UNSUPPORTED, "pileup of %lld observations exceeds 4096", (long long)max_obs);
     enum { S_COL0 = 20, S_CAT = 29, S_OFF, S_EV, S_MARG, S_AF, S_MB };
     const double *cols[9] = {obs->prob_mapping, obs->prob_mismapping, obs->prob_alt, obs->prob_ref,
                              obs->prob_missed_allele, obs->prob_sample_alt, obs->prob_double_overlap,
@@ -1051,7 +1095,7 @@ int vlr_posterior_batch(vlr_ctx *ctx, int64_t n_sites, const vlr_model *model,
     dc.prob_ref = d_cols[3] - r0; dc.prob_missed_allele = d_cols[4] - r0; dc.prob_sample_alt = d_cols[5] - r0;
     dc.prob_double_overlap = d_cols[6] - r0; dc.prob_single_overlap = d_cols[7] - r0;
     dc.prob_hit_base = d_cols[8] - r0; dc.cat = d_cat - r0;
-    int rc = vlr_posterior_batch_dev(ctx, n_sites, model, &dc, d_off, d_ev, d_marg, d_af, d_mb);
+    int rc = vlr_posterior_batch_dev(ctx, n_sites, model, &dc, d_off, (int32_t)max_obs, d_ev, d_marg, d_af, d_mb);
     if (rc != VLR_OK) return rc;
     VLR_CUDA(ctx, cudaMemcpyAsync(out_event_ln, d_ev, (size_t)n_sites * NE * 8, cudaMemcpyDeviceToHost, st));
     VLR_CUDA(ctx, cudaMemcpyAsync(out_marginal, d_marg, (size_t)n_sites * 8, cudaMemcpyDeviceToHost, st));

@@ -43,7 +43,7 @@ def test_c3_shape_unbanded(ctx, oracle, flags):
 @pytest.mark.parametrize("gi", [0, 1, 2])
 def test_ragged_unbanded(ctx, oracle, gi):
     gap = _gap_sets()[gi]
-    w = synth.make_ragged_pairs(300, seed=100 + gi, max_ly=256, max_lx=600)
+    w = synth.make_ragged_pairs(300, seed=100 + gi, max_ly=248, max_lx=600)
     got = ctx.pairhmm_batch(w["hap_bytes"], w["hap_off"], w["read_bases"], w["read_quals"],
                             w["read_off"], gap)
     want = oracle.pairhmm_batch(w["hap_bytes"], w["hap_off"], w["read_bases"], w["read_quals"],
@@ -109,7 +109,7 @@ def test_errors_are_loud(ctx):
     read = np.frombuffer(b"A" * 300, dtype=np.uint8)
     with pytest.raises(P.VlrError):
         ctx.pairhmm_batch(hap, np.array([0, 400]), read, np.full(300, 30, np.uint8),
-                          np.array([0, 300]), gap)  # 300 rows > 256: unsupported for now
+                          np.array([0, 300]), gap)  # 300 rows > 248: unsupported for now
     with pytest.raises(P.VlrError):
         ctx.pairhmm_batch(hap, np.array([0, 400]), read[:10], np.full(10, 30, np.uint8),
                           np.array([0, 10]), gap, pair_hap=np.array([3], np.int32),

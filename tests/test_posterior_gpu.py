@@ -90,6 +90,13 @@ def test_tumor_normal_snv_ragged(ctx, oracle):
     _check(ctx, oracle, scn, cols, cat, off)
 
 
+def test_deep_pileups_beyond_max_depth(ctx, oracle):
+    """600 observations per pileup (default --max-depth is 200): shared-memory staging scales."""
+    scn = scenario.single_sample(continuous=True, resolution=21)
+    cols, cat, off, _ = synth.make_pileups(6, [600], seed=13)
+    _check(ctx, oracle, scn, cols, cat, off)
+
+
 def test_trio_with_branching_tree(ctx, oracle):
     scn = scenario.trio(with_biases=True)
     cols, cat, off, _ = synth.make_pileups(60, [30, 30, 30], seed=synth.SEED_C5)
@@ -182,9 +189,9 @@ def test_likelihood_items_and_reference_identities(ctx, oracle):
 
 def test_posterior_errors_are_loud(ctx):
     scn = scenario.single_sample()
-    cols, cat, off, _ = synth.make_pileups(2, [300], seed=1)
+    cols, cat, off, _ = synth.make_pileups(1, [5000], seed=1)
     with pytest.raises(P.VlrError):
-        ctx.posterior_batch(scn, cols, cat, off)  # 300 observations > 256 per pileup
+        ctx.posterior_batch(scn, cols, cat, off)  # 5000 observations > 4096 per pileup
     bad = scenario.single_sample()
     bad["nodes"][0]["sample"] = 5
     cols, cat, off, _ = synth.make_pileups(2, [10], seed=1)
