@@ -108,13 +108,43 @@ int vlr_pairhmm_batch_dev(vlr_ctx *ctx, int64_t n_pairs,
 int vlr_measure_fp64_peak(vlr_ctx *ctx, double *out_tflops);
 
 /* ---- Myers best hit: replaces EditDistanceCalculation::calc_best_hit
- *      (edit_distance.rs:56-154); same haps/reads/pairs layout as above (host buffers) ------ */
+ *      (edit_distance.rs:56-154); same haps/reads/pairs layout as above (host buffers).
+ * out_dist = EditDistanceHit::dist (-1: no hit), out_start = alignments[0].start,
+ * out_end = min(alignments.last().start + len_y + dist, len_x), out_n_best = number of best end
+ * positions; best_indel_operations (131-144): count in out_n_indel_ops (nullable) and the first
+ * VLR_MAX_INDEL_OPS of them in out_indel_ops[k*VLR_MAX_INDEL_OPS ..] (nullable; 2 = Del, 3 = Ins,
+ * forward order).  Read windows up to 256 rows. ------ */
+#define VLR_MAX_INDEL_OPS 32
 int vlr_besthit_batch(vlr_ctx *ctx, int64_t n_pairs,
                       const uint8_t *hap_bytes, const int64_t *hap_off, int64_t n_haps,
                       const uint8_t *read_bases, const int64_t *read_off, int64_t n_reads,
                       const int32_t *pair_hap, const int32_t *pair_read,
                       int32_t *out_dist, int32_t *out_start, int32_t *out_end,
-                      int32_t *out_n_best);
+                      int32_t *out_n_best, int32_t *out_n_indel_ops, uint8_t *out_indel_ops);
+
+/* ---- fused Realigner::allele_support for merged candidate regions (realignment/mod.rs:225-319
+ *      with prob_allele 338-385): region r aligns read window region_read[r] against the
+ *      haplotypes region_haps[region_hap_off[r] .. region_hap_off[r+1]) (indices into the hap
+ *      CSR); the first region_n_ref[r] of them are candidates of the ref allele, the rest of the
+ *      alt allele.  shrink_extra[h] (nullable = all 0): >= 0: the window is shrunk to the hit
+ *      (pairhmm.rs:38-44) and extended by that many bytes (insertion.rs:219-222); < 0: not
+ *      shrinkable (breakend alleles, breakends.rs:649-664).
+ *      Device pipeline: K2 best hits -> minimal-distance haplotypes -> dist == 0 ? certainty_est
+ *      : banded pair-HMM (band dist+2) -> max over haplotypes -> normalisation / 0.5 fallbacks.
+ *      Outputs per region: normalised prob_ref / prob_alt, raw (unnormalised) values (nullable),
+ *      edit distances of the chosen hits, and the alt hit's best_indel_operations. ------ */
+int vlr_allele_support_batch(vlr_ctx *ctx, int64_t n_regions, const int32_t *region_read,
+                             const int32_t *region_hap_off, const int32_t *region_haps,
+                             const int32_t *region_n_ref,
+                             const uint8_t *hap_bytes, const int64_t *hap_off, int64_t n_haps,
+                             const int32_t *shrink_extra,
+                             const uint8_t *read_bases, const uint8_t *read_quals,
+                             const int64_t *read_off, int64_t n_reads,
+                             const vlr_gap_params *gap, uint32_t flags,
+                             double *out_prob_ref, double *out_prob_alt,
+                             double *out_raw_ref, double *out_raw_alt,
+                             int32_t *out_ref_dist, int32_t *out_alt_dist,
+                             int32_t *out_n_indel_ops, uint8_t *out_indel_ops);
 
 /* ---- pileup likelihood + posterior: replaces Likelihood::compute (likelihood.rs:118-152,
  *      215-245) and GenericPosterior/Model::compute (generic.rs:124-365, calling.rs:568-677) --

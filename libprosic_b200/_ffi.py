@@ -13,6 +13,7 @@ VLR_OK = 0
 HMM_SUM3_APPROX = 1
 HMM_PATH_CLOSE = 2
 HMM_DEFAULT = HMM_SUM3_APPROX
+MAX_INDEL_OPS = 32
 
 NODE_SET, NODE_RANGE, NODE_FALSE, NODE_SKIP = 0, 1, 2, 3
 
@@ -73,7 +74,7 @@ EXPORTS = [
     "vlr_version", "vlr_ctx_create", "vlr_ctx_destroy", "vlr_last_error", "vlr_ctx_set_stream",
     "vlr_ctx_synchronize", "vlr_ctx_launch_count", "vlr_pairhmm_batch",
     "vlr_pairhmm_workspace_bytes", "vlr_pairhmm_batch_dev", "vlr_measure_fp64_peak",
-    "vlr_besthit_batch", "vlr_likelihood_batch", "vlr_posterior_batch", "vlr_posterior_batch_dev",
+    "vlr_besthit_batch", "vlr_allele_support_batch", "vlr_likelihood_batch", "vlr_posterior_batch", "vlr_posterior_batch_dev",
 ]
 
 _lib = None
@@ -107,7 +108,9 @@ def load():
     L.vlr_pairhmm_batch_dev.argtypes = [vp, i64, vp, vp, i64, vp, vp, vp, i64, vp, vp, vp,
                                         C.POINTER(GapParams), u32, vp, C.c_size_t, vp]
     L.vlr_measure_fp64_peak.argtypes = [vp, _DP]
-    L.vlr_besthit_batch.argtypes = [vp, i64, vp, vp, i64, vp, vp, i64, vp, vp, vp, vp, vp, vp]
+    L.vlr_besthit_batch.argtypes = [vp, i64, vp, vp, i64, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.vlr_allele_support_batch.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, i64,
+                                           C.POINTER(GapParams), u32, vp, vp, vp, vp, vp, vp, vp, vp]
     L.vlr_likelihood_batch.argtypes = [vp, i64, i32, C.POINTER(ObsColumns), vp, vp, i32, vp, i64, vp]
     L.vlr_posterior_batch.argtypes = [vp, i64, C.POINTER(Model), C.POINTER(ObsColumns), vp, vp, vp,
                                       vp, vp]

@@ -106,6 +106,54 @@ class Context:
             _ptr(max_edit_dist), C.byref(gap.c), int(flags), _ptr(out)))
         return out
 
+    def besthit_batch(self, hap_bytes, hap_off, read_bases, read_off, pair_hap=None, pair_read=None):
+        """calc_best_hit for every pair: dict(dist, start, end, n_best, n_indel_ops, indel_ops)."""
+        hap_bytes = _arr(hap_bytes, np.uint8)
+        hap_off = _arr(hap_off, np.int64)
+        read_bases = _arr(read_bases, np.uint8)
+        read_off = _arr(read_off, np.int64)
+        pair_hap = _arr(pair_hap, np.int32)
+        pair_read = _arr(pair_read, np.int32)
+        n_haps, n_reads = len(hap_off) - 1, len(read_off) - 1
+        n = len(pair_hap) if pair_hap is not None else (len(pair_read) if pair_read is not None
+                                                        else min(n_haps, n_reads))
+        out = {k: np.empty(n, np.int32) for k in ("dist", "start", "end", "n_best", "n_indel_ops")}
+        ops = np.zeros((n, _ffi.MAX_INDEL_OPS), np.uint8)
+        self._check(self.lib.vlr_besthit_batch(
+            self.h, n, _ptr(hap_bytes), _ptr(hap_off), n_haps, _ptr(read_bases), _ptr(read_off),
+            n_reads, _ptr(pair_hap), _ptr(pair_read), _ptr(out["dist"]), _ptr(out["start"]),
+            _ptr(out["end"]), _ptr(out["n_best"]), _ptr(out["n_indel_ops"]), _ptr(ops)))
+        out["indel_ops"] = ops
+        return out
+
+    def allele_support_batch(self, region_read, region_hap_off, region_haps, region_n_ref, hap_bytes,
+                             hap_off, read_bases, read_quals, read_off, gap, shrink_extra=None,
+                             flags=_ffi.HMM_DEFAULT):
+        """Fused Realigner::allele_support per merged region (see include/vlr_gpu.h)."""
+        region_read = _arr(region_read, np.int32)
+        region_hap_off = _arr(region_hap_off, np.int32)
+        region_haps = _arr(region_haps, np.int32)
+        region_n_ref = _arr(region_n_ref, np.int32)
+        hap_bytes = _arr(hap_bytes, np.uint8)
+        hap_off = _arr(hap_off, np.int64)
+        read_bases = _arr(read_bases, np.uint8)
+        read_quals = _arr(read_quals, np.uint8)
+        read_off = _arr(read_off, np.int64)
+        shrink_extra = _arr(shrink_extra, np.int32)
+        n = len(region_read)
+        out = dict(prob_ref=np.empty(n), prob_alt=np.empty(n), raw_ref=np.empty(n), raw_alt=np.empty(n),
+                   ref_dist=np.empty(n, np.int32), alt_dist=np.empty(n, np.int32),
+                   n_indel_ops=np.empty(n, np.int32),
+                   indel_ops=np.zeros((n, _ffi.MAX_INDEL_OPS), np.uint8))
+        self._check(self.lib.vlr_allele_support_batch(
+            self.h, n, _ptr(region_read), _ptr(region_hap_off), _ptr(region_haps), _ptr(region_n_ref),
+            _ptr(hap_bytes), _ptr(hap_off), len(hap_off) - 1, _ptr(shrink_extra), _ptr(read_bases),
+            _ptr(read_quals), _ptr(read_off), len(read_off) - 1, C.byref(gap.c), int(flags),
+            _ptr(out["prob_ref"]), _ptr(out["prob_alt"]), _ptr(out["raw_ref"]), _ptr(out["raw_alt"]),
+            _ptr(out["ref_dist"]), _ptr(out["alt_dist"]), _ptr(out["n_indel_ops"]),
+            _ptr(out["indel_ops"])))
+        return out
+
     def pairhmm_workspace_bytes(self, n_pairs, max_len_x=0, max_len_y=0):
         return int(self.lib.vlr_pairhmm_workspace_bytes(n_pairs, max_len_x, max_len_y))
 

@@ -1,0 +1,535 @@
+// myers.cu -- K2: Myers bit-vector best hit with traceback, and the fused allele-support pipeline.
+//
+// Replaces EditDistanceCalculation::calc_best_hit (reference
+// src/variants/evidence/realignment/edit_distance.rs:56-154, on top of
+// bio::pattern_matching::myers) and, in vlr_allele_support_batch, the per-region part of
+// Realigner::allele_support / prob_allele (realignment/mod.rs:225-319, 338-385):
+//   best hit per (read window, haplotype) -> minimal-distance haplotypes per allele ->
+//   dist == 0 ? certainty_est : banded pair-HMM on the window shrunk to the hit (pairhmm.rs:38-44)
+//   -> max over haplotypes -> normalisation / 0.5 fallbacks.
+//
+// One thread per (read, haplotype) pair: the pattern is the read window (<= 248 rows = 4 words of
+// 64 bits), the text the haplotype window.  Each thread keeps the vertical-delta bit-vectors
+// (Pv, Mv) of every column in a private global scratch slot so that the traceback can evaluate
+// any D[j][i] with two masked popcounts per word -- the same information bio's lazy matcher
+// records.  Integer work only; results are bit-exact against the oracle.
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "pairhmm_host.cuh"
+
+namespace vlr {
+
+constexpr int kMyW = 4;               // 64-bit words per column (pattern <= 256 rows)
+constexpr int kMaxIndelOps = VLR_MAX_INDEL_OPS;
+static_assert((kMaxIndelOps & (kMaxIndelOps - 1)) == 0, "ring size must be a power of two");
+
+struct HitOut {
+    int32_t dist, start, end, n_best, n_indel;
+};
+
+struct MyersArgs {
+    const uint8_t *hap;
+    const int64_t *hap_off;
+    const uint8_t *rbase;
+    const int64_t *read_off;
+    const int32_t *pair_hap, *pair_read;
+    int64_t n_pairs;
+    int32_t *cursor;
+    uint64_t *scratch;        // per worker: (max_lx + 1) * 2 * kMyW words
+    int32_t *scratch_dm;      // per worker: (max_lx + 1) bottom distances
+    int64_t scratch_stride;   // columns per worker
+    HitOut *out;
+    uint8_t *out_ops;         // [n_pairs][kMaxIndelOps]
+};
+
+__device__ __forceinline__ int up_char(int c) { return (unsigned)(c - 'a') < 26u ? c - 32 : c; }
+__device__ __forceinline__ int sym_of(int c) {  // A C G T N -> 0..4, anything else 5
+    return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : c == 'N' ? 4 : 5;
+}
+
+// D[j][i] from the stored column state (i >= 1): bottom distance minus the vertical deltas of
+// rows j+1..m
+__device__ __forceinline__ int dist_at(const uint64_t *col, int dm, int j, int m) {
+    int d = dm;
+#pragma unroll
+    for (int w = 0; w < kMyW; ++w) {
+        const int lo = w * 64, hi = min(m, lo + 64);
+        if (hi <= lo || j >= hi) continue;
+        const int from = max(j, lo) - lo;  // bit index of row from+1
+        uint64_t mask = (hi - lo == 64 ? ~0ull : ((1ull << (hi - lo)) - 1ull)) & (~0ull << from);
+        d -= __popcll(col[w] & mask);
+        d += __popcll(col[kMyW + w] & mask);
+    }
+    return d;
+}
+
+__global__ void __launch_bounds__(128) besthit_kernel(MyersArgs g) {
+    const int64_t worker = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    uint64_t *cols = g.scratch + worker * g.scratch_stride * (2 * kMyW);
+    int32_t *dms = g.scratch_dm + worker * g.scratch_stride;
+    for (;;) {
+        const int64_t k = (int64_t)atomicAdd(g.cursor, 1);
+        if (k >= g.n_pairs) break;
+        const int64_t h = g.pair_hap ? g.pair_hap[k] : k;
+        const int64_t rd = g.pair_read ? g.pair_read[k] : k;
+        const int64_t ho = g.hap_off[h], ro = g.read_off[rd];
+        const int n = (int)(g.hap_off[h + 1] - ho), m = (int)(g.read_off[rd + 1] - ro);
+        HitOut res = {0, 0, 0, 0, 0};
+        if (n <= 0 || m <= 0 || m > 64 * kMyW) {
+            res.dist = -1;  // no hit (calc_best_hit returns None for an empty text)
+            g.out[k] = res;
+            continue;
+        }
+        const uint8_t *pat = g.rbase + ro, *txt = g.hap + ho;
+        // pattern masks for A C G T N
+        uint64_t peq[5][kMyW];
+#pragma unroll
+        for (int s = 0; s < 5; ++s)
+#pragma unroll
+            for (int w = 0; w < kMyW; ++w) peq[s][w] = 0;
+        for (int j = 0; j < m; ++j) {
+            const int s = sym_of(pat[j]);
+            if (s < 5) peq[s][j >> 6] |= 1ull << (j & 63);
+        }
+        uint64_t Pv[kMyW], Mv[kMyW];
+#pragma unroll
+        for (int w = 0; w < kMyW; ++w) { Pv[w] = ~0ull; Mv[w] = 0; }
+        const int W = (m + 63) >> 6, lastbit = (m - 1) & 63;
+        int score = m, best = 1 << 30, n_best = 0, first_best = 0, last_best = 0;
+        for (int i = 0; i < n; ++i) {
+            const int c = up_char(txt[i]);
+            const int s = sym_of(c);
+            int hin = 0;
+#pragma unroll
+            for (int w = 0; w < kMyW; ++w) {
+                if (w >= W) break;
+                uint64_t Eq;
+                if (s < 5) Eq = peq[s][w];
+                else {  // rare symbol: build the mask on the fly
+                    Eq = 0;
+                    for (int j = w * 64; j < min(m, w * 64 + 64); ++j)
+                        if (pat[j] == c) Eq |= 1ull << (j & 63);
+                }
+                const uint64_t pv = Pv[w], mv = Mv[w];
+                const uint64_t Xv = Eq | mv;
+                if (hin < 0) Eq |= 1ull;
+                const uint64_t Xh = (((Eq & pv) + pv) ^ pv) | Eq;
+                uint64_t Ph = mv | ~(Xh | pv);
+                uint64_t Mh = pv & Xh;
+                const int top = (w == W - 1) ? lastbit : 63;
+                const int hout = (int)((Ph >> top) & 1ull) - (int)((Mh >> top) & 1ull);
+                Ph <<= 1; Mh <<= 1;
+                if (hin < 0) Mh |= 1ull; else if (hin > 0) Ph |= 1ull;
+                Pv[w] = Mh | ~(Xv | Ph);
+                Mv[w] = Ph & Xv;
+                hin = hout;
+            }
+            score += hin;
+            uint64_t *col = cols + (int64_t)(i + 1) * (2 * kMyW);
+#pragma unroll
+            for (int w = 0; w < kMyW; ++w) { col[w] = Pv[w]; col[kMyW + w] = Mv[w]; }
+            dms[i + 1] = score;
+            if (score < best) { best = score; n_best = 1; first_best = i + 1; last_best = i + 1; }
+            else if (score == best) { n_best++; last_best = i + 1; }
+        }
+        // tracebacks of every best end position (edit_distance.rs:88-97), in increasing position
+        int start_first = 0, start_last = 0, best_nindel = 1 << 30, best_nops = 0;
+        uint8_t best_ops[kMaxIndelOps];
+        for (int e = first_best; e <= last_best; ++e) {
+            if (dms[e] != best) continue;
+            int j = m, i = e, nindel = 0;
+            uint8_t ops[kMaxIndelOps];  // ring of the indel ops in traceback (reverse) order
+            while (j > 0) {
+                const int d = i > 0 ? dist_at(cols + (int64_t)i * (2 * kMyW), dms[i], j, m) : j;
+                const int dup = i > 0 ? dist_at(cols + (int64_t)i * (2 * kMyW), dms[i], j - 1, m) : j - 1;
+                if (d == dup + 1) {  // vertical delta +1: Ins
+                    ops[nindel & (kMaxIndelOps - 1)] = 3;
+                    nindel++; j--;
+                    continue;
+                }
+                const int dl = i > 1 ? dist_at(cols + (int64_t)(i - 1) * (2 * kMyW), dms[i - 1], j, m) : j;
+                if (i > 0 && dl + 1 == d) {  // Del
+                    ops[nindel & (kMaxIndelOps - 1)] = 2;
+                    nindel++; i--;
+                    continue;
+                }
+                j--; i--;  // Match / Subst
+            }
+            if (e == first_best) start_first = i;
+            start_last = i;
+            if (nindel < best_nindel) {  // fewest indel ops, first on ties (min_by_key)
+                best_nindel = nindel;
+                best_nops = min(nindel, kMaxIndelOps);
+                // forward order: op t is traceback entry nindel-1-t (the ring keeps the last 32 of those)
+                for (int t = 0; t < best_nops; ++t) best_ops[t] = ops[(nindel - 1 - t) & (kMaxIndelOps - 1)];
+            }
+        }
+        res.dist = best;
+        res.start = start_first;
+        res.end = min(start_last + m + best, n);
+        res.n_best = n_best;
+        res.n_indel = best_nindel;
+        g.out[k] = res;
+        if (g.out_ops)
+            for (int t = 0; t < best_nops; ++t) g.out_ops[k * kMaxIndelOps + t] = best_ops[t];
+    }
+}
+
+// ---------------------------------------------------------------- fused allele support
+struct SupportArgs {
+    int64_t n_regions;
+    const int32_t *region_read, *region_hap_off, *region_haps, *region_n_ref;
+    const int32_t *shrink_extra;   // per haplotype (nullable)
+    const int64_t *hap_off, *read_off;
+    const uint8_t *rqual;
+    const double *qlut;
+    const HitOut *hits;            // per slot
+    const uint8_t *hit_ops;
+    // pair-HMM work list, per slot
+    int64_t *win_start;
+    int32_t *win_len, *pair_read, *med;
+    double *slot_prob;             // certainty for dist == 0 slots; HMM output otherwise
+    uint8_t *slot_mode;            // 0 skip, 1 certainty, 2 hmm
+    // outputs
+    double *prob_ref, *prob_alt, *raw_ref, *raw_alt;
+    int32_t *ref_dist, *alt_dist, *n_indel;
+    uint8_t *indel_ops;
+};
+
+// prob_allele, first half (mod.rs:346-362): keep the haplotypes with minimal edit distance and
+// prepare their pair-HMM windows (shrink_to_hit, pairhmm.rs:38-44)
+__global__ void support_select_kernel(SupportArgs g) {
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < g.n_regions;
+         r += (int64_t)gridDim.x * blockDim.x) {
+        const int s0 = g.region_hap_off[r], s1 = g.region_hap_off[r + 1];
+        const int nref = g.region_n_ref[r];
+        const int rd = g.region_read[r];
+        const int64_t ro = g.read_off[rd];
+        const int ly = (int)(g.read_off[rd + 1] - ro);
+        for (int allele = 0; allele < 2; ++allele) {
+            const int a0 = allele == 0 ? s0 : s0 + nref, a1 = allele == 0 ? s0 + nref : s1;
+            int best = -1;
+            for (int s = a0; s < a1; ++s) {
+                const int d = g.hits[s].dist;
+                if (d >= 0 && (best < 0 || d < best)) best = d;
+            }
+            for (int s = a0; s < a1; ++s) {
+                const HitOut hit = g.hits[s];
+                const int h = g.region_haps[s];
+                g.pair_read[s] = rd;
+                g.win_start[s] = g.hap_off[h];
+                g.win_len[s] = 0;
+                g.med[s] = -1;
+                g.slot_mode[s] = 0;
+                g.slot_prob[s] = -INFINITY;
+                if (hit.dist < 0 || hit.dist != best) continue;
+                if (hit.dist == 0) {
+                    // certainty_est (pairhmm.rs:208-210): sum of ln(1 - eps_j) in read order
+                    double p = 0.0;
+                    for (int j = 0; j < ly; ++j) p += g.qlut[g.rqual[ro + j] * kQlutStride + 3];
+                    g.slot_prob[s] = p;
+                    g.slot_mode[s] = 1;
+                } else {
+                    const int lx = (int)(g.hap_off[h + 1] - g.hap_off[h]);
+                    int ws = 0, we = lx;
+                    const int extra = g.shrink_extra ? g.shrink_extra[h] : 0;
+                    if (extra >= 0) {  // < 0: not shrinkable (breakend alleles, quirk Q6)
+                        const int ref_len = lx - extra;
+                        ws = max(hit.start - 2, 0);
+                        we = min(hit.end + 2, ref_len) + extra;
+                    }
+                    g.win_start[s] = g.hap_off[h] + ws;
+                    g.win_len[s] = we - ws;
+                    g.med[s] = hit.dist + 2;  // dist_upper_bound (edit_distance.rs:180-182)
+                    g.slot_mode[s] = 2;
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ double ln_add_exp_s(double a, double b) {
+    const double p0 = fmax(a, b), p1 = fmin(a, b);
+    if (p0 == -INFINITY) return -INFINITY;
+    if (p1 == -INFINITY) return p0;
+    return p0 + log1p(exp(p1 - p0));
+}
+
+// prob_allele second half (mod.rs:364-383) + the region epilogue of allele_support (283-301)
+__global__ void support_epilogue_kernel(SupportArgs g) {
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < g.n_regions;
+         r += (int64_t)gridDim.x * blockDim.x) {
+        const int s0 = g.region_hap_off[r], s1 = g.region_hap_off[r + 1];
+        const int nref = g.region_n_ref[r];
+        double prob[2] = {-INFINITY, -INFINITY};
+        int best_slot[2] = {-1, -1};
+        for (int allele = 0; allele < 2; ++allele) {
+            const int a0 = allele == 0 ? s0 : s0 + nref, a1 = allele == 0 ? s0 + nref : s1;
+            bool have = false;
+            for (int s = a0; s < a1; ++s) {
+                const int mode = g.slot_mode[s];
+                if (mode == 0) continue;
+                const double p = g.slot_prob[s];
+                if (mode == 1) {  // perfect match: unconditional overwrite
+                    prob[allele] = p; best_slot[allele] = s; have = true;
+                } else if (!have || p > prob[allele]) {
+                    prob[allele] = p; best_slot[allele] = s; have = true;
+                }
+            }
+        }
+        double pr = prob[0], pa = prob[1];
+        if (g.raw_ref) g.raw_ref[r] = pr;
+        if (g.raw_alt) g.raw_alt[r] = pa;
+        if (pr != -INFINITY && pa != -INFINITY) {  // normalise only if both are non-zero
+            const double tot = ln_add_exp_s(pa, pr);
+            pr -= tot;
+            pa -= tot;
+        }
+        if (pr == -INFINITY && pa == -INFINITY) pr = pa = -0.6931471805599453;  // Prob(0.5)
+        g.prob_ref[r] = pr;
+        g.prob_alt[r] = pa;
+        g.ref_dist[r] = best_slot[0] >= 0 ? g.hits[best_slot[0]].dist : -1;
+        g.alt_dist[r] = best_slot[1] >= 0 ? g.hits[best_slot[1]].dist : -1;
+        int ni = 0;
+        if (best_slot[1] >= 0) {
+            ni = g.hits[best_slot[1]].n_indel;
+            if (g.indel_ops)
+                for (int t = 0; t < min(ni, kMaxIndelOps); ++t)
+                    g.indel_ops[r * kMaxIndelOps + t] = g.hit_ops[(int64_t)best_slot[1] * kMaxIndelOps + t];
+        }
+        g.n_indel[r] = ni;
+    }
+}
+
+// launches K2 over device-resident pairs; returns workers used
+static int launch_besthit(vlr_ctx *ctx, MyersArgs &a, int64_t max_lx, int slot_base) {
+    cudaStream_t st = ctx->stream;
+    const size_t per_worker = (size_t)(max_lx + 1) * (2 * kMyW * 8 + 4);
+    int64_t workers = (int64_t)ctx->sm_count * 256;
+    const size_t budget = (size_t)2 << 30;
+    if ((size_t)workers * per_worker > budget) workers = (int64_t)(budget / per_worker);
+    workers = workers / 128 * 128;
+    if (workers < 128) return set_err(ctx, VLR_ERR_UNSUPPORTED, "haplotype window of %lld bytes is too long for the Myers scratch", (long long)max_lx);
+    if (workers > a.n_pairs) workers = (a.n_pairs + 127) / 128 * 128;
+    uint64_t *scratch = (uint64_t *)dev_scratch(ctx, slot_base, (size_t)workers * (max_lx + 1) * (2 * kMyW * 8));
+    int32_t *dm = (int32_t *)dev_scratch(ctx, slot_base + 1, (size_t)workers * (max_lx + 1) * 4);
+    int32_t *cnt = (int32_t *)dev_scratch(ctx, slot_base + 2, 64);
+    if (!scratch || !dm || !cnt) return set_err(ctx, VLR_ERR_NOMEM, "scratch allocation failed");
+    VLR_CUDA(ctx, cudaMemsetAsync(cnt, 0, 64, st));
+    a.scratch = scratch;
+    a.scratch_dm = dm;
+    a.scratch_stride = max_lx + 1;
+    a.cursor = cnt;
+    besthit_kernel<<<(int)(workers / 128), 128, 0, st>>>(a);
+    VLR_LAUNCH_CHECK(ctx);
+    return VLR_OK;
+}
+
+}  // namespace vlr
+
+using namespace vlr;
+
+extern "C" {
+
+int vlr_besthit_batch(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *hap_bytes, const int64_t *hap_off,
+                      int64_t n_haps, const uint8_t *read_bases, const int64_t *read_off,
+                      int64_t n_reads, const int32_t *pair_hap, const int32_t *pair_read,
+                      int32_t *out_dist, int32_t *out_start, int32_t *out_end, int32_t *out_n_best,
+                      int32_t *out_n_indel_ops, uint8_t *out_indel_ops) {
+    if (!ctx) return VLR_ERR_INVALID;
+    if (n_pairs < 0 || n_pairs > 0x7fffffff) return set_err(ctx, VLR_ERR_INVALID, "n_pairs out of range");
+    if (n_pairs == 0) return VLR_OK;
+    if (!hap_bytes || !hap_off || !read_bases || !read_off || !out_dist || !out_start || !out_end ||
+        !out_n_best || n_haps <= 0 || n_reads <= 0)
+        return set_err(ctx, VLR_ERR_INVALID, "null/empty argument");
+    if ((!pair_hap && n_haps < n_pairs) || (!pair_read && n_reads < n_pairs))
+        return set_err(ctx, VLR_ERR_INVALID, "identity pair mapping needs n_haps/n_reads >= n_pairs");
+    VLR_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    int64_t max_lx = 0, max_ly = 0;
+    for (int64_t h = 0; h < n_haps; ++h) {
+        if (hap_off[h + 1] < hap_off[h]) return set_err(ctx, VLR_ERR_INVALID, "hap_off not monotone");
+        max_lx = std::max(max_lx, hap_off[h + 1] - hap_off[h]);
+    }
+    for (int64_t r = 0; r < n_reads; ++r) {
+        if (read_off[r + 1] < read_off[r]) return set_err(ctx, VLR_ERR_INVALID, "read_off not monotone");
+        max_ly = std::max(max_ly, read_off[r + 1] - read_off[r]);
+    }
+    if (max_ly > 64 * kMyW) return set_err(ctx, VLR_ERR_UNSUPPORTED, "read window of %lld rows exceeds %d", (long long)max_ly, 64 * kMyW);
+    if (pair_hap || pair_read)
+        for (int64_t k = 0; k < n_pairs; ++k) {
+            if (pair_hap && (pair_hap[k] < 0 || pair_hap[k] >= n_haps)) return set_err(ctx, VLR_ERR_INVALID, "pair_hap out of range");
+            if (pair_read && (pair_read[k] < 0 || pair_read[k] >= n_reads)) return set_err(ctx, VLR_ERR_INVALID, "pair_read out of range");
+        }
+    enum { S_HAP = 40, S_HOFF, S_RB, S_ROFF, S_PH, S_PR, S_OUT, S_OPS, S_SCR };
+    const int64_t hap_lo = hap_off[0], rd_lo = read_off[0];
+    const size_t hb = (size_t)(hap_off[n_haps] - hap_lo), rb = (size_t)(read_off[n_reads] - rd_lo);
+    uint8_t *d_hap = (uint8_t *)dev_scratch(ctx, S_HAP, hb + 64);
+    int64_t *d_hoff = (int64_t *)dev_scratch(ctx, S_HOFF, (size_t)(n_haps + 1) * 8);
+    uint8_t *d_rb = (uint8_t *)dev_scratch(ctx, S_RB, rb + 16);
+    int64_t *d_roff = (int64_t *)dev_scratch(ctx, S_ROFF, (size_t)(n_reads + 1) * 8);
+    int32_t *d_ph = pair_hap ? (int32_t *)dev_scratch(ctx, S_PH, (size_t)n_pairs * 4) : nullptr;
+    int32_t *d_pr = pair_read ? (int32_t *)dev_scratch(ctx, S_PR, (size_t)n_pairs * 4) : nullptr;
+    HitOut *d_out = (HitOut *)dev_scratch(ctx, S_OUT, (size_t)n_pairs * sizeof(HitOut));
+    uint8_t *d_ops = (uint8_t *)dev_scratch(ctx, S_OPS, (size_t)n_pairs * kMaxIndelOps);
+    if (!d_hap || !d_hoff || !d_rb || !d_roff || !d_out || !d_ops || (pair_hap && !d_ph) || (pair_read && !d_pr))
+        return set_err(ctx, VLR_ERR_NOMEM, "scratch allocation failed");
+    VLR_CUDA(ctx, cudaMemcpyAsync(d_hap, hap_bytes + hap_lo, hb, cudaMemcpyHostToDevice, st));
+    VLR_CUDA(ctx, cudaMemcpyAsync(d_hoff, hap_off, (size_t)(n_haps + 1) * 8, cudaMemcpyHostToDevice, st));
+    VLR_CUDA(ctx, cudaMemcpyAsync(d_rb, read_bases + rd_lo, rb, cudaMemcpyHostToDevice, st));
+    VLR_CUDA(ctx, cudaMemcpyAsync(d_roff, read_off, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (pair_hap) VLR_CUDA(ctx, cudaMemcpyAsync(d_ph, pair_hap, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, st));
+    if (pair_read) VLR_CUDA(ctx, cudaMemcpyAsync(d_pr, pair_read, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, st));
+    VLR_CUDA(ctx, cudaMemsetAsync(d_ops, 0, (size_t)n_pairs * kMaxIndelOps, st));
+    MyersArgs a;
+    memset(&a, 0, sizeof(a));
+    a.hap = d_hap - hap_lo; a.hap_off = d_hoff; a.rbase = d_rb - rd_lo; a.read_off = d_roff;
+    a.pair_hap = d_ph; a.pair_read = d_pr; a.n_pairs = n_pairs; a.out = d_out; a.out_ops = d_ops;
+    int rc = launch_besthit(ctx, a, max_lx, S_SCR);
+    if (rc != VLR_OK) return rc;
+    std::vector<HitOut> h((size_t)n_pairs);
+    VLR_CUDA(ctx, cudaMemcpyAsync(h.data(), d_out, (size_t)n_pairs * sizeof(HitOut), cudaMemcpyDeviceToHost, st));
+    if (out_indel_ops)
+        VLR_CUDA(ctx, cudaMemcpyAsync(out_indel_ops, d_ops, (size_t)n_pairs * kMaxIndelOps, cudaMemcpyDeviceToHost, st));
+    VLR_CUDA(ctx, cudaStreamSynchronize(st));
+    for (int64_t k = 0; k < n_pairs; ++k) {
+        out_dist[k] = h[k].dist; out_start[k] = h[k].start; out_end[k] = h[k].end;
+        out_n_best[k] = h[k].n_best;
+        if (out_n_indel_ops) out_n_indel_ops[k] = h[k].n_indel;
+    }
+    return VLR_OK;
+}
+
+int vlr_allele_support_batch(vlr_ctx *ctx, int64_t n_regions, const int32_t *region_read,
+                             const int32_t *region_hap_off, const int32_t *region_haps,
+                             const int32_t *region_n_ref, const uint8_t *hap_bytes,
+                             const int64_t *hap_off, int64_t n_haps, const int32_t *shrink_extra,
+                             const uint8_t *read_bases, const uint8_t *read_quals,
+                             const int64_t *read_off, int64_t n_reads, const vlr_gap_params *gap,
+                             uint32_t flags, double *out_prob_ref, double *out_prob_alt,
+                             double *out_raw_ref, double *out_raw_alt, int32_t *out_ref_dist,
+                             int32_t *out_alt_dist, int32_t *out_n_indel_ops, uint8_t *out_indel_ops) {
+    if (!ctx) return VLR_ERR_INVALID;
+    if (n_regions < 0 || n_regions > 0x3fffffff) return set_err(ctx, VLR_ERR_INVALID, "n_regions out of range");
+    if (n_regions == 0) return VLR_OK;
+    if (!region_read || !region_hap_off || !region_haps || !region_n_ref || !hap_bytes || !hap_off ||
+        !read_bases || !read_quals || !read_off || !gap || !out_prob_ref || !out_prob_alt ||
+        !out_ref_dist || !out_alt_dist || !out_n_indel_ops || n_haps <= 0 || n_reads <= 0)
+        return set_err(ctx, VLR_ERR_INVALID, "null/empty argument");
+    VLR_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int64_t n_slots = region_hap_off[n_regions];
+    if (n_slots <= 0 || n_slots > 0x7fffffff) return set_err(ctx, VLR_ERR_INVALID, "bad region_hap_off");
+    int64_t max_lx = 0, max_ly = 0;
+    for (int64_t h = 0; h < n_haps; ++h) {
+        if (hap_off[h + 1] < hap_off[h]) return set_err(ctx, VLR_ERR_INVALID, "hap_off not monotone");
+        max_lx = std::max(max_lx, hap_off[h + 1] - hap_off[h]);
+        if (shrink_extra && shrink_extra[h] > hap_off[h + 1] - hap_off[h])
+            return set_err(ctx, VLR_ERR_INVALID, "shrink_extra[%lld] exceeds the window", (long long)h);
+    }
+    for (int64_t r = 0; r < n_reads; ++r) {
+        if (read_off[r + 1] < read_off[r]) return set_err(ctx, VLR_ERR_INVALID, "read_off not monotone");
+        max_ly = std::max(max_ly, read_off[r + 1] - read_off[r]);
+    }
+    if (max_ly > 248) return set_err(ctx, VLR_ERR_UNSUPPORTED, "read window of %lld rows exceeds 248", (long long)max_ly);
+    for (int64_t r = 0; r < n_regions; ++r) {
+        const int s0 = region_hap_off[r], s1 = region_hap_off[r + 1];
+        if (s1 < s0 || region_n_ref[r] < 0 || region_n_ref[r] > s1 - s0 || region_read[r] < 0 || region_read[r] >= n_reads)
+            return set_err(ctx, VLR_ERR_INVALID, "region %lld is malformed", (long long)r);
+    }
+    for (int64_t s = 0; s < n_slots; ++s)
+        if (region_haps[s] < 0 || region_haps[s] >= n_haps) return set_err(ctx, VLR_ERR_INVALID, "region_haps out of range");
+    enum { S_HAP = 40, S_HOFF, S_RB, S_ROFF, S_PH, S_PR, S_OUT, S_OPS, S_SCR, S_SCR2, S_SCR3,
+           S_RQ, S_RR, S_RHO, S_RNR, S_SE, S_WS0, S_WL, S_MED, S_SP, S_SM, S_O1, S_O2, S_O3, S_O4, S_O5,
+           S_O6, S_O7, S_O8, S_PWS };
+    const int64_t hap_lo = hap_off[0], rd_lo = read_off[0];
+    const size_t hb = (size_t)(hap_off[n_haps] - hap_lo), rb = (size_t)(read_off[n_reads] - rd_lo);
+    auto D = [&](int slot, size_t bytes) { return dev_scratch(ctx, slot, bytes ? bytes : 8); };
+    uint8_t *d_hap = (uint8_t *)D(S_HAP, hb + 64);
+    int64_t *d_hoff = (int64_t *)D(S_HOFF, (size_t)(n_haps + 1) * 8);
+    uint8_t *d_rb = (uint8_t *)D(S_RB, rb + 16), *d_rq = (uint8_t *)D(S_RQ, rb + 16);
+    int64_t *d_roff = (int64_t *)D(S_ROFF, (size_t)(n_reads + 1) * 8);
+    int32_t *d_rr = (int32_t *)D(S_RR, (size_t)n_regions * 4), *d_rho = (int32_t *)D(S_RHO, (size_t)(n_regions + 1) * 4);
+    int32_t *d_rh = (int32_t *)D(S_PH, (size_t)n_slots * 4), *d_rnr = (int32_t *)D(S_RNR, (size_t)n_regions * 4);
+    int32_t *d_se = shrink_extra ? (int32_t *)D(S_SE, (size_t)n_haps * 4) : nullptr;
+    int32_t *d_slot_read = (int32_t *)D(S_PR, (size_t)n_slots * 4);
+    HitOut *d_hits = (HitOut *)D(S_OUT, (size_t)n_slots * sizeof(HitOut));
+    uint8_t *d_ops = (uint8_t *)D(S_OPS, (size_t)n_slots * kMaxIndelOps);
+    int64_t *d_ws = (int64_t *)D(S_WS0, (size_t)n_slots * 8);
+    int32_t *d_wl = (int32_t *)D(S_WL, (size_t)n_slots * 4), *d_med = (int32_t *)D(S_MED, (size_t)n_slots * 4);
+    double *d_sp = (double *)D(S_SP, (size_t)n_slots * 8);
+    uint8_t *d_sm = (uint8_t *)D(S_SM, (size_t)n_slots);
+    double *d_pref = (double *)D(S_O1, (size_t)n_regions * 8), *d_palt = (double *)D(S_O2, (size_t)n_regions * 8);
+    double *d_rref = (double *)D(S_O3, (size_t)n_regions * 8), *d_ralt = (double *)D(S_O4, (size_t)n_regions * 8);
+    int32_t *d_rd = (int32_t *)D(S_O5, (size_t)n_regions * 4), *d_ad = (int32_t *)D(S_O6, (size_t)n_regions * 4);
+    int32_t *d_ni = (int32_t *)D(S_O7, (size_t)n_regions * 4);
+    uint8_t *d_io = (uint8_t *)D(S_O8, (size_t)n_regions * kMaxIndelOps);
+    const size_t pws_bytes = vlr_pairhmm_workspace_bytes(n_slots, 0, 0);
+    void *d_pws = D(S_PWS, pws_bytes);
+    if (!d_hap || !d_hoff || !d_rb || !d_rq || !d_roff || !d_rr || !d_rho || !d_rh || !d_rnr ||
+        (shrink_extra && !d_se) || !d_slot_read || !d_hits || !d_ops || !d_ws || !d_wl || !d_med ||
+        !d_sp || !d_sm || !d_pref || !d_palt || !d_rref || !d_ralt || !d_rd || !d_ad || !d_ni || !d_io || !d_pws)
+        return set_err(ctx, VLR_ERR_NOMEM, "scratch allocation failed");
+    // slot -> read index (the Myers pairs)
+    std::vector<int32_t> slot_read((size_t)n_slots);
+    for (int64_t r = 0; r < n_regions; ++r)
+        for (int s = region_hap_off[r]; s < region_hap_off[r + 1]; ++s) slot_read[s] = region_read[r];
+    auto H2D = [&](void *d, const void *h, size_t b) { return cudaMemcpyAsync(d, h, b, cudaMemcpyHostToDevice, st); };
+    VLR_CUDA(ctx, H2D(d_hap, hap_bytes + hap_lo, hb));
+    VLR_CUDA(ctx, H2D(d_hoff, hap_off, (size_t)(n_haps + 1) * 8));
+    VLR_CUDA(ctx, H2D(d_rb, read_bases + rd_lo, rb));
+    VLR_CUDA(ctx, H2D(d_rq, read_quals + rd_lo, rb));
+    VLR_CUDA(ctx, H2D(d_roff, read_off, (size_t)(n_reads + 1) * 8));
+    VLR_CUDA(ctx, H2D(d_rr, region_read, (size_t)n_regions * 4));
+    VLR_CUDA(ctx, H2D(d_rho, region_hap_off, (size_t)(n_regions + 1) * 4));
+    VLR_CUDA(ctx, H2D(d_rh, region_haps, (size_t)n_slots * 4));
+    VLR_CUDA(ctx, H2D(d_rnr, region_n_ref, (size_t)n_regions * 4));
+    if (shrink_extra) VLR_CUDA(ctx, H2D(d_se, shrink_extra, (size_t)n_haps * 4));
+    VLR_CUDA(ctx, H2D(d_slot_read, slot_read.data(), (size_t)n_slots * 4));
+    VLR_CUDA(ctx, cudaStreamSynchronize(st));  // slot_read is a stack-owned staging vector
+    VLR_CUDA(ctx, cudaMemsetAsync(d_ops, 0, (size_t)n_slots * kMaxIndelOps, st));
+    VLR_CUDA(ctx, cudaMemsetAsync(d_io, 0, (size_t)n_regions * kMaxIndelOps, st));
+    // 1. best hit of every (read window, haplotype) slot
+    MyersArgs ma;
+    memset(&ma, 0, sizeof(ma));
+    ma.hap = d_hap - hap_lo; ma.hap_off = d_hoff; ma.rbase = d_rb - rd_lo; ma.read_off = d_roff;
+    ma.pair_hap = d_rh; ma.pair_read = d_slot_read; ma.n_pairs = n_slots; ma.out = d_hits; ma.out_ops = d_ops;
+    int rc = launch_besthit(ctx, ma, max_lx, S_SCR);
+    if (rc != VLR_OK) return rc;
+    // 2. minimal-distance selection, certainty short-circuit, HMM windows
+    SupportArgs sa;
+    memset(&sa, 0, sizeof(sa));
+    sa.n_regions = n_regions; sa.region_read = d_rr; sa.region_hap_off = d_rho; sa.region_haps = d_rh;
+    sa.region_n_ref = d_rnr; sa.shrink_extra = d_se; sa.hap_off = d_hoff; sa.read_off = d_roff;
+    sa.rqual = d_rq - rd_lo; sa.qlut = ctx->d_qlut; sa.hits = d_hits; sa.hit_ops = d_ops;
+    sa.win_start = d_ws; sa.win_len = d_wl; sa.pair_read = d_slot_read; sa.med = d_med;
+    sa.slot_prob = d_sp; sa.slot_mode = d_sm;
+    sa.prob_ref = d_pref; sa.prob_alt = d_palt; sa.raw_ref = d_rref; sa.raw_alt = d_ralt;
+    sa.ref_dist = d_rd; sa.alt_dist = d_ad; sa.n_indel = d_ni; sa.indel_ops = d_io;
+    const int grid = (int)std::min<int64_t>((n_regions + 127) / 128, (int64_t)ctx->sm_count * 8);
+    support_select_kernel<<<grid, 128, 0, st>>>(sa);
+    VLR_LAUNCH_CHECK(ctx);
+    // 3. banded pair-HMM on the shrunk windows (mode-2 slots; others have an empty window)
+    rc = pairhmm_windows_dev(ctx, n_slots, d_hap - hap_lo, d_ws, d_wl, d_rb - rd_lo, d_rq - rd_lo,
+                             d_roff, d_slot_read, d_med, d_sm, gap, flags, d_pws, pws_bytes, d_sp);
+    if (rc != VLR_OK) return rc;
+    // 4. max over haplotypes, normalisation, fallbacks
+    support_epilogue_kernel<<<grid, 128, 0, st>>>(sa);
+    VLR_LAUNCH_CHECK(ctx);
+    auto D2H = [&](void *h, const void *d, size_t b) { return cudaMemcpyAsync(h, d, b, cudaMemcpyDeviceToHost, st); };
+    VLR_CUDA(ctx, D2H(out_prob_ref, d_pref, (size_t)n_regions * 8));
+    VLR_CUDA(ctx, D2H(out_prob_alt, d_palt, (size_t)n_regions * 8));
+    if (out_raw_ref) VLR_CUDA(ctx, D2H(out_raw_ref, d_rref, (size_t)n_regions * 8));
+    if (out_raw_alt) VLR_CUDA(ctx, D2H(out_raw_alt, d_ralt, (size_t)n_regions * 8));
+    VLR_CUDA(ctx, D2H(out_ref_dist, d_rd, (size_t)n_regions * 4));
+    VLR_CUDA(ctx, D2H(out_alt_dist, d_ad, (size_t)n_regions * 4));
+    VLR_CUDA(ctx, D2H(out_n_indel_ops, d_ni, (size_t)n_regions * 4));
+    if (out_indel_ops) VLR_CUDA(ctx, D2H(out_indel_ops, d_io, (size_t)n_regions * kMaxIndelOps));
+    VLR_CUDA(ctx, cudaStreamSynchronize(st));
+    return VLR_OK;
+}
+
+}  // extern "C"

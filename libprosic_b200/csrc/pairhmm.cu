@@ -5,6 +5,7 @@
 
 #include <vector>
 
+#include "pairhmm_host.cuh"
 #include "pairhmm_kernel.cuh"
 
 namespace vlr {
@@ -28,12 +29,13 @@ constexpr int kCntCount = 0, kCntOff = 8, kCntScatter = 16, kCntWork = 24, kCntF
               kCntFbWork = 33, kCntTotal = 64;
 
 __global__ void classify_kernel(int64_t n_pairs, const int64_t *read_off, const int32_t *pair_read,
-                                int32_t *counters) {
+                                const uint8_t *mode, int32_t *counters) {
     __shared__ int s_cnt[kNumClasses];
     if (threadIdx.x < kNumClasses) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n_pairs;
          p += (int64_t)gridDim.x * blockDim.x) {
+        if (mode && mode[p] != 2) continue;
         const int64_t rd = pair_read ? (int64_t)pair_read[p] : p;
         const int ly = (int)(read_off[rd + 1] - read_off[rd]);
         atomicAdd(&s_cnt[class_of_len(ly)], 1);
@@ -54,9 +56,10 @@ __global__ void class_scan_kernel(int32_t *counters) {
 }
 
 __global__ void scatter_kernel(int64_t n_pairs, const int64_t *read_off, const int32_t *pair_read,
-                               int32_t *counters, int32_t *list) {
+                               const uint8_t *mode, int32_t *counters, int32_t *list) {
     for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n_pairs;
          p += (int64_t)gridDim.x * blockDim.x) {
+        if (mode && mode[p] != 2) continue;
         const int64_t rd = pair_read ? (int64_t)pair_read[p] : p;
         const int ly = (int)(read_off[rd + 1] - read_off[rd]);
         const int k = class_of_len(ly);
@@ -140,27 +143,22 @@ static PairWs carve_ws(void *ws, int64_t n_pairs) {
 
 using namespace vlr;
 
-extern "C" {
-
-size_t vlr_pairhmm_workspace_bytes(int64_t n_pairs, int64_t max_len_x, int64_t max_len_y) {
-    (void)max_len_x; (void)max_len_y;
-    return pair_ws_bytes(n_pairs < 1 ? 1 : n_pairs);
-}
-
-int vlr_pairhmm_batch_dev(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *d_hap_bytes,
-                          const int64_t *d_hap_off, int64_t n_haps, const uint8_t *d_read_bases,
-                          const uint8_t *d_read_quals, const int64_t *d_read_off, int64_t n_reads,
-                          const int32_t *d_pair_hap, const int32_t *d_pair_read,
-                          const int32_t *d_max_edit_dist, const vlr_gap_params *gap, uint32_t flags,
-                          void *d_workspace, size_t workspace_bytes, double *d_out_lnprob) {
+static int pairhmm_core_dev(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *d_hap_bytes,
+                            const int64_t *d_hap_off, int64_t n_haps, const uint8_t *d_read_bases,
+                            const uint8_t *d_read_quals, const int64_t *d_read_off, int64_t n_reads,
+                            const int32_t *d_pair_hap, const int32_t *d_pair_read,
+                            const int32_t *d_max_edit_dist, const int64_t *d_win_start,
+                            const int32_t *d_win_len, const uint8_t *d_mode,
+                            const vlr_gap_params *gap, uint32_t flags, void *d_workspace,
+                            size_t workspace_bytes, double *d_out_lnprob) {
     if (!ctx) return VLR_ERR_INVALID;
     if (n_pairs < 0 || n_pairs > 0x7fffffff)
         return set_err(ctx, VLR_ERR_INVALID, "n_pairs out of range");
     if (n_pairs == 0) return VLR_OK;
-    if (!d_hap_bytes || !d_hap_off || !d_read_bases || !d_read_quals || !d_read_off || !gap ||
+    if (!d_hap_bytes || (!d_hap_off && !d_win_start) || !d_read_bases || !d_read_quals || !d_read_off || !gap ||
         !d_workspace || !d_out_lnprob)
         return set_err(ctx, VLR_ERR_INVALID, "null pointer argument");
-    if ((!d_pair_hap && n_haps < n_pairs) || (!d_pair_read && n_reads < n_pairs))
+    if ((!d_win_start && !d_pair_hap && n_haps < n_pairs) || (!d_pair_read && n_reads < n_pairs))
         return set_err(ctx, VLR_ERR_INVALID, "identity pair mapping needs n_haps/n_reads >= n_pairs");
     if (workspace_bytes < pair_ws_bytes(n_pairs))
         return set_err(ctx, VLR_ERR_INVALID, "workspace too small");
@@ -170,17 +168,18 @@ int vlr_pairhmm_batch_dev(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *d_hap_by
     VLR_CUDA(ctx, cudaMemsetAsync(w.counters, 0, kCntTotal * sizeof(int32_t), st));
     const int64_t want = (n_pairs + 255) / 256, cap = (int64_t)ctx->sm_count * 8;
     const int cgrid = (int)(want < cap ? want : cap);
-    classify_kernel<<<cgrid, 256, 0, st>>>(n_pairs, d_read_off, d_pair_read, w.counters);
+    classify_kernel<<<cgrid, 256, 0, st>>>(n_pairs, d_read_off, d_pair_read, d_mode, w.counters);
     VLR_LAUNCH_CHECK(ctx);
     class_scan_kernel<<<1, 32, 0, st>>>(w.counters);
     VLR_LAUNCH_CHECK(ctx);
-    scatter_kernel<<<cgrid, 256, 0, st>>>(n_pairs, d_read_off, d_pair_read, w.counters, w.list);
+    scatter_kernel<<<cgrid, 256, 0, st>>>(n_pairs, d_read_off, d_pair_read, d_mode, w.counters, w.list);
     VLR_LAUNCH_CHECK(ctx);
 
     HmmArgs a;
     a.hap = d_hap_bytes; a.hap_off = d_hap_off;
     a.rbase = d_read_bases; a.rqual = d_read_quals; a.read_off = d_read_off;
     a.pair_hap = d_pair_hap; a.pair_read = d_pair_read; a.med = d_max_edit_dist;
+    a.win_start = d_win_start; a.win_len = d_win_len;
     a.fb_list = w.fb_list; a.fb_count = w.counters + kCntFb;
     a.out = d_out_lnprob; a.qlut = ctx->d_qlut;
     make_consts(gap, flags, &a.lin, &a.ln);
@@ -218,6 +217,38 @@ int vlr_pairhmm_batch_dev(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *d_hap_by
     mark_unsupported_kernel<<<32, 256, 0, st>>>(w.list, w.counters, d_out_lnprob);
     VLR_LAUNCH_CHECK(ctx);
     return VLR_OK;
+}
+
+
+namespace vlr {
+int pairhmm_windows_dev(vlr_ctx *ctx, int64_t n_slots, const uint8_t *d_hap_base,
+                        const int64_t *d_win_start, const int32_t *d_win_len,
+                        const uint8_t *d_read_bases, const uint8_t *d_read_quals,
+                        const int64_t *d_read_off, const int32_t *d_pair_read, const int32_t *d_med,
+                        const uint8_t *d_mode, const vlr_gap_params *gap, uint32_t flags,
+                        void *d_workspace, size_t workspace_bytes, double *d_out) {
+    return pairhmm_core_dev(ctx, n_slots, d_hap_base, nullptr, 0, d_read_bases, d_read_quals, d_read_off,
+                            (int64_t)1 << 40, nullptr, d_pair_read, d_med, d_win_start, d_win_len, d_mode,
+                            gap, flags, d_workspace, workspace_bytes, d_out);
+}
+}  // namespace vlr
+
+extern "C" {
+
+size_t vlr_pairhmm_workspace_bytes(int64_t n_pairs, int64_t max_len_x, int64_t max_len_y) {
+    (void)max_len_x; (void)max_len_y;
+    return pair_ws_bytes(n_pairs < 1 ? 1 : n_pairs);
+}
+
+int vlr_pairhmm_batch_dev(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *d_hap_bytes,
+                          const int64_t *d_hap_off, int64_t n_haps, const uint8_t *d_read_bases,
+                          const uint8_t *d_read_quals, const int64_t *d_read_off, int64_t n_reads,
+                          const int32_t *d_pair_hap, const int32_t *d_pair_read,
+                          const int32_t *d_max_edit_dist, const vlr_gap_params *gap, uint32_t flags,
+                          void *d_workspace, size_t workspace_bytes, double *d_out_lnprob) {
+    return pairhmm_core_dev(ctx, n_pairs, d_hap_bytes, d_hap_off, n_haps, d_read_bases, d_read_quals,
+                            d_read_off, n_reads, d_pair_hap, d_pair_read, d_max_edit_dist, nullptr,
+                            nullptr, nullptr, gap, flags, d_workspace, workspace_bytes, d_out_lnprob);
 }
 
 int vlr_pairhmm_batch(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *hap_bytes,

@@ -48,6 +48,8 @@ struct HmmArgs {
     const int32_t *pair_hap;
     const int32_t *pair_read;
     const int32_t *med;
+    const int64_t *win_start;  // optional explicit haplotype windows (fused allele support)
+    const int32_t *win_len;
     const int32_t *list;      // pair ids handled by this launch (device)
     const int32_t *list_off;  // device offset into `list` (nullable)
     const int32_t *count;  // number of entries of `list` (device)
@@ -347,8 +349,8 @@ __global__ void __launch_bounds__(kWarps * 32, Occ<R>::kMinBlocks) pairhmm_kerne
         const int pair = list ? list[p] : p;
         const int64_t hidx = g.pair_hap ? (int64_t)g.pair_hap[pair] : (int64_t)pair;
         const int64_t rd = g.pair_read ? (int64_t)g.pair_read[pair] : (int64_t)pair;
-        const int64_t ho = g.hap_off[hidx];
-        const int lx = (int)(g.hap_off[hidx + 1] - ho);
+        const int64_t ho = g.win_start ? g.win_start[pair] : g.hap_off[hidx];
+        const int lx = g.win_start ? g.win_len[pair] : (int)(g.hap_off[hidx + 1] - ho);
         const int64_t ro = g.read_off[rd];
         const int ly = (int)(g.read_off[rd + 1] - ro);
         int band = kMedMax;
