@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--cpu-sample-pairs", type=int, default=0, help="0 = auto (about 15 s)")
     ap.add_argument("--p2-sites", type=int, default=262144, help="C2 sites per step and GPU (part 2)")
     ap.add_argument("--skip-part2", action="store_true")
+    ap.add_argument("--c4-pairs", type=int, default=1184, help="long-read pairs of the C4 subsample (0 = skip)")
+    ap.add_argument("--as-reads", type=int, default=262144, help="reads per step for the fused allele-support run")
     ap.add_argument("--part2-only", default="", help="run only this part-2 workload (profiling aid)")
     return ap.parse_args()
 
@@ -286,6 +288,109 @@ def bench_part2(args, ctx, torch, dist, dev, stream, rank, world, name, wl, time
     return res
 
 
+def bench_allele_support(args, ctx, w, flags, rank, world, torch, dist, dev):
+    """Part 1 as the pipeline runs it (Realigner::allele_support per read): Myers best hits,
+    minimal-distance selection, certainty short-circuit, banded pair-HMM on the shrunk windows,
+    normalisation -- one fused device pipeline behind vlr_allele_support_batch (host buffers,
+    end to end)."""
+    import libprosic_b200 as P
+    n_reads = min(len(w["read_off"]) - 1, args.as_reads)
+    site_of = w["site_of"][:n_reads]
+    region_read = np.arange(n_reads, dtype=np.int32)
+    region_haps = (2 * site_of[:, None] + np.arange(2)[None, :]).reshape(-1).astype(np.int32)
+    region_hap_off = np.arange(0, 2 * n_reads + 1, 2, dtype=np.int32)
+    region_n_ref = np.ones(n_reads, dtype=np.int32)
+    gap = P.GapParams()
+
+    def run():
+        return ctx.allele_support_batch(region_read, region_hap_off, region_haps, region_n_ref,
+                                        w["hap_bytes"], w["hap_off"], w["read_bases"], w["read_quals"],
+                                        w["read_off"][:n_reads + 1], gap, flags=flags)
+    out = run()
+    run()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = run()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    cells = 2.0 * n_reads * 150 * 300
+    res = {"workload": "C3 reads: Realigner::allele_support per read (ref + alt haplotype, band dist+2)",
+           "reads_per_gpu": int(n_reads), "value": n_reads * world * args.steps / dt, "unit": "reads/s",
+           "effective_gcups_full_matrix": cells * world * args.steps / dt / 1e9,
+           "ms_per_step": 1e3 * dt / args.steps, "timing": "host wall clock around the synchronous C-ABI call",
+           "frac_pairs_certainty_shortcut": float(np.mean(np.concatenate([out["ref_dist"], out["alt_dist"]]) == 0))}
+    if rank == 0:
+        import oracle as O
+        n_cpu = 64
+        t0 = time.perf_counter()
+        worst = 0.0
+        for r in range(n_cpu):
+            ids = region_haps[2 * r:2 * r + 2]
+            hp = [w["hap_bytes"][w["hap_off"][h]:w["hap_off"][h + 1]] for h in ids]
+            want = O.allele_support_region([hp[0]], [hp[1]], w["read_bases"][w["read_off"][r]:w["read_off"][r + 1]],
+                                           w["read_quals"][w["read_off"][r]:w["read_off"][r + 1]],
+                                           gap.as_ln_array(), flags=flags)
+            worst = max(worst, abs(want["prob_ref"] - out["prob_ref"][r]), abs(want["prob_alt"] - out["prob_alt"][r]))
+        cdt = time.perf_counter() - t0
+        res["parity_max_abs_ln"] = worst
+        res["cpu_baseline"] = {"value": n_cpu / cdt, "unit": "reads/s", "cores": 1, "kind": "port",
+                               "sample": "%d reads, 1 thread, %.1f s (oracle: DP-matrix edit distance + log-space banded HMM)" % (n_cpu, cdt)}
+    return res
+
+
+def bench_c4(args, ctx, torch, dist, dev, rank, world, timed):
+    """Config C4 (long reads 15 kb x 20 kb haplotype windows), labelled SUBSAMPLE of the 1 M pairs:
+    strip-wise K1 with per-strip renormalisation; gap parameters raised as in SURVEY 8(d)."""
+    import libprosic_b200 as P
+    from libprosic_b200 import synth
+    n = args.c4_pairs
+    w = synth.make_long_read_pairs(n, seed=synth.SEED_C4 + rank)
+    # one small pair appended for the oracle spot check (a 15 kb x 20 kb pair takes ~25 s on the CPU)
+    small = synth.make_long_read_pairs(1, seed=7, read_len=1500, hap_len=2200)
+    hap = np.concatenate([w["hap_bytes"], small["hap_bytes"]])
+    hoff = np.concatenate([w["hap_off"], w["hap_off"][-1:] + small["hap_off"][1:]])
+    rb = np.concatenate([w["read_bases"], small["read_bases"]])
+    rq = np.concatenate([w["read_quals"], small["read_quals"]])
+    roff = np.concatenate([w["read_off"], w["read_off"][-1:] + small["read_off"][1:]])
+    gap = P.GapParams(0.02, 0.02, 0.3, 0.3)
+    npairs = n + 1
+    d_hap = torch.zeros(len(hap) + 64, dtype=torch.uint8, device=dev)
+    d_hap[:len(hap)] = torch.from_numpy(hap).to(dev)
+    d_hoff, d_roff = torch.from_numpy(hoff).to(dev), torch.from_numpy(roff).to(dev)
+    d_rb, d_rq = torch.from_numpy(rb).to(dev), torch.from_numpy(rq).to(dev)
+    ws_bytes = ctx.pairhmm_workspace_bytes(npairs, 20000, 15000)
+    d_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(npairs, dtype=torch.float64, device=dev)
+
+    def step():
+        ctx.pairhmm_batch_dev(npairs, d_hap.data_ptr(), d_hoff.data_ptr(), npairs, d_rb.data_ptr(),
+                              d_rq.data_ptr(), d_roff.data_ptr(), npairs, 0, 0, 0, gap, P.HMM_DEFAULT,
+                              d_ws.data_ptr(), ws_bytes, d_out.data_ptr())
+    step()
+    ms = timed(step, 1)
+    cells = w["cells"] + small["cells"]
+    res = {"workload": "C4 long reads: 15 kb reads x 20 kb haplotype windows, gap open .02 / extend .3, "
+                       "SUBSAMPLE of %d of the 1 M pairs per GPU" % n,
+           "pairs_per_gpu": n, "value": cells * world / (ms * 1e-3) / 1e9, "unit": "GCUPS",
+           "ms_per_step": ms, "m_state_sum": "ln_sum3_exp_approx (reference)"}
+    if rank == 0:
+        import oracle as O
+        got = float(d_out[n].item())
+        want = O.pairhmm_prob_related(small["hap_bytes"], small["read_bases"], small["read_quals"],
+                                      gap.as_ln_array(), -1, P.HMM_DEFAULT)
+        res["parity_abs_ln_on_1500x2200_pair"] = abs(got - want)
+        out = d_out[:n].cpu().numpy()
+        res["ln_prob_range"] = [float(out.min()), float(out.max())]
+        res["finite"] = bool(np.isfinite(out).all())
+    return res
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -404,9 +509,16 @@ def main():
         parity = float(np.max(np.abs(got - want)))
         same_e2e = bool(np.array_equal(h_out.numpy(), d_out.cpu().numpy()))
 
+    allele_support = None
+    if not args.skip_part2:
+        allele_support = bench_allele_support(args, ctx, w, flags, rank, world, torch, dist, dev)
+    c4 = None
+    if not args.skip_part2 and args.c4_pairs > 0:
+        del d, d_hap, d_ws, d_out
+        torch.cuda.empty_cache()
+        c4 = bench_c4(args, ctx, torch, dist, dev, rank, world, timed)
     part2 = {}
     if not args.skip_part2:
-        del d, d_hap, d_ws, d_out
         torch.cuda.empty_cache()
         for name, wl in part2_workloads(args).items():
             if args.part2_only and name != args.part2_only:
@@ -458,6 +570,8 @@ def main():
             "other_mode": {"m_state_sum": "ln_sum3_exp_approx" if args.exact_sum else "exact",
                            "value": total_cells * args.steps / (ms_other * 1e-3) / 1e9, "unit": "GCUPS"},
             "parity_max_abs_ln": parity,
+            "allele_support": allele_support,
+            "c4_long_reads": c4,
             "sites_per_sec": part2,
             "clocks": clocks,
         }

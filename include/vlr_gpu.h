@@ -91,7 +91,9 @@ int vlr_pairhmm_batch(vlr_ctx *ctx, int64_t n_pairs,
  * context's stream, nothing is copied or synchronised.  Any byte alignment of the windows is
  * accepted (the kernel aligns its TMA bulk copies down to 16 bytes); the hap buffer must be
  * readable for 32 bytes past hap_off[n_haps] and 16 bytes before hap_off[0].  `workspace` must
- * hold vlr_pairhmm_workspace_bytes(n_pairs) bytes.  Read windows longer than 248 rows yield NaN.
+ * hold vlr_pairhmm_workspace_bytes(n_pairs, max_len_x, max_len_y) bytes.  Read windows longer
+ * than 248 rows take the strip-wise long-read variant (unbanded only; NaN if banded or if the
+ * workspace was sized without max_len_x / max_len_y).
  */
 size_t vlr_pairhmm_workspace_bytes(int64_t n_pairs, int64_t max_len_x, int64_t max_len_y);
 int vlr_pairhmm_batch_dev(vlr_ctx *ctx, int64_t n_pairs,

@@ -26,7 +26,8 @@ __host__ __device__ inline int class_of_len(int ly) {
 // counters layout (int32): [0..7] class counts, [8..15] class offsets, [16..23] scatter cursors,
 // [24..31] work cursors (one per class launch), [32] fallback count, [33] fallback work cursor
 constexpr int kCntCount = 0, kCntOff = 8, kCntScatter = 16, kCntWork = 24, kCntFb = 32,
-              kCntFbWork = 33, kCntTotal = 64;
+              kCntFbWork = 33, kCntFbLong = 34, kCntFbLongWork = 35, kCntTotal = 64;
+constexpr int64_t kLongWarpsCap = 160 * kLongBlocksPerSm * kWarps;  // boundary-row slots (<= 160 SMs)
 
 __global__ void classify_kernel(int64_t n_pairs, const int64_t *read_off, const int32_t *pair_read,
                                 const uint8_t *mode, int32_t *counters) {
@@ -90,6 +91,11 @@ static cudaError_t launch_lin(bool banded, bool approx, int cls, bool ext, const
     return approx ? launch_pairhmm_lin<false, true>(cls, ext, a, sm_count, st)
                   : launch_pairhmm_lin<false, false>(cls, ext, a, sm_count, st);
 }
+static cudaError_t launch_long(bool approx, bool ext, bool log_space, const HmmArgs &a, int sm_count,
+                               cudaStream_t st) {
+    return approx ? launch_pairhmm_long<true>(ext, log_space, a, sm_count, st)
+                  : launch_pairhmm_long<false>(ext, log_space, a, sm_count, st);
+}
 static cudaError_t launch_log(bool banded, bool approx, const HmmArgs &a, int sm_count,
                               cudaStream_t st) {
     if (banded)
@@ -121,12 +127,14 @@ static void make_consts(const vlr_gap_params *gp, uint32_t flags, HmmConsts *lin
 }
 
 struct PairWs {
-    int32_t *counters;  // kCntTotal
-    int32_t *list;      // n_pairs
-    int32_t *fb_list;   // n_pairs
+    int32_t *counters;      // kCntTotal
+    int32_t *list;          // n_pairs
+    int32_t *fb_list;       // n_pairs
+    int32_t *fb_long_list;  // n_pairs
+    double *long_ws;        // boundary rows of the long-read variant
 };
 static size_t pair_ws_bytes(int64_t n_pairs) {
-    return align_up(kCntTotal * sizeof(int32_t), 256) + 2 * align_up((size_t)n_pairs * 4 + 4, 256);
+    return align_up(kCntTotal * sizeof(int32_t), 256) + 3 * align_up((size_t)n_pairs * 4 + 4, 256);
 }
 static PairWs carve_ws(void *ws, int64_t n_pairs) {
     PairWs w;
@@ -136,6 +144,10 @@ static PairWs carve_ws(void *ws, int64_t n_pairs) {
     w.list = (int32_t *)p;
     p += align_up((size_t)n_pairs * 4 + 4, 256);
     w.fb_list = (int32_t *)p;
+    p += align_up((size_t)n_pairs * 4 + 4, 256);
+    w.fb_long_list = (int32_t *)p;
+    p += align_up((size_t)n_pairs * 4 + 4, 256);
+    w.long_ws = (double *)p;
     return w;
 }
 
@@ -165,6 +177,9 @@ static int pairhmm_core_dev(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *d_hap_
     VLR_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     PairWs w = carve_ws(d_workspace, n_pairs);
+    // whatever the caller allocated beyond the bookkeeping is boundary-row space for long reads
+    const int64_t long_stride =
+        (int64_t)((workspace_bytes - pair_ws_bytes(n_pairs)) / (size_t)(kLongWarpsCap * 6 * sizeof(double)));
     VLR_CUDA(ctx, cudaMemsetAsync(w.counters, 0, kCntTotal * sizeof(int32_t), st));
     const int64_t want = (n_pairs + 255) / 256, cap = (int64_t)ctx->sm_count * 8;
     const int cgrid = (int)(want < cap ? want : cap);
@@ -182,6 +197,7 @@ static int pairhmm_core_dev(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *d_hap_
     a.win_start = d_win_start; a.win_len = d_win_len;
     a.fb_list = w.fb_list; a.fb_count = w.counters + kCntFb;
     a.out = d_out_lnprob; a.qlut = ctx->d_qlut;
+    a.long_ws = w.long_ws; a.long_stride = long_stride;
     make_consts(gap, flags, &a.lin, &a.ln);
     const bool banded = d_max_edit_dist != nullptr;
     const bool approx = (flags & VLR_HMM_SUM3_APPROX) != 0;
@@ -214,8 +230,29 @@ static int pairhmm_core_dev(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *d_hap_
             return set_err(ctx, VLR_ERR_CUDA, "pairhmm launch failed: %s", cudaGetErrorString(e));
         ctx->launches++;
     }
-    mark_unsupported_kernel<<<32, 256, 0, st>>>(w.list, w.counters, d_out_lnprob);
-    VLR_LAUNCH_CHECK(ctx);
+    if (!banded && !d_win_start && long_stride > 0 && ctx->sm_count <= 160) {
+        // read windows longer than 248 rows: strip-wise variant (+ its log-space pass)
+        HmmArgs al = a;
+        al.list = w.list;
+        al.list_off = w.counters + kCntOff + 7;
+        al.count = w.counters + kCntCount + 7;
+        al.cursor = w.counters + kCntWork + 7;
+        al.fb_list = w.fb_long_list;
+        al.fb_count = w.counters + kCntFbLong;
+        cudaError_t e = launch_long(approx, ext, false, al, ctx->sm_count, st);
+        if (e != cudaSuccess) return set_err(ctx, VLR_ERR_CUDA, "pairhmm launch failed: %s", cudaGetErrorString(e));
+        ctx->launches++;
+        al.list = w.fb_long_list;
+        al.list_off = nullptr;
+        al.count = w.counters + kCntFbLong;
+        al.cursor = w.counters + kCntFbLongWork;
+        e = launch_long(approx, ext, true, al, ctx->sm_count, st);
+        if (e != cudaSuccess) return set_err(ctx, VLR_ERR_CUDA, "pairhmm launch failed: %s", cudaGetErrorString(e));
+        ctx->launches++;
+    } else {
+        mark_unsupported_kernel<<<32, 256, 0, st>>>(w.list, w.counters, d_out_lnprob);
+        VLR_LAUNCH_CHECK(ctx);
+    }
     return VLR_OK;
 }
 
@@ -236,8 +273,10 @@ int pairhmm_windows_dev(vlr_ctx *ctx, int64_t n_slots, const uint8_t *d_hap_base
 extern "C" {
 
 size_t vlr_pairhmm_workspace_bytes(int64_t n_pairs, int64_t max_len_x, int64_t max_len_y) {
-    (void)max_len_x; (void)max_len_y;
-    return pair_ws_bytes(n_pairs < 1 ? 1 : n_pairs);
+    size_t b = pair_ws_bytes(n_pairs < 1 ? 1 : n_pairs);
+    if (max_len_y > 248 && max_len_x > 0)  // boundary rows of the strip-wise long-read variant
+        b += (size_t)kLongWarpsCap * 6 * sizeof(double) * (size_t)(max_len_x + 32);
+    return b;
 }
 
 int vlr_pairhmm_batch_dev(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *d_hap_bytes,
@@ -274,8 +313,8 @@ int vlr_pairhmm_batch(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *hap_bytes,
         if (l < 0) return set_err(ctx, VLR_ERR_INVALID, "read_off not monotone");
         if (l > max_ly) max_ly = l;
     }
-    if (max_ly > 248)
-        return set_err(ctx, VLR_ERR_UNSUPPORTED, "read window of %lld rows exceeds 248",
+    if (max_ly > 248 && max_edit_dist)
+        return set_err(ctx, VLR_ERR_UNSUPPORTED, "banded read window of %lld rows exceeds 248",
                        (long long)max_ly);
     if (pair_hap || pair_read)
         for (int64_t k = 0; k < n_pairs; ++k) {
@@ -286,8 +325,11 @@ int vlr_pairhmm_batch(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *hap_bytes,
         }
     const int64_t hap_lo = hap_off[0], hap_hi = hap_off[n_haps];
     const int64_t rd_lo = read_off[0], rd_hi = read_off[n_reads];
-    for (int64_t h = 0; h < n_haps; ++h)
+    int64_t max_lx = 0;
+    for (int64_t h = 0; h < n_haps; ++h) {
         if (hap_off[h + 1] < hap_off[h]) return set_err(ctx, VLR_ERR_INVALID, "hap_off not monotone");
+        if (hap_off[h + 1] - hap_off[h] > max_lx) max_lx = hap_off[h + 1] - hap_off[h];
+    }
     enum { S_HAP = 0, S_HOFF, S_RB, S_RQ, S_ROFF, S_PH, S_PR, S_MED, S_WS, S_OUT };
     const size_t hap_bytes_n = (size_t)(hap_hi - hap_lo), rd_bytes_n = (size_t)(rd_hi - rd_lo);
     uint8_t *d_hap = (uint8_t *)dev_scratch(ctx, S_HAP, hap_bytes_n + 64);
@@ -298,7 +340,7 @@ int vlr_pairhmm_batch(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *hap_bytes,
     int32_t *d_ph = pair_hap ? (int32_t *)dev_scratch(ctx, S_PH, (size_t)n_pairs * 4) : nullptr;
     int32_t *d_pr = pair_read ? (int32_t *)dev_scratch(ctx, S_PR, (size_t)n_pairs * 4) : nullptr;
     int32_t *d_med = max_edit_dist ? (int32_t *)dev_scratch(ctx, S_MED, (size_t)n_pairs * 4) : nullptr;
-    const size_t ws_bytes = pair_ws_bytes(n_pairs);
+    const size_t ws_bytes = vlr_pairhmm_workspace_bytes(n_pairs, max_lx, max_ly);
     void *d_ws = dev_scratch(ctx, S_WS, ws_bytes);
     double *d_out = (double *)dev_scratch(ctx, S_OUT, (size_t)n_pairs * 8);
     if (!d_hap || !d_hoff || !d_rb || !d_rq || !d_roff || !d_ws || !d_out || (pair_hap && !d_ph) ||

@@ -56,6 +56,8 @@ struct HmmArgs {
     int32_t *cursor;       // dynamic work counter (device, zero at launch)
     int32_t *fb_list;      // pairs that need the log-space pass
     int32_t *fb_count;
+    double *long_ws;       // long-read variant: per-warp boundary rows, 6 * long_stride doubles
+    int64_t long_stride;   // columns per boundary row
     double *out;
     const double *qlut;
     HmmConsts lin, ln;
@@ -446,12 +448,248 @@ __global__ void __launch_bounds__(kWarps * 32, Occ<R>::kMinBlocks) pairhmm_kerne
     }
 }
 
+
+// ---------------------------------------------------------------- long reads (config C4)
+// Read windows longer than 248 rows are swept in horizontal strips of 31 lanes x 8 rows.  The
+// bottom row (M, X, Y per column) of a strip goes to a per-warp global buffer and comes back as
+// the row-above inputs of lane 0 in the next strip (prefetched 32 columns at a time through
+// registers into shared memory).  In scaled linear space every strip is renormalised: the
+// largest value of the boundary row is brought back to 2^960 by an exact power of two that is
+// applied while the boundary chunk is loaded, and the exponents are summed (a 15 kb read loses
+// ~e^-4000, far outside fp64 otherwise).
+constexpr int kLongR = 8;
+constexpr int kStripRows = 31 * kLongR;
+
+template <bool APPROX, bool EXT, typename A>
+__global__ void __launch_bounds__(kWarps * 32, 2) pairhmm_long_kernel(HmmArgs g) {
+    constexpr int R = kLongR;
+    __shared__ __align__(128) uint8_t s_hap[kWarps][kRing];
+    __shared__ __align__(8) uint64_t s_bar[kWarps][2];
+    __shared__ double s_bnd[kWarps][3][32];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    HapRing h;
+    h.ring = s_hap[warp];
+    h.bar = s_bar[warp];
+    if (lane == 0) {
+        mbar_init(&h.bar[0], 1);
+        mbar_init(&h.bar[1], 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    h.parity0 = 0;
+    h.parity1 = 0;
+    const HmmConsts c = A::kLog ? g.ln : g.lin;
+    const int n = *g.count;
+    const int32_t *list = g.list ? g.list + (g.list_off ? *g.list_off : 0) : nullptr;
+    double *ws = g.long_ws + ((int64_t)blockIdx.x * kWarps + warp) * 6 * g.long_stride;
+
+    for (;;) {
+        int p = 0;
+        if (lane == 0) p = atomicAdd(g.cursor, 1);
+        p = __shfl_sync(0xffffffffu, p, 0);
+        if (p >= n) break;
+        const int pair = list ? list[p] : p;
+        const int64_t hidx = g.pair_hap ? (int64_t)g.pair_hap[pair] : (int64_t)pair;
+        const int64_t rd = g.pair_read ? (int64_t)g.pair_read[pair] : (int64_t)pair;
+        const int64_t ho = g.hap_off[hidx];
+        const int lx = (int)(g.hap_off[hidx + 1] - ho);
+        const int64_t ro = g.read_off[rd];
+        const int ly = (int)(g.read_off[rd + 1] - ro);
+        if (lx <= 0 || ly <= 0 || lx > g.long_stride) {
+            if (lane == 0) g.out[pair] = lx > g.long_stride ? NAN : -INFINITY;
+            continue;
+        }
+        const int shift = (int)((uintptr_t)(g.hap + ho) & 15);
+        h.hsrc = g.hap + ho - shift;
+        h.lxs = lx + shift;
+        h.n_chunks = (h.lxs + kChunk - 1) / kChunk;
+        const int n_strips = (ly + kStripRows - 1) / kStripRows;
+        int64_t e_total = 0;   // sum of the per-strip rescaling exponents (linear space)
+        int kshift = 0;        // exponent applied to the incoming boundary row
+        bool dead = false;
+        double acc = A::zero();
+        int last_lane = 0;
+
+        for (int strip = 0; strip < n_strips; ++strip) {
+            const int j0 = strip * kStripRows;
+            const int ns = min(kStripRows, ly - j0);
+            last_lane = (ns - 1) / R;
+            const int last_r = (ns - 1) - last_lane * R;
+            const bool last_strip = strip == n_strips - 1;
+            double *bin = ws + (int64_t)(strip & 1) * 3 * g.long_stride;
+            double *bout = ws + (int64_t)((strip + 1) & 1) * 3 * g.long_stride;
+            __syncwarp();
+            if (lane == 0) {
+                const uint32_t bytes = (uint32_t)min(kChunk, (h.lxs + 15) & ~15);
+                mbar_expect_tx(&h.bar[0], bytes);
+                tma_load_1d(h.ring, h.hsrc, bytes, &h.bar[0]);
+            }
+            PairState<R> s;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int j = j0 + lane * R + r;
+                if (lane * R + r < ns) {
+                    const int q = g.rqual[ro + j];
+                    s.rb[r] = g.rbase[ro + j];
+                    if (A::kLog) {
+                        const double ln_eps = (double)q * -0.23025850929940456;
+                        s.pm[r] = g.qlut[q * kQlutStride + 3];
+                        s.pmm[r] = ln_eps + -1.098712293668443;
+                        s.cyo[r] = ln_eps + c.t_gx;
+                        s.cye[r] = ln_eps + c.t_gxe;
+                    } else {
+                        const double eps = g.qlut[q * kQlutStride + 0];
+                        s.pm[r] = g.qlut[q * kQlutStride + 1];
+                        s.pmm[r] = g.qlut[q * kQlutStride + 2];
+                        s.cyo[r] = eps * c.t_gx;
+                        s.cye[r] = eps * c.t_gxe;
+                    }
+                } else {
+                    s.rb[r] = -1;
+                    s.pm[r] = s.pmm[r] = s.cyo[r] = s.cye[r] = A::zero();
+                }
+                s.M[r] = s.X[r] = s.Y[r] = A::zero();
+                s.med[r] = kMedMax;
+            }
+            s.bM = s.bX = s.bY = A::zero();
+            s.dM = (lane == 0 && strip == 0) ? A::one() : A::zero();
+            s.dX = s.dY = A::zero();
+            s.acc = A::zero();
+            double bmax = A::zero();
+            // prefetch registers for the incoming boundary chunk (columns t .. t+31)
+            double pfM = A::zero(), pfX = A::zero(), pfY = A::zero();
+            if (strip > 0 && lane < lx) {
+                pfM = __ldcg(&bin[lane]); pfX = __ldcg(&bin[g.long_stride + lane]); pfY = __ldcg(&bin[2 * g.long_stride + lane]);
+            }
+            mbar_wait(&h.bar[0], h.parity0);
+            h.parity0 ^= 1;
+            const int T = lx + last_lane;
+            const int src = (lane + 31) & 31;
+            for (int t = 0; t < T; ++t) {
+                // ---- haplotype ring maintenance (as hmm_sweep)
+                const int ts = t + shift;
+                const int ph = ts & (kChunk - 1);
+                if (ph == 32) {
+                    const int cnext = (ts >> 8) + 1;
+                    if (cnext < h.n_chunks && lane == 0) {
+                        const int off = cnext * kChunk;
+                        const uint32_t bytes = (uint32_t)min(kChunk, ((h.lxs - off) + 15) & ~15);
+                        uint64_t *b = &h.bar[cnext & 1];
+                        mbar_expect_tx(b, bytes);
+                        tma_load_1d(h.ring + (cnext & 1) * kChunk, h.hsrc + off, bytes, b);
+                    }
+                } else if (ph == 0 && t > 0) {
+                    const int cidx = ts >> 8;
+                    if (cidx < h.n_chunks) {
+                        if (cidx & 1) { mbar_wait(&h.bar[1], h.parity1); h.parity1 ^= 1; }
+                        else { mbar_wait(&h.bar[0], h.parity0); h.parity0 ^= 1; }
+                    }
+                }
+                // ---- incoming boundary chunk: registers -> shared, prefetch the next one
+                if (strip > 0 && (t & 31) == 0) {
+                    __syncwarp();
+                    double vM = pfM, vX = pfX, vY = pfY;
+                    if (!A::kLog && kshift != 0) { vM = scalbn(vM, kshift); vX = scalbn(vX, kshift); vY = scalbn(vY, kshift); }
+                    s_bnd[warp][0][lane] = vM; s_bnd[warp][1][lane] = vX; s_bnd[warp][2][lane] = vY;
+                    const int cn = t + 32 + lane;
+                    pfM = pfX = pfY = A::zero();
+                    if (cn < lx) {
+                        pfM = __ldcg(&bin[cn]); pfX = __ldcg(&bin[g.long_stride + cn]); pfY = __ldcg(&bin[2 * g.long_stride + cn]);
+                    }
+                    __syncwarp();
+                }
+                const int i = t - lane;
+                int xb = h.ring[(i + shift) & (kRing - 1)];
+                if ((unsigned)(xb - 'a') < 26u) xb -= 32;
+                double uM = __shfl_sync(0xffffffffu, s.bM, src);
+                double uX = __shfl_sync(0xffffffffu, s.bX, src);
+                double uY = __shfl_sync(0xffffffffu, s.bY, src);
+                if (strip > 0 && lane == 0) {  // row above = bottom row of the previous strip
+                    const bool in = t < lx;
+                    uM = in ? s_bnd[warp][0][t & 31] : A::zero();
+                    uX = in ? s_bnd[warp][1][t & 31] : A::zero();
+                    uY = in ? s_bnd[warp][2][t & 31] : A::zero();
+                }
+                double diagM = s.dM, diagX = s.dX, diagY = s.dY, upM = uM, upY = uY;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const bool match = xb == s.rb[r];
+                    const double e = match ? s.pm[r] : s.pmm[r];
+                    const double nM = A::mul(e, A::template sum3<APPROX, EXT>(c, diagM, diagX, diagY));
+                    const double nX = A::template dot2<EXT>(c.t_gy, s.M[r], c.t_gye, s.X[r]);
+                    const double nY = A::template dot2<EXT>(s.cyo[r], upM, s.cye[r], upY);
+                    diagM = s.M[r]; diagX = s.X[r]; diagY = s.Y[r];
+                    s.M[r] = nM; s.X[r] = nX; s.Y[r] = nY;
+                    upM = nM; upY = nY;
+                }
+                s.dM = (lane == 0 && strip == 0) ? A::one() : uM;
+                s.dX = uX;
+                s.dY = uY;
+                s.bM = s.M[R - 1]; s.bX = s.X[R - 1]; s.bY = s.Y[R - 1];
+                if (last_strip) {
+                    double tsum = A::zero();
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        if (r == last_r) tsum = A::add(A::add(s.M[r], s.X[r]), s.Y[r]);
+                    s.acc = A::add(s.acc, tsum);
+                } else if (lane == 30 && (unsigned)i < (unsigned)lx) {
+                    // full strip: lane 30 holds its last row; hand it to the next strip
+                    __stcg(&bout[i], s.bM); __stcg(&bout[g.long_stride + i], s.bX); __stcg(&bout[2 * g.long_stride + i], s.bY);
+                    if (!A::kLog) bmax = fmax(bmax, fmax(s.bM, fmax(s.bX, s.bY)));
+                }
+            }
+            if (last_strip) {
+                acc = __shfl_sync(0xffffffffu, s.acc, last_lane);
+            } else if (!A::kLog) {
+                // renormalise: bring the largest boundary value back to 2^960
+                bmax = __shfl_sync(0xffffffffu, bmax, 30);
+                if (!(bmax > 0.0) || !(bmax < 1.0e307)) { dead = true; break; }
+                const int k = 960 - ilogb(bmax);
+                kshift = k;
+                e_total += k;
+            }
+            __threadfence_block();
+        }
+        if (lane == 0) {
+            double res;
+            if (A::kLog) {
+                res = acc;
+            } else if (dead || !(acc >= 4.3e-283 && acc < 1.0e307)) {
+                const int slot = atomicAdd(g.fb_count, 1);
+                g.fb_list[slot] = pair;
+                res = NAN;
+            } else {
+                res = log(acc) - c_scale_ln - (double)e_total * 0.6931471805599453;
+            }
+            if (res > 0.0) res = 0.0;
+            g.out[pair] = res;
+        }
+    }
+}
+
 // ---------------------------------------------------------------- launch table (pairhmm_inst_*.cu)
 // cls: 0..6 -> R = 1,2,3,4,5,6,8
 template <bool BANDED, bool APPROX>
 cudaError_t launch_pairhmm_lin(int cls, bool ext, const HmmArgs &a, int sm_count, cudaStream_t st);
 template <bool BANDED, bool APPROX>
 cudaError_t launch_pairhmm_log(const HmmArgs &a, int sm_count, cudaStream_t st);
+// long reads (unbanded only): linear pass and its log-space fallback
+template <bool APPROX>
+cudaError_t launch_pairhmm_long(bool ext, bool log_space, const HmmArgs &a, int sm_count, cudaStream_t st);
+constexpr int kLongBlocksPerSm = 2;
+
+#define VLR_PAIRHMM_LONG_INSTANTIATE(APPROX)                                                      \
+    template <>                                                                                   \
+    cudaError_t launch_pairhmm_long<APPROX>(bool ext, bool log_space, const HmmArgs &a,           \
+                                            int sm_count, cudaStream_t st) {                      \
+        const int grid = sm_count * kLongBlocksPerSm;                                             \
+        if (log_space) pairhmm_long_kernel<APPROX, true, Log><<<grid, kWarps * 32, 0, st>>>(a);   \
+        else if (ext) pairhmm_long_kernel<APPROX, true, Lin><<<grid, kWarps * 32, 0, st>>>(a);    \
+        else pairhmm_long_kernel<APPROX, false, Lin><<<grid, kWarps * 32, 0, st>>>(a);            \
+        return cudaGetLastError();                                                                \
+    }
 
 #define VLR_PAIRHMM_INSTANTIATE(BANDED, APPROX)                                                   \
     template <int R, bool EXT>                                                                    \

@@ -240,3 +240,29 @@ def make_pileups(n_sites, depths, seed=SEED_C2, kind="snv", af_sets=None, purity
     cols["prob_single_overlap"] = _ln1mexp(cols["prob_double_overlap"])  # prob_overlap()
     cat = pack_cat(strand, orient, np.where(major, 0, 1), softclip, indel, np.ones(n, dtype=int))
     return cols, cat, obs_off, true_af
+
+
+def make_long_read_pairs(n_pairs, seed=SEED_C4, read_len=15000, hap_len=20000, sub=0.08, ins=0.02,
+                         dele=0.02):
+    """Config C4: long reads (Q ~ clip(N(15,4),3,30), 8 % substitutions, 2 % insertions, 2 %
+    deletions) against longer haplotype windows; one pair per read."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    haps = _ACGT[rng.integers(0, 4, size=(n_pairs, hap_len))]
+    reads, quals = [], []
+    for k in range(n_pairs):
+        s = int(rng.integers(0, hap_len - read_len + 1))
+        r = haps[k, s:s + read_len].copy()
+        m = rng.random(read_len) < sub
+        r[m] = _ACGT[rng.integers(0, 4, int(m.sum()))]
+        r = r[rng.random(read_len) > dele]
+        pos = np.sort(rng.integers(0, len(r), int(ins * len(r))))
+        r = np.insert(r, pos, _ACGT[rng.integers(0, 4, len(pos))])[:read_len]
+        reads.append(r)
+        quals.append(_quals(rng, len(r), 15.0, 4.0, 3, 30))
+    read_off = np.zeros(n_pairs + 1, dtype=np.int64)
+    read_off[1:] = np.cumsum([len(r) for r in reads])
+    hap_off = np.arange(0, (n_pairs + 1) * hap_len, hap_len, dtype=np.int64)
+    cells = int(sum(len(r) for r in reads)) * hap_len
+    return dict(hap_bytes=np.ascontiguousarray(haps.reshape(-1)), hap_off=hap_off,
+                read_bases=np.concatenate(reads), read_quals=np.concatenate(quals),
+                read_off=read_off, cells=cells)

@@ -109,8 +109,43 @@ def test_errors_are_loud(ctx):
     read = np.frombuffer(b"A" * 300, dtype=np.uint8)
     with pytest.raises(P.VlrError):
         ctx.pairhmm_batch(hap, np.array([0, 400]), read, np.full(300, 30, np.uint8),
-                          np.array([0, 300]), gap)  # 300 rows > 248: unsupported for now
+                          np.array([0, 300]), gap, max_edit_dist=np.array([5], np.int32))  # banded + long
     with pytest.raises(P.VlrError):
         ctx.pairhmm_batch(hap, np.array([0, 400]), read[:10], np.full(10, 30, np.uint8),
                           np.array([0, 10]), gap, pair_hap=np.array([3], np.int32),
                           pair_read=np.array([0], np.int32))
+
+
+@pytest.mark.parametrize("gi,flags", [(0, P.HMM_DEFAULT), (1, P.HMM_DEFAULT), (1, 0)])
+def test_long_reads_strips(ctx, oracle, gi, flags):
+    """Config C4 shape in miniature: read windows of 250..1400 rows against longer haplotypes
+    (strip-wise sweep with per-strip renormalisation), mixed with short pairs in one batch."""
+    gap = _gap_sets()[gi]
+    rng = np.random.default_rng(40 + gi)
+    A = np.frombuffer(b"ACGT", dtype=np.uint8)
+    haps, reads, quals = [], [], []
+    for k in range(24):
+        ly = int(rng.integers(249, 1400)) if k % 4 else int(rng.integers(20, 200))
+        lx = ly + int(rng.integers(10, 600))
+        hap = A[rng.integers(0, 4, lx)]
+        s = int(rng.integers(0, lx - ly))
+        read = hap[s:s + ly].copy()
+        q = np.clip(np.rint(rng.normal(15, 4, ly)), 3, 30).astype(np.uint8)   # long-read error model
+        sub = rng.random(ly) < 0.08
+        read[sub] = A[rng.integers(0, 4, int(sub.sum()))]
+        keep = rng.random(ly) > 0.02
+        read = read[keep]
+        q = q[keep]
+        ins = np.sort(rng.integers(0, len(read), int(0.02 * len(read))))
+        read = np.insert(read, ins, A[rng.integers(0, 4, len(ins))])
+        q = np.insert(q, ins, 10)
+        if k == 5:
+            read = A[rng.integers(0, 4, len(read))]  # unrelated: deep underflow -> log-space pass
+        haps.append(hap); reads.append(read); quals.append(q)
+    hap_off = np.concatenate([[0], np.cumsum([len(h) for h in haps])]).astype(np.int64)
+    read_off = np.concatenate([[0], np.cumsum([len(r) for r in reads])]).astype(np.int64)
+    hb, rb, rq = np.concatenate(haps), np.concatenate(reads), np.concatenate(quals)
+    got = ctx.pairhmm_batch(hb, hap_off, rb, rq, read_off, gap, flags=flags)
+    want = oracle.pairhmm_batch(hb, hap_off, rb, rq, read_off, gap.as_ln_array(), flags=flags)
+    assert (want < -700).any()   # beyond plain fp64 range: renormalisation is exercised
+    _compare(got, want, tol=1e-6)
