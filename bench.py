@@ -180,7 +180,7 @@ def part2_workloads(args):
                             desc="C2 scenario A: 1 sample x 30 obs, universe {0,.5,1}, SNV bias configs",
                             flops=FLOPS_PER_EVAL_SINGLE),
         "c3_tumor_normal": dict(scn=scenario.tumor_normal(purity=0.75, indel=True), depths=[40, 100],
-                                kind="indel", n_sites=max(1024, args.p2_sites // 64),
+                                kind="indel", n_sites=max(1024, args.p2_sites // 8),
                                 af_sets=[[(0, .6), (.5, .3), (1, .1)], [(0, .4), (.3, .4), (.05, .2)]],
                                 purity=[1.0, 0.75],
                                 desc="C3 part 2: built-in tumor/normal scenario, 40x normal + 100x tumor, "

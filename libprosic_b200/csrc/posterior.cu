@@ -84,6 +84,7 @@ struct PostArgs {
     int32_t *out_map_bias;
     int32_t *status;        // [0] = number of sites that overflowed a kernel limit
     int32_t obs_cap;        // observations per (site, sample) the shared staging can hold
+    int64_t gs_cap;         // doubles of per-team shared memory for the blocked contaminated path
 };
 __device__ __forceinline__ int m_ncfg_cap(const PostArgs &g) { return g.m.n_cfg; }
 
@@ -236,6 +237,8 @@ struct TeamShared {
     double sum_m[kMaxSamples];
     double other_rate[kMaxCfg];
     int allowed[kMaxCfg];
+    int alist[kMaxCfg];   // allowed configurations, compacted
+    int n_allowed, slow;
     double ev_ln[kMaxEvents];
     // reduction scratch
     double red_mx[4], red_sum[4];
@@ -297,6 +300,67 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// Product of the per-observation terms T'_i of one likelihood key, checked variant: mantissas are
+// multiplied (two chains), biased exponents summed in an integer; terms outside the normal range
+// are handed to the log-space path.  finish(): ln prod = (sum e - 1023*count)*ln2 + ln(mantissas).
+struct ProdAcc {
+    double m0, m1, lnslow;
+    int ex, nslow;
+    __device__ __forceinline__ void init() { m0 = 1.0; m1 = 1.0; lnslow = 0.0; ex = 0; nslow = 0; }
+    __device__ __forceinline__ bool add(double T, int i) {
+        const int hi = __double2hiint(T);
+        // sign 0 and 24 <= biased exponent < 2000 (normal, away from both ends)
+        if ((unsigned)(hi - 0x01800000) >= (unsigned)(0x7d000000 - 0x01800000)) return false;
+        ex += hi >> 20;
+        const double mt = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(T));
+        if (i & 1) m1 *= mt; else m0 *= mt;
+        if ((i & 255) == 255) {  // keep the mantissa products inside fp64 range
+            const double mm = m0 * m1;
+            const int h2 = __double2hiint(mm);
+            ex += (h2 >> 20) - 1023;
+            m0 = __hiloint2double((h2 & 0x000fffff) | 0x3ff00000, __double2loint(mm));
+            m1 = 1.0;
+        }
+        return true;
+    }
+    // exact ln T_i of an out-of-range term; sum_m already holds m_i, so it is taken out again
+    __device__ __forceinline__ void slow(double lt, double mi) {
+        lnslow += (mi == -INFINITY) ? lt : lt - mi;
+        nslow++;
+    }
+    __device__ __forceinline__ double finish(double sum_m, int n) const {
+        if (n == 0) return 0.0;  // empty pileup: fold identity ln 1 (likelihood.rs:135,227)
+        const double lm = (double)(ex - 1023 * (n - nslow)) * 0.6931471805599453 + log_ni(m0 * m1);
+        if (nslow == 0) return sum_m + lm;
+        return (sum_m == -INFINITY) ? lnslow + lm : sum_m + lm + lnslow;
+    }
+};
+
+// Unchecked variant for pileups whose terms are known to lie in [2^-240, 4] (k_i >= 2^-240, all
+// factors finite): NB running products per thread, the exponent is pulled out of each product once
+// per four observations (m in [1,2) times four terms stays above 2^-960).
+constexpr double kTermMin = 5.659799424266695e-73;  // 2^-240
+template <int NB>
+struct ProdBlock {
+    double m[NB];
+    int ex[NB];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) { m[b] = 1.0; ex[b] = 0; }
+    }
+    __device__ __forceinline__ void renorm() {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const int hi = __double2hiint(m[b]);
+            ex[b] += hi >> 20;
+            m[b] = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(m[b]));
+        }
+    }
+    __device__ __forceinline__ double finish(int b, double sum_m, int nren) const {
+        return sum_m + ((double)(ex[b] - 1023 * nren) * 0.6931471805599453 + log_ni(m[b]));
+    }
+};
+
 // s_i(af): effective probability to sample the alt allele (likelihood.rs:25-38)
 __device__ __forceinline__ double s_eff(double af, double sigma) {
     if (af == 1.0) return 1.0;
@@ -319,9 +383,11 @@ __global__ void __launch_bounds__(kTeamThreadsMax, 3) posterior_kernel(PostArgs 
     // per-team staging of one sample's observations: OC = {cR, kk, sigma, m_i}, BC = beta*cA per cfg
     extern __shared__ __align__(16) unsigned char s_dyn[];
     const int obs_cap = g.obs_cap;
-    const size_t per_team = (size_t)obs_cap * sizeof(double4) + (size_t)obs_cap * m_ncfg_cap(g) * sizeof(double);
+    const size_t per_team = (size_t)obs_cap * sizeof(double4) +
+                            (size_t)obs_cap * m_ncfg_cap(g) * sizeof(double) + (size_t)g.gs_cap * sizeof(double);
     double4 *OC = (double4 *)(s_dyn + (size_t)team_in_cta * per_team);
     double *BC = (double *)(OC + obs_cap);
+    double *GS = BC + (size_t)obs_cap * m_ncfg_cap(g);  // blocked contaminated path (may be empty)
     const int team_global = blockIdx.x * kTeamsPerCta + team_in_cta;
     double *table = g.table + (int64_t)team_global * g.table_stride;
     const DevModel &m = g.m;
@@ -532,6 +598,12 @@ __global__ void __launch_bounds__(kTeamThreadsMax, 3) posterior_kernel(PostArgs 
             S.allowed[c] = ok;
         }
         team_sync<TEAM>();
+        if (tt == 0) {
+            int k = 0;
+            #pragma unroll 1
+            for (int c = 0; c < m.n_cfg; ++c) if (S.allowed[c]) S.alist[k++] = c;
+            S.n_allowed = k;
+        }
 
         // ---- 4. likelihood tables.  Per sample: the team stages the observation constants
         // (scaled linear space) and the per-(observation, bias cfg) factor beta*cA in shared memory,
@@ -549,6 +621,9 @@ __global__ void __launch_bounds__(kTeamThreadsMax, 3) posterior_kernel(PostArgs 
             const int nkeys = nv * bynv;
             const int ncfg = m.n_cfg;
             team_sync<TEAM>();  // previous sample's shared constants are no longer read
+            if (tt == 0) S.slow = 0;
+            team_sync<TEAM>();
+            bool fast_ok = true;
             #pragma unroll 1
             for (int i = tt; i < n; i += TT) {
                 const int64_t row = o0 + i;
@@ -567,62 +642,168 @@ __global__ void __launch_bounds__(kTeamThreadsMax, 3) posterior_kernel(PostArgs 
                 const unsigned cat = g.obs.cat[row];
                 const double sN = VLR_CAT_STRAND(cat) == 2 ? exp_ni(g.obs.prob_double_overlap[row])
                                                            : 0.5 * exp_ni(g.obs.prob_single_overlap[row]);
-                OC[i] = make_double4(cR, kk, exp_ni(g.obs.prob_sample_alt[row]), mi);
+                const double sigma = exp_ni(g.obs.prob_sample_alt[row]);
+                OC[i] = make_double4(cR, kk, sigma, mi);
+                // unchecked products need every term T_i in [2^-240, 4]: k_i bounds it from below
+                fast_ok &= kk >= kTermMin && kk <= 2.0 && cR >= 0.0 && cR <= 2.0 && sigma >= 0.0 && sigma <= 1.0;
                 #pragma unroll 1
-                for (int c = 0; c < ncfg; ++c)
-                    BC[i * ncfg + c] = S.allowed[c]
-                                           ? bias_lin(m.cfg[c], S.other_rate[c], cat, sN, hb) * cA : 0.0;
+                for (int c = 0; c < ncfg; ++c) {
+                    const double b = S.allowed[c] ? bias_lin(m.cfg[c], S.other_rate[c], cat, sN, hb) * cA : 0.0;
+                    BC[i * ncfg + c] = b;
+                    fast_ok &= b >= 0.0 && b <= 2.0;  // false for NaN (configurations the reference panics on)
+                }
             }
+            if (!fast_ok) S.slow = 1;
             team_sync<TEAM>();
-            const int npairs = nkeys * ncfg;
-            #pragma unroll 1
-            for (int q = tt; q < npairs; q += TT) {
-                const int c = q / nkeys, key = q - c * nkeys;
-                if (!S.allowed[c]) continue;  // gated out: never requested (generic.rs:258-262)
-                const int vi = key / bynv, vb = key - vi * bynv;
-                const double af_p = S.val[v0 + vi];
-                const double af_s = cont ? S.val[byv0 + vb] : 0.0;
-                double mant0 = 1.0, mant1 = 1.0, lnslow = 0.0;
-                int ex = 0;
-                bool slow_any = false;
-#pragma unroll 2
-                for (int i = 0; i < n; ++i) {
-                    const double4 oc = OC[i];            // cR, kk, sigma, m_i
-                    const double bcA = BC[i * ncfg + c];
-                    double z = s_eff(af_p, oc.z);
-                    double zr = 1.0 - z;
-                    if (cont) {
-                        const double z2 = s_eff(af_s, oc.z);
-                        zr = rho * zr + (1.0 - rho) * (1.0 - z2);
-                        z = rho * z + (1.0 - rho) * z2;
+            const double sum_m = S.sum_m[smp];
+            const int na = S.n_allowed;
+            const bool fast = S.slow == 0;
+            const int VBP = (bynv + 7) & ~7;
+            double *tab = table + S.tab_off[smp];
+            const int64_t tcs = S.tab_cfg_stride[smp];
+            if (fast && cont && (int64_t)na * n * VBP <= g.gs_cap) {
+                // ---- 4a. contaminated sample, blocked: thread = (primary value, cfg), eight
+                // secondary values in registers.  GS[ca][i][vb] = (1-rho)*F_i(af_vb) + k_i is staged
+                // once; the primary part rho*F_i(af_vi) is computed once per observation and shared
+                // by the eight products: 2.5 fp64 instructions per evaluation.
+                #pragma unroll 1
+                for (int idx = tt; idx < na * n * VBP; idx += TT) {
+                    const int vb = idx % VBP, r = idx / VBP;
+                    const int i = r % n, ca = r / n;
+                    double v = 1.0;  // padding columns: harmless factor
+                    if (vb < bynv) {
+                        const double4 oc = OC[i];
+                        const double af = S.val[byv0 + vb];
+                        const double z = af == 1.0 ? 1.0 : af * oc.z;
+                        const double F = fma(1.0 - z, oc.x, z * BC[i * ncfg + S.alist[ca]]);
+                        v = fma(1.0 - rho, F, oc.y);
                     }
-                    const double T = fma(zr, oc.x, fma(z, bcA, oc.y));
-                    const int hi = __double2hiint(T);
-                    const int e = (hi >> 20) & 0x7ff;  // the sign bit is 0 for every valid T
-                    if (hi > 0 && e > 23 && e < 2000) {
-                        ex += e - 1023;
-                        const double mt = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(T));
-                        if (i & 1) mant1 *= mt; else mant0 *= mt;
-                    } else {
-                        // zero / subnormal / NaN: recompute this observation in log space
-                        const double lt = ln_T_exact(g.obs, o0 + i, m.cfg[c], S.other_rate[c], af_p, af_s,
-                                                     cont, rho);
-                        lnslow += (oc.w == -INFINITY) ? lt : lt - oc.w;  // sum_m already holds m_i
-                        slow_any = true;
-                    }
-                    if ((i & 127) == 127) {  // keep the mantissa products inside fp64 range
-                        const double mm = mant0 * mant1;
-                        const int h2 = __double2hiint(mm);
-                        ex += ((h2 >> 20) & 0x7ff) - 1023;
-                        mant0 = __hiloint2double((h2 & 0x000fffff) | 0x3ff00000, __double2loint(mm));
-                        mant1 = 1.0;
+                    GS[idx] = v;
+                }
+                team_sync<TEAM>();
+                const int nvp = (nv + 31) & ~31;  // warps are uniform in cfg: GS reads broadcast
+                #pragma unroll 1
+                for (int q = tt; q < na * nvp; q += TT) {
+                    const int ca = q / nvp, vi = q - ca * nvp;
+                    if (vi >= nv) continue;
+                    const int c = S.alist[ca];
+                    const double af = S.val[v0 + vi];
+                    const double afm = af == 1.0 ? 0.0 : af, afa = af == 1.0 ? 1.0 : 0.0;  // z = afm*sigma + afa
+                    const double *bc = BC + c;
+                    #pragma unroll 1
+                    for (int vb0 = 0; vb0 < VBP; vb0 += 8) {
+                        const double *gs = GS + (int64_t)ca * n * VBP + vb0;
+                        ProdBlock<8> P;
+                        P.init();
+                        int nren = 0;
+                        auto body = [&](int i) {
+                            const double4 oc = OC[i];
+                            const double z = fma(afm, oc.z, afa);
+                            const double gp = rho * fma(1.0 - z, oc.x, z * bc[i * ncfg]);
+                            const double2 *gv = (const double2 *)(gs + i * VBP);
+                            const double2 g0 = gv[0], g1 = gv[1], g2 = gv[2], g3 = gv[3];
+                            P.m[0] *= gp + g0.x; P.m[1] *= gp + g0.y; P.m[2] *= gp + g1.x; P.m[3] *= gp + g1.y;
+                            P.m[4] *= gp + g2.x; P.m[5] *= gp + g2.y; P.m[6] *= gp + g3.x; P.m[7] *= gp + g3.y;
+                        };
+                        int i = 0;
+                        #pragma unroll 1
+                        for (; i + 4 <= n; i += 4) {
+                            body(i); body(i + 1); body(i + 2); body(i + 3);
+                            P.renorm(); ++nren;
+                        }
+                        if (i < n) {
+                            #pragma unroll 1
+                            for (; i < n; ++i) body(i);
+                            P.renorm(); ++nren;
+                        }
+                        #pragma unroll
+                        for (int b = 0; b < 8; ++b)
+                            if (vb0 + b < bynv)
+                                __stcg(&tab[(int64_t)c * tcs + (int64_t)vi * bynv + vb0 + b], P.finish(b, sum_m, nren));
                     }
                 }
-                const double lm = (double)ex * 0.6931471805599453 + log_ni(mant0 * mant1);
-                double L = S.sum_m[smp] + lm;
-                if (slow_any) L = (S.sum_m[smp] == -INFINITY) ? lnslow + lm : L + lnslow;
-                if (n == 0) L = 0.0;  // empty pileup: fold identity ln 1 (likelihood.rs:135,227)
-                __stcg(&table[S.tab_off[smp] + (int64_t)c * S.tab_cfg_stride[smp] + key], L);
+            } else if (fast) {
+                // ---- 4b. unchecked direct evaluation: thread = (four primary values, secondary
+                // value, cfg); exponent extraction once per four observations
+                const int ng = (nv + 3) >> 2;
+                const int nitems = na * bynv * ng;
+                #pragma unroll 1
+                for (int q = tt; q < nitems; q += TT) {
+                    const int vg = q % ng, r = q / ng;
+                    const int vb = r % bynv, c = S.alist[r / bynv];
+                    double afm[4], afa[4];
+                    #pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const double af = S.val[v0 + min(vg * 4 + k, nv - 1)];
+                        afm[k] = af == 1.0 ? 0.0 : af;
+                        afa[k] = af == 1.0 ? 1.0 : 0.0;
+                    }
+                    const double af_s = cont ? S.val[byv0 + vb] : 0.0;
+                    const double asm_ = af_s == 1.0 ? 0.0 : af_s, asa = af_s == 1.0 ? 1.0 : 0.0;
+                    const double rho1 = 1.0 - rho;
+                    const double *bc = BC + c;
+                    ProdBlock<4> P;
+                    P.init();
+                    int nren = 0;
+                    auto body = [&](int i) {
+                        const double4 oc = OC[i];
+                        const double bcA = bc[i * ncfg];
+                        const double z2 = cont ? rho1 * fma(asm_, oc.z, asa) : 0.0;
+                        #pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            double z = fma(afm[k], oc.z, afa[k]);
+                            if (cont) z = fma(rho, z, z2);
+                            P.m[k] *= fma(1.0 - z, oc.x, fma(z, bcA, oc.y));
+                        }
+                    };
+                    int i = 0;
+                    #pragma unroll 1
+                    for (; i + 4 <= n; i += 4) {
+                        body(i); body(i + 1); body(i + 2); body(i + 3);
+                        P.renorm(); ++nren;
+                    }
+                    if (i < n) {
+                        #pragma unroll 1
+                        for (; i < n; ++i) body(i);
+                        P.renorm(); ++nren;
+                    }
+                    #pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (vg * 4 + k < nv)
+                            __stcg(&tab[(int64_t)c * tcs + (int64_t)(vg * 4 + k) * bynv + vb], P.finish(k, sum_m, nren));
+                }
+            } else {
+                // ---- 4c. checked evaluation: every term is range-tested, terms outside the normal
+                // fp64 range (zero, subnormal, NaN) are recomputed in log space
+                const int npairs = nkeys * ncfg;
+                #pragma unroll 1
+                for (int q = tt; q < npairs; q += TT) {
+                    const int c = q / nkeys, key = q - c * nkeys;
+                    if (!S.allowed[c]) continue;  // gated out: never requested (generic.rs:258-262)
+                    const int vi = key / bynv, vb = key - vi * bynv;
+                    const double af_p = S.val[v0 + vi];
+                    const double af_s = cont ? S.val[byv0 + vb] : 0.0;
+                    ProdAcc acc;
+                    acc.init();
+#pragma unroll 2
+                    for (int i = 0; i < n; ++i) {
+                        const double4 oc = OC[i];            // cR, kk, sigma, m_i
+                        const double bcA = BC[i * ncfg + c];
+                        double z = s_eff(af_p, oc.z);
+                        double zr = 1.0 - z;
+                        if (cont) {
+                            const double z2 = s_eff(af_s, oc.z);
+                            zr = rho * zr + (1.0 - rho) * (1.0 - z2);
+                            z = rho * z + (1.0 - rho) * z2;
+                        }
+                        if (!acc.add(fma(zr, oc.x, fma(z, bcA, oc.y)), i)) {
+                            const double lt = ln_T_exact(g.obs, o0 + i, m.cfg[c], S.other_rate[c], af_p,
+                                                         af_s, cont, rho);
+                            acc.slow(lt, oc.w);
+                        }
+                    }
+                    __stcg(&tab[(int64_t)c * tcs + key], acc.finish(sum_m, n));
+                }
             }
         }
         team_sync<TEAM>();
@@ -960,11 +1141,25 @@ int vlr_posterior_batch_dev(vlr_ctx *ctx, int64_t n_sites, const vlr_model *mode
     const int64_t tbound = table_bound(model, H);
     // team size: whole CTA for big tables (tumor/normal-like), one warp per site for small ones
     const int obs_cap = std::max(8, (max_obs_per_pileup + 7) & ~7);
-    const size_t team_smem = (size_t)obs_cap * sizeof(double4) + (size_t)obs_cap * H.cfg.size() * sizeof(double);
+    size_t team_smem = (size_t)obs_cap * sizeof(double4) + (size_t)obs_cap * H.cfg.size() * sizeof(double);
+    // blocked contaminated path: cfgs x observations x (values of the contaminant, padded to 8)
+    int64_t gs_cap = 0;
+    {
+        int64_t nvb[kMaxSamples] = {0};
+        for (const DevSpectrum &sp : H.spectra) {
+            int64_t c = sp.kind == VLR_NODE_RANGE ? (int64_t)model->resolution[sp.sample] + 1 : sp.n_vafs;
+            if (sp.kind == VLR_NODE_RANGE && c < 5) c = 5;
+            nvb[sp.sample] += c;
+        }
+        for (int smp = 0; smp < model->n_samples; ++smp)
+            if (model->contaminated[smp])
+                gs_cap = std::max(gs_cap, (int64_t)H.cfg.size() * obs_cap * ((nvb[model->by[smp]] + 7) & ~(int64_t)7));
+        if (team_smem + (size_t)gs_cap * 8 > 72 * 1024) gs_cap = 0;  // does not fit: direct evaluation
+    }
+    team_smem += (size_t)gs_cap * 8;
     const bool big = tbound > 2048 || 4 * team_smem > 64 * 1024;
     const int teams_per_cta = big ? 1 : 4;
-    const size_t dyn_smem = (size_t)teams_per_cta *
-                            ((size_t)obs_cap * sizeof(double4) + (size_t)obs_cap * H.cfg.size() * sizeof(double));
+    const size_t dyn_smem = (size_t)teams_per_cta * team_smem;
     if (dyn_smem > 160 * 1024)
         return set_err(ctx, VLR_ERR_UNSUPPORTED,
                        "%d observations x %d bias configurations do not fit the shared-memory staging",
@@ -1034,6 +1229,7 @@ int vlr_posterior_batch_dev(vlr_ctx *ctx, int64_t n_sites, const vlr_model *mode
     a.out_map_af = d_out_map_af;
     a.out_map_bias = d_out_map_bias;
     a.obs_cap = obs_cap;
+    a.gs_cap = gs_cap;
     if (big) {
         VLR_CUDA(ctx, cudaFuncSetAttribute(posterior_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
         posterior_kernel<4><<<grid, kTeamThreadsMax, dyn_smem, st>>>(a);
