@@ -26,7 +26,8 @@ __host__ __device__ inline int class_of_len(int ly) {
 // counters layout (int32): [0..7] class counts, [8..15] class offsets, [16..23] scatter cursors,
 // [24..31] work cursors (one per class launch), [32] fallback count, [33] fallback work cursor
 constexpr int kCntCount = 0, kCntOff = 8, kCntScatter = 16, kCntWork = 24, kCntFb = 32,
-              kCntFbWork = 33, kCntFbLong = 34, kCntFbLongWork = 35, kCntTotal = 64;
+              kCntFbWork = 33, kCntFbLong = 34, kCntFbLongWork = 35, kCntGen = 36, kCntGenWork = 37,
+              kCntTotal = 64;
 constexpr int64_t kLongWarpsCap = 160 * kLongBlocksPerSm * kWarps;  // boundary-row slots (<= 160 SMs)
 
 __global__ void classify_kernel(int64_t n_pairs, const int64_t *read_off, const int32_t *pair_read,
@@ -96,6 +97,14 @@ static cudaError_t launch_long(bool approx, bool ext, bool log_space, const HmmA
     return approx ? launch_pairhmm_long<true>(ext, log_space, a, sm_count, st)
                   : launch_pairhmm_long<false>(ext, log_space, a, sm_count, st);
 }
+static cudaError_t launch_generic(bool banded, bool approx, const HmmArgs &a, int sm_count,
+                                  cudaStream_t st) {
+    if (banded)
+        return approx ? launch_pairhmm_generic<true, true>(a, sm_count, st)
+                      : launch_pairhmm_generic<true, false>(a, sm_count, st);
+    return approx ? launch_pairhmm_generic<false, true>(a, sm_count, st)
+                  : launch_pairhmm_generic<false, false>(a, sm_count, st);
+}
 static cudaError_t launch_log(bool banded, bool approx, const HmmArgs &a, int sm_count,
                               cudaStream_t st) {
     if (banded)
@@ -124,6 +133,12 @@ static void make_consts(const vlr_gap_params *gp, uint32_t flags, HmmConsts *lin
     ln->t_gy = gy; ln->t_gye = gye; ln->t_gx = gx; ln->t_gxe = gxe;
     lin->t_mm = exp(ln->t_mm); lin->t_xm = exp(ln->t_xm); lin->t_ym = exp(ln->t_ym);
     lin->t_gy = exp(gy); lin->t_gye = exp(gye); lin->t_gx = exp(gx); lin->t_gxe = exp(gxe);
+    // scaled-state kernels keep M' = t_mm * M (pairhmm_kernel.cuh, hmm_step<..., LUT = true>)
+    lin->t_gy_s = lin->t_gy / lin->t_mm;
+    lin->t_gx_s = lin->t_gx / lin->t_mm;
+    lin->inv_tmm = 1.0 / lin->t_mm;
+    lin->one_s = VLR_SCALE * lin->t_mm;
+    ln->t_gy_s = ln->t_gx_s = ln->inv_tmm = ln->one_s = NAN;  // unused in log space
 }
 
 struct PairWs {
@@ -131,10 +146,11 @@ struct PairWs {
     int32_t *list;          // n_pairs
     int32_t *fb_list;       // n_pairs
     int32_t *fb_long_list;  // n_pairs
+    int32_t *gen_list;      // n_pairs
     double *long_ws;        // boundary rows of the long-read variant
 };
 static size_t pair_ws_bytes(int64_t n_pairs) {
-    return align_up(kCntTotal * sizeof(int32_t), 256) + 3 * align_up((size_t)n_pairs * 4 + 4, 256);
+    return align_up(kCntTotal * sizeof(int32_t), 256) + 4 * align_up((size_t)n_pairs * 4 + 4, 256);
 }
 static PairWs carve_ws(void *ws, int64_t n_pairs) {
     PairWs w;
@@ -146,6 +162,8 @@ static PairWs carve_ws(void *ws, int64_t n_pairs) {
     w.fb_list = (int32_t *)p;
     p += align_up((size_t)n_pairs * 4 + 4, 256);
     w.fb_long_list = (int32_t *)p;
+    p += align_up((size_t)n_pairs * 4 + 4, 256);
+    w.gen_list = (int32_t *)p;
     p += align_up((size_t)n_pairs * 4 + 4, 256);
     w.long_ws = (double *)p;
     return w;
@@ -196,6 +214,7 @@ static int pairhmm_core_dev(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *d_hap_
     a.pair_hap = d_pair_hap; a.pair_read = d_pair_read; a.med = d_max_edit_dist;
     a.win_start = d_win_start; a.win_len = d_win_len;
     a.fb_list = w.fb_list; a.fb_count = w.counters + kCntFb;
+    a.gen_list = w.gen_list; a.gen_count = w.counters + kCntGen;
     a.out = d_out_lnprob; a.qlut = ctx->d_qlut;
     a.long_ws = w.long_ws; a.long_stride = long_stride;
     make_consts(gap, flags, &a.lin, &a.ln);
@@ -214,6 +233,18 @@ static int pairhmm_core_dev(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *d_hap_
         ac.count = w.counters + kCntCount + cls;
         ac.cursor = w.counters + kCntWork + cls;
         cudaError_t e = launch_lin(banded, approx, cls, ext, ac, ctx->sm_count, st);
+        if (e != cudaSuccess)
+            return set_err(ctx, VLR_ERR_CUDA, "pairhmm launch failed: %s", cudaGetErrorString(e));
+        ctx->launches++;
+    }
+    // reads with a base outside ACGT (N, IUPAC codes): same arithmetic, emission by byte compare
+    {
+        HmmArgs ac = a;
+        ac.list = w.gen_list;
+        ac.list_off = nullptr;
+        ac.count = w.counters + kCntGen;
+        ac.cursor = w.counters + kCntGenWork;
+        cudaError_t e = launch_generic(banded, approx, ac, ctx->sm_count, st);
         if (e != cudaSuccess)
             return set_err(ctx, VLR_ERR_CUDA, "pairhmm launch failed: %s", cudaGetErrorString(e));
         ctx->launches++;

@@ -37,6 +37,9 @@ __device__ __constant__ double c_scale_ln = 665.4212933375474;  // 960 * ln 2
 
 struct HmmConsts {  // linear or ln, depending on the arithmetic policy
     double t_mm, t_xm, t_ym, t_gy, t_gye, t_gx, t_gxe;
+    // scaled-state variant (the M state carries the factor t_mm, see hmm_step<..., LUT = true>):
+    // t_gy / t_mm, t_gx / t_mm, 1 / t_mm, 2^960 * t_mm  (linear space only)
+    double t_gy_s, t_gx_s, inv_tmm, one_s;
 };
 
 struct HmmArgs {
@@ -56,6 +59,8 @@ struct HmmArgs {
     int32_t *cursor;       // dynamic work counter (device, zero at launch)
     int32_t *fb_list;      // pairs that need the log-space pass
     int32_t *fb_count;
+    int32_t *gen_list;     // pairs whose read holds a non-ACGT base: generic (select) kernel
+    int32_t *gen_count;
     double *long_ws;       // long-read variant: per-warp boundary rows, 6 * long_stride doubles
     int64_t long_stride;   // columns per boundary row
     double *out;
@@ -122,23 +127,39 @@ struct Lin {  // scaled linear space
     __device__ static double dot2(double a, double b, double c, double d) {
         return EXT ? fma(a, b, c * d) : a * b;
     }
-    // sum over the three predecessors of the M state
-    template <bool APPROX, bool EXT>
+    // sum over the three predecessors of the M state (SCALED: dM already carries t_mm)
+    template <bool APPROX, bool EXT, bool SCALED = false>
     __device__ static double sum3(const HmmConsts &k, double dM, double dX, double dY) {
         if (APPROX) {
             // bio pairhmm ln_sum3_exp_approx: return the maximum alone if the second largest term is
             // more than e^-10 below it, else the exact sum.  "second < max*e^-10" <=> exactly one of
-            // the three terms reaches max*e^-10.
-            const double a = k.t_mm * dM;
+            // the three terms reaches max*e^-10.  Written in PTX so that the three threshold
+            // predicates feed one select (the C++ form compiles to nested 64-bit selects).
+            const double a = SCALED ? dM : k.t_mm * dM;
             const double b = EXT ? k.t_xm * dX : dX;
             const double c = EXT ? k.t_ym * dY : dY;
-            const double hi = a > b ? a : b;
-            const double mx = hi > c ? hi : c;
-            const double thr = mx * 4.5399929762484854e-05;  // e^-10
-            const bool pa = a >= thr, pb = b >= thr, pc = c >= thr;
-            const bool two = (pa && pb) || (pc && (pa || pb));
-            return two ? (a + b + c) : mx;
+            const double s = a + b + c;
+            double r;
+            asm("{\n\t"
+                ".reg .pred p, q, pa, pb, pc, t, u;\n\t"
+                ".reg .f64 hi, mx, thr;\n\t"
+                "setp.gt.f64 p, %1, %2;\n\t"
+                "selp.f64 hi, %1, %2, p;\n\t"
+                "setp.gt.f64 q, hi, %3;\n\t"
+                "selp.f64 mx, hi, %3, q;\n\t"
+                "mul.f64 thr, mx, 0d3F07CD79B5647C9B;\n\t"  // e^-10
+                "setp.ge.f64 pa, %1, thr;\n\t"
+                "setp.ge.f64 pb, %2, thr;\n\t"
+                "setp.ge.f64 pc, %3, thr;\n\t"
+                "and.pred t, pa, pb;\n\t"
+                "or.pred u, pa, pb;\n\t"
+                "and.pred u, u, pc;\n\t"
+                "or.pred t, t, u;\n\t"
+                "selp.f64 %0, %4, mx, t;\n\t"
+                "}" : "=d"(r) : "d"(a), "d"(b), "d"(c), "d"(s));
+            return r;
         }
+        if (SCALED) return EXT ? fma(k.t_ym, dY, fma(k.t_xm, dX, dM)) : dM + (dX + dY);
         if (EXT) return fma(k.t_ym, dY, fma(k.t_xm, dX, k.t_mm * dM));
         return fma(k.t_mm, dM, dX + dY);
     }
@@ -154,7 +175,7 @@ struct Log {  // natural-log space, the literal arithmetic of the reference
     __device__ static double dot2(double a, double b, double c, double d) {
         return ln_add_exp_d(a + b, c + d);
     }
-    template <bool APPROX, bool EXT>
+    template <bool APPROX, bool EXT, bool SCALED = false>
     __device__ static double sum3(const HmmConsts &k, double dM, double dX, double dY) {
         double p0 = k.t_mm + dM, p1 = k.t_xm + dX, p2 = k.t_ym + dY, t;
         if (p1 < p2) { t = p1; p1 = p2; p2 = t; }
@@ -185,7 +206,8 @@ struct PairState {
     int med[R];                            // band bookkeeping (min edit distance)
     double bM, bX, bY, dM, dX, dY;         // bottom row of last column; diagonal inputs of row 0
     int bMed, dMed;
-    double acc;
+    double acc, acc2;                      // free-end sums (scaled state: M' and X + Y apart)
+    double one0;                           // lane 0: start mass of the row-0 boundary; else 0
 };
 
 // Ring of haplotype bytes: two 256-byte slots filled by TMA; `pos` is the ring position
@@ -199,14 +221,45 @@ struct HapRing {
     uint32_t parity0, parity1;
 };
 
+// LUT kernels keep base CODES in the ring (A, C, G, T -> 0..3, anything else -> 4, case folded as
+// to_ascii_uppercase does, pairhmm.rs:190): the chunk is converted in place right after it landed,
+// 8 bytes per lane.
+__device__ __forceinline__ uint32_t base_codes4(uint32_t w) {
+    const uint32_t u = w & 0xDFDFDFDFu;
+    return 0x04040404u - (__vcmpeq4(u, 0x41414141u) & 0x04040404u) - (__vcmpeq4(u, 0x43434343u) & 0x03030303u) -
+           (__vcmpeq4(u, 0x47474747u) & 0x02020202u) - (__vcmpeq4(u, 0x54545454u) & 0x01010101u);
+}
+__device__ __forceinline__ void encode_chunk(uint8_t *slot, int lane) {
+    uint2 *p = reinterpret_cast<uint2 *>(slot) + lane;
+    uint2 v = *p;
+    v.x = base_codes4(v.x);
+    v.y = base_codes4(v.y);
+    *p = v;
+    __syncwarp();
+}
+__device__ __forceinline__ int base_code1(int b) {
+    b &= 0xDF;
+    return b == 'A' ? 0 : (b == 'C' ? 1 : (b == 'G' ? 2 : (b == 'T' ? 3 : 4)));
+}
+
+constexpr int kLutCols = 5;  // emission LUT: [row][code][lane]
+
 // One anti-diagonal step (lane `lane` computes column t - lane).  LR >= 0: compile-time index of
 // the last read row inside lane `last_lane` (free-end accumulation); LR < 0: run-time `last_r`.
-template <int R, int LR, bool BANDED, bool APPROX, bool EXT, typename A>
+// LUT = true (scaled linear space only): the ring holds base codes, the emission factor comes
+// from the per-warp shared-memory table lut[(r*5 + code)*32] (already multiplied by t_mm: the M
+// state carries that factor, which removes one multiplication per cell), and the row-0 start mass
+// is added instead of selected.
+template <int R, int LR, bool BANDED, bool APPROX, bool EXT, bool LUT, typename A>
 __device__ __forceinline__ void hmm_step(PairState<R> &s, const HmmConsts &c, const uint8_t *ring,
-                                         int t, int lane, int shift, int band, int last_r) {
+                                         const double *lut, int t, int lane, int shift, int band,
+                                         int last_r) {
     const int i = t - lane;
     int xb = ring[(i + shift) & (kRing - 1)];
-    if ((unsigned)(xb - 'a') < 26u) xb -= 32;  // to_ascii_uppercase (pairhmm.rs:190)
+    if (!LUT) {
+        if ((unsigned)(xb - 'a') < 26u) xb -= 32;  // to_ascii_uppercase (pairhmm.rs:190)
+    }
+    const double *lcol = lut + xb * 32;
 
     // receive the bottom row of the lane above (its column i).  The rotation makes lane 0 read
     // lane 31, which is always a padding lane (R = ceil(len_y / 31)) whose state is identically
@@ -224,10 +277,17 @@ __device__ __forceinline__ void hmm_step(PairState<R> &s, const HmmConsts &c, co
     int diagMed = s.dMed, upMed = uMed;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        const bool match = xb == s.rb[r];
-        const double e = match ? s.pm[r] : s.pmm[r];
-        double nM = A::mul(e, A::template sum3<APPROX, EXT>(c, diagM, diagX, diagY));
-        double nX = A::template dot2<EXT>(c.t_gy, s.M[r], c.t_gye, s.X[r]);
+        bool match = false;
+        double e;
+        if (LUT) {
+            e = lcol[r * (kLutCols * 32)];
+            if (BANDED) match = xb == s.rb[r];
+        } else {
+            match = xb == s.rb[r];
+            e = match ? s.pm[r] : s.pmm[r];
+        }
+        double nM = A::mul(e, A::template sum3<APPROX, EXT, LUT>(c, diagM, diagX, diagY));
+        double nX = A::template dot2<EXT>(LUT ? c.t_gy_s : c.t_gy, s.M[r], c.t_gye, s.X[r]);
         double nY = A::template dot2<EXT>(s.cyo[r], upM, s.cye[r], upY);
         if (BANDED) {
             // PairHMM band: skip the cell if all three predecessors exceed max_edit_dist
@@ -247,8 +307,10 @@ __device__ __forceinline__ void hmm_step(PairState<R> &s, const HmmConsts &c, co
         s.M[r] = nM; s.X[r] = nX; s.Y[r] = nY;
         upM = nM; upY = nY;
     }
-    // next column's diagonal inputs of my row 0 are this column's "up" values
-    s.dM = lane == 0 ? A::one() : uM;
+    // next column's diagonal inputs of my row 0 are this column's "up" values; lane 0 sees the
+    // free-start mass fm[prev][0] = 1 there (uM is exactly zero for lane 0)
+    if (A::kLog) s.dM = lane == 0 ? A::one() : uM;
+    else s.dM = uM + s.one0;
     s.dX = uX;
     s.dY = uY;
     s.bM = s.M[R - 1]; s.bX = s.X[R - 1]; s.bY = s.Y[R - 1];
@@ -257,22 +319,32 @@ __device__ __forceinline__ void hmm_step(PairState<R> &s, const HmmConsts &c, co
     // free end: add the last read row of this column (prob_cols).  Only the accumulator of lane
     // `last_lane` is used; its column is always inside [0, len_x) or still all-zero (i < 0).
     if (LR >= 0) {
-        s.acc = A::add(s.acc, A::add(A::add(s.M[LR >= 0 ? LR : 0], s.X[LR >= 0 ? LR : 0]),
-                                     s.Y[LR >= 0 ? LR : 0]));
+        if (LUT) {
+            s.acc += s.M[LR >= 0 ? LR : 0];
+            s.acc2 += s.X[LR >= 0 ? LR : 0] + s.Y[LR >= 0 ? LR : 0];
+        } else {
+            s.acc = A::add(s.acc, A::add(A::add(s.M[LR >= 0 ? LR : 0], s.X[LR >= 0 ? LR : 0]),
+                                         s.Y[LR >= 0 ? LR : 0]));
+        }
     } else {
-        double tsum = A::zero();
+        double tsum = A::zero(), tm = A::zero();
 #pragma unroll
         for (int r = 0; r < R; ++r)
-            if (r == last_r) tsum = A::add(A::add(s.M[r], s.X[r]), s.Y[r]);
-        s.acc = A::add(s.acc, tsum);
+            if (r == last_r) {
+                if (LUT) { tm = s.M[r]; tsum = s.X[r] + s.Y[r]; }
+                else tsum = A::add(A::add(s.M[r], s.X[r]), s.Y[r]);
+            }
+        if (LUT) { s.acc += tm; s.acc2 += tsum; }
+        else s.acc = A::add(s.acc, tsum);
     }
 }
 
 // Sweep all columns of one pair.  Ring maintenance happens only at segment boundaries
 // (ring position == 0 or 32 mod 256), the inner loop is branch-free.
-template <int R, int LR, bool BANDED, bool APPROX, bool EXT, typename A>
-__device__ __forceinline__ void hmm_sweep(PairState<R> &s, const HmmConsts &c, HapRing &h, int T,
-                                          int lane, int shift, int band, int last_r) {
+template <int R, int LR, bool BANDED, bool APPROX, bool EXT, bool LUT, typename A>
+__device__ __forceinline__ void hmm_sweep(PairState<R> &s, const HmmConsts &c, HapRing &h,
+                                          const double *lut, int T, int lane, int shift, int band,
+                                          int last_r) {
     int t = 0;
     while (t < T) {
         const int ts = t + shift;
@@ -283,6 +355,8 @@ __device__ __forceinline__ void hmm_sweep(PairState<R> &s, const HmmConsts &c, H
                 const int off = cnext * kChunk;
                 const uint32_t bytes = (uint32_t)min(kChunk, ((h.lxs - off) + 15) & ~15);
                 uint64_t *b = &h.bar[cnext & 1];
+                // the slot was read (and, with LUT, rewritten) through the generic proxy
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_expect_tx(b, bytes);
                 tma_load_1d(h.ring + (cnext & 1) * kChunk, h.hsrc + off, bytes, b);
             }
@@ -291,45 +365,54 @@ __device__ __forceinline__ void hmm_sweep(PairState<R> &s, const HmmConsts &c, H
             if (cidx < h.n_chunks) {
                 if (cidx & 1) { mbar_wait(&h.bar[1], h.parity1); h.parity1 ^= 1; }
                 else { mbar_wait(&h.bar[0], h.parity0); h.parity0 ^= 1; }
+                if (LUT) encode_chunk(h.ring + (cidx & 1) * kChunk, lane);
             }
         }
         const int next_ts = ph < 32 ? (ts & ~(kChunk - 1)) + 32 : (ts & ~(kChunk - 1)) + kChunk;
         const int t_end = min(T, next_ts - shift);
 #pragma unroll 2
         for (; t < t_end; ++t)
-            hmm_step<R, LR, BANDED, APPROX, EXT, A>(s, c, h.ring, t, lane, shift, band, last_r);
+            hmm_step<R, LR, BANDED, APPROX, EXT, LUT, A>(s, c, h.ring, lut, t, lane, shift, band, last_r);
     }
 }
 
-template <int R, int LR, bool BANDED, bool APPROX, bool EXT, typename A>
+template <int R, int LR, bool BANDED, bool APPROX, bool EXT, bool LUT, typename A>
 struct SweepDispatch {
     __device__ __forceinline__ static void run(PairState<R> &s, const HmmConsts &c, HapRing &h,
-                                               int T, int lane, int shift, int band, int last_r) {
+                                               const double *lut, int T, int lane, int shift,
+                                               int band, int last_r) {
         if (last_r == LR)
-            hmm_sweep<R, LR, BANDED, APPROX, EXT, A>(s, c, h, T, lane, shift, band, last_r);
+            hmm_sweep<R, LR, BANDED, APPROX, EXT, LUT, A>(s, c, h, lut, T, lane, shift, band, last_r);
         else
-            SweepDispatch<R, LR - 1, BANDED, APPROX, EXT, A>::run(s, c, h, T, lane, shift, band,
-                                                                  last_r);
+            SweepDispatch<R, LR - 1, BANDED, APPROX, EXT, LUT, A>::run(s, c, h, lut, T, lane, shift,
+                                                                       band, last_r);
     }
 };
-template <int R, bool BANDED, bool APPROX, bool EXT, typename A>
-struct SweepDispatch<R, -1, BANDED, APPROX, EXT, A> {
+template <int R, bool BANDED, bool APPROX, bool EXT, bool LUT, typename A>
+struct SweepDispatch<R, -1, BANDED, APPROX, EXT, LUT, A> {
     __device__ __forceinline__ static void run(PairState<R> &s, const HmmConsts &c, HapRing &h,
-                                               int T, int lane, int shift, int band, int last_r) {
-        hmm_sweep<R, -1, BANDED, APPROX, EXT, A>(s, c, h, T, lane, shift, band, last_r);
+                                               const double *lut, int T, int lane, int shift,
+                                               int band, int last_r) {
+        hmm_sweep<R, -1, BANDED, APPROX, EXT, LUT, A>(s, c, h, lut, T, lane, shift, band, last_r);
     }
 };
 
-template <int R, bool BANDED, bool APPROX, bool EXT, typename A>
+template <int R, bool BANDED, bool APPROX, bool EXT, bool LUT, typename A>
 __global__ void __launch_bounds__(kWarps * 32, Occ<R>::kMinBlocks) pairhmm_kernel(HmmArgs g) {
+    static_assert(!LUT || !A::kLog, "the emission LUT exists in scaled linear space only");
     __shared__ __align__(128) uint8_t s_hap[kWarps][kRing];
     __shared__ __align__(8) uint64_t s_bar[kWarps][2];
+    __shared__ __align__(16) double s_lut[kWarps][LUT ? R * kLutCols * 32 : 1];
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     HapRing h;
     h.ring = s_hap[warp];
     h.bar = s_bar[warp];
+    double *lut = s_lut[warp] + (LUT ? lane : 0);
+    // LUT: ring bytes index the emission table, so the ring must hold valid codes (0..4) at every
+    // position a lane may touch, including the wrap-around reads of columns outside [0, len_x)
+    if (LUT) reinterpret_cast<uint4 *>(h.ring)[lane] = make_uint4(0, 0, 0, 0);
     if (lane == 0) {
         mbar_init(&h.bar[0], 1);
         mbar_init(&h.bar[1], 1);
@@ -366,28 +449,17 @@ __global__ void __launch_bounds__(kWarps * 32, Occ<R>::kMinBlocks) pairhmm_kerne
             continue;
         }
 
-        // ---- stage the first haplotype chunk (TMA) while the row constants are loaded.
-        // Bulk copies need 16-byte aligned sources: copy from the aligned-down address and shift
-        // the ring index by the misalignment.
-        const int shift = (int)((uintptr_t)(g.hap + ho) & 15);
-        h.hsrc = g.hap + ho - shift;
-        h.lxs = lx + shift;
-        h.n_chunks = (h.lxs + kChunk - 1) / kChunk;
-        __syncwarp();  // every lane is done with the ring contents of the previous pair
-        if (lane == 0) {
-            const uint32_t bytes = (uint32_t)min(kChunk, (h.lxs + 15) & ~15);
-            mbar_expect_tx(&h.bar[0], bytes);
-            tma_load_1d(h.ring, h.hsrc, bytes, &h.bar[0]);
-        }
-
         // ---- per-row constants (ReadEmission, pairhmm.rs:160-200)
         PairState<R> s;
+        bool odd_base = false;  // a read base outside ACGT: the 5-column LUT cannot express it
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int j = lane * R + r;
             if (j < ly) {
                 const int q = g.rqual[ro + j];
-                s.rb[r] = g.rbase[ro + j];
+                const int b = g.rbase[ro + j];
+                s.rb[r] = LUT ? base_code1(b) : b;
+                if (LUT) odd_base |= s.rb[r] == 4;
                 if (A::kLog) {
                     const double ln_eps = (double)q * -0.23025850929940456;
                     s.pm[r] = g.qlut[q * kQlutStride + 3];
@@ -398,7 +470,7 @@ __global__ void __launch_bounds__(kWarps * 32, Occ<R>::kMinBlocks) pairhmm_kerne
                     const double eps = g.qlut[q * kQlutStride + 0];
                     s.pm[r] = g.qlut[q * kQlutStride + 1];
                     s.pmm[r] = g.qlut[q * kQlutStride + 2];
-                    s.cyo[r] = eps * c.t_gx;
+                    s.cyo[r] = eps * (LUT ? c.t_gx_s : c.t_gx);
                     s.cye[r] = eps * c.t_gxe;
                 }
             } else {  // padding row below the read: stays at zero mass
@@ -408,26 +480,56 @@ __global__ void __launch_bounds__(kWarps * 32, Occ<R>::kMinBlocks) pairhmm_kerne
             s.M[r] = s.X[r] = s.Y[r] = A::zero();
             s.med[r] = kMedMax;
         }
+        if (LUT) {
+            if (__any_sync(0xffffffffu, odd_base)) {
+                if (lane == 0) g.gen_list[atomicAdd(g.gen_count, 1)] = pair;
+                continue;
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const double em = s.pm[r] * c.t_mm, emm = s.pmm[r] * c.t_mm;
+#pragma unroll
+                for (int k = 0; k < kLutCols; ++k) lut[(r * kLutCols + k) * 32] = k == s.rb[r] ? em : emm;
+            }
+        }
+
+        // ---- stage the first haplotype chunk (TMA).  Bulk copies need 16-byte aligned sources:
+        // copy from the aligned-down address and shift the ring index by the misalignment.
+        const int shift = (int)((uintptr_t)(g.hap + ho) & 15);
+        h.hsrc = g.hap + ho - shift;
+        h.lxs = lx + shift;
+        h.n_chunks = (h.lxs + kChunk - 1) / kChunk;
+        __syncwarp();  // every lane is done with the ring contents of the previous pair
+        if (lane == 0) {
+            const uint32_t bytes = (uint32_t)min(kChunk, (h.lxs + 15) & ~15);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&h.bar[0], bytes);
+            tma_load_1d(h.ring, h.hsrc, bytes, &h.bar[0]);
+        }
         const int last_lane = (ly - 1) / R;
         const int last_r = (ly - 1) - last_lane * R;
         s.bM = s.bX = s.bY = A::zero();
-        s.dM = lane == 0 ? A::one() : A::zero();
+        s.one0 = lane == 0 ? (LUT ? c.one_s : A::one()) : A::zero();
+        s.dM = s.one0;
         s.dX = s.dY = A::zero();
         s.bMed = kMedMax;
         s.dMed = lane == 0 ? 0 : kMedMax;
         s.acc = A::zero();
+        s.acc2 = A::zero();
 
         mbar_wait(&h.bar[0], h.parity0);
         h.parity0 ^= 1;
+        if (LUT) encode_chunk(h.ring, lane);
 
         const int T = lx + last_lane;
         // the log-space instantiation keeps one loop body (run-time last row); the linear one is
         // specialised on the last-row index so that the free-end sum costs three adds per step
-        SweepDispatch<R, A::kLog ? -1 : R - 1, BANDED, APPROX, EXT, A>::run(s, c, h, T, lane, shift,
-                                                                            band, last_r);
+        SweepDispatch<R, A::kLog ? -1 : R - 1, BANDED, APPROX, EXT, LUT, A>::run(s, c, h, lut, T, lane,
+                                                                                 shift, band, last_r);
 
         // ---- result lives in lane last_lane
-        const double acc = __shfl_sync(0xffffffffu, s.acc, last_lane);
+        double acc = __shfl_sync(0xffffffffu, s.acc, last_lane);
+        if (LUT) acc = fma(acc, c.inv_tmm, __shfl_sync(0xffffffffu, s.acc2, last_lane));
         if (lane == 0) {
             double res;
             if (A::kLog) {
@@ -675,6 +777,9 @@ template <bool BANDED, bool APPROX>
 cudaError_t launch_pairhmm_lin(int cls, bool ext, const HmmArgs &a, int sm_count, cudaStream_t st);
 template <bool BANDED, bool APPROX>
 cudaError_t launch_pairhmm_log(const HmmArgs &a, int sm_count, cudaStream_t st);
+// scaled linear space without the emission LUT (any byte alphabet), R = 8, gap extension on
+template <bool BANDED, bool APPROX>
+cudaError_t launch_pairhmm_generic(const HmmArgs &a, int sm_count, cudaStream_t st);
 // long reads (unbanded only): linear pass and its log-space fallback
 template <bool APPROX>
 cudaError_t launch_pairhmm_long(bool ext, bool log_space, const HmmArgs &a, int sm_count, cudaStream_t st);
@@ -694,7 +799,7 @@ constexpr int kLongBlocksPerSm = 2;
 #define VLR_PAIRHMM_INSTANTIATE(BANDED, APPROX)                                                   \
     template <int R, bool EXT>                                                                    \
     static cudaError_t launch_r(const HmmArgs &a, int sm_count, cudaStream_t st) {                \
-        pairhmm_kernel<R, BANDED, APPROX, EXT, Lin>                                               \
+        pairhmm_kernel<R, BANDED, APPROX, EXT, true, Lin>                                         \
             <<<sm_count * Occ<R>::kMinBlocks, kWarps * 32, 0, st>>>(a);                           \
         return cudaGetLastError();                                                                \
     }                                                                                             \
@@ -713,9 +818,16 @@ constexpr int kLongBlocksPerSm = 2;
         }                                                                                         \
     }                                                                                             \
     template <>                                                                                   \
+    cudaError_t launch_pairhmm_generic<BANDED, APPROX>(const HmmArgs &a, int sm_count,            \
+                                                       cudaStream_t st) {                         \
+        pairhmm_kernel<8, BANDED, APPROX, true, false, Lin>                                       \
+            <<<sm_count * Occ<8>::kMinBlocks, kWarps * 32, 0, st>>>(a);                           \
+        return cudaGetLastError();                                                                \
+    }                                                                                             \
+    template <>                                                                                   \
     cudaError_t launch_pairhmm_log<BANDED, APPROX>(const HmmArgs &a, int sm_count,                \
                                                    cudaStream_t st) {                             \
-        pairhmm_kernel<8, BANDED, APPROX, true, Log>                                              \
+        pairhmm_kernel<8, BANDED, APPROX, true, false, Log>                                       \
             <<<sm_count * Occ<8>::kMinBlocks, kWarps * 32, 0, st>>>(a);                           \
         return cudaGetLastError();                                                                \
     }
