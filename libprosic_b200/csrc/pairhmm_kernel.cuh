@@ -20,6 +20,7 @@
 // range are re-run by the same kernel instantiated with log-space arithmetic (still on the GPU).
 #pragma once
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -194,7 +195,7 @@ struct Log {  // natural-log space, the literal arithmetic of the reference
 // ---------------------------------------------------------------- the kernel
 template <int R>
 struct Occ {
-    static constexpr int kMinBlocks = R <= 3 ? 5 : (R <= 4 ? 4 : (R <= 6 ? 3 : 2));
+    static constexpr int kMinBlocks = R <= 3 ? 5 : (R <= 5 ? 4 : (R <= 6 ? 3 : 2));
 };
 
 // Per-pair state that lives in registers across the sweep.
@@ -784,6 +785,12 @@ cudaError_t launch_pairhmm_generic(const HmmArgs &a, int sm_count, cudaStream_t 
 template <bool APPROX>
 cudaError_t launch_pairhmm_long(bool ext, bool log_space, const HmmArgs &a, int sm_count, cudaStream_t st);
 constexpr int kLongBlocksPerSm = 2;
+// persistent-grid size per SM; VLR_K1_BLOCKS_PER_SM overrides it (tuning aid)
+inline int blocks_per_sm(int dflt) {
+    const char *e = getenv("VLR_K1_BLOCKS_PER_SM");
+    const int v = e ? atoi(e) : 0;
+    return v > 0 ? v : dflt;
+}
 
 #define VLR_PAIRHMM_LONG_INSTANTIATE(APPROX)                                                      \
     template <>                                                                                   \
@@ -800,7 +807,7 @@ constexpr int kLongBlocksPerSm = 2;
     template <int R, bool EXT>                                                                    \
     static cudaError_t launch_r(const HmmArgs &a, int sm_count, cudaStream_t st) {                \
         pairhmm_kernel<R, BANDED, APPROX, EXT, true, Lin>                                         \
-            <<<sm_count * Occ<R>::kMinBlocks, kWarps * 32, 0, st>>>(a);                           \
+            <<<sm_count * blocks_per_sm(Occ<R>::kMinBlocks), kWarps * 32, 0, st>>>(a);            \
         return cudaGetLastError();                                                                \
     }                                                                                             \
     template <>                                                                                   \
