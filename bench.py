@@ -29,6 +29,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOPS_PER_CELL = 14.0  # algorithmic fp64 flops per pair-HMM cell update
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel (pairhmm_kernel<5,0,1,0,1,Lin>),
+# one launch at the default workload (7168 sites x 140 reads): `ncu --set full` capture summarised in
+# profiles/r1_ncu_k1_pairhmm_R5_approx_lut_default_summary.txt (347.3 MB read + 18.6 MB written)
+NCU_TRAFFIC_DEFAULT = {"sites": 7168, "reads_per_site": 140, "exact_sum": False, "bytes": 365.9e6}
 
 
 def parse():
@@ -41,7 +45,8 @@ def parse():
     ap.add_argument("--reads-per-site", type=int, default=140)
     ap.add_argument("--exact-sum", action="store_true",
                     help="time the exact M-state sum instead of bio's ln_sum3_exp_approx")
-    ap.add_argument("--cpu-sample-pairs", type=int, default=0, help="0 = auto (about 15 s)")
+    ap.add_argument("--cpu-sample-pairs", type=int, default=0, help="0 = auto (about 12 s)")
+    ap.add_argument("--cpu-sample-sites", type=int, default=0, help="0 = auto (5-10 s per workload)")
     ap.add_argument("--p2-sites", type=int, default=262144, help="C2 sites per step and GPU (part 2)")
     ap.add_argument("--skip-part2", action="store_true")
     ap.add_argument("--c4-pairs", type=int, default=1184, help="long-read pairs of the C4 subsample (0 = skip)")
@@ -186,6 +191,12 @@ def part2_workloads(args):
                                 desc="C3 part 2: built-in tumor/normal scenario, 40x normal + 100x tumor, "
                                      "purity .75, tumor grid 101 x normal grid 5, indel bias configs (1+3)",
                                 flops=FLOPS_PER_EVAL_CONTAM),
+        "c5_trio": dict(scn=scenario.trio(with_biases=True), depths=[30, 30, 30], kind="snv",
+                        n_sites=args.p2_sites // 2,
+                        af_sets=[[(0, .9), (.5, .07), (1, .03)]] * 3, purity=None,
+                        desc="C5 shape: trio (child, father, mother) x 30 obs, genotype universe {0,.5,1} "
+                             "per sample, joint events over 27 AF tuples, SNV bias configs, flat prior",
+                        flops=FLOPS_PER_EVAL_SINGLE),
     }
 
 
@@ -260,7 +271,7 @@ def bench_part2(args, ctx, torch, dist, dev, stream, rank, world, name, wl, time
                    "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
                    "ms_per_step": ms_e2e / args.steps}}
     if rank == 0:
-        n_cpu = 200 if ns == 1 else 24
+        n_cpu = min(n_sites, args.cpu_sample_sites or (16384 if ns == 1 else (4096 if ns == 3 else 256)))
         ores, cpu_sps, cpu_dt = oracle_part2(wl, cols, cat, off, n_cpu)
         ev = d_ev.cpu().numpy().reshape(n_sites, ne)[:n_cpu]
         want = np.array([r["event_ln"] for r in ores])
@@ -275,7 +286,7 @@ def bench_part2(args, ctx, torch, dist, dev, stream, rank, world, name, wl, time
         # distinct likelihood evaluations per site (cache-miss semantics of likelihood.rs:128,221):
         # oracle count of distinct keys x observations of the sample they run over
         keys = float(np.mean([r["n_evals"] for r in ores]))
-        evals = keys * (wl["depths"][-1] if ns > 1 else wl["depths"][0])
+        evals = keys * (wl["depths"][-1] if ns == 2 else wl["depths"][0])
         sps_gpu = n_sites * args.steps / (ms * 1e-3)
         res["evals_per_site"] = evals
         res["roofline"] = {"bound": "fp64", "achieved": sps_gpu * evals * wl["flops"] / 1e12,
@@ -327,7 +338,7 @@ def bench_allele_support(args, ctx, w, flags, rank, world, torch, dist, dev):
            "frac_pairs_certainty_shortcut": float(np.mean(np.concatenate([out["ref_dist"], out["alt_dist"]]) == 0))}
     if rank == 0:
         import oracle as O
-        n_cpu = 64
+        n_cpu = min(n_reads, 4096)
         t0 = time.perf_counter()
         worst = 0.0
         for r in range(n_cpu):
@@ -540,7 +551,7 @@ def main():
         in_bytes = sum(int(host[k].numel() * host[k].element_size()) for k in host)
         cores = os.cpu_count() or 1
         # bounded CPU sample of the same workload, one thread (the reference is single-threaded)
-        n_cpu = args.cpu_sample_pairs or 256
+        n_cpu = min(n_pairs, args.cpu_sample_pairs or 8192)
         g1, dt1, _ = cpu_sample(w, n_cpu, 1, flags)
         line = {
             "metric": "pairhmm_gcups", "value": gcups, "unit": "GCUPS", "n_gpus": world,
@@ -558,7 +569,15 @@ def main():
                     "identical_to_device_path": same_e2e},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": ach_tf / peak_tf if peak_tf else None, "traffic": None,
+                         "frac": ach_tf / peak_tf if peak_tf else None,
+                         "traffic": (NCU_TRAFFIC_DEFAULT["bytes"]
+                                     if (args.sites, args.reads_per_site, args.exact_sum) ==
+                                     (NCU_TRAFFIC_DEFAULT["sites"], NCU_TRAFFIC_DEFAULT["reads_per_site"],
+                                      NCU_TRAFFIC_DEFAULT["exact_sum"]) else None),
+                         "traffic_unit": "bytes per launch of the dominant kernel (ncu, profiles/)",
+                         "algorithmic_bytes_per_launch": in_bytes + n_pairs * 8,
+                         "bound_note": "the path is bound by the fp64 pipe, not by HBM or tensor cores "
+                                       "(SURVEY.md 8d): 0.004 B/cell; the HBM figure is under 'hbm'",
                          "peak_source": "vlr_measure_fp64_peak (DFMA chains, measured live); "
                                         "MEASURED_PEAKS.json has no fp64 entry",
                          "flops_per_cell": FLOPS_PER_CELL,
