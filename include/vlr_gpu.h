@@ -63,6 +63,7 @@ typedef struct {
 /* flags */
 #define VLR_HMM_SUM3_APPROX 1u /* bio's ln_sum3_exp_approx in the M-state sum (reference behaviour) */
 #define VLR_HMM_PATH_CLOSE 2u  /* close-gap constants paired as PathHMMRealigner (mod.rs:469-470)   */
+#define VLR_REALIGN_FAST 4u    /* vlr_allele_support_batch: --pairhmm-mode fast (PathHMMRealigner)     */
 #define VLR_HMM_DEFAULT VLR_HMM_SUM3_APPROX
 
 /*
@@ -124,6 +125,18 @@ int vlr_besthit_batch(vlr_ctx *ctx, int64_t n_pairs,
                       int32_t *out_dist, int32_t *out_start, int32_t *out_end,
                       int32_t *out_n_best, int32_t *out_n_indel_ops, uint8_t *out_indel_ops);
 
+/* ---- PathHMM: replaces PathHMMRealigner::calculate_prob_allele (`--pairhmm-mode fast`,
+ *      realignment/mod.rs:499-576): ln probability of the best Myers alignment path (maximum over
+ *      the alignments of every best end position, transition table of mod.rs:459-486, emissions
+ *      of pairhmm.rs:182-200).  Same layout as vlr_besthit_batch plus the base qualities;
+ *      out_dist (nullable) = the hit's edit distance, -1 and NaN probability if there is no hit. */
+int vlr_pathhmm_batch(vlr_ctx *ctx, int64_t n_pairs,
+                      const uint8_t *hap_bytes, const int64_t *hap_off, int64_t n_haps,
+                      const uint8_t *read_bases, const uint8_t *read_quals,
+                      const int64_t *read_off, int64_t n_reads,
+                      const int32_t *pair_hap, const int32_t *pair_read,
+                      const vlr_gap_params *gap, double *out_lnprob, int32_t *out_dist);
+
 /* ---- fused Realigner::allele_support for merged candidate regions (realignment/mod.rs:225-319
  *      with prob_allele 338-385): region r aligns read window region_read[r] against the
  *      haplotypes region_haps[region_hap_off[r] .. region_hap_off[r+1]) (indices into the hap
@@ -132,7 +145,8 @@ int vlr_besthit_batch(vlr_ctx *ctx, int64_t n_pairs,
  *      (pairhmm.rs:38-44) and extended by that many bytes (insertion.rs:219-222); < 0: not
  *      shrinkable (breakend alleles, breakends.rs:649-664).
  *      Device pipeline: K2 best hits -> minimal-distance haplotypes -> dist == 0 ? certainty_est
- *      : banded pair-HMM (band dist+2) -> max over haplotypes -> normalisation / 0.5 fallbacks.
+ *      : banded pair-HMM (band dist+2; with VLR_REALIGN_FAST in flags: best-path probability
+ *      of PathHMMRealigner instead) -> max over haplotypes -> normalisation / 0.5 fallbacks.
  *      Outputs per region: normalised prob_ref / prob_alt, raw (unnormalised) values (nullable),
  *      edit distances of the chosen hits, and the alt hit's best_indel_operations. ------ */
 int vlr_allele_support_batch(vlr_ctx *ctx, int64_t n_regions, const int32_t *region_read,

@@ -12,6 +12,7 @@ SO_PATH = os.path.join(_HERE, "libvlr_b200.so")
 VLR_OK = 0
 HMM_SUM3_APPROX = 1
 HMM_PATH_CLOSE = 2
+REALIGN_FAST = 4  # vlr_allele_support_batch: --pairhmm-mode fast (PathHMMRealigner)
 HMM_DEFAULT = HMM_SUM3_APPROX
 MAX_INDEL_OPS = 32
 
@@ -74,7 +75,7 @@ EXPORTS = [
     "vlr_version", "vlr_ctx_create", "vlr_ctx_destroy", "vlr_last_error", "vlr_ctx_set_stream",
     "vlr_ctx_synchronize", "vlr_ctx_launch_count", "vlr_pairhmm_batch",
     "vlr_pairhmm_workspace_bytes", "vlr_pairhmm_batch_dev", "vlr_measure_fp64_peak",
-    "vlr_besthit_batch", "vlr_allele_support_batch", "vlr_likelihood_batch", "vlr_posterior_batch", "vlr_posterior_batch_dev",
+    "vlr_besthit_batch", "vlr_pathhmm_batch", "vlr_allele_support_batch", "vlr_likelihood_batch", "vlr_posterior_batch", "vlr_posterior_batch_dev",
 ]
 
 _lib = None
@@ -109,6 +110,7 @@ def load():
                                         C.POINTER(GapParams), u32, vp, C.c_size_t, vp]
     L.vlr_measure_fp64_peak.argtypes = [vp, _DP]
     L.vlr_besthit_batch.argtypes = [vp, i64, vp, vp, i64, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.vlr_pathhmm_batch.argtypes = [vp, i64, vp, vp, i64, vp, vp, vp, i64, vp, vp, vp, vp, vp]
     L.vlr_allele_support_batch.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, i64,
                                            C.POINTER(GapParams), u32, vp, vp, vp, vp, vp, vp, vp, vp]
     L.vlr_likelihood_batch.argtypes = [vp, i64, i32, C.POINTER(ObsColumns), vp, vp, i32, vp, i64, vp]

@@ -126,6 +126,26 @@ class Context:
         out["indel_ops"] = ops
         return out
 
+    def pathhmm_batch(self, hap_bytes, hap_off, read_bases, read_quals, read_off, gap,
+                      pair_hap=None, pair_read=None):
+        """PathHMMRealigner::calculate_prob_allele (fast mode): (ln prob of the best path, dist)."""
+        hap_bytes = _arr(hap_bytes, np.uint8)
+        hap_off = _arr(hap_off, np.int64)
+        read_bases = _arr(read_bases, np.uint8)
+        read_quals = _arr(read_quals, np.uint8)
+        read_off = _arr(read_off, np.int64)
+        pair_hap = _arr(pair_hap, np.int32)
+        pair_read = _arr(pair_read, np.int32)
+        n_haps, n_reads = len(hap_off) - 1, len(read_off) - 1
+        n = len(pair_hap) if pair_hap is not None else (len(pair_read) if pair_read is not None
+                                                        else min(n_haps, n_reads))
+        out, dist = np.empty(n, np.float64), np.empty(n, np.int32)
+        self._check(self.lib.vlr_pathhmm_batch(
+            self.h, n, _ptr(hap_bytes), _ptr(hap_off), n_haps, _ptr(read_bases), _ptr(read_quals),
+            _ptr(read_off), n_reads, _ptr(pair_hap), _ptr(pair_read), C.byref(gap.c), _ptr(out),
+            _ptr(dist)))
+        return out, dist
+
     def allele_support_batch(self, region_read, region_hap_off, region_haps, region_n_ref, hap_bytes,
                              hap_off, read_bases, read_quals, read_off, gap, shrink_extra=None,
                              flags=_ffi.HMM_DEFAULT):

@@ -43,6 +43,12 @@ struct MyersArgs {
     int64_t scratch_stride;   // columns per worker
     HitOut *out;
     uint8_t *out_ops;         // [n_pairs][kMaxIndelOps]
+    // PathHMM ("fast" realignment mode, realignment/mod.rs:499-576): probability of the best
+    // alignment path(s); needs the base qualities and the transition table (nullable)
+    const uint8_t *rqual;
+    const double *qlut;
+    double *out_path;
+    double no_gap, close_x, close_y, reopen_x, reopen_y, gap_x, gap_y;
 };
 
 __device__ __forceinline__ int up_char(int c) { return (unsigned)(c - 'a') < 26u ? c - 32 : c; }
@@ -81,6 +87,7 @@ __global__ void __launch_bounds__(128) besthit_kernel(MyersArgs g) {
         if (n <= 0 || m <= 0 || m > 64 * kMyW) {
             res.dist = -1;  // no hit (calc_best_hit returns None for an empty text)
             g.out[k] = res;
+            if (g.out_path) g.out_path[k] = NAN;
             continue;
         }
         const uint8_t *pat = g.rbase + ro, *txt = g.hap + ho;
@@ -138,25 +145,53 @@ __global__ void __launch_bounds__(128) besthit_kernel(MyersArgs g) {
         // tracebacks of every best end position (edit_distance.rs:88-97), in increasing position
         int start_first = 0, start_last = 0, best_nindel = 1 << 30, best_nops = 0;
         uint8_t best_ops[kMaxIndelOps];
+        const bool want_path = g.out_path != nullptr;
+        double best_path = -INFINITY;
+        bool have_path = false;
         for (int e = first_best; e <= last_best; ++e) {
             if (dms[e] != best) continue;
             int j = m, i = e, nindel = 0;
             uint8_t ops[kMaxIndelOps];  // ring of the indel ops in traceback (reverse) order
+            // PathHMM: the walk runs backwards, so the transition INTO the operation found last
+            // step (`next`) is added once its predecessor is known; emissions as found
+            double path = 0.0;
+            int next = -1;  // 0 match/subst, 2 del, 3 ins
+            auto trans = [&](int prev, int cur) -> double {
+                if (cur == 0) return prev == 2 ? g.close_y : (prev == 3 ? g.close_x : (prev == 0 ? g.no_gap : 0.0));
+                if (cur == 2) return prev == 2 ? g.reopen_y : (prev == 3 ? g.close_x + g.gap_y : g.gap_y);
+                return prev == 3 ? g.reopen_x : (prev == 2 ? g.close_y + g.gap_x : g.gap_x);
+            };
             while (j > 0) {
                 const int d = i > 0 ? dist_at(cols + (int64_t)i * (2 * kMyW), dms[i], j, m) : j;
                 const int dup = i > 0 ? dist_at(cols + (int64_t)i * (2 * kMyW), dms[i], j - 1, m) : j - 1;
+                int op;
                 if (d == dup + 1) {  // vertical delta +1: Ins
                     ops[nindel & (kMaxIndelOps - 1)] = 3;
                     nindel++; j--;
-                    continue;
+                    op = 3;
+                    if (want_path) path += (double)g.rqual[ro + j] * -0.23025850929940456;  // prob_emit_y
+                } else {
+                    const int dl = i > 1 ? dist_at(cols + (int64_t)(i - 1) * (2 * kMyW), dms[i - 1], j, m) : j;
+                    if (i > 0 && dl + 1 == d) {  // Del (prob_emit_x = ln 1)
+                        ops[nindel & (kMaxIndelOps - 1)] = 2;
+                        nindel++; i--;
+                        op = 2;
+                    } else {
+                        j--; i--;  // Match / Subst
+                        op = 0;
+                        if (want_path) {
+                            const int q = g.rqual[ro + j];
+                            path += pat[j] == up_char(txt[i]) ? g.qlut[q * kQlutStride + 3]
+                                                              : (double)q * -0.23025850929940456 + -1.098712293668443;
+                        }
+                    }
                 }
-                const int dl = i > 1 ? dist_at(cols + (int64_t)(i - 1) * (2 * kMyW), dms[i - 1], j, m) : j;
-                if (i > 0 && dl + 1 == d) {  // Del
-                    ops[nindel & (kMaxIndelOps - 1)] = 2;
-                    nindel++; i--;
-                    continue;
-                }
-                j--; i--;  // Match / Subst
+                if (want_path && next >= 0) path += trans(op, next);
+                next = op;
+            }
+            if (want_path) {
+                if (next >= 0) path += trans(-1, next);
+                if (!have_path || path > best_path) { best_path = path; have_path = true; }
             }
             if (e == first_best) start_first = i;
             start_last = i;
@@ -173,6 +208,7 @@ __global__ void __launch_bounds__(128) besthit_kernel(MyersArgs g) {
         res.n_best = n_best;
         res.n_indel = best_nindel;
         g.out[k] = res;
+        if (want_path) g.out_path[k] = best_path;
         if (g.out_ops)
             for (int t = 0; t < best_nops; ++t) g.out_ops[k * kMaxIndelOps + t] = best_ops[t];
     }
@@ -188,6 +224,7 @@ struct SupportArgs {
     const double *qlut;
     const HitOut *hits;            // per slot
     const uint8_t *hit_ops;
+    const double *path_prob;       // per slot, fast mode only (else nullptr)
     // pair-HMM work list, per slot
     int64_t *win_start;
     int32_t *win_len, *pair_read, *med;
@@ -232,6 +269,10 @@ __global__ void support_select_kernel(SupportArgs g) {
                     for (int j = 0; j < ly; ++j) p += g.qlut[g.rqual[ro + j] * kQlutStride + 3];
                     g.slot_prob[s] = p;
                     g.slot_mode[s] = 1;
+                } else if (g.path_prob) {
+                    // --pairhmm-mode fast: probability of the best alignment path(s)
+                    g.slot_prob[s] = g.path_prob[s];
+                    g.slot_mode[s] = 3;
                 } else {
                     const int lx = (int)(g.hap_off[h + 1] - g.hap_off[h]);
                     int ws = 0, we = lx;
@@ -304,6 +345,24 @@ __global__ void support_epilogue_kernel(SupportArgs g) {
     }
 }
 
+// PathHMMRealigner::new (realignment/mod.rs:459-486): transition table of the fast mode
+static void set_path_consts(MyersArgs &a, const vlr_gap_params *gp) {
+    auto l1me = [](double p) -> double { return p < -0.693 ? log1p(-exp(p)) : log(-expm1(p)); };
+    auto lae = [](double x, double y) -> double {
+        const double p0 = x > y ? x : y, p1 = x > y ? y : x;
+        if (p0 == -INFINITY) return -INFINITY;
+        if (p1 == -INFINITY) return p0;
+        return p0 + log1p(exp(p1 - p0));
+    };
+    a.gap_x = gp->prob_gap_x;
+    a.gap_y = gp->prob_gap_y;
+    a.no_gap = l1me(lae(gp->prob_gap_x, gp->prob_gap_y));
+    a.close_x = l1me(gp->prob_gap_x_extend);
+    a.close_y = l1me(gp->prob_gap_y_extend);
+    a.reopen_x = lae(gp->prob_gap_x_extend, a.close_x + gp->prob_gap_x);
+    a.reopen_y = lae(gp->prob_gap_y_extend, a.close_y + gp->prob_gap_y);
+}
+
 // launches K2 over device-resident pairs; returns workers used
 static int launch_besthit(vlr_ctx *ctx, MyersArgs &a, int64_t max_lx, int slot_base) {
     cudaStream_t st = ctx->stream;
@@ -332,18 +391,17 @@ static int launch_besthit(vlr_ctx *ctx, MyersArgs &a, int64_t max_lx, int slot_b
 
 using namespace vlr;
 
-extern "C" {
-
-int vlr_besthit_batch(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *hap_bytes, const int64_t *hap_off,
-                      int64_t n_haps, const uint8_t *read_bases, const int64_t *read_off,
-                      int64_t n_reads, const int32_t *pair_hap, const int32_t *pair_read,
-                      int32_t *out_dist, int32_t *out_start, int32_t *out_end, int32_t *out_n_best,
-                      int32_t *out_n_indel_ops, uint8_t *out_indel_ops) {
+static int besthit_host(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *hap_bytes, const int64_t *hap_off,
+                        int64_t n_haps, const uint8_t *read_bases, const uint8_t *read_quals,
+                        const int64_t *read_off, int64_t n_reads, const int32_t *pair_hap,
+                        const int32_t *pair_read, const vlr_gap_params *gap, int32_t *out_dist,
+                        int32_t *out_start, int32_t *out_end, int32_t *out_n_best,
+                        int32_t *out_n_indel_ops, uint8_t *out_indel_ops, double *out_path) {
     if (!ctx) return VLR_ERR_INVALID;
     if (n_pairs < 0 || n_pairs > 0x7fffffff) return set_err(ctx, VLR_ERR_INVALID, "n_pairs out of range");
     if (n_pairs == 0) return VLR_OK;
-    if (!hap_bytes || !hap_off || !read_bases || !read_off || !out_dist || !out_start || !out_end ||
-        !out_n_best || n_haps <= 0 || n_reads <= 0)
+    if (!hap_bytes || !hap_off || !read_bases || !read_off || n_haps <= 0 || n_reads <= 0 ||
+        (out_path ? (!read_quals || !gap) : (!out_dist || !out_start || !out_end || !out_n_best)))
         return set_err(ctx, VLR_ERR_INVALID, "null/empty argument");
     if ((!pair_hap && n_haps < n_pairs) || (!pair_read && n_reads < n_pairs))
         return set_err(ctx, VLR_ERR_INVALID, "identity pair mapping needs n_haps/n_reads >= n_pairs");
@@ -364,7 +422,7 @@ int vlr_besthit_batch(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *hap_bytes, c
             if (pair_hap && (pair_hap[k] < 0 || pair_hap[k] >= n_haps)) return set_err(ctx, VLR_ERR_INVALID, "pair_hap out of range");
             if (pair_read && (pair_read[k] < 0 || pair_read[k] >= n_reads)) return set_err(ctx, VLR_ERR_INVALID, "pair_read out of range");
         }
-    enum { S_HAP = 40, S_HOFF, S_RB, S_ROFF, S_PH, S_PR, S_OUT, S_OPS, S_SCR };
+    enum { S_HAP = 40, S_HOFF, S_RB, S_ROFF, S_PH, S_PR, S_OUT, S_OPS, S_SCR, S_SCR2, S_SCR3, S_RQ, S_PATH = 75 };
     const int64_t hap_lo = hap_off[0], rd_lo = read_off[0];
     const size_t hb = (size_t)(hap_off[n_haps] - hap_lo), rb = (size_t)(read_off[n_reads] - rd_lo);
     uint8_t *d_hap = (uint8_t *)dev_scratch(ctx, S_HAP, hb + 64);
@@ -388,19 +446,56 @@ int vlr_besthit_batch(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *hap_bytes, c
     memset(&a, 0, sizeof(a));
     a.hap = d_hap - hap_lo; a.hap_off = d_hoff; a.rbase = d_rb - rd_lo; a.read_off = d_roff;
     a.pair_hap = d_ph; a.pair_read = d_pr; a.n_pairs = n_pairs; a.out = d_out; a.out_ops = d_ops;
+    double *d_path = nullptr;
+    if (out_path) {
+        uint8_t *d_rq = (uint8_t *)dev_scratch(ctx, S_RQ, rb + 16);
+        d_path = (double *)dev_scratch(ctx, S_PATH, (size_t)n_pairs * 8);
+        if (!d_rq || !d_path) return set_err(ctx, VLR_ERR_NOMEM, "scratch allocation failed");
+        VLR_CUDA(ctx, cudaMemcpyAsync(d_rq, read_quals + rd_lo, rb, cudaMemcpyHostToDevice, st));
+        a.rqual = d_rq - rd_lo; a.qlut = ctx->d_qlut; a.out_path = d_path;
+        set_path_consts(a, gap);
+    }
     int rc = launch_besthit(ctx, a, max_lx, S_SCR);
     if (rc != VLR_OK) return rc;
+    if (out_path)
+        VLR_CUDA(ctx, cudaMemcpyAsync(out_path, d_path, (size_t)n_pairs * 8, cudaMemcpyDeviceToHost, st));
     std::vector<HitOut> h((size_t)n_pairs);
     VLR_CUDA(ctx, cudaMemcpyAsync(h.data(), d_out, (size_t)n_pairs * sizeof(HitOut), cudaMemcpyDeviceToHost, st));
     if (out_indel_ops)
         VLR_CUDA(ctx, cudaMemcpyAsync(out_indel_ops, d_ops, (size_t)n_pairs * kMaxIndelOps, cudaMemcpyDeviceToHost, st));
     VLR_CUDA(ctx, cudaStreamSynchronize(st));
     for (int64_t k = 0; k < n_pairs; ++k) {
-        out_dist[k] = h[k].dist; out_start[k] = h[k].start; out_end[k] = h[k].end;
-        out_n_best[k] = h[k].n_best;
+        if (out_dist) out_dist[k] = h[k].dist;
+        if (out_start) out_start[k] = h[k].start;
+        if (out_end) out_end[k] = h[k].end;
+        if (out_n_best) out_n_best[k] = h[k].n_best;
         if (out_n_indel_ops) out_n_indel_ops[k] = h[k].n_indel;
     }
     return VLR_OK;
+}
+
+extern "C" {
+
+int vlr_besthit_batch(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *hap_bytes, const int64_t *hap_off,
+                      int64_t n_haps, const uint8_t *read_bases, const int64_t *read_off,
+                      int64_t n_reads, const int32_t *pair_hap, const int32_t *pair_read,
+                      int32_t *out_dist, int32_t *out_start, int32_t *out_end, int32_t *out_n_best,
+                      int32_t *out_n_indel_ops, uint8_t *out_indel_ops) {
+    return besthit_host(ctx, n_pairs, hap_bytes, hap_off, n_haps, read_bases, nullptr, read_off, n_reads,
+                        pair_hap, pair_read, nullptr, out_dist, out_start, out_end, out_n_best,
+                        out_n_indel_ops, out_indel_ops, nullptr);
+}
+
+int vlr_pathhmm_batch(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *hap_bytes, const int64_t *hap_off,
+                      int64_t n_haps, const uint8_t *read_bases, const uint8_t *read_quals,
+                      const int64_t *read_off, int64_t n_reads, const int32_t *pair_hap,
+                      const int32_t *pair_read, const vlr_gap_params *gap, double *out_lnprob,
+                      int32_t *out_dist) {
+    if (!ctx) return VLR_ERR_INVALID;
+    if (!out_lnprob) return set_err(ctx, VLR_ERR_INVALID, "null/empty argument");
+    return besthit_host(ctx, n_pairs, hap_bytes, hap_off, n_haps, read_bases, read_quals, read_off,
+                        n_reads, pair_hap, pair_read, gap, out_dist, nullptr, nullptr, nullptr, nullptr,
+                        nullptr, out_lnprob);
 }
 
 int vlr_allele_support_batch(vlr_ctx *ctx, int64_t n_regions, const int32_t *region_read,
@@ -444,7 +539,7 @@ int vlr_allele_support_batch(vlr_ctx *ctx, int64_t n_regions, const int32_t *reg
         if (region_haps[s] < 0 || region_haps[s] >= n_haps) return set_err(ctx, VLR_ERR_INVALID, "region_haps out of range");
     enum { S_HAP = 40, S_HOFF, S_RB, S_ROFF, S_PH, S_PR, S_OUT, S_OPS, S_SCR, S_SCR2, S_SCR3,
            S_RQ, S_RR, S_RHO, S_RNR, S_SE, S_WS0, S_WL, S_MED, S_SP, S_SM, S_O1, S_O2, S_O3, S_O4, S_O5,
-           S_O6, S_O7, S_O8, S_PWS };
+           S_O6, S_O7, S_O8, S_PWS, S_PATH = 75 };
     const int64_t hap_lo = hap_off[0], rd_lo = read_off[0];
     const size_t hb = (size_t)(hap_off[n_haps] - hap_lo), rb = (size_t)(read_off[n_reads] - rd_lo);
     auto D = [&](int slot, size_t bytes) { return dev_scratch(ctx, slot, bytes ? bytes : 8); };
@@ -497,6 +592,14 @@ int vlr_allele_support_batch(vlr_ctx *ctx, int64_t n_regions, const int32_t *reg
     memset(&ma, 0, sizeof(ma));
     ma.hap = d_hap - hap_lo; ma.hap_off = d_hoff; ma.rbase = d_rb - rd_lo; ma.read_off = d_roff;
     ma.pair_hap = d_rh; ma.pair_read = d_slot_read; ma.n_pairs = n_slots; ma.out = d_hits; ma.out_ops = d_ops;
+    const bool fast = (flags & VLR_REALIGN_FAST) != 0;
+    double *d_path = nullptr;
+    if (fast) {
+        d_path = (double *)D(S_PATH, (size_t)n_slots * 8);
+        if (!d_path) return set_err(ctx, VLR_ERR_NOMEM, "scratch allocation failed");
+        ma.rqual = d_rq - rd_lo; ma.qlut = ctx->d_qlut; ma.out_path = d_path;
+        set_path_consts(ma, gap);
+    }
     int rc = launch_besthit(ctx, ma, max_lx, S_SCR);
     if (rc != VLR_OK) return rc;
     // 2. minimal-distance selection, certainty short-circuit, HMM windows
@@ -505,6 +608,7 @@ int vlr_allele_support_batch(vlr_ctx *ctx, int64_t n_regions, const int32_t *reg
     sa.n_regions = n_regions; sa.region_read = d_rr; sa.region_hap_off = d_rho; sa.region_haps = d_rh;
     sa.region_n_ref = d_rnr; sa.shrink_extra = d_se; sa.hap_off = d_hoff; sa.read_off = d_roff;
     sa.rqual = d_rq - rd_lo; sa.qlut = ctx->d_qlut; sa.hits = d_hits; sa.hit_ops = d_ops;
+    sa.path_prob = d_path;
     sa.win_start = d_ws; sa.win_len = d_wl; sa.pair_read = d_slot_read; sa.med = d_med;
     sa.slot_prob = d_sp; sa.slot_mode = d_sm;
     sa.prob_ref = d_pref; sa.prob_alt = d_palt; sa.raw_ref = d_rref; sa.raw_alt = d_ralt;
@@ -513,9 +617,11 @@ int vlr_allele_support_batch(vlr_ctx *ctx, int64_t n_regions, const int32_t *reg
     support_select_kernel<<<grid, 128, 0, st>>>(sa);
     VLR_LAUNCH_CHECK(ctx);
     // 3. banded pair-HMM on the shrunk windows (mode-2 slots; others have an empty window)
-    rc = pairhmm_windows_dev(ctx, n_slots, d_hap - hap_lo, d_ws, d_wl, d_rb - rd_lo, d_rq - rd_lo,
-                             d_roff, d_slot_read, d_med, d_sm, gap, flags, d_pws, pws_bytes, d_sp);
-    if (rc != VLR_OK) return rc;
+    if (!fast) {
+        rc = pairhmm_windows_dev(ctx, n_slots, d_hap - hap_lo, d_ws, d_wl, d_rb - rd_lo, d_rq - rd_lo,
+                                 d_roff, d_slot_read, d_med, d_sm, gap, flags, d_pws, pws_bytes, d_sp);
+        if (rc != VLR_OK) return rc;
+    }
     // 4. max over haplotypes, normalisation, fallbacks
     support_epilogue_kernel<<<grid, 128, 0, st>>>(sa);
     VLR_LAUNCH_CHECK(ctx);

@@ -215,6 +215,24 @@ def best_hit(hap, read, want_alignments=False):
     return res
 
 
+def pathhmm_prob(hap, read, qual, gap_ln):
+    """PathHMMRealigner::calculate_prob_allele on the best hit of (read, hap); None without a hit."""
+    hit = best_hit(hap, read, want_alignments=True)
+    if hit is None:
+        return None
+    h, hp = _u8(hap)
+    r, rp = _u8(read)
+    q, qp = _u8(qual)
+    g, gp = _f64(gap_ln)
+    starts = np.ascontiguousarray(hit["starts"], dtype=np.int32)
+    ops = np.concatenate(hit["alignments"]).astype(np.uint8) if hit["alignments"] else np.zeros(1, np.uint8)
+    off = np.concatenate([[0], np.cumsum([len(a) for a in hit["alignments"]])]).astype(np.int32)
+    fn = lib().vlro_pathhmm_prob
+    fn.restype = C.c_double
+    return float(fn(hp, len(h), rp, qp, len(r), gp, len(starts), starts.ctypes.data_as(_I32P),
+                    ops.ctypes.data_as(_U8P), off.ctypes.data_as(_I32P)))
+
+
 def allele_support_region(ref_haps, alt_haps, read, qual, gap_ln, shrink_extra=None,
                           flags=HMM_SUM3_APPROX, fast_mode=False):
     """ref_haps / alt_haps: lists of uint8 arrays.  shrink_extra: list (ref haps then alt haps)."""

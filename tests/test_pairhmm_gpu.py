@@ -149,3 +149,38 @@ def test_long_reads_strips(ctx, oracle, gi, flags):
     want = oracle.pairhmm_batch(hb, hap_off, rb, rq, read_off, gap.as_ln_array(), flags=flags)
     assert (want < -700).any()   # beyond plain fp64 range: renormalisation is exercised
     _compare(got, want, tol=1e-6)
+
+
+@pytest.mark.parametrize("flags", [P.HMM_DEFAULT, 0])
+def test_non_acgt_bases(ctx, oracle, flags):
+    """Reads and haplotypes with N / IUPAC codes and lower case: read-side codes route the pair to
+    the byte-compare kernel (the emission LUT has columns for A, C, G, T and 'anything else');
+    N == N is a match (pairhmm.rs:190-191)."""
+    rng = np.random.default_rng(77)
+    alphabet = np.frombuffer(b"ACGTNRYacgtn", dtype=np.uint8)
+    read_alpha = np.frombuffer(b"ACGTNR", dtype=np.uint8)
+    haps, reads, quals = [], [], []
+    for k in range(96):
+        lx, ly = int(rng.integers(40, 330)), int(rng.integers(5, 200))
+        pw = np.array([.22, .22, .22, .22, .03, .01, .01, .02, .02, .01, .01, .01])
+        hap = alphabet[rng.choice(len(alphabet), lx, p=pw / pw.sum())]
+        if k % 3 == 0:    # read bases all ACGT, haplotype with codes: stays on the LUT kernel
+            read = read_alpha[rng.integers(0, 4, ly)]
+        else:
+            read = read_alpha[rng.choice(6, ly, p=[.23, .23, .23, .23, .06, .02])]
+        if ly <= lx and k % 2 == 0:  # make the read resemble the haplotype
+            s = int(rng.integers(0, lx - ly + 1))
+            up = hap[s:s + ly].copy()
+            up[(up >= 97)] -= 32
+            keep = rng.random(ly) < 0.9
+            read = np.where(keep, up, read)
+        haps.append(hap); reads.append(read)
+        quals.append(rng.integers(2, 42, ly).astype(np.uint8))
+    hap_off = np.concatenate([[0], np.cumsum([len(h) for h in haps])]).astype(np.int64)
+    read_off = np.concatenate([[0], np.cumsum([len(r) for r in reads])]).astype(np.int64)
+    gap = P.GapParams(1e-3, 2e-3, 0.1, 0.1)
+    got = ctx.pairhmm_batch(np.concatenate(haps), hap_off, np.concatenate(reads), np.concatenate(quals),
+                            read_off, gap, flags=flags)
+    want = np.array([oracle.pairhmm_prob_related(haps[k], reads[k], quals[k], gap.as_ln_array(), -1, flags)
+                     for k in range(96)])
+    _compare(got, want)

@@ -128,3 +128,42 @@ def test_allele_support_regions(ctx, oracle, multi_alt, flags):
         assert np.array_equal(got["indel_ops"][r][:len(want["indel_ops"])], want["indel_ops"][:32]), r
         n_inf += want["informative"]
     assert n_inf > 20  # most reads must discriminate the alleles for the test to mean anything
+
+
+def test_pathhmm_fast_mode(ctx, oracle):
+    """--pairhmm-mode fast (PathHMMRealigner, realignment/mod.rs:499-576): probability of the best
+    Myers alignment path, all three gap settings (extension and re-open terms included)."""
+    for gi, gap in enumerate([P.GapParams(), P.GapParams(0.02, 0.03, 0.3, 0.3), P.GapParams(1e-3, 2e-3, 0.1, 0.2)]):
+        w = synth.make_ragged_pairs(150, seed=900 + gi, max_ly=200, max_lx=400)
+        got, dist = ctx.pathhmm_batch(w["hap_bytes"], w["hap_off"], w["read_bases"], w["read_quals"],
+                                      w["read_off"], gap)
+        for k in range(150):
+            hap = w["hap_bytes"][w["hap_off"][k]:w["hap_off"][k + 1]]
+            read = w["read_bases"][w["read_off"][k]:w["read_off"][k + 1]]
+            qual = w["read_quals"][w["read_off"][k]:w["read_off"][k + 1]]
+            want = oracle.pathhmm_prob(hap, read, qual, gap.as_ln_array())
+            if want is None:
+                assert dist[k] == -1 and np.isnan(got[k]), k
+                continue
+            assert dist[k] == oracle.best_hit(hap, read)["dist"], k
+            assert (np.isneginf(got[k]) and np.isneginf(want)) or abs(got[k] - want) <= 1e-6, (gi, k, got[k], want)
+
+
+def test_allele_support_fast_mode(ctx, oracle):
+    rng = np.random.default_rng(23)
+    R = _make_regions(rng, 10, 10, True)
+    gap = P.GapParams()
+    got = ctx.allele_support_batch(R["region_read"], R["region_hap_off"], R["region_haps"],
+                                   R["region_n_ref"], R["hap_bytes"], R["hap_off"], R["read_bases"],
+                                   R["read_quals"], R["read_off"], gap, shrink_extra=R["extra"],
+                                   flags=P.HMM_DEFAULT | P.REALIGN_FAST)
+    for r in range(len(R["region_read"])):
+        ids = R["region_haps"][R["region_hap_off"][r]:R["region_hap_off"][r + 1]]
+        rd = R["region_read"][r]
+        want = oracle.allele_support_region(
+            [R["haps"][ids[0]]], [R["haps"][h] for h in ids[1:]], R["reads"][rd], R["quals"][rd],
+            gap.as_ln_array(), shrink_extra=[int(R["extra"][h]) for h in ids], fast_mode=True)
+        for key in ("prob_ref", "prob_alt", "raw_ref", "raw_alt"):
+            g, w = got[key][r], want[key]
+            assert (np.isneginf(g) and np.isneginf(w)) or abs(g - w) <= 1e-6, (r, key, g, w)
+        assert got["ref_dist"][r] == want["ref_dist"] and got["alt_dist"][r] == want["alt_dist"], r
