@@ -254,12 +254,25 @@ typedef struct {
     const int32_t *roots;
     const vlr_event *events;
     const vlr_biases *biases;
+    /* Prior (bio::stats::bayesian::model::Prior::compute, prior.rs:788-805; joint = prior +
+     * likelihood, generic.rs:317-365): ln prior of every leaf AF vector in the order of
+     * vlr_model_leaves, or NULL = flat (ln 1).  The prior is data-independent, so the host
+     * evaluates its unchanged Prior once per event universe.  Only for models whose tree paths
+     * bind VAF sets (ploidy-derived universes, e.g. pedigrees): the grid points of a Range depend
+     * on the site's depth (generic.rs:109-122). */
+    const double *prior_ln;
+    int64_t n_prior;
 } vlr_model;
+
+/* Leaves (event, tree path, value combination; last sample fastest) of a set-only model:
+ * out_event[leaf] and out_afs[leaf*n_samples + m], both nullable to query the count alone. */
+int vlr_model_leaves(vlr_ctx *ctx, const vlr_model *model, int64_t capacity, int64_t *out_n_leaves,
+                     int32_t *out_event, double *out_afs);
 
 /*
  * Whole part 2 for a batch of sites: bias learning + gating (bias/mod.rs:30-83, 192-223),
  * AF-grid likelihoods, VAF-tree integration (Simpson, generic.rs:196-208), marginal, MAP.
- * Prior: flat (ln 1) when prior_ln == NULL.
+ * Prior: model->prior_ln (flat = ln 1 when NULL).
  *   out_event_ln[s*n_events + e]  unnormalised ln posterior of event e (Posterior::compute)
  *   out_marginal[s]               ln marginal (Model::compute)
  *   out_map_af[s*n_samples + m]   MAP allele frequency (calling.rs:635-677)

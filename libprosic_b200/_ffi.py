@@ -68,14 +68,15 @@ class Model(C.Structure):
                 ("n_biases", C.c_int32), ("resolution", C.c_void_p), ("contaminated", C.c_void_p),
                 ("by", C.c_void_p), ("purity", C.c_void_p), ("nodes", C.c_void_p),
                 ("children", C.c_void_p), ("vafs", C.c_void_p), ("roots", C.c_void_p),
-                ("events", C.c_void_p), ("biases", C.c_void_p)]
+                ("events", C.c_void_p), ("biases", C.c_void_p), ("prior_ln", C.c_void_p),
+                ("n_prior", C.c_int64)]
 
 
 EXPORTS = [
     "vlr_version", "vlr_ctx_create", "vlr_ctx_destroy", "vlr_last_error", "vlr_ctx_set_stream",
     "vlr_ctx_synchronize", "vlr_ctx_launch_count", "vlr_pairhmm_batch",
     "vlr_pairhmm_workspace_bytes", "vlr_pairhmm_batch_dev", "vlr_measure_fp64_peak",
-    "vlr_besthit_batch", "vlr_pathhmm_batch", "vlr_allele_support_batch", "vlr_likelihood_batch", "vlr_posterior_batch", "vlr_posterior_batch_dev",
+    "vlr_besthit_batch", "vlr_pathhmm_batch", "vlr_allele_support_batch", "vlr_likelihood_batch", "vlr_model_leaves", "vlr_posterior_batch", "vlr_posterior_batch_dev",
 ]
 
 _lib = None
@@ -114,6 +115,7 @@ def load():
     L.vlr_allele_support_batch.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, i64,
                                            C.POINTER(GapParams), u32, vp, vp, vp, vp, vp, vp, vp, vp]
     L.vlr_likelihood_batch.argtypes = [vp, i64, i32, C.POINTER(ObsColumns), vp, vp, i32, vp, i64, vp]
+    L.vlr_model_leaves.argtypes = [vp, C.POINTER(Model), i64, vp, vp, vp]
     L.vlr_posterior_batch.argtypes = [vp, i64, C.POINTER(Model), C.POINTER(ObsColumns), vp, vp, vp,
                                       vp, vp]
     L.vlr_posterior_batch_dev.argtypes = [vp, i64, C.POINTER(Model), C.POINTER(ObsColumns), vp, i32,

@@ -227,10 +227,29 @@ class Context:
         vf = np.asarray(vafs if vafs else [0.0], np.float64)
         rt = np.asarray(roots, np.int32)
         keep.extend([nodes, events, biases, res, cont, by, pur, ch, vf, rt])
+        prior = scn.get("prior_ln")  # ln prior per leaf in vlr_model_leaves order (None = flat)
+        if prior is not None:
+            prior = np.ascontiguousarray(prior, dtype=np.float64)
+            keep.append(prior)
         return Model(scn["n_samples"], len(scn["events"]), len(scn["nodes"]), len(flat),
                      res.ctypes.data, cont.ctypes.data, by.ctypes.data, pur.ctypes.data,
                      C.addressof(nodes), ch.ctypes.data, vf.ctypes.data, rt.ctypes.data,
-                     C.addressof(events), C.addressof(biases))
+                     C.addressof(events), C.addressof(biases),
+                     prior.ctypes.data if prior is not None else None,
+                     len(prior) if prior is not None else 0)
+
+    def model_leaves(self, scn):
+        """Leaf AF vectors of a set-only scenario: (event index per leaf, afs[n_leaves, n_samples])."""
+        keep = []
+        scn = dict(scn)
+        scn.pop("prior_ln", None)
+        model = self.build_model(scn, keep)
+        n = C.c_int64()
+        self._check(self.lib.vlr_model_leaves(self.h, C.byref(model), 0, C.byref(n), None, None))
+        ev = np.empty(n.value, np.int32)
+        afs = np.empty((n.value, scn["n_samples"]), np.float64)
+        self._check(self.lib.vlr_model_leaves(self.h, C.byref(model), n.value, C.byref(n), _ptr(ev), _ptr(afs)))
+        return ev, afs
 
     def posterior_batch(self, scn, cols, cat, obs_off):
         """Model::compute for every site: returns dict(event_ln[n_sites, n_events], marginal,

@@ -53,6 +53,14 @@ struct DevPath {
 struct DevEventBias {  // one (event, bias configuration) entry
     int32_t event, cfg;
 };
+// one (event, bias configuration, tree path) segment of the integration, in the order the
+// reference visits them (events, then the event's bias list, then tree paths)
+struct DevSeg {
+    int32_t event, ebi, cfg, art, path, _pad;
+    int64_t leaf_off;            // first prior-table entry of (event, path); -1 without a prior
+    int16_t spec[kMaxSamples];   // spectrum bound by the path, per sample
+    int16_t nv[kMaxSamples];     // its number of values; -1 = Range (the site's grid size)
+};
 struct DevEvent {
     int32_t is_artifact;
     int32_t path_off, n_paths;
@@ -61,7 +69,7 @@ struct DevEvent {
 };
 
 struct DevModel {
-    int32_t n_samples, n_events, n_spectra, n_paths, n_cfg, n_eb;
+    int32_t n_samples, n_events, n_spectra, n_paths, n_cfg, n_eb, n_segs;
     int32_t resolution[kMaxSamples], contaminated[kMaxSamples], by[kMaxSamples];
     double purity[kMaxSamples];
     const DevSpectrum *spectra;
@@ -70,6 +78,8 @@ struct DevModel {
     const DevEventBias *eb;
     const vlr_biases *cfg;
     const double *vafs;
+    const DevSeg *segs;
+    const double *prior;  // ln prior per leaf (event, path, combination), nullptr = flat
 };
 
 struct PostArgs {
@@ -85,6 +95,7 @@ struct PostArgs {
     int32_t *status;        // [0] = number of sites that overflowed a kernel limit
     int32_t obs_cap;        // observations per (site, sample) the shared staging can hold
     int64_t gs_cap;         // doubles of per-team shared memory for the blocked contaminated path
+    int64_t tab_cap;        // doubles of per-team shared memory for the likelihood table (0: global)
 };
 __device__ __forceinline__ int m_ncfg_cap(const PostArgs &g) { return g.m.n_cfg; }
 
@@ -384,12 +395,15 @@ __global__ void __launch_bounds__(kTeamThreadsMax, 3) posterior_kernel(PostArgs 
     extern __shared__ __align__(16) unsigned char s_dyn[];
     const int obs_cap = g.obs_cap;
     const size_t per_team = (size_t)obs_cap * sizeof(double4) +
-                            (size_t)obs_cap * m_ncfg_cap(g) * sizeof(double) + (size_t)g.gs_cap * sizeof(double);
+                            (size_t)obs_cap * m_ncfg_cap(g) * sizeof(double) +
+                            (size_t)(g.gs_cap + g.tab_cap) * sizeof(double);
     double4 *OC = (double4 *)(s_dyn + (size_t)team_in_cta * per_team);
     double *BC = (double *)(OC + obs_cap);
     double *GS = BC + (size_t)obs_cap * m_ncfg_cap(g);  // blocked contaminated path (may be empty)
     const int team_global = blockIdx.x * kTeamsPerCta + team_in_cta;
-    double *table = g.table + (int64_t)team_global * g.table_stride;
+    // likelihood table of the site: shared memory when it fits, else per-team global scratch
+    double *table = g.tab_cap ? GS + g.gs_cap : g.table + (int64_t)team_global * g.table_stride;
+    __shared__ double s_part[kTeamsPerCta][TEAM][2][kMaxEvents];  // per-warp (max, sum) of every event
     const DevModel &m = g.m;
     const int NS = m.n_samples;
 
@@ -719,7 +733,7 @@ __global__ void __launch_bounds__(kTeamThreadsMax, 3) posterior_kernel(PostArgs 
                         #pragma unroll
                         for (int b = 0; b < 8; ++b)
                             if (vb0 + b < bynv)
-                                __stcg(&tab[(int64_t)c * tcs + (int64_t)vi * bynv + vb0 + b], P.finish(b, sum_m, nren));
+                                tab[(int64_t)c * tcs + (int64_t)vi * bynv + vb0 + b] = P.finish(b, sum_m, nren);
                     }
                 }
             } else if (fast) {
@@ -770,7 +784,7 @@ __global__ void __launch_bounds__(kTeamThreadsMax, 3) posterior_kernel(PostArgs 
                     #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         if (vg * 4 + k < nv)
-                            __stcg(&tab[(int64_t)c * tcs + (int64_t)(vg * 4 + k) * bynv + vb], P.finish(k, sum_m, nren));
+                            tab[(int64_t)c * tcs + (int64_t)(vg * 4 + k) * bynv + vb] = P.finish(k, sum_m, nren);
                 }
             } else {
                 // ---- 4c. checked evaluation: every term is range-tested, terms outside the normal
@@ -802,97 +816,115 @@ __global__ void __launch_bounds__(kTeamThreadsMax, 3) posterior_kernel(PostArgs 
                             acc.slow(lt, oc.w);
                         }
                     }
-                    __stcg(&tab[(int64_t)c * tcs + key], acc.finish(sum_m, n));
+                    tab[(int64_t)c * tcs + key] = acc.finish(sum_m, n);
                 }
             }
         }
         team_sync<TEAM>();
 
-        // ---- 5. integrate: per event a log-sum-exp over (bias cfg, path, grid combination)
+        // ---- 5. integrate: per event a log-sum-exp over (bias cfg, path, grid combination).
+        // The (event, bias cfg, path) segments come flattened from the host in the reference's
+        // visiting order; every thread takes grid combinations tt, tt+TT, ... of each segment and
+        // keeps an online (max, sum) of the current event, flushed per warp at event boundaries.
         double bestJ[2] = {-INFINITY, -INFINITY};  // [0] any, [1] non-artifact
         int bestId[2][3] = {{0x7fffffff, 0, 0}, {0x7fffffff, 0, 0}};
         bool have[2] = {false, false};
-        #pragma unroll 1
-        for (int e = 0; e < m.n_events; ++e) {
-            const DevEvent ev = m.events[e];
+        {
             double mx = -INFINITY, sum = 0.0;
+            int cur_e = -1;
+            auto flush = [&](int e) {
+                double M = mx;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) M = fmax(M, __shfl_xor_sync(0xffffffffu, M, o));
+                double part = (mx == -INFINITY) ? 0.0 : sum * exp_ni(mx - M);
+                if (isnan(sum)) part = NAN;
+                part = warp_sum(part);
+                if (lane == 0) {
+                    s_part[team_in_cta][wt][0][e] = M;
+                    s_part[team_in_cta][wt][1][e] = part;
+                }
+            };
             #pragma unroll 1
-            for (int q = 0; q < ev.n_eb; ++q) {
-                const int ebi = ev.eb_off + q;
-                const int c = m.eb[ebi].cfg;
+            for (int k = tt; k < TEAM * 2 * kMaxEvents; k += TT)  // events without any segment
+                (&s_part[team_in_cta][0][0][0])[k] = ((k / kMaxEvents) & 1) ? 0.0 : -INFINITY;
+            team_sync<TEAM>();
+            #pragma unroll 1
+            for (int sidx = 0; sidx < m.n_segs; ++sidx) {
+                const DevSeg *sg = &m.segs[sidx];
+                const int ev_id = sg->event;
+                if (ev_id != cur_e) {
+                    if (cur_e >= 0) flush(cur_e);
+                    cur_e = ev_id; mx = -INFINITY; sum = 0.0;
+                }
+                const int c = sg->cfg;
                 if (!S.allowed[c]) continue;
-                const bool art = m.cfg[c].strand | m.cfg[c].orientation | m.cfg[c].read_position |
-                                 m.cfg[c].softclip | m.cfg[c].divindel;
+                const bool art = sg->art != 0;
+                const int ebi = sg->ebi, p = sg->path;
+                unsigned cnt[kMaxSamples];
+                int base[kMaxSamples];
+                unsigned total = 1;
                 #pragma unroll 1
-                for (int p = 0; p < ev.n_paths; ++p) {
-                    const DevPath &path = m.paths[ev.path_off + p];
-                    int cnt[kMaxSamples], base[kMaxSamples];
-                    int64_t total = 1;
+                for (int smp = 0; smp < NS; ++smp) {
+                    const int nvs = sg->nv[smp];
+                    cnt[smp] = nvs < 0 ? (unsigned)S.grid[smp] : (unsigned)nvs;
+                    base[smp] = S.spec_off[sg->spec[smp]] - S.sample_voff[smp];  // value index within sample
+                    total *= cnt[smp];
+                }
+                const double *prior = m.prior ? m.prior + sg->leaf_off : nullptr;
+                #pragma unroll 1
+                for (unsigned combo = tt; combo < total; combo += TT) {
+                    unsigned rem = combo;
+                    int vidx[kMaxSamples];
+                    double lw = 0.0;
+                    // mixed radix, LAST sample fastest
+                    #pragma unroll 1
+                    for (int smp = NS - 1; smp >= 0; --smp) {
+                        const unsigned q = rem / cnt[smp];
+                        vidx[smp] = base[smp] + (int)(rem - q * cnt[smp]);
+                        rem = q;
+                        lw += S.lnw[S.sample_voff[smp] + vidx[smp]];
+                    }
+                    double J = prior ? prior[combo] : 0.0;  // Prior::compute (prior.rs:788-805) via the host's table
                     #pragma unroll 1
                     for (int smp = 0; smp < NS; ++smp) {
-                        const int sp = path.spec[smp];
-                        const DevSpectrum spc = m.spectra[sp];
-                        cnt[smp] = spc.kind == VLR_NODE_RANGE ? S.grid[smp] : spc.n_vafs;
-                        base[smp] = S.spec_off[sp] - S.sample_voff[smp];  // value index within sample
-                        total *= cnt[smp];
+                        const int key = m.contaminated[smp] ? vidx[smp] * S.sample_nv[m.by[smp]] + vidx[m.by[smp]]
+                                                            : vidx[smp];
+                        J += table[S.tab_off[smp] + (int64_t)c * S.tab_cfg_stride[smp] + key];
                     }
-                    #pragma unroll 1
-                    for (int64_t combo = tt; combo < total; combo += TT) {
-                        int64_t rem = combo;
-                        int vidx[kMaxSamples];
-                        double lw = 0.0;
-                        // mixed radix, LAST sample fastest
-                        #pragma unroll 1
-                        for (int smp = NS - 1; smp >= 0; --smp) {
-                            const int d = (int)(rem % cnt[smp]);
-                            rem /= cnt[smp];
-                            vidx[smp] = base[smp] + d;
-                            lw += S.lnw[S.sample_voff[smp] + vidx[smp]];
-                        }
-                        double J = 0.0;  // flat prior (ln 1)
-                        #pragma unroll 1
-                        for (int smp = 0; smp < NS; ++smp) {
-                            const int64_t key = m.contaminated[smp]
-                                                    ? (int64_t)vidx[smp] * S.sample_nv[m.by[smp]] + vidx[m.by[smp]]
-                                                    : (int64_t)vidx[smp];
-                            J += __ldcg(&table[S.tab_off[smp] + (int64_t)c * S.tab_cfg_stride[smp] + key]);
-                        }
-                        // joint_probs bookkeeping for the MAP (ties: lowest (eb, path, combo))
+                    // joint_probs bookkeeping for the MAP (ties: lowest (eb, path, combo))
+                    if (!isnan(J)) {
+                        #pragma unroll
                         for (int w = 0; w < 2; ++w) {
                             if (w == 1 && art) continue;
-                            const bool better = map_better(m, S, J, ebi, p, (int)combo, have[w], bestJ[w],
-                                                           bestId[w][0], bestId[w][1], bestId[w][2]);
-                            if (better && !isnan(J)) {
+                            if (map_better(m, S, J, ebi, p, (int)combo, have[w], bestJ[w], bestId[w][0],
+                                           bestId[w][1], bestId[w][2])) {
                                 have[w] = true; bestJ[w] = J;
                                 bestId[w][0] = ebi; bestId[w][1] = p; bestId[w][2] = (int)combo;
                             }
                         }
-                        const double t = J + lw;
-                        if (isnan(t)) { sum = NAN; }
-                        else if (t > mx) { sum = sum * exp_ni(mx - t) + 1.0; mx = t; }
-                        else if (t != -INFINITY) sum += exp_ni(t - mx);
                     }
+                    const double t = J + lw;
+                    if (isnan(t)) { sum = NAN; }
+                    else if (t > mx) { sum = sum * exp_ni(mx - t) + 1.0; mx = t; }
+                    else if (t != -INFINITY) sum += exp_ni(t - mx);
                 }
             }
-            // reduce (mx, sum) over the team: max first, then one rescale per lane, then a plain sum
-            double M = mx;
+            if (cur_e >= 0) flush(cur_e);
+            team_sync<TEAM>();
+            #pragma unroll 1
+            for (int e = tt; e < m.n_events; e += TT) {
+                double M = -INFINITY;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) M = fmax(M, __shfl_xor_sync(0xffffffffu, M, o));
-            if (TEAM > 1) {
-                if (lane == 0) S.red_mx[wt] = M;
-                team_sync<TEAM>();
-                M = fmax(fmax(S.red_mx[0], S.red_mx[1]), fmax(S.red_mx[2], S.red_mx[3]));
+                for (int k = 0; k < TEAM; ++k) M = fmax(M, s_part[team_in_cta][k][0][e]);
+                double tot = 0.0;
+#pragma unroll
+                for (int k = 0; k < TEAM; ++k) {
+                    const double pm_ = s_part[team_in_cta][k][0][e];
+                    if (pm_ != -INFINITY) tot += s_part[team_in_cta][k][1][e] * (TEAM > 1 ? exp_ni(pm_ - M) : 1.0);
+                    else if (isnan(s_part[team_in_cta][k][1][e])) tot = NAN;
+                }
+                S.ev_ln[e] = (M == -INFINITY && !isnan(tot)) ? -INFINITY : m.events[e].bias_prior + M + log_ni(tot);
             }
-            double part = (mx == -INFINITY) ? 0.0 : sum * exp_ni(mx - M);
-            part = warp_sum(part);
-            if (TEAM > 1) {
-                if (lane == 0) S.red_sum[wt] = part;
-                team_sync<TEAM>();
-                part = S.red_sum[0] + S.red_sum[1] + S.red_sum[2] + S.red_sum[3];
-                team_sync<TEAM>();
-            }
-            mx = M; sum = part;
-            if (tt == 0) S.ev_ln[e] = (mx == -INFINITY) ? -INFINITY : ev.bias_prior + mx + log_ni(sum);
         }
         // ---- MAP reduction (ties -> lowest id)
         for (int w = 0; w < 2; ++w) {
@@ -999,7 +1031,10 @@ struct HostModel {
     std::vector<DevEventBias> eb;
     std::vector<vlr_biases> cfg;
     std::vector<double> vafs;
-    int max_paths_combos_hint = 0;
+    std::vector<DevSeg> segs;
+    std::vector<int64_t> path_leaf_off;  // per path: first leaf (prior-table entry), -1 if it binds a Range
+    int64_t n_leaves = 0;                // leaves of all-Set paths
+    bool any_range_path = false;
 };
 
 static bool same_cfg(const vlr_biases &a, const vlr_biases &b) {
@@ -1094,6 +1129,39 @@ static int flatten_model(vlr_ctx *ctx, const vlr_model *mdl, HostModel &H) {
         H.paths.insert(H.paths.end(), out.begin(), out.end());
         H.events.push_back(de);
     }
+    // leaves (event, path, combination) in visiting order: the index space of the prior table
+    H.path_leaf_off.assign(H.paths.size(), -1);
+    for (size_t pi = 0; pi < H.paths.size(); ++pi) {
+        int64_t combos = 1;
+        bool all_set = true;
+        for (int smp = 0; smp < NS; ++smp) {
+            const DevSpectrum &sp = H.spectra[H.paths[pi].spec[smp]];
+            if (sp.kind == VLR_NODE_RANGE) all_set = false;
+            else combos *= sp.n_vafs;
+        }
+        if (all_set) { H.path_leaf_off[pi] = H.n_leaves; H.n_leaves += combos; }
+        else H.any_range_path = true;
+    }
+    for (int e = 0; e < mdl->n_events; ++e) {
+        const DevEvent &de = H.events[e];
+        for (int q = 0; q < de.n_eb; ++q)
+            for (int pth = 0; pth < de.n_paths; ++pth) {
+                DevSeg sg;
+                memset(&sg, 0, sizeof(sg));
+                sg.event = e; sg.ebi = de.eb_off + q; sg.cfg = H.eb[de.eb_off + q].cfg; sg.path = pth;
+                const vlr_biases &b = H.cfg[sg.cfg];
+                sg.art = (b.strand || b.orientation || b.read_position || b.softclip || b.divindel) ? 1 : 0;
+                sg.leaf_off = H.path_leaf_off[de.path_off + pth];
+                for (int smp = 0; smp < NS; ++smp) {
+                    const int spi = H.paths[de.path_off + pth].spec[smp];
+                    sg.spec[smp] = (int16_t)spi;
+                    sg.nv[smp] = H.spectra[spi].kind == VLR_NODE_RANGE ? (int16_t)-1 : (int16_t)H.spectra[spi].n_vafs;
+                    if (H.spectra[spi].kind != VLR_NODE_RANGE && H.spectra[spi].n_vafs > 32767)
+                        return set_err(ctx, VLR_ERR_UNSUPPORTED, "VAF set with more than 32767 values");
+                }
+                H.segs.push_back(sg);
+            }
+    }
     if ((int)H.spectra.size() > kMaxSpectra) return set_err(ctx, VLR_ERR_UNSUPPORTED, "too many distinct VAF spectra");
     if ((int)H.cfg.size() > kMaxCfg) return set_err(ctx, VLR_ERR_UNSUPPORTED, "too many bias configurations");
     return VLR_OK;
@@ -1103,8 +1171,8 @@ static int flatten_model(vlr_ctx *ctx, const vlr_model *mdl, HostModel &H) {
 static int64_t table_bound(const vlr_model *mdl, const HostModel &H) {
     int64_t nv[kMaxSamples] = {0};
     for (const DevSpectrum &sp : H.spectra) {
-        int64_t c = sp.kind == VLR_NODE_RANGE ? (int64_t)mdl->resolution[sp.sample] + 1 : sp.n_vafs;
-        if (sp.kind == VLR_NODE_RANGE && c < 5) c = 5;
+        // grid = min(max(n_obs + 1, 5), resolution) made odd (generic.rs:109-122) <= resolution | 1
+        const int64_t c = sp.kind == VLR_NODE_RANGE ? (int64_t)(mdl->resolution[sp.sample] | 1) : sp.n_vafs;
         nv[sp.sample] += c;
     }
     int64_t tot = 0;
@@ -1147,8 +1215,7 @@ int vlr_posterior_batch_dev(vlr_ctx *ctx, int64_t n_sites, const vlr_model *mode
     {
         int64_t nvb[kMaxSamples] = {0};
         for (const DevSpectrum &sp : H.spectra) {
-            int64_t c = sp.kind == VLR_NODE_RANGE ? (int64_t)model->resolution[sp.sample] + 1 : sp.n_vafs;
-            if (sp.kind == VLR_NODE_RANGE && c < 5) c = 5;
+            const int64_t c = sp.kind == VLR_NODE_RANGE ? (int64_t)(model->resolution[sp.sample] | 1) : sp.n_vafs;
             nvb[sp.sample] += c;
         }
         for (int smp = 0; smp < model->n_samples; ++smp)
@@ -1157,6 +1224,10 @@ int vlr_posterior_batch_dev(vlr_ctx *ctx, int64_t n_sites, const vlr_model *mode
         if (team_smem + (size_t)gs_cap * 8 > 72 * 1024) gs_cap = 0;  // does not fit: direct evaluation
     }
     team_smem += (size_t)gs_cap * 8;
+    // likelihood table of one site in shared memory when it is small enough
+    const int64_t tab_cap = (tbound <= 4096 && team_smem + (size_t)tbound * 8 <= 72 * 1024)
+                                ? ((tbound + 3) & ~(int64_t)3) : 0;  // keeps the teams' carve-outs 32-byte aligned
+    team_smem += (size_t)tab_cap * 8;
     const bool big = tbound > 2048 || 4 * team_smem > 64 * 1024;
     const int teams_per_cta = big ? 1 : 4;
     const size_t dyn_smem = (size_t)teams_per_cta * team_smem;
@@ -1164,16 +1235,28 @@ int vlr_posterior_batch_dev(vlr_ctx *ctx, int64_t n_sites, const vlr_model *mode
         return set_err(ctx, VLR_ERR_UNSUPPORTED,
                        "%d observations x %d bias configurations do not fit the shared-memory staging",
                        max_obs_per_pileup, (int)H.cfg.size());
-    const int grid = ctx->sm_count * (dyn_smem > 48 * 1024 ? 2 : 3);
+    // static shared memory: TeamShared (~8 KB per team) + event partials (4 KB)
+    const size_t cta_smem = dyn_smem + (size_t)teams_per_cta * 8704 + 4096 + 1024;
+    const int grid = ctx->sm_count * (int)std::max<size_t>(1, std::min<size_t>(3, (size_t)(220 * 1024) / cta_smem));
     const int64_t n_teams = (int64_t)grid * teams_per_cta;
     if (tbound > ((int64_t)1 << 24))
         return set_err(ctx, VLR_ERR_UNSUPPORTED, "likelihood table of %lld entries per site is too large", (long long)tbound);
+    const bool has_prior = model->prior_ln != nullptr;
+    if (has_prior) {
+        if (H.any_range_path)
+            return set_err(ctx, VLR_ERR_UNSUPPORTED, "a prior table needs every tree path to bind VAF sets only "
+                                                     "(grid points of a Range depend on the site's depth)");
+        if (model->n_prior != H.n_leaves)
+            return set_err(ctx, VLR_ERR_INVALID, "prior table has %lld entries, the model has %lld leaves",
+                           (long long)model->n_prior, (long long)H.n_leaves);
+    }
     enum { S_MODEL = 16, S_TABLE, S_CNT };
     // model blob
     const size_t b_spec = H.spectra.size() * sizeof(DevSpectrum), b_path = H.paths.size() * sizeof(DevPath),
                  b_ev = H.events.size() * sizeof(DevEvent), b_eb = H.eb.size() * sizeof(DevEventBias),
-                 b_cfg = H.cfg.size() * sizeof(vlr_biases), b_vaf = H.vafs.size() * sizeof(double);
-    size_t off[7];
+                 b_cfg = H.cfg.size() * sizeof(vlr_biases), b_vaf = H.vafs.size() * sizeof(double),
+                 b_seg = H.segs.size() * sizeof(DevSeg), b_pri = has_prior ? (size_t)H.n_leaves * 8 : 0;
+    size_t off[9];
     off[0] = 0;
     off[1] = align_up(off[0] + b_spec, 16);
     off[2] = align_up(off[1] + b_path, 16);
@@ -1181,9 +1264,11 @@ int vlr_posterior_batch_dev(vlr_ctx *ctx, int64_t n_sites, const vlr_model *mode
     off[4] = align_up(off[3] + b_eb, 16);
     off[5] = align_up(off[4] + b_cfg, 16);
     off[6] = align_up(off[5] + b_vaf, 16);
-    uint8_t *h_blob = (uint8_t *)pin_scratch(ctx, 4, off[6] + 16);
-    uint8_t *d_blob = (uint8_t *)dev_scratch(ctx, S_MODEL, off[6] + 16);
-    double *d_table = (double *)dev_scratch(ctx, S_TABLE, (size_t)(n_teams * tbound + 8) * sizeof(double));
+    off[7] = align_up(off[6] + b_seg, 16);
+    off[8] = align_up(off[7] + b_pri, 16);
+    uint8_t *h_blob = (uint8_t *)pin_scratch(ctx, 4, off[8] + 16);
+    uint8_t *d_blob = (uint8_t *)dev_scratch(ctx, S_MODEL, off[8] + 16);
+    double *d_table = (double *)dev_scratch(ctx, S_TABLE, (size_t)((tab_cap ? 0 : n_teams * tbound) + 8) * sizeof(double));
     int32_t *d_cnt = (int32_t *)dev_scratch(ctx, S_CNT, 256);
     if (!h_blob || !d_blob || !d_table || !d_cnt) return set_err(ctx, VLR_ERR_NOMEM, "scratch allocation failed");
     // the pinned blob may still be in flight from a previous call on this stream
@@ -1194,7 +1279,9 @@ int vlr_posterior_batch_dev(vlr_ctx *ctx, int64_t n_sites, const vlr_model *mode
     memcpy(h_blob + off[3], H.eb.data(), b_eb);
     memcpy(h_blob + off[4], H.cfg.data(), b_cfg);
     memcpy(h_blob + off[5], H.vafs.data(), b_vaf);
-    VLR_CUDA(ctx, cudaMemcpyAsync(d_blob, h_blob, off[6], cudaMemcpyHostToDevice, st));
+    memcpy(h_blob + off[6], H.segs.data(), b_seg);
+    if (has_prior) memcpy(h_blob + off[7], model->prior_ln, b_pri);
+    VLR_CUDA(ctx, cudaMemcpyAsync(d_blob, h_blob, off[8], cudaMemcpyHostToDevice, st));
     VLR_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, 256, st));
     PostArgs a;
     memset(&a, 0, sizeof(a));
@@ -1217,6 +1304,9 @@ int vlr_posterior_batch_dev(vlr_ctx *ctx, int64_t n_sites, const vlr_model *mode
     a.m.eb = (const DevEventBias *)(d_blob + off[3]);
     a.m.cfg = (const vlr_biases *)(d_blob + off[4]);
     a.m.vafs = (const double *)(d_blob + off[5]);
+    a.m.segs = (const DevSeg *)(d_blob + off[6]);
+    a.m.n_segs = (int)H.segs.size();
+    a.m.prior = has_prior ? (const double *)(d_blob + off[7]) : nullptr;
     a.obs = *d_obs;
     a.obs_off = d_obs_off;
     a.n_sites = n_sites;
@@ -1230,6 +1320,7 @@ int vlr_posterior_batch_dev(vlr_ctx *ctx, int64_t n_sites, const vlr_model *mode
     a.out_map_bias = d_out_map_bias;
     a.obs_cap = obs_cap;
     a.gs_cap = gs_cap;
+    a.tab_cap = tab_cap;
     if (big) {
         VLR_CUDA(ctx, cudaFuncSetAttribute(posterior_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
         posterior_kernel<4><<<grid, kTeamThreadsMax, dyn_smem, st>>>(a);
@@ -1238,6 +1329,38 @@ int vlr_posterior_batch_dev(vlr_ctx *ctx, int64_t n_sites, const vlr_model *mode
         posterior_kernel<1><<<grid, kTeamThreadsMax, dyn_smem, st>>>(a);
     }
     VLR_LAUNCH_CHECK(ctx);
+    return VLR_OK;
+}
+
+int vlr_model_leaves(vlr_ctx *ctx, const vlr_model *model, int64_t capacity, int64_t *out_n_leaves,
+                     int32_t *out_event, double *out_afs) {
+    if (!ctx) return VLR_ERR_INVALID;
+    if (!model || !out_n_leaves) return set_err(ctx, VLR_ERR_INVALID, "bad argument");
+    HostModel H;
+    int rc = flatten_model(ctx, model, H);
+    if (rc != VLR_OK) return rc;
+    if (H.any_range_path)
+        return set_err(ctx, VLR_ERR_UNSUPPORTED, "leaves are enumerable only when every tree path binds VAF sets");
+    *out_n_leaves = H.n_leaves;
+    if (!out_event && !out_afs) return VLR_OK;
+    if (capacity < H.n_leaves) return set_err(ctx, VLR_ERR_INVALID, "capacity %lld < %lld leaves", (long long)capacity, (long long)H.n_leaves);
+    const int NS = model->n_samples;
+    for (int e = 0; e < model->n_events; ++e)
+        for (int pth = 0; pth < H.events[e].n_paths; ++pth) {
+            const int pi = H.events[e].path_off + pth;
+            int64_t combos = 1;
+            for (int smp = 0; smp < NS; ++smp) combos *= H.spectra[H.paths[pi].spec[smp]].n_vafs;
+            for (int64_t combo = 0; combo < combos; ++combo) {
+                const int64_t leaf = H.path_leaf_off[pi] + combo;
+                if (out_event) out_event[leaf] = e;
+                int64_t rem = combo;
+                for (int smp = NS - 1; smp >= 0; --smp) {  // LAST sample is the fastest digit
+                    const DevSpectrum &sp = H.spectra[H.paths[pi].spec[smp]];
+                    if (out_afs) out_afs[leaf * NS + smp] = H.vafs[sp.vaf_off + rem % sp.n_vafs];
+                    rem /= sp.n_vafs;
+                }
+            }
+        }
     return VLR_OK;
 }
 

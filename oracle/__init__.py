@@ -343,9 +343,14 @@ class ModelSpec:
                        len(flat_biases))
 
 
-def model_compute(spec, pileup_views):
-    """Returns dict(event_ln, marginal, map_af, map_bias, n_evals, status)."""
+PRIOR_FN = C.CFUNCTYPE(C.c_double, C.POINTER(C.c_double), C.c_int, C.c_void_p)
+
+
+def model_compute(spec, pileup_views, prior=None):
+    """Returns dict(event_ln, marginal, map_af, map_bias, n_evals, status).
+    prior: optional callable(list of allele frequencies) -> ln prior (Prior::compute)."""
     ns = spec.n_samples
+    cb = PRIOR_FN(lambda afs, n, _u: float(prior([afs[k] for k in range(n)]))) if prior else None
     arr = (Pileup * ns)(*[pv.c for pv in pileup_views])
     ev = np.zeros(len(spec.events_py), np.float64)
     marg = C.c_double()
@@ -354,6 +359,6 @@ def model_compute(spec, pileup_views):
     ne = C.c_int64()
     st = lib().vlro_model_compute(C.byref(spec.c), arr, ev.ctypes.data_as(_DP), C.byref(marg),
                                   maf.ctypes.data_as(_DP), mb.ctypes.data_as(_I32P), C.byref(ne),
-                                  None, None)
+                                  C.cast(cb, C.c_void_p) if cb else None, None)
     return dict(event_ln=ev, marginal=marg.value, map_af=maf, map_bias=mb, n_evals=ne.value,
                 status=st)

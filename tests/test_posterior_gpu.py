@@ -197,3 +197,51 @@ def test_posterior_errors_are_loud(ctx):
     cols, cat, off, _ = synth.make_pileups(2, [10], seed=1)
     with pytest.raises(P.VlrError):
         ctx.posterior_batch(bad, cols, cat, off)
+
+
+def _mendel_prior(afs, het=0.001):
+    """Pedigree-shaped prior over diploid genotypes (child, father, mother): population prior of
+    the parents and Mendelian transmission to the child -- a stand-in for Prior::compute
+    (prior.rs:288-431, 674-786); what matters here is that it is a non-flat, AF-vector dependent
+    ln prior evaluated by the host."""
+    def pop(a):
+        return {0.0: math.log(1 - 1.5 * het), 0.5: math.log(het), 1.0: math.log(0.5 * het)}[a]
+
+    def gam(a):
+        return {0.0: (1.0, 0.0), 0.5: (0.5, 0.5), 1.0: (0.0, 1.0)}[a]
+    c, f, m = afs
+    pf, pm = gam(f), gam(m)
+    n_alt = int(round(2 * c))
+    p = sum(pf[i] * pm[j] for i in range(2) for j in range(2) if i + j == n_alt)
+    p = 0.999 * p + 0.001 / 3.0  # de-novo mass keeps every genotype possible
+    return pop(f) + pop(m) + math.log(p)
+
+
+def test_trio_with_prior_table(ctx, oracle):
+    """Non-flat prior: the host evaluates its Prior for the leaves vlr_model_leaves reports and
+    passes the table; event posteriors and MAP genotypes must follow the oracle's callback."""
+    scn = dict(scenario.trio(with_biases=True))
+    ev, afs = ctx.model_leaves(scn)
+    assert len(ev) == 1 + 2 * (9 + 9 + 1) and afs.shape[1] == 3  # absent + (event, artifact event) x leaves
+    scn["prior_ln"] = np.array([_mendel_prior(list(a)) for a in afs])
+    cols, cat, off, _ = synth.make_pileups(96, [25, 30, 20], seed=5150, kind="snv",
+                                           af_sets=[[(0, .5), (.5, .35), (1, .15)]] * 3, ragged=True,
+                                           artifact_frac=0.05)
+    got = ctx.posterior_batch(scn, cols, cat, off)
+    flat = ctx.posterior_batch({k: v for k, v in scn.items() if k != "prior_ln"}, cols, cat, off)
+    assert np.nanmax(np.abs(got["event_ln"] - flat["event_ln"])) > 1.0  # the prior does matter
+    spec = _oracle_spec(oracle, scn)
+    for s in range(96):
+        pv = [oracle.PileupView(cols, cat, int(off[s * 3 + k]), int(off[s * 3 + k + 1])) for k in range(3)]
+        w = oracle.model_compute(spec, pv, prior=_mendel_prior)
+        _close(got["event_ln"][s], w["event_ln"])
+        _close(got["marginal"][s], w["marginal"])
+        assert np.array_equal(got["map_af"][s], w["map_af"], equal_nan=True), (s, got["map_af"][s], w["map_af"])
+
+
+def test_prior_table_rejected_for_ranges(ctx):
+    scn = dict(scenario.single_sample(continuous=True))
+    scn["prior_ln"] = np.zeros(4)
+    cols, cat, off, _ = synth.make_pileups(4, [10], seed=1, kind="snv")
+    with pytest.raises(P.VlrError):
+        ctx.posterior_batch(scn, cols, cat, off)
