@@ -563,18 +563,22 @@ __global__ void __launch_bounds__(kWarps * 32, Occ<R>::kMinBlocks) pairhmm_kerne
 constexpr int kLongR = 8;
 constexpr int kStripRows = 31 * kLongR;
 
-template <bool APPROX, bool EXT, typename A>
+template <bool APPROX, bool EXT, bool LUT, typename A>
 __global__ void __launch_bounds__(kWarps * 32, 2) pairhmm_long_kernel(HmmArgs g) {
+    static_assert(!LUT || !A::kLog, "the emission LUT exists in scaled linear space only");
     constexpr int R = kLongR;
     __shared__ __align__(128) uint8_t s_hap[kWarps][kRing];
     __shared__ __align__(8) uint64_t s_bar[kWarps][2];
     __shared__ double s_bnd[kWarps][3][32];
+    __shared__ __align__(16) double s_lut[kWarps][LUT ? R * kLutCols * 32 : 1];
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     HapRing h;
     h.ring = s_hap[warp];
     h.bar = s_bar[warp];
+    double *lut = s_lut[warp] + (LUT ? lane : 0);
+    if (LUT) reinterpret_cast<uint4 *>(h.ring)[lane] = make_uint4(0, 0, 0, 0);  // valid codes everywhere
     if (lane == 0) {
         mbar_init(&h.bar[0], 1);
         mbar_init(&h.bar[1], 1);
@@ -604,6 +608,19 @@ __global__ void __launch_bounds__(kWarps * 32, 2) pairhmm_long_kernel(HmmArgs g)
             if (lane == 0) g.out[pair] = lx > g.long_stride ? NAN : -INFINITY;
             continue;
         }
+        if (LUT) {
+            // a read base outside ACGT cannot be expressed by the 5-column LUT: such pairs (rare in
+            // long reads) take the byte-compare log-space instantiation
+            bool odd_base = false;
+            for (int j = lane; j < ly; j += 32) odd_base |= base_code1(g.rbase[ro + j]) == 4;
+            if (__any_sync(0xffffffffu, odd_base)) {
+                if (lane == 0) {
+                    g.fb_list[atomicAdd(g.fb_count, 1)] = pair;
+                    g.out[pair] = NAN;
+                }
+                continue;
+            }
+        }
         const int shift = (int)((uintptr_t)(g.hap + ho) & 15);
         h.hsrc = g.hap + ho - shift;
         h.lxs = lx + shift;
@@ -626,6 +643,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) pairhmm_long_kernel(HmmArgs g)
             __syncwarp();
             if (lane == 0) {
                 const uint32_t bytes = (uint32_t)min(kChunk, (h.lxs + 15) & ~15);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_expect_tx(&h.bar[0], bytes);
                 tma_load_1d(h.ring, h.hsrc, bytes, &h.bar[0]);
             }
@@ -635,7 +653,8 @@ __global__ void __launch_bounds__(kWarps * 32, 2) pairhmm_long_kernel(HmmArgs g)
                 const int j = j0 + lane * R + r;
                 if (lane * R + r < ns) {
                     const int q = g.rqual[ro + j];
-                    s.rb[r] = g.rbase[ro + j];
+                    const int b = g.rbase[ro + j];
+                    s.rb[r] = LUT ? base_code1(b) : b;
                     if (A::kLog) {
                         const double ln_eps = (double)q * -0.23025850929940456;
                         s.pm[r] = g.qlut[q * kQlutStride + 3];
@@ -646,7 +665,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) pairhmm_long_kernel(HmmArgs g)
                         const double eps = g.qlut[q * kQlutStride + 0];
                         s.pm[r] = g.qlut[q * kQlutStride + 1];
                         s.pmm[r] = g.qlut[q * kQlutStride + 2];
-                        s.cyo[r] = eps * c.t_gx;
+                        s.cyo[r] = eps * (LUT ? c.t_gx_s : c.t_gx);
                         s.cye[r] = eps * c.t_gxe;
                     }
                 } else {
@@ -656,10 +675,20 @@ __global__ void __launch_bounds__(kWarps * 32, 2) pairhmm_long_kernel(HmmArgs g)
                 s.M[r] = s.X[r] = s.Y[r] = A::zero();
                 s.med[r] = kMedMax;
             }
+            if (LUT) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const double em = s.pm[r] * c.t_mm, emm = s.pmm[r] * c.t_mm;
+#pragma unroll
+                    for (int k = 0; k < kLutCols; ++k) lut[(r * kLutCols + k) * 32] = k == s.rb[r] ? em : emm;
+                }
+            }
             s.bM = s.bX = s.bY = A::zero();
-            s.dM = (lane == 0 && strip == 0) ? A::one() : A::zero();
+            s.one0 = (lane == 0 && strip == 0) ? (LUT ? c.one_s : A::one()) : A::zero();
+            s.dM = s.one0;
             s.dX = s.dY = A::zero();
             s.acc = A::zero();
+            s.acc2 = A::zero();
             double bmax = A::zero();
             // prefetch registers for the incoming boundary chunk (columns t .. t+31)
             double pfM = A::zero(), pfX = A::zero(), pfY = A::zero();
@@ -668,6 +697,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) pairhmm_long_kernel(HmmArgs g)
             }
             mbar_wait(&h.bar[0], h.parity0);
             h.parity0 ^= 1;
+            if (LUT) encode_chunk(h.ring, lane);
             const int T = lx + last_lane;
             const int src = (lane + 31) & 31;
             for (int t = 0; t < T; ++t) {
@@ -680,6 +710,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) pairhmm_long_kernel(HmmArgs g)
                         const int off = cnext * kChunk;
                         const uint32_t bytes = (uint32_t)min(kChunk, ((h.lxs - off) + 15) & ~15);
                         uint64_t *b = &h.bar[cnext & 1];
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         mbar_expect_tx(b, bytes);
                         tma_load_1d(h.ring + (cnext & 1) * kChunk, h.hsrc + off, bytes, b);
                     }
@@ -688,6 +719,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) pairhmm_long_kernel(HmmArgs g)
                     if (cidx < h.n_chunks) {
                         if (cidx & 1) { mbar_wait(&h.bar[1], h.parity1); h.parity1 ^= 1; }
                         else { mbar_wait(&h.bar[0], h.parity0); h.parity0 ^= 1; }
+                        if (LUT) encode_chunk(h.ring + (cidx & 1) * kChunk, lane);
                     }
                 }
                 // ---- incoming boundary chunk: registers -> shared, prefetch the next one
@@ -705,7 +737,10 @@ __global__ void __launch_bounds__(kWarps * 32, 2) pairhmm_long_kernel(HmmArgs g)
                 }
                 const int i = t - lane;
                 int xb = h.ring[(i + shift) & (kRing - 1)];
-                if ((unsigned)(xb - 'a') < 26u) xb -= 32;
+                if (!LUT) {
+                    if ((unsigned)(xb - 'a') < 26u) xb -= 32;
+                }
+                const double *lcol = lut + xb * 32;
                 double uM = __shfl_sync(0xffffffffu, s.bM, src);
                 double uX = __shfl_sync(0xffffffffu, s.bX, src);
                 double uY = __shfl_sync(0xffffffffu, s.bY, src);
@@ -718,25 +753,31 @@ __global__ void __launch_bounds__(kWarps * 32, 2) pairhmm_long_kernel(HmmArgs g)
                 double diagM = s.dM, diagX = s.dX, diagY = s.dY, upM = uM, upY = uY;
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    const bool match = xb == s.rb[r];
-                    const double e = match ? s.pm[r] : s.pmm[r];
-                    const double nM = A::mul(e, A::template sum3<APPROX, EXT>(c, diagM, diagX, diagY));
-                    const double nX = A::template dot2<EXT>(c.t_gy, s.M[r], c.t_gye, s.X[r]);
+                    double e;
+                    if (LUT) e = lcol[r * (kLutCols * 32)];
+                    else e = xb == s.rb[r] ? s.pm[r] : s.pmm[r];
+                    const double nM = A::mul(e, A::template sum3<APPROX, EXT, LUT>(c, diagM, diagX, diagY));
+                    const double nX = A::template dot2<EXT>(LUT ? c.t_gy_s : c.t_gy, s.M[r], c.t_gye, s.X[r]);
                     const double nY = A::template dot2<EXT>(s.cyo[r], upM, s.cye[r], upY);
                     diagM = s.M[r]; diagX = s.X[r]; diagY = s.Y[r];
                     s.M[r] = nM; s.X[r] = nX; s.Y[r] = nY;
                     upM = nM; upY = nY;
                 }
-                s.dM = (lane == 0 && strip == 0) ? A::one() : uM;
+                if (A::kLog) s.dM = (lane == 0 && strip == 0) ? A::one() : uM;
+                else s.dM = uM + s.one0;
                 s.dX = uX;
                 s.dY = uY;
                 s.bM = s.M[R - 1]; s.bX = s.X[R - 1]; s.bY = s.Y[R - 1];
                 if (last_strip) {
-                    double tsum = A::zero();
+                    double tsum = A::zero(), tm = A::zero();
 #pragma unroll
                     for (int r = 0; r < R; ++r)
-                        if (r == last_r) tsum = A::add(A::add(s.M[r], s.X[r]), s.Y[r]);
-                    s.acc = A::add(s.acc, tsum);
+                        if (r == last_r) {
+                            if (LUT) { tm = s.M[r]; tsum = s.X[r] + s.Y[r]; }
+                            else tsum = A::add(A::add(s.M[r], s.X[r]), s.Y[r]);
+                        }
+                    if (LUT) { s.acc += tm; s.acc2 += tsum; }
+                    else s.acc = A::add(s.acc, tsum);
                 } else if (lane == 30 && (unsigned)i < (unsigned)lx) {
                     // full strip: lane 30 holds its last row; hand it to the next strip
                     __stcg(&bout[i], s.bM); __stcg(&bout[g.long_stride + i], s.bX); __stcg(&bout[2 * g.long_stride + i], s.bY);
@@ -745,6 +786,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) pairhmm_long_kernel(HmmArgs g)
             }
             if (last_strip) {
                 acc = __shfl_sync(0xffffffffu, s.acc, last_lane);
+                if (LUT) acc = fma(acc, c.inv_tmm, __shfl_sync(0xffffffffu, s.acc2, last_lane));
             } else if (!A::kLog) {
                 // renormalise: bring the largest boundary value back to 2^960
                 bmax = __shfl_sync(0xffffffffu, bmax, 30);
@@ -797,9 +839,9 @@ inline int blocks_per_sm(int dflt) {
     cudaError_t launch_pairhmm_long<APPROX>(bool ext, bool log_space, const HmmArgs &a,           \
                                             int sm_count, cudaStream_t st) {                      \
         const int grid = sm_count * kLongBlocksPerSm;                                             \
-        if (log_space) pairhmm_long_kernel<APPROX, true, Log><<<grid, kWarps * 32, 0, st>>>(a);   \
-        else if (ext) pairhmm_long_kernel<APPROX, true, Lin><<<grid, kWarps * 32, 0, st>>>(a);    \
-        else pairhmm_long_kernel<APPROX, false, Lin><<<grid, kWarps * 32, 0, st>>>(a);            \
+        if (log_space) pairhmm_long_kernel<APPROX, true, false, Log><<<grid, kWarps * 32, 0, st>>>(a); \
+        else if (ext) pairhmm_long_kernel<APPROX, true, true, Lin><<<grid, kWarps * 32, 0, st>>>(a);   \
+        else pairhmm_long_kernel<APPROX, false, true, Lin><<<grid, kWarps * 32, 0, st>>>(a);           \
         return cudaGetLastError();                                                                \
     }
 
