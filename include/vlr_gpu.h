@@ -291,6 +291,41 @@ int vlr_posterior_batch_dev(vlr_ctx *ctx, int64_t n_sites, const vlr_model *mode
                             int32_t max_obs_per_pileup, double *d_out_event_ln,
                             double *d_out_marginal, double *d_out_map_af, int32_t *d_out_map_bias);
 
+/* ---- observation wire format: the INFO fields between `preprocess` and `call` -------------
+ * Replaces read_observations / write_observations (src/calling/variants/preprocessing/mod.rs:
+ * 452-598, OBSERVATION_FORMAT_VERSION "8"; format 7 = the same without INDEL_OPERATIONS) and
+ * MiniLogProb (src/utils/mod.rs:381-407).  Each field is the BCF INFO integer vector of one
+ * record (bincode bytes as u16 little endian); fields are indexed by VLR_OBS_*.  Host functions,
+ * no context needed. */
+#define VLR_OBS_PROB_MAPPING 0
+#define VLR_OBS_PROB_REF 1
+#define VLR_OBS_PROB_ALT 2
+#define VLR_OBS_PROB_MISSED_ALLELE 3
+#define VLR_OBS_PROB_SAMPLE_ALT 4
+#define VLR_OBS_PROB_DOUBLE_OVERLAP 5
+#define VLR_OBS_PROB_HIT_BASE 6
+#define VLR_OBS_STRAND 7
+#define VLR_OBS_READ_ORIENTATION 8
+#define VLR_OBS_READ_POSITION 9
+#define VLR_OBS_SOFTCLIPPED 10
+#define VLR_OBS_INDEL_OPERATIONS 11
+#define VLR_OBS_PAIRED 12
+#define VLR_OBS_N_FIELDS 13
+/* Decode one record into rows of the observation columns: out_cols[0..8] are the nine column
+ * pointers in vlr_obs_columns order (already advanced to the record's first row), out_cat the
+ * packed categoricals.  prob_mismapping / prob_single_overlap are derived as ObservationBuilder
+ * does (observation.rs:218-226).  fields[VLR_OBS_INDEL_OPERATIONS] may be NULL (format 7):
+ * IndelOperations::None.  With out_cols == NULL and out_cat == NULL only *out_n_obs is set. */
+int vlr_obs_decode(const int32_t *const *fields, const int32_t *n_values, int64_t capacity,
+                   int64_t *out_n_obs, double *const *out_cols, uint16_t *out_cat);
+/* Encode n_obs rows (cols[0..8] in vlr_obs_columns order; the derived columns 1 and 7 are not
+ * read) as format 8: each out_fields[f] receives at most `capacity` values
+ * (vlr_obs_encoded_bound(n_obs) suffices), out_n_values[f] their count.  Applies
+ * MiniLogProb::new (f16 iff p < -10 and the f16 value keeps the integer part, else f32). */
+int64_t vlr_obs_encoded_bound(int64_t n_obs);
+int vlr_obs_encode(int64_t n_obs, const double *const *cols, const uint16_t *cat,
+                   int32_t *const *out_fields, int64_t capacity, int32_t *out_n_values);
+
 #ifdef __cplusplus
 }
 #endif

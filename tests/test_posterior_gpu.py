@@ -245,3 +245,30 @@ def test_prior_table_rejected_for_ranges(ctx):
     cols, cat, off, _ = synth.make_pileups(4, [10], seed=1, kind="snv")
     with pytest.raises(P.VlrError):
         ctx.posterior_batch(scn, cols, cat, off)
+
+
+@pytest.mark.parametrize("snv", [True, False])
+@pytest.mark.parametrize("continuous", [True, False])
+def test_real_pileups_from_reference_records(ctx, oracle, snv, continuous):
+    """Part 2 on REAL observation records (written by the reference's `preprocess`, extracted from
+    its testcases into tests/golden/obs_records.json and decoded by the library's codec): GPU
+    posteriors, marginals and MAP allele frequencies against the oracle."""
+    import json
+    import os
+    from libprosic_b200 import obs_codec as lc
+    recs = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "obs_records.json")))
+    names = lc.COLUMNS
+    parts = {c: [] for c in names}
+    cats, off = [], [0]
+    for r in recs:
+        cols, cat = lc.decode_record(r["fields"])
+        for c in names:
+            parts[c].append(cols[c])
+        cats.append(cat)
+        off.append(off[-1] + len(cat))
+    cols = {c: np.concatenate(parts[c]) for c in names}
+    scn = scenario.single_sample(continuous=continuous, snv=snv)
+    got, want = _check(ctx, oracle, scn, cols, np.concatenate(cats), np.array(off, np.int64))
+    # the records are real calls: most sites must put their mass on a present-variant event
+    present = sum(1 for w in want if np.argmax(w["event_ln"]) != 0)
+    assert present >= len(recs) // 2
