@@ -291,6 +291,20 @@ int vlr_posterior_batch_dev(vlr_ctx *ctx, int64_t n_sites, const vlr_model *mode
                             int32_t max_obs_per_pileup, double *d_out_event_ln,
                             double *d_out_marginal, double *d_out_map_af, int32_t *d_out_map_bias);
 
+/* ---- values of the final call record: replaces the numeric part of the BCF writer of
+ *      `varlociraptor call` (src/calling/variants/mod.rs:99-399, calling.rs:573-602).
+ * event_is_artifact[e] marks the artifact twin of an event (model::Event::is_artifact); the
+ * output has one column per non-artifact event, in order, plus a final "artifact" column:
+ *   out_prob[s*(n_named+1) + k]  PROB_<EVENT> = |PHRED(posterior)| as f32 (mod.rs:326-333); BCF
+ *                                float-missing bits when every pileup of the site is empty
+ *   out_af[s*n_samples + m]      AF as f32 (mod.rs:185)
+ *   out_dp[s*n_samples + m]      DP = round(exp(ln_sum_exp(prob_mapping))) (observation.rs:31-36)
+ * Inputs are the outputs of vlr_posterior_batch and the prob_mapping column (host buffers). */
+int vlr_call_records(vlr_ctx *ctx, int64_t n_sites, int32_t n_events, int32_t n_samples,
+                     const uint8_t *event_is_artifact, const double *event_ln,
+                     const double *marginal, const double *map_af, const double *prob_mapping,
+                     const int64_t *obs_off, float *out_prob, float *out_af, int32_t *out_dp);
+
 /* ---- observation wire format: the INFO fields between `preprocess` and `call` -------------
  * Replaces read_observations / write_observations (src/calling/variants/preprocessing/mod.rs:
  * 452-598, OBSERVATION_FORMAT_VERSION "8"; format 7 = the same without INDEL_OPERATIONS) and

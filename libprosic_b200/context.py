@@ -238,6 +238,28 @@ class Context:
                      prior.ctypes.data if prior is not None else None,
                      len(prior) if prior is not None else 0)
 
+    def call_records(self, scn, post, prob_mapping, obs_off):
+        """BCF values of the call records: dict(prob[n_sites, n_named + 1] f32 PHRED, af f32, dp i32,
+        names).  post = the dict posterior_batch returned."""
+        is_art = np.array([any(scn["biases"][b][k] for k in ("strand", "orientation", "read_position",
+                                                             "softclip", "divindel"))
+                           for b in (ev["biases"][0] for ev in scn["events"])], np.uint8)
+        ev = np.ascontiguousarray(post["event_ln"], np.float64)
+        n_sites, ne = ev.shape
+        ns = scn["n_samples"]
+        marg = np.ascontiguousarray(post["marginal"], np.float64)
+        maf = np.ascontiguousarray(post["map_af"], np.float64)
+        pm = np.ascontiguousarray(prob_mapping, np.float64)
+        off = np.ascontiguousarray(obs_off, np.int64)
+        n_named = int((is_art == 0).sum())
+        prob = np.empty((n_sites, n_named + 1), np.float32)
+        af = np.empty((n_sites, ns), np.float32)
+        dp = np.empty((n_sites, ns), np.int32)
+        self._check(self.lib.vlr_call_records(self.h, n_sites, ne, ns, _ptr(is_art), _ptr(ev), _ptr(marg),
+                                              _ptr(maf), _ptr(pm), _ptr(off), _ptr(prob), _ptr(af), _ptr(dp)))
+        names = [e["name"] for e, a in zip(scn["events"], is_art) if not a] + ["artifact"]
+        return dict(prob=prob, af=af, dp=dp, names=names)
+
     def model_leaves(self, scn):
         """Leaf AF vectors of a set-only scenario: (event index per leaf, afs[n_leaves, n_samples])."""
         keep = []

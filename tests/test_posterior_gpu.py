@@ -272,3 +272,35 @@ def test_real_pileups_from_reference_records(ctx, oracle, snv, continuous):
     # the records are real calls: most sites must put their mass on a present-variant event
     present = sum(1 for w in want if np.argmax(w["event_ln"]) != 0)
     assert present >= len(recs) // 2
+
+
+def test_call_record_values(ctx, oracle):
+    """PROB_* (PHRED f32), AF (f32) and DP of the final call record (calling/variants/mod.rs:185-187,
+    309-333): bit-identical f32 / int values for the same posterior outputs, float-missing for
+    sites without observations."""
+    from oracle import call_records as ocr
+    scn = scenario.tumor_normal(purity=0.75, indel=True)
+    cols, cat, off, _ = synth.make_pileups(64, [12, 25], seed=99, kind="indel", ragged=True,
+                                           af_sets=[[(0, .6), (.5, .4)], [(0, .4), (.3, .6)]], purity=[1.0, 0.75])
+    off = off.copy()
+    post = ctx.posterior_batch(scn, cols, cat, off)
+    got = ctx.call_records(scn, post, cols["prob_mapping"], off)
+    assert got["names"] == ["absent", "somatic_tumor", "somatic_normal", "germline_het", "germline_hom", "artifact"]
+    is_art = [any(scn["biases"][b][k] for k in ("strand", "orientation", "read_position", "softclip", "divindel"))
+              for b in (ev["biases"][0] for ev in scn["events"])]
+    n_missing = 0
+    for s in range(64):
+        pms = [cols["prob_mapping"][off[s * 2 + m]:off[s * 2 + m + 1]] for m in range(2)]
+        prob, af, dp = ocr.call_record(post["event_ln"][s], post["marginal"][s], post["map_af"][s], is_art, pms)
+        assert np.array_equal(got["dp"][s], dp), (s, got["dp"][s], dp)
+        assert np.array_equal(got["af"][s].view(np.uint32), af.view(np.uint32)), s
+        if all(len(p) == 0 for p in pms):
+            n_missing += 1
+            assert (got["prob"][s].view(np.uint32) == 0x7F800001).all(), s
+            continue
+        # f32 rounding of values that agree to 1e-13: allow the last f32 bit
+        a, b = got["prob"][s].astype(np.float64), prob.astype(np.float64)
+        fin = np.isfinite(b)
+        assert np.array_equal(np.isfinite(a), fin), s
+        assert np.all(np.abs(a[fin] - b[fin]) <= 1.2e-7 * np.maximum(1.0, np.abs(b[fin]))), (s, a, b)
+    assert np.mean(got["prob"][np.isfinite(got["prob"])] >= 0) == 1.0
