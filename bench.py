@@ -126,7 +126,7 @@ def cpu_sample(w, n_pairs, threads, flags):
             run(k)
     else:
         with ThreadPoolExecutor(max_workers=threads) as ex:  # ctypes releases the GIL
-            list(ex.map(run, range(n_pairs), chunksize=8))
+            list(ex.map(run, range(n_pairs), chunksize=4))
     dt = time.perf_counter() - t0
     cells = sum(int(ho[int(h) + 1] - ho[int(h)]) * int(ro[int(r) + 1] - ro[int(r)])
                 for h, r in zip(ph, pr))
@@ -141,11 +141,12 @@ def run_reference(args, rank, world):
     cores = os.cpu_count() or 1
     flags = 0 if args.exact_sum else 1
     small = argparse.Namespace(**vars(args))
-    small.sites, small.reads_per_site = 8, 140
+    small.sites, small.reads_per_site = 256, 140   # 71 680 pairs of the headline workload's shape
     w = gen_workload(small, 0)
-    # calibrate the per-step sample to ~3 s on all cores
-    g, dt, _ = cpu_sample(w, 64, cores, flags)
-    per_step = int(max(64, min(len(w["pair_hap"]), 64 * 3.0 / max(dt, 1e-3))))
+    # calibrate the per-step sample to ~5 s on all cores
+    probe = min(len(w["pair_hap"]), cores * 48)
+    g, dt, _ = cpu_sample(w, probe, cores, flags)
+    per_step = int(max(probe, min(len(w["pair_hap"]), probe * 5.0 / max(dt, 1e-3))))
     for _ in range(max(args.warmup, 0) and 1):
         cpu_sample(w, per_step, cores, flags)
     tot_cells, tot_t = 0, 0.0
