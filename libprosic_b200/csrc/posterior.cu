@@ -30,6 +30,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -65,6 +66,7 @@ struct DevEvent {
     int32_t is_artifact;
     int32_t path_off, n_paths;
     int32_t eb_off, n_eb;
+    int32_t seg_off, n_seg;  // the event's (bias, path) segments in DevModel::segs
     double bias_prior;  // ln .5 (+ ln 1/|biases| for artifact events), generic.rs:251-255
 };
 
@@ -96,6 +98,7 @@ struct PostArgs {
     int32_t obs_cap;        // observations per (site, sample) the shared staging can hold
     int64_t gs_cap;         // doubles of per-team shared memory for the blocked contaminated path
     int64_t tab_cap;        // doubles of per-team shared memory for the likelihood table (0: global)
+    int32_t seg_cap;        // ints of per-team shared memory for the segment sizes (n_segs, padded)
 };
 __device__ __forceinline__ int m_ncfg_cap(const PostArgs &g) { return g.m.n_cfg; }
 
@@ -396,13 +399,14 @@ __global__ void __launch_bounds__(kTeamThreadsMax, 3) posterior_kernel(PostArgs 
     const int obs_cap = g.obs_cap;
     const size_t per_team = (size_t)obs_cap * sizeof(double4) +
                             (size_t)obs_cap * m_ncfg_cap(g) * sizeof(double) +
-                            (size_t)(g.gs_cap + g.tab_cap) * sizeof(double);
+                            (size_t)(g.gs_cap + g.tab_cap) * sizeof(double) + (size_t)g.seg_cap * sizeof(int);
     double4 *OC = (double4 *)(s_dyn + (size_t)team_in_cta * per_team);
     double *BC = (double *)(OC + obs_cap);
     double *GS = BC + (size_t)obs_cap * m_ncfg_cap(g);  // blocked contaminated path (may be empty)
     const int team_global = blockIdx.x * kTeamsPerCta + team_in_cta;
     // likelihood table of the site: shared memory when it fits, else per-team global scratch
     double *table = g.tab_cap ? GS + g.gs_cap : g.table + (int64_t)team_global * g.table_stride;
+    int *seg_cnt = (int *)(GS + g.gs_cap + g.tab_cap);  // grid combinations per segment (0 = gated out)
     __shared__ double s_part[kTeamsPerCta][TEAM][2][kMaxEvents];  // per-warp (max, sum) of every event
     const DevModel &m = g.m;
     const int NS = m.n_samples;
@@ -737,55 +741,61 @@ __global__ void __launch_bounds__(kTeamThreadsMax, 3) posterior_kernel(PostArgs 
                     }
                 }
             } else if (fast) {
-                // ---- 4b. unchecked direct evaluation: thread = (four primary values, secondary
-                // value, cfg); exponent extraction once per four observations
-                const int ng = (nv + 3) >> 2;
-                const int nitems = na * bynv * ng;
-                #pragma unroll 1
-                for (int q = tt; q < nitems; q += TT) {
-                    const int vg = q % ng, r = q / ng;
-                    const int vb = r % bynv, c = S.alist[r / bynv];
-                    double afm[4], afa[4];
-                    #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const double af = S.val[v0 + min(vg * 4 + k, nv - 1)];
-                        afm[k] = af == 1.0 ? 0.0 : af;
-                        afa[k] = af == 1.0 ? 1.0 : 0.0;
-                    }
-                    const double af_s = cont ? S.val[byv0 + vb] : 0.0;
-                    const double asm_ = af_s == 1.0 ? 0.0 : af_s, asa = af_s == 1.0 ? 1.0 : 0.0;
-                    const double rho1 = 1.0 - rho;
-                    const double *bc = BC + c;
-                    ProdBlock<4> P;
-                    P.init();
-                    int nren = 0;
-                    auto body = [&](int i) {
-                        const double4 oc = OC[i];
-                        const double bcA = bc[i * ncfg];
-                        const double z2 = cont ? rho1 * fma(asm_, oc.z, asa) : 0.0;
-                        #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            double z = fma(afm[k], oc.z, afa[k]);
-                            if (cont) z = fma(rho, z, z2);
-                            P.m[k] *= fma(1.0 - z, oc.x, fma(z, bcA, oc.y));
-                        }
-                    };
-                    int i = 0;
+                // ---- 4b. unchecked direct evaluation: thread = (NVB primary values, secondary
+                // value, cfg); exponent extraction once per four observations.  NVB = 4 amortises
+                // the shared-memory reads; small tables (few values) take NVB = 1 to fill the lanes.
+                auto direct = [&](auto nvb_tag) {
+                    constexpr int NVB = decltype(nvb_tag)::value;
+                    const int ng = (nv + NVB - 1) / NVB;
+                    const int nitems = na * bynv * ng;
                     #pragma unroll 1
-                    for (; i + 4 <= n; i += 4) {
-                        body(i); body(i + 1); body(i + 2); body(i + 3);
-                        P.renorm(); ++nren;
-                    }
-                    if (i < n) {
+                    for (int q = tt; q < nitems; q += TT) {
+                        const int vg = q % ng, r = q / ng;
+                        const int vb = r % bynv, c = S.alist[r / bynv];
+                        double afm[NVB], afa[NVB];
+                        #pragma unroll
+                        for (int k = 0; k < NVB; ++k) {
+                            const double af = S.val[v0 + min(vg * NVB + k, nv - 1)];
+                            afm[k] = af == 1.0 ? 0.0 : af;
+                            afa[k] = af == 1.0 ? 1.0 : 0.0;
+                        }
+                        const double af_s = cont ? S.val[byv0 + vb] : 0.0;
+                        const double asm_ = af_s == 1.0 ? 0.0 : af_s, asa = af_s == 1.0 ? 1.0 : 0.0;
+                        const double rho1 = 1.0 - rho;
+                        const double *bc = BC + c;
+                        ProdBlock<NVB> P;
+                        P.init();
+                        int nren = 0;
+                        auto body = [&](int i) {
+                            const double4 oc = OC[i];
+                            const double bcA = bc[i * ncfg];
+                            const double z2 = cont ? rho1 * fma(asm_, oc.z, asa) : 0.0;
+                            #pragma unroll
+                            for (int k = 0; k < NVB; ++k) {
+                                double z = fma(afm[k], oc.z, afa[k]);
+                                if (cont) z = fma(rho, z, z2);
+                                P.m[k] *= fma(1.0 - z, oc.x, fma(z, bcA, oc.y));
+                            }
+                        };
+                        int i = 0;
                         #pragma unroll 1
-                        for (; i < n; ++i) body(i);
-                        P.renorm(); ++nren;
+                        for (; i + 4 <= n; i += 4) {
+                            body(i); body(i + 1); body(i + 2); body(i + 3);
+                            P.renorm(); ++nren;
+                        }
+                        if (i < n) {
+                            #pragma unroll 1
+                            for (; i < n; ++i) body(i);
+                            P.renorm(); ++nren;
+                        }
+                        #pragma unroll
+                        for (int k = 0; k < NVB; ++k)
+                            if (vg * NVB + k < nv)
+                                tab[(int64_t)c * tcs + (int64_t)(vg * NVB + k) * bynv + vb] = P.finish(k, sum_m, nren);
                     }
-                    #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if (vg * 4 + k < nv)
-                            tab[(int64_t)c * tcs + (int64_t)(vg * 4 + k) * bynv + vb] = P.finish(k, sum_m, nren);
-                }
+                };
+                if (na * bynv * ((nv + 3) >> 2) >= TT) direct(std::integral_constant<int, 4>());
+                else direct(std::integral_constant<int, 1>());
             } else {
                 // ---- 4c. checked evaluation: every term is range-tested, terms outside the normal
                 // fp64 range (zero, subnormal, NaN) are recomputed in log space
@@ -831,7 +841,6 @@ __global__ void __launch_bounds__(kTeamThreadsMax, 3) posterior_kernel(PostArgs 
         bool have[2] = {false, false};
         {
             double mx = -INFINITY, sum = 0.0;
-            int cur_e = -1;
             auto flush = [&](int e) {
                 double M = mx;
 #pragma unroll
@@ -844,35 +853,53 @@ __global__ void __launch_bounds__(kTeamThreadsMax, 3) posterior_kernel(PostArgs 
                     s_part[team_in_cta][wt][1][e] = part;
                 }
             };
+            // 5a. grid combinations of every segment at this site (0 if its bias cfg is gated out)
             #pragma unroll 1
-            for (int k = tt; k < TEAM * 2 * kMaxEvents; k += TT)  // events without any segment
-                (&s_part[team_in_cta][0][0][0])[k] = ((k / kMaxEvents) & 1) ? 0.0 : -INFINITY;
-            team_sync<TEAM>();
-            #pragma unroll 1
-            for (int sidx = 0; sidx < m.n_segs; ++sidx) {
-                const DevSeg *sg = &m.segs[sidx];
-                const int ev_id = sg->event;
-                if (ev_id != cur_e) {
-                    if (cur_e >= 0) flush(cur_e);
-                    cur_e = ev_id; mx = -INFINITY; sum = 0.0;
-                }
-                const int c = sg->cfg;
-                if (!S.allowed[c]) continue;
-                const bool art = sg->art != 0;
-                const int ebi = sg->ebi, p = sg->path;
-                unsigned cnt[kMaxSamples];
-                int base[kMaxSamples];
-                unsigned total = 1;
+            for (int k = tt; k < m.n_segs; k += TT) {
+                const DevSeg *sg = &m.segs[k];
+                unsigned total = S.allowed[sg->cfg] ? 1u : 0u;
                 #pragma unroll 1
                 for (int smp = 0; smp < NS; ++smp) {
                     const int nvs = sg->nv[smp];
-                    cnt[smp] = nvs < 0 ? (unsigned)S.grid[smp] : (unsigned)nvs;
-                    base[smp] = S.spec_off[sg->spec[smp]] - S.sample_voff[smp];  // value index within sample
-                    total *= cnt[smp];
+                    total *= nvs < 0 ? (unsigned)S.grid[smp] : (unsigned)nvs;
                 }
-                const double *prior = m.prior ? m.prior + sg->leaf_off : nullptr;
+                seg_cnt[k] = (int)total;
+            }
+            team_sync<TEAM>();
+            // 5b. event by event: the lanes stride over ALL terms of the event (across its
+            // segments), so that events made of many single-term segments still fill the lanes
+            #pragma unroll 1
+            for (int e = 0; e < m.n_events; ++e) {
+                const int s_lo = m.events[e].seg_off, s_hi = s_lo + m.events[e].n_seg;
+                mx = -INFINITY; sum = 0.0;
+                int sidx = s_lo;
+                unsigned seg_base = 0;          // first term of segment sidx within the event
+                int loaded = -1;                // segment whose radix tables are in cnt[] / base[]
+                unsigned cnt[kMaxSamples];
+                int base[kMaxSamples];
+                int c = 0, ebi = 0, p = -1;
+                bool art = false;
+                const double *prior = nullptr;
                 #pragma unroll 1
-                for (unsigned combo = tt; combo < total; combo += TT) {
+                for (unsigned t = tt;; t += TT) {
+                    while (sidx < s_hi && t >= seg_base + (unsigned)seg_cnt[sidx]) seg_base += (unsigned)seg_cnt[sidx++];
+                    if (sidx >= s_hi) break;
+                    if (sidx != loaded) {
+                        const DevSeg *sg = &m.segs[sidx];
+                        c = sg->cfg; ebi = sg->ebi; art = sg->art != 0;
+                        if (sg->path != p) {  // radix tables depend on the tree path only
+                            p = sg->path;
+                            #pragma unroll 1
+                            for (int smp = 0; smp < NS; ++smp) {
+                                const int nvs = sg->nv[smp];
+                                cnt[smp] = nvs < 0 ? (unsigned)S.grid[smp] : (unsigned)nvs;
+                                base[smp] = S.spec_off[sg->spec[smp]] - S.sample_voff[smp];  // value index within sample
+                            }
+                            prior = m.prior ? m.prior + sg->leaf_off : nullptr;
+                        }
+                        loaded = sidx;
+                    }
+                    const unsigned combo = t - seg_base;
                     unsigned rem = combo;
                     int vidx[kMaxSamples];
                     double lw = 0.0;
@@ -903,13 +930,13 @@ __global__ void __launch_bounds__(kTeamThreadsMax, 3) posterior_kernel(PostArgs 
                             }
                         }
                     }
-                    const double t = J + lw;
-                    if (isnan(t)) { sum = NAN; }
-                    else if (t > mx) { sum = sum * exp_ni(mx - t) + 1.0; mx = t; }
-                    else if (t != -INFINITY) sum += exp_ni(t - mx);
+                    const double tv = J + lw;
+                    if (isnan(tv)) { sum = NAN; }
+                    else if (tv > mx) { sum = sum * exp_ni(mx - tv) + 1.0; mx = tv; }
+                    else if (tv != -INFINITY) sum += exp_ni(tv - mx);
                 }
+                flush(e);
             }
-            if (cur_e >= 0) flush(cur_e);
             team_sync<TEAM>();
             #pragma unroll 1
             for (int e = tt; e < m.n_events; e += TT) {
@@ -946,47 +973,60 @@ __global__ void __launch_bounds__(kTeamThreadsMax, 3) posterior_kernel(PostArgs 
         }
         team_sync<TEAM>();
 
-        // ---- 6. outputs (one thread): marginal, is_artifact, MAP allele frequencies
-        if (tt == 0) {
+        // ---- 6. outputs (first warp of the team, lanes over events): marginal, artifact event,
+        // then one thread picks the MAP allele frequencies
+        bool is_artifact = true;
+        if (wt == 0) {
             const int NE = m.n_events;
             double M = -INFINITY;
             bool nan_any = false;
             #pragma unroll 1
-            for (int e = 0; e < NE; ++e) { nan_any |= isnan(S.ev_ln[e]); M = fmax(M, S.ev_ln[e]); }
+            for (int e = lane; e < NE; e += 32) { const double v = S.ev_ln[e]; nan_any |= isnan(v); M = fmax(M, v); }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) M = fmax(M, __shfl_xor_sync(0xffffffffu, M, o));
+            nan_any = __any_sync(0xffffffffu, nan_any);
+            // LogProb::ln_sum_exp: pmax (first maximum) + ln_1p(sum of the others)
+            int imax = 0x7fffffff;
+            #pragma unroll 1
+            for (int e = lane; e < NE; e += 32) if (S.ev_ln[e] == M) imax = min(imax, e);
+            imax = __reduce_min_sync(0xffffffffu, imax);
+            double acc = 0.0;
+            #pragma unroll 1
+            for (int e = lane; e < NE; e += 32) {
+                const double v = S.ev_ln[e];
+                if (e != imax && v != -INFINITY && !nan_any && M != -INFINITY) acc += exp_ni(v - M);
+                g.out_event_ln[site * NE + e] = v;
+            }
+            acc = warp_sum(acc);
             double marg;
             if (nan_any) marg = NAN;
             else if (M == -INFINITY) marg = -INFINITY;
-            else {
-                // LogProb::ln_sum_exp: pmax + ln_1p(sum of the others)
-                int imax = 0;
-                #pragma unroll 1
-                for (int e = 1; e < NE; ++e) if (S.ev_ln[e] > S.ev_ln[imax]) imax = e;
-                double acc = 0.0;
-                #pragma unroll 1
-                for (int e = 0; e < NE; ++e)
-                    if (e != imax && S.ev_ln[e] != -INFINITY) acc += exp_ni(S.ev_ln[e] - S.ev_ln[imax]);
-                marg = S.ev_ln[imax] + log1p_ni(acc);
-            }
-            #pragma unroll 1
-            for (int e = 0; e < NE; ++e) g.out_event_ln[site * NE + e] = S.ev_ln[e];
-            g.out_marginal[site] = marg;
+            else marg = M + log1p_ni(acc);
+            if (lane == 0) g.out_marginal[site] = marg;
             // artifact event = ln_sum_exp of artifact posteriors (calling.rs:581-598)
             double am = -INFINITY;
             #pragma unroll 1
-            for (int e = 0; e < NE; ++e) if (m.events[e].is_artifact) am = fmax(am, S.ev_ln[e] - marg);
+            for (int e = lane; e < NE; e += 32)
+                if (m.events[e].is_artifact) am = fmax(am, S.ev_ln[e] - marg);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) am = fmax(am, __shfl_xor_sync(0xffffffffu, am, o));
             double prob_art = -INFINITY;
             if (am != -INFINITY && !isnan(am)) {
-                double acc = 0.0;
+                double acc2 = 0.0;
                 #pragma unroll 1
-                for (int e = 0; e < NE; ++e)
+                for (int e = lane; e < NE; e += 32)
                     if (m.events[e].is_artifact && S.ev_ln[e] - marg != -INFINITY)
-                        acc += exp_ni(S.ev_ln[e] - marg - am);
-                prob_art = am + log_ni(acc);
-            } else if (isnan(am)) prob_art = NAN;
-            bool is_artifact = true;
+                        acc2 += exp_ni(S.ev_ln[e] - marg - am);
+                acc2 = warp_sum(acc2);
+                prob_art = am + log_ni(acc2);
+            }
+            bool viol = false;
             #pragma unroll 1
-            for (int e = 0; e < NE; ++e)
-                if (!m.events[e].is_artifact && !((S.ev_ln[e] - marg) < prob_art)) is_artifact = false;
+            for (int e = lane; e < NE; e += 32)
+                if (!m.events[e].is_artifact && !((S.ev_ln[e] - marg) < prob_art)) viol = true;
+            is_artifact = !__any_sync(0xffffffffu, viol);
+        }
+        if (tt == 0) {
             const int w = is_artifact ? 0 : 1;
             double j = -INFINITY; int i0 = 0x7fffffff, i1 = 0, i2 = 0;
             for (int k = 0; k < TEAM; ++k) {
@@ -1143,7 +1183,9 @@ static int flatten_model(vlr_ctx *ctx, const vlr_model *mdl, HostModel &H) {
         else H.any_range_path = true;
     }
     for (int e = 0; e < mdl->n_events; ++e) {
-        const DevEvent &de = H.events[e];
+        DevEvent &de = H.events[e];
+        de.seg_off = (int)H.segs.size();
+        de.n_seg = de.n_eb * de.n_paths;
         for (int q = 0; q < de.n_eb; ++q)
             for (int pth = 0; pth < de.n_paths; ++pth) {
                 DevSeg sg;
@@ -1228,6 +1270,8 @@ int vlr_posterior_batch_dev(vlr_ctx *ctx, int64_t n_sites, const vlr_model *mode
     const int64_t tab_cap = (tbound <= 4096 && team_smem + (size_t)tbound * 8 <= 72 * 1024)
                                 ? ((tbound + 3) & ~(int64_t)3) : 0;  // keeps the teams' carve-outs 32-byte aligned
     team_smem += (size_t)tab_cap * 8;
+    const int seg_cap = ((int)H.segs.size() + 7) & ~7;  // ints; keeps the carve-outs 32-byte aligned
+    team_smem += (size_t)seg_cap * 4;
     const bool big = tbound > 2048 || 4 * team_smem > 64 * 1024;
     const int teams_per_cta = big ? 1 : 4;
     const size_t dyn_smem = (size_t)teams_per_cta * team_smem;
@@ -1321,6 +1365,7 @@ int vlr_posterior_batch_dev(vlr_ctx *ctx, int64_t n_sites, const vlr_model *mode
     a.obs_cap = obs_cap;
     a.gs_cap = gs_cap;
     a.tab_cap = tab_cap;
+    a.seg_cap = seg_cap;
     if (big) {
         VLR_CUDA(ctx, cudaFuncSetAttribute(posterior_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
         posterior_kernel<4><<<grid, kTeamThreadsMax, dyn_smem, st>>>(a);
