@@ -250,6 +250,15 @@ def bench_part2(args, ctx, torch, dist, dev, stream, rank, world, name, wl, time
     def step_e2e():
         return ctx.posterior_batch(scn, np_cols, np_cat, h_off.numpy())
 
+    # compact entry: the seven stored fields as f32 (lossless for MiniLogProb-quantised values)
+    stored = ("prob_mapping", "prob_alt", "prob_ref", "prob_missed_allele", "prob_sample_alt",
+              "prob_double_overlap", "prob_hit_base")
+    h_cols32 = {n: torch.from_numpy(np.ascontiguousarray(cols[n], dtype=np.float32)).pin_memory() for n in stored}
+    np_cols32 = {n: h_cols32[n].numpy() for n in stored}
+
+    def step_e2e_f32():
+        return ctx.posterior_batch_f32(scn, np_cols32, np_cat, h_off.numpy())
+
     for _ in range(max(args.warmup, 3)):
         step_dev()
     l0 = ctx.launch_count()
@@ -263,6 +272,15 @@ def bench_part2(args, ctx, torch, dist, dev, stream, rank, world, name, wl, time
         t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e2e = float(t.item())
+    out32 = step_e2e_f32()
+    t0 = time.perf_counter()
+    timed(step_e2e_f32, args.steps)
+    ms_e2e32 = (time.perf_counter() - t0) * 1e3
+    if world > 1:
+        t = torch.tensor([ms_e2e32], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e32 = float(t.item())
+    in_bytes32 = sum(int(v.numel() * 4) for v in h_cols32.values()) + int(h_cat.numel() * 2 + h_off.numel() * 8)
     in_bytes = sum(int(v.numel() * v.element_size()) for v in h_cols.values()) + \
         int(h_cat.numel() * 2 + h_off.numel() * 8)
     out_bytes = n_sites * (ne * 8 + 8 + ns * 12)
@@ -270,8 +288,15 @@ def bench_part2(args, ctx, torch, dist, dev, stream, rank, world, name, wl, time
            "unit": "sites/s", "ms_per_step": ms / args.steps, "gpu_launches": int(launches),
            "e2e": {"value": n_sites * world * args.steps / (ms_e2e * 1e-3), "unit": "sites/s",
                    "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
-                   "ms_per_step": ms_e2e / args.steps}}
+                   "ms_per_step": ms_e2e / args.steps},
+           "e2e_f32": {"value": n_sites * world * args.steps / (ms_e2e32 * 1e-3), "unit": "sites/s",
+                       "h2d_bytes_per_step": in_bytes32, "d2h_bytes_per_step": out_bytes,
+                       "ms_per_step": ms_e2e32 / args.steps,
+                       "note": "vlr_posterior_batch_f32: stored fields as f32, derived columns on the device"}}
     if rank == 0:
+        res["e2e_f32"]["max_abs_ln_vs_f64_entry"] = float(np.nanmax(np.abs(np.where(
+            np.isfinite(out32["event_ln"]) & np.isfinite(out_e2e["event_ln"]),
+            out32["event_ln"] - out_e2e["event_ln"], 0.0))))
         n_cpu = min(n_sites, args.cpu_sample_sites or (16384 if ns == 1 else (4096 if ns == 3 else 256)))
         ores, cpu_sps, cpu_dt = oracle_part2(wl, cols, cat, off, n_cpu)
         ev = d_ev.cpu().numpy().reshape(n_sites, ne)[:n_cpu]

@@ -283,6 +283,27 @@ int vlr_posterior_batch(vlr_ctx *ctx, int64_t n_sites, const vlr_model *model,
                         double *out_event_ln, double *out_marginal, double *out_map_af,
                         int32_t *out_map_bias);
 
+/* Compact host-buffer variant: the seven STORED observation fields as f32 (30 bytes per
+ * observation instead of 74 over PCIe).  The wire format holds every value as f16 or f32
+ * (MiniLogProb, utils/mod.rs:381-407), so f32 is lossless for real `preprocess` output; the two
+ * derived columns are computed on the device as ObservationBuilder does (observation.rs:218-226).
+ * Both host-buffer variants stream the batch in chunks: H2D of chunk c+1 overlaps the kernels of
+ * chunk c (pass pinned host memory for the copies to be asynchronous). */
+typedef struct {
+    const float *prob_mapping;
+    const float *prob_alt;
+    const float *prob_ref;
+    const float *prob_missed_allele;
+    const float *prob_sample_alt;
+    const float *prob_double_overlap;
+    const float *prob_hit_base;
+    const uint16_t *cat;
+} vlr_obs_columns_f32;
+int vlr_posterior_batch_f32(vlr_ctx *ctx, int64_t n_sites, const vlr_model *model,
+                            const vlr_obs_columns_f32 *obs, const int64_t *obs_off,
+                            double *out_event_ln, double *out_marginal, double *out_map_af,
+                            int32_t *out_map_bias);
+
 /* device-resident variant (obs columns / obs_off / outputs are device pointers; `model` stays a
  * host struct).  max_obs_per_pileup: upper bound of observations per (site, sample), e.g.
  * --max-depth (cli.rs:246-252); sites exceeding it get NaN outputs. */

@@ -63,6 +63,11 @@ class Event(C.Structure):
                 ("n_biases", C.c_int32)]
 
 
+class ObsColumnsF32(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("prob_mapping", "prob_alt", "prob_ref", "prob_missed_allele",
+                                          "prob_sample_alt", "prob_double_overlap", "prob_hit_base", "cat")]
+
+
 class Model(C.Structure):
     _fields_ = [("n_samples", C.c_int32), ("n_events", C.c_int32), ("n_nodes", C.c_int32),
                 ("n_biases", C.c_int32), ("resolution", C.c_void_p), ("contaminated", C.c_void_p),
@@ -76,7 +81,7 @@ EXPORTS = [
     "vlr_version", "vlr_ctx_create", "vlr_ctx_destroy", "vlr_last_error", "vlr_ctx_set_stream",
     "vlr_ctx_synchronize", "vlr_ctx_launch_count", "vlr_pairhmm_batch",
     "vlr_pairhmm_workspace_bytes", "vlr_pairhmm_batch_dev", "vlr_measure_fp64_peak",
-    "vlr_besthit_batch", "vlr_pathhmm_batch", "vlr_allele_support_batch", "vlr_likelihood_batch", "vlr_call_records", "vlr_model_leaves", "vlr_obs_decode", "vlr_obs_encode", "vlr_obs_encoded_bound", "vlr_posterior_batch", "vlr_posterior_batch_dev",
+    "vlr_besthit_batch", "vlr_pathhmm_batch", "vlr_allele_support_batch", "vlr_likelihood_batch", "vlr_call_records", "vlr_model_leaves", "vlr_obs_decode", "vlr_obs_encode", "vlr_obs_encoded_bound", "vlr_posterior_batch", "vlr_posterior_batch_f32", "vlr_posterior_batch_dev",
 ]
 
 _lib = None
@@ -123,6 +128,8 @@ def load():
     L.vlr_model_leaves.argtypes = [vp, C.POINTER(Model), i64, vp, vp, vp]
     L.vlr_posterior_batch.argtypes = [vp, i64, C.POINTER(Model), C.POINTER(ObsColumns), vp, vp, vp,
                                       vp, vp]
+    L.vlr_posterior_batch_f32.argtypes = [vp, i64, C.POINTER(Model), C.POINTER(ObsColumnsF32), vp, vp, vp,
+                                          vp, vp]
     L.vlr_posterior_batch_dev.argtypes = [vp, i64, C.POINTER(Model), C.POINTER(ObsColumns), vp, i32,
                                           vp, vp, vp, vp]
     _lib = L

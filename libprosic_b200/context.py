@@ -291,6 +291,28 @@ class Context:
                                                  _ptr(mb)))
         return dict(event_ln=ev, marginal=marg, map_af=maf, map_bias=mb)
 
+    def posterior_batch_f32(self, scn, cols32, cat, obs_off):
+        """Compact variant: the seven stored fields as float32 arrays (dict), derived columns on the
+        device.  Same outputs as posterior_batch."""
+        from ._ffi import ObsColumnsF32
+        keep = []
+        model = self.build_model(scn, keep)
+        names = ("prob_mapping", "prob_alt", "prob_ref", "prob_missed_allele", "prob_sample_alt",
+                 "prob_double_overlap", "prob_hit_base")
+        arrs = [np.ascontiguousarray(cols32[n], dtype=np.float32) for n in names]
+        catc = np.ascontiguousarray(cat, dtype=np.uint16)
+        oc = ObsColumnsF32(*[a.ctypes.data for a in arrs], catc.ctypes.data)
+        obs_off = np.ascontiguousarray(obs_off, dtype=np.int64)
+        ns, ne = scn["n_samples"], len(scn["events"])
+        n_sites = (len(obs_off) - 1) // ns
+        ev = np.empty((n_sites, ne), np.float64)
+        marg = np.empty(n_sites, np.float64)
+        maf = np.empty((n_sites, ns), np.float64)
+        mb = np.empty((n_sites, ns), np.int32)
+        self._check(self.lib.vlr_posterior_batch_f32(self.h, n_sites, C.byref(model), C.byref(oc),
+                                                     _ptr(obs_off), _ptr(ev), _ptr(marg), _ptr(maf), _ptr(mb)))
+        return dict(event_ln=ev, marginal=marg, map_af=maf, map_bias=mb)
+
     def posterior_batch_dev(self, scn, n_sites, d_cols, d_cat, d_obs_off, max_obs, d_ev, d_marg, d_maf,
                             d_mb, _cache={}):
         """Device-pointer variant (ints).  d_cols: dict name -> device pointer."""

@@ -24,6 +24,9 @@ struct vlr_ctx {
     };
     std::vector<Buf> dev_bufs;   // indexed by slot
     std::vector<Buf> pin_bufs;
+    // host-buffer entry points overlap H2D of chunk c+1 with the kernels of chunk c
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
 };
 
 namespace vlr {
@@ -32,6 +35,8 @@ int set_err(vlr_ctx *ctx, int code, const char *fmt, ...);
 // returns device scratch of at least `bytes` in slot `slot` (grow-only), nullptr on failure
 void *dev_scratch(vlr_ctx *ctx, int slot, size_t bytes);
 void *pin_scratch(vlr_ctx *ctx, int slot, size_t bytes);
+// creates the copy stream and its events on first use; VLR_OK or an error code
+int ensure_copy_stream(vlr_ctx *ctx);
 
 #define VLR_CUDA(ctx, call)                                                                  \
     do {                                                                                     \

@@ -47,11 +47,21 @@ void *pin_scratch(vlr_ctx *ctx, int slot, size_t bytes) {
     return grow(ctx->pin_bufs, slot, bytes, true);
 }
 
+int ensure_copy_stream(vlr_ctx *ctx) {
+    if (ctx->copy_stream) return VLR_OK;
+    VLR_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+        VLR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_h2d[k], cudaEventDisableTiming));
+        VLR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_done[k], cudaEventDisableTiming));
+    }
+    return VLR_OK;
+}
+
 }  // namespace vlr
 
 extern "C" {
 
-int vlr_version(void) { return 100; }
+int vlr_version(void) { return 101; }
 
 int vlr_ctx_create(int device, vlr_ctx **out) {
     if (!out) return VLR_ERR_INVALID;
@@ -99,6 +109,14 @@ void vlr_ctx_destroy(vlr_ctx *ctx) {
     for (auto &b : ctx->dev_bufs) if (b.p) cudaFree(b.p);
     for (auto &b : ctx->pin_bufs) if (b.p) cudaFreeHost(b.p);
     if (ctx->d_qlut) cudaFree(ctx->d_qlut);
+    if (ctx->copy_stream) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamDestroy(ctx->copy_stream);
+        for (int k = 0; k < 2; ++k) {
+            if (ctx->ev_h2d[k]) cudaEventDestroy(ctx->ev_h2d[k]);
+            if (ctx->ev_done[k]) cudaEventDestroy(ctx->ev_done[k]);
+        }
+    }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }

@@ -1409,11 +1409,39 @@ int vlr_model_leaves(vlr_ctx *ctx, const vlr_model *model, int64_t capacity, int
     return VLR_OK;
 }
 
-int vlr_posterior_batch(vlr_ctx *ctx, int64_t n_sites, const vlr_model *model,
-                        const vlr_obs_columns *obs, const int64_t *obs_off, double *out_event_ln,
-                        double *out_marginal, double *out_map_af, int32_t *out_map_bias) {
-    if (!ctx) return VLR_ERR_INVALID;
-    if (!model || !obs || !obs_off || !out_event_ln || !out_marginal || !out_map_af || !out_map_bias ||
+// ---- host-buffer pipeline: the batch is cut into chunks of sites; H2D of chunk c+1 (copy
+// stream) overlaps the kernels and D2H of chunk c (main stream), two sets of device buffers.
+// T = double: the nine columns as given.  T = float: the seven stored columns (de-quantised
+// MiniLogProb values are exactly representable in f32), widened on the device, where the two
+// derived columns are computed as ObservationBuilder does (observation.rs:218-226).
+}  // extern "C"
+
+namespace vlr {
+
+__global__ void widen_obs_kernel(int64_t n, const float *pm, const float *pa, const float *pr, const float *pmiss,
+                                 const float *psa, const float *pdo, const float *phb, double *o_pm,
+                                 double *o_pmm, double *o_pa, double *o_pr, double *o_pmiss, double *o_psa,
+                                 double *o_pdo, double *o_pso, double *o_phb) {
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        const double m = (double)pm[k], d = (double)pdo[k];
+        o_pm[k] = m;
+        o_pmm[k] = ln_one_minus_exp_d(m);
+        o_pa[k] = (double)pa[k];
+        o_pr[k] = (double)pr[k];
+        o_pmiss[k] = (double)pmiss[k];
+        o_psa[k] = (double)psa[k];
+        o_pdo[k] = d;
+        o_pso[k] = ln_one_minus_exp_d(d);
+        o_phb[k] = (double)phb[k];
+    }
+}
+
+template <typename T>
+static int posterior_pipeline(vlr_ctx *ctx, int64_t n_sites, const vlr_model *model, const T *const *cols,
+                              int n_cols_in, const uint16_t *cat, const int64_t *obs_off,
+                              double *out_event_ln, double *out_marginal, double *out_map_af,
+                              int32_t *out_map_bias) {
+    if (!model || !cols || !cat || !obs_off || !out_event_ln || !out_marginal || !out_map_af || !out_map_bias ||
         n_sites < 0)
         return set_err(ctx, VLR_ERR_INVALID, "bad argument");
     if (n_sites == 0) return VLR_OK;
@@ -1421,9 +1449,9 @@ int vlr_posterior_batch(vlr_ctx *ctx, int64_t n_sites, const vlr_model *model,
     cudaStream_t st = ctx->stream;
     const int NS = model->n_samples, NE = model->n_events;
     if (NS < 1 || NS > kMaxSamples) return set_err(ctx, VLR_ERR_UNSUPPORTED, "n_samples must be 1..8");
+    if (NE < 1 || NE > kMaxEvents) return set_err(ctx, VLR_ERR_UNSUPPORTED, "n_events must be 1..%d", kMaxEvents);
     const int64_t n_off = n_sites * NS + 1;
-    const int64_t r0 = obs_off[0], r1 = obs_off[n_off - 1];
-    const int64_t n_rows = r1 - r0;
+    const int64_t n_rows = obs_off[n_off - 1] - obs_off[0];
     int64_t max_obs = 0;
     for (int64_t k = 0; k + 1 < n_off; ++k) {
         const int64_t l = obs_off[k + 1] - obs_off[k];
@@ -1431,42 +1459,133 @@ int vlr_posterior_batch(vlr_ctx *ctx, int64_t n_sites, const vlr_model *model,
         if (l > max_obs) max_obs = l;
     }
     if (max_obs > 4096) return set_err(ctx, VLR_ERR_UNSUPPORTED, "pileup of %lld observations exceeds 4096", (long long)max_obs);
-    enum { S_COL0 = 20, S_CAT = 29, S_OFF, S_EV, S_MARG, S_AF, S_MB };
+    for (int c = 0; c < n_cols_in; ++c)
+        if (!cols[c] && n_rows > 0) return set_err(ctx, VLR_ERR_INVALID, "null observation column");
+    int rc = ensure_copy_stream(ctx);
+    if (rc != VLR_OK) return rc;
+    // ---- chunk boundaries (in sites), ~24 MB of input per chunk
+    const double in_bytes = (double)n_rows * (n_cols_in * sizeof(T) + 2) + (double)n_off * 8;
+    int n_chunks = (int)std::min<double>(64.0, std::max<double>(1.0, ceil(in_bytes / (24.0 * 1048576.0))));
+    if ((int64_t)n_chunks > n_sites) n_chunks = (int)n_sites;
+    std::vector<int64_t> cs((size_t)n_chunks + 1);
+    cs[0] = 0;
+    for (int c = 1; c < n_chunks; ++c) {
+        const int64_t want = obs_off[0] + n_rows * c / n_chunks;
+        int64_t lo = cs[c - 1] + 1, hi = n_sites - (n_chunks - c);  // keep every chunk non-empty
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) / 2;
+            if (obs_off[mid * NS] < want) lo = mid + 1; else hi = mid;
+        }
+        cs[c] = lo;
+    }
+    cs[n_chunks] = n_sites;
+    int64_t max_rows = 0, max_sites = 0;
+    for (int c = 0; c < n_chunks; ++c) {
+        max_rows = std::max(max_rows, obs_off[cs[c + 1] * NS] - obs_off[cs[c] * NS]);
+        max_sites = std::max(max_sites, cs[c + 1] - cs[c]);
+    }
+    // ---- two sets of device buffers
+    constexpr bool kWiden = sizeof(T) == 4;
+    enum { S_BASE = 100, S_PER = 24 };  // per set: 0..8 fp64 columns, 9 cat, 10 off, 11..14 outputs, 15..21 f32 staging
+    double *d_cols[2][9];
+    T *d_in[2][9];
+    uint16_t *d_cat[2];
+    int64_t *d_off[2];
+    double *d_ev[2], *d_marg[2], *d_af[2];
+    int32_t *d_mb[2];
+    for (int b = 0; b < 2; ++b) {
+        const int base = S_BASE + b * S_PER;
+        for (int c = 0; c < 9; ++c) {
+            d_cols[b][c] = (double *)dev_scratch(ctx, base + c, (size_t)(max_rows + 1) * 8);
+            if (!d_cols[b][c]) return set_err(ctx, VLR_ERR_NOMEM, "scratch allocation failed");
+        }
+        for (int c = 0; c < n_cols_in; ++c) {
+            d_in[b][c] = kWiden ? (T *)dev_scratch(ctx, base + 15 + c, (size_t)(max_rows + 1) * sizeof(T))
+                                : (T *)d_cols[b][c];
+            if (!d_in[b][c]) return set_err(ctx, VLR_ERR_NOMEM, "scratch allocation failed");
+        }
+        d_cat[b] = (uint16_t *)dev_scratch(ctx, base + 9, (size_t)(max_rows + 1) * 2);
+        d_off[b] = (int64_t *)dev_scratch(ctx, base + 10, (size_t)(max_sites * NS + 1) * 8);
+        d_ev[b] = (double *)dev_scratch(ctx, base + 11, (size_t)max_sites * NE * 8);
+        d_marg[b] = (double *)dev_scratch(ctx, base + 12, (size_t)max_sites * 8);
+        d_af[b] = (double *)dev_scratch(ctx, base + 13, (size_t)max_sites * NS * 8);
+        d_mb[b] = (int32_t *)dev_scratch(ctx, base + 14, (size_t)max_sites * NS * 4);
+        if (!d_cat[b] || !d_off[b] || !d_ev[b] || !d_marg[b] || !d_af[b] || !d_mb[b])
+            return set_err(ctx, VLR_ERR_NOMEM, "scratch allocation failed");
+    }
+    // earlier work of this context may still read the buffers the copy stream is about to overwrite
+    VLR_CUDA(ctx, cudaStreamSynchronize(st));
+    cudaStream_t cp = ctx->copy_stream;
+    for (int c = 0; c <= n_chunks; ++c) {
+        if (c < n_chunks) {  // H2D of chunk c
+            const int b = c & 1;
+            const int64_t s0 = cs[c], s1 = cs[c + 1];
+            const int64_t r0 = obs_off[s0 * NS], rows = obs_off[s1 * NS] - r0;
+            if (c >= 2) VLR_CUDA(ctx, cudaStreamWaitEvent(cp, ctx->ev_done[b], 0));
+            for (int k = 0; k < n_cols_in && rows > 0; ++k)
+                VLR_CUDA(ctx, cudaMemcpyAsync(d_in[b][k], cols[k] + r0, (size_t)rows * sizeof(T), cudaMemcpyHostToDevice, cp));
+            if (rows > 0) VLR_CUDA(ctx, cudaMemcpyAsync(d_cat[b], cat + r0, (size_t)rows * 2, cudaMemcpyHostToDevice, cp));
+            VLR_CUDA(ctx, cudaMemcpyAsync(d_off[b], obs_off + s0 * NS, (size_t)((s1 - s0) * NS + 1) * 8, cudaMemcpyHostToDevice, cp));
+            VLR_CUDA(ctx, cudaEventRecord(ctx->ev_h2d[b], cp));
+        }
+        if (c >= 1) {  // kernels + D2H of chunk c-1
+            const int b = (c - 1) & 1;
+            const int64_t s0 = cs[c - 1], s1 = cs[c];
+            const int64_t r0 = obs_off[s0 * NS], rows = obs_off[s1 * NS] - r0;
+            VLR_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_h2d[b], 0));
+            if (kWiden && rows > 0) {
+                const float *const *f = (const float *const *)d_in[b];
+                const int grid = (int)std::min<int64_t>((rows + 255) / 256, (int64_t)ctx->sm_count * 8);
+                widen_obs_kernel<<<grid, 256, 0, st>>>(rows, f[0], f[1], f[2], f[3], f[4], f[5], f[6], d_cols[b][0],
+                                                       d_cols[b][1], d_cols[b][2], d_cols[b][3], d_cols[b][4],
+                                                       d_cols[b][5], d_cols[b][6], d_cols[b][7], d_cols[b][8]);
+                VLR_LAUNCH_CHECK(ctx);
+            }
+            vlr_obs_columns dc;  // offsets stay absolute: rebase the device pointers
+            dc.prob_mapping = d_cols[b][0] - r0; dc.prob_mismapping = d_cols[b][1] - r0; dc.prob_alt = d_cols[b][2] - r0;
+            dc.prob_ref = d_cols[b][3] - r0; dc.prob_missed_allele = d_cols[b][4] - r0; dc.prob_sample_alt = d_cols[b][5] - r0;
+            dc.prob_double_overlap = d_cols[b][6] - r0; dc.prob_single_overlap = d_cols[b][7] - r0;
+            dc.prob_hit_base = d_cols[b][8] - r0; dc.cat = d_cat[b] - r0;
+            rc = vlr_posterior_batch_dev(ctx, s1 - s0, model, &dc, d_off[b], (int32_t)max_obs, d_ev[b], d_marg[b],
+                                         d_af[b], d_mb[b]);
+            if (rc != VLR_OK) return rc;
+            const int64_t ns_ = s1 - s0;
+            VLR_CUDA(ctx, cudaMemcpyAsync(out_event_ln + s0 * NE, d_ev[b], (size_t)ns_ * NE * 8, cudaMemcpyDeviceToHost, st));
+            VLR_CUDA(ctx, cudaMemcpyAsync(out_marginal + s0, d_marg[b], (size_t)ns_ * 8, cudaMemcpyDeviceToHost, st));
+            VLR_CUDA(ctx, cudaMemcpyAsync(out_map_af + s0 * NS, d_af[b], (size_t)ns_ * NS * 8, cudaMemcpyDeviceToHost, st));
+            VLR_CUDA(ctx, cudaMemcpyAsync(out_map_bias + s0 * NS, d_mb[b], (size_t)ns_ * NS * 4, cudaMemcpyDeviceToHost, st));
+            VLR_CUDA(ctx, cudaEventRecord(ctx->ev_done[b], st));
+        }
+    }
+    VLR_CUDA(ctx, cudaStreamSynchronize(st));
+    return VLR_OK;
+}
+
+}  // namespace vlr
+
+extern "C" {
+
+int vlr_posterior_batch(vlr_ctx *ctx, int64_t n_sites, const vlr_model *model,
+                        const vlr_obs_columns *obs, const int64_t *obs_off, double *out_event_ln,
+                        double *out_marginal, double *out_map_af, int32_t *out_map_bias) {
+    if (!ctx) return VLR_ERR_INVALID;
+    if (!obs) return set_err(ctx, VLR_ERR_INVALID, "bad argument");
     const double *cols[9] = {obs->prob_mapping, obs->prob_mismapping, obs->prob_alt, obs->prob_ref,
                              obs->prob_missed_allele, obs->prob_sample_alt, obs->prob_double_overlap,
                              obs->prob_single_overlap, obs->prob_hit_base};
-    double *d_cols[9];
-    for (int c = 0; c < 9; ++c) {
-        if (!cols[c] && n_rows > 0) return set_err(ctx, VLR_ERR_INVALID, "null observation column");
-        d_cols[c] = (double *)dev_scratch(ctx, S_COL0 + c, (size_t)(n_rows + 1) * 8);
-        if (!d_cols[c]) return set_err(ctx, VLR_ERR_NOMEM, "scratch allocation failed");
-        if (n_rows > 0)
-            VLR_CUDA(ctx, cudaMemcpyAsync(d_cols[c], cols[c] + r0, (size_t)n_rows * 8, cudaMemcpyHostToDevice, st));
-    }
-    uint16_t *d_cat = (uint16_t *)dev_scratch(ctx, S_CAT, (size_t)(n_rows + 1) * 2);
-    int64_t *d_off = (int64_t *)dev_scratch(ctx, S_OFF, (size_t)n_off * 8);
-    double *d_ev = (double *)dev_scratch(ctx, S_EV, (size_t)n_sites * NE * 8);
-    double *d_marg = (double *)dev_scratch(ctx, S_MARG, (size_t)n_sites * 8);
-    double *d_af = (double *)dev_scratch(ctx, S_AF, (size_t)n_sites * NS * 8);
-    int32_t *d_mb = (int32_t *)dev_scratch(ctx, S_MB, (size_t)n_sites * NS * 4);
-    if (!d_cat || !d_off || !d_ev || !d_marg || !d_af || !d_mb)
-        return set_err(ctx, VLR_ERR_NOMEM, "scratch allocation failed");
-    if (n_rows > 0)
-        VLR_CUDA(ctx, cudaMemcpyAsync(d_cat, obs->cat + r0, (size_t)n_rows * 2, cudaMemcpyHostToDevice, st));
-    VLR_CUDA(ctx, cudaMemcpyAsync(d_off, obs_off, (size_t)n_off * 8, cudaMemcpyHostToDevice, st));
-    vlr_obs_columns dc;
-    dc.prob_mapping = d_cols[0] - r0; dc.prob_mismapping = d_cols[1] - r0; dc.prob_alt = d_cols[2] - r0;
-    dc.prob_ref = d_cols[3] - r0; dc.prob_missed_allele = d_cols[4] - r0; dc.prob_sample_alt = d_cols[5] - r0;
-    dc.prob_double_overlap = d_cols[6] - r0; dc.prob_single_overlap = d_cols[7] - r0;
-    dc.prob_hit_base = d_cols[8] - r0; dc.cat = d_cat - r0;
-    int rc = vlr_posterior_batch_dev(ctx, n_sites, model, &dc, d_off, (int32_t)max_obs, d_ev, d_marg, d_af, d_mb);
-    if (rc != VLR_OK) return rc;
-    VLR_CUDA(ctx, cudaMemcpyAsync(out_event_ln, d_ev, (size_t)n_sites * NE * 8, cudaMemcpyDeviceToHost, st));
-    VLR_CUDA(ctx, cudaMemcpyAsync(out_marginal, d_marg, (size_t)n_sites * 8, cudaMemcpyDeviceToHost, st));
-    VLR_CUDA(ctx, cudaMemcpyAsync(out_map_af, d_af, (size_t)n_sites * NS * 8, cudaMemcpyDeviceToHost, st));
-    VLR_CUDA(ctx, cudaMemcpyAsync(out_map_bias, d_mb, (size_t)n_sites * NS * 4, cudaMemcpyDeviceToHost, st));
-    VLR_CUDA(ctx, cudaStreamSynchronize(st));
-    return VLR_OK;
+    return posterior_pipeline<double>(ctx, n_sites, model, cols, 9, obs->cat, obs_off, out_event_ln, out_marginal,
+                                      out_map_af, out_map_bias);
+}
+
+int vlr_posterior_batch_f32(vlr_ctx *ctx, int64_t n_sites, const vlr_model *model,
+                            const vlr_obs_columns_f32 *obs, const int64_t *obs_off, double *out_event_ln,
+                            double *out_marginal, double *out_map_af, int32_t *out_map_bias) {
+    if (!ctx) return VLR_ERR_INVALID;
+    if (!obs) return set_err(ctx, VLR_ERR_INVALID, "bad argument");
+    const float *cols[7] = {obs->prob_mapping, obs->prob_alt, obs->prob_ref, obs->prob_missed_allele,
+                            obs->prob_sample_alt, obs->prob_double_overlap, obs->prob_hit_base};
+    return posterior_pipeline<float>(ctx, n_sites, model, cols, 7, obs->cat, obs_off, out_event_ln, out_marginal,
+                                     out_map_af, out_map_bias);
 }
 
 }  // extern "C"

@@ -304,3 +304,30 @@ def test_call_record_values(ctx, oracle):
         assert np.array_equal(np.isfinite(a), fin), s
         assert np.all(np.abs(a[fin] - b[fin]) <= 1.2e-7 * np.maximum(1.0, np.abs(b[fin]))), (s, a, b)
     assert np.mean(got["prob"][np.isfinite(got["prob"])] >= 0) == 1.0
+
+
+def test_chunked_pipeline_and_f32_entry(ctx, oracle):
+    """The host-buffer entry points stream the batch in chunks (H2D of chunk c+1 overlaps the
+    kernels of chunk c): a batch large enough for several chunks, ragged depths, must give the
+    same numbers as the oracle on a sample of sites, and the compact f32 entry (derived columns on
+    the device) the same as the f64 entry."""
+    scn = scenario.tumor_normal(purity=0.75, indel=True)
+    cols, cat, off, _ = synth.make_pileups(6000, [40, 100], seed=321, kind="indel", ragged=True,
+                                           af_sets=[[(0, .6), (.5, .3), (1, .1)], [(0, .4), (.3, .4), (.05, .2)]],
+                                           purity=[1.0, 0.75], artifact_frac=0.05)
+    assert len(cat) * 74 > 2 * 24 * 2 ** 20  # at least three chunks of ~24 MB
+    got = ctx.posterior_batch(scn, cols, cat, off)
+    sites = list(range(0, 6000, 499)) + [5999]
+    want = _oracle_run(oracle, scn, cols, cat, off, sites)
+    for s, w in zip(sites, want):
+        _close(got["event_ln"][s], w["event_ln"])
+        assert np.array_equal(got["map_af"][s], w["map_af"], equal_nan=True), s
+    cols32 = {k: v.astype(np.float32) for k, v in cols.items()}
+    for k in ("prob_mapping", "prob_alt", "prob_ref", "prob_missed_allele", "prob_sample_alt",
+              "prob_double_overlap", "prob_hit_base"):
+        assert np.array_equal(cols32[k].astype(np.float64), cols[k], equal_nan=True), k  # quantised inputs
+    got32 = ctx.posterior_batch_f32(scn, cols32, cat, off)
+    _close(got32["event_ln"], got["event_ln"], 1e-9)
+    _close(got32["marginal"], got["marginal"], 1e-9)
+    assert np.array_equal(got32["map_af"], got["map_af"], equal_nan=True)
+    assert np.array_equal(got32["map_bias"], got["map_bias"])
