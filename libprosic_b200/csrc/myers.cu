@@ -18,6 +18,8 @@
 
 #include <vector>
 
+#include <stdlib.h>
+
 #include "pairhmm_host.cuh"
 
 namespace vlr {
@@ -367,8 +369,10 @@ static void set_path_consts(MyersArgs &a, const vlr_gap_params *gp) {
 static int launch_besthit(vlr_ctx *ctx, MyersArgs &a, int64_t max_lx, int slot_base) {
     cudaStream_t st = ctx->stream;
     const size_t per_worker = (size_t)(max_lx + 1) * (2 * kMyW * 8 + 4);
-    int64_t workers = (int64_t)ctx->sm_count * 256;
-    const size_t budget = (size_t)2 << 30;
+    // one thread per pair, latency bound (scratch stores, local-memory masks): many resident warps
+    const char *wenv = getenv("VLR_K2_THREADS_PER_SM");
+    int64_t workers = (int64_t)ctx->sm_count * (wenv && atoi(wenv) > 0 ? atoi(wenv) : 512);
+    const size_t budget = (size_t)6 << 30;
     if ((size_t)workers * per_worker > budget) workers = (int64_t)(budget / per_worker);
     workers = workers / 128 * 128;
     if (workers < 128) return set_err(ctx, VLR_ERR_UNSUPPORTED, "haplotype window of %lld bytes is too long for the Myers scratch", (long long)max_lx);

@@ -3,6 +3,7 @@
 #include <math.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "pairhmm_host.cuh"
@@ -347,12 +348,14 @@ int vlr_pairhmm_batch(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *hap_bytes,
     if (max_ly > 248 && max_edit_dist)
         return set_err(ctx, VLR_ERR_UNSUPPORTED, "banded read window of %lld rows exceeds 248",
                        (long long)max_ly);
+    bool reads_in_pair_order = pair_hap && pair_read;  // pair_read non-decreasing: reads can stream in chunks
     if (pair_hap || pair_read)
         for (int64_t k = 0; k < n_pairs; ++k) {
             if (pair_hap && (pair_hap[k] < 0 || pair_hap[k] >= n_haps))
                 return set_err(ctx, VLR_ERR_INVALID, "pair_hap[%lld] out of range", (long long)k);
             if (pair_read && (pair_read[k] < 0 || pair_read[k] >= n_reads))
                 return set_err(ctx, VLR_ERR_INVALID, "pair_read[%lld] out of range", (long long)k);
+            if (reads_in_pair_order && k > 0 && pair_read[k] < pair_read[k - 1]) reads_in_pair_order = false;
         }
     const int64_t hap_lo = hap_off[0], hap_hi = hap_off[n_haps];
     const int64_t rd_lo = read_off[0], rd_hi = read_off[n_reads];
@@ -380,18 +383,74 @@ int vlr_pairhmm_batch(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *hap_bytes,
     // H2D straight from the caller's buffers (full speed when they are pinned)
     VLR_CUDA(ctx, cudaMemcpyAsync(d_hap, hap_bytes + hap_lo, hap_bytes_n, cudaMemcpyHostToDevice, st));
     VLR_CUDA(ctx, cudaMemcpyAsync(d_hoff, hap_off, (size_t)(n_haps + 1) * 8, cudaMemcpyHostToDevice, st));
-    VLR_CUDA(ctx, cudaMemcpyAsync(d_rb, read_bases + rd_lo, rd_bytes_n, cudaMemcpyHostToDevice, st));
-    VLR_CUDA(ctx, cudaMemcpyAsync(d_rq, read_quals + rd_lo, rd_bytes_n, cudaMemcpyHostToDevice, st));
     VLR_CUDA(ctx, cudaMemcpyAsync(d_roff, read_off, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
-    if (pair_hap) VLR_CUDA(ctx, cudaMemcpyAsync(d_ph, pair_hap, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, st));
-    if (pair_read) VLR_CUDA(ctx, cudaMemcpyAsync(d_pr, pair_read, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, st));
-    if (max_edit_dist)
-        VLR_CUDA(ctx, cudaMemcpyAsync(d_med, max_edit_dist, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, st));
-    // offsets are absolute into the caller's arrays: rebase the device pointers instead of the offsets
-    int rc = vlr_pairhmm_batch_dev(ctx, n_pairs, d_hap - hap_lo, d_hoff, n_haps, d_rb - rd_lo,
-                                   d_rq - rd_lo, d_roff, n_reads, d_ph, d_pr, d_med, gap, flags, d_ws,
-                                   ws_bytes, d_out);
-    if (rc != VLR_OK) return rc;
+    const double stream_bytes = 2.0 * (double)rd_bytes_n + 12.0 * (double)n_pairs;
+    int n_chunks = reads_in_pair_order ? (int)std::min<double>(32.0, floor(stream_bytes / (32.0 * 1048576.0))) : 1;
+    if (n_chunks > 1 && ensure_copy_stream(ctx) != VLR_OK) n_chunks = 1;
+    if (n_chunks <= 1) {
+        VLR_CUDA(ctx, cudaMemcpyAsync(d_rb, read_bases + rd_lo, rd_bytes_n, cudaMemcpyHostToDevice, st));
+        VLR_CUDA(ctx, cudaMemcpyAsync(d_rq, read_quals + rd_lo, rd_bytes_n, cudaMemcpyHostToDevice, st));
+        if (pair_hap) VLR_CUDA(ctx, cudaMemcpyAsync(d_ph, pair_hap, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, st));
+        if (pair_read) VLR_CUDA(ctx, cudaMemcpyAsync(d_pr, pair_read, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, st));
+        if (max_edit_dist)
+            VLR_CUDA(ctx, cudaMemcpyAsync(d_med, max_edit_dist, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, st));
+        // offsets are absolute into the caller's arrays: rebase the device pointers instead of the offsets
+        int rc = vlr_pairhmm_batch_dev(ctx, n_pairs, d_hap - hap_lo, d_hoff, n_haps, d_rb - rd_lo,
+                                       d_rq - rd_lo, d_roff, n_reads, d_ph, d_pr, d_med, gap, flags, d_ws,
+                                       ws_bytes, d_out);
+        if (rc != VLR_OK) return rc;
+    } else {
+        // Pairs reference their reads in non-decreasing order: stream reads and pair lists in
+        // chunks on the copy stream while the main stream computes the previous chunk.  All device
+        // buffers are full size, so chunks never alias; one event per chunk orders copy -> kernel.
+        cudaStream_t cp = ctx->copy_stream;
+        std::vector<cudaEvent_t> evs((size_t)n_chunks, nullptr);
+        cudaEvent_t ev_start = nullptr;
+        auto cleanup = [&]() {
+            for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
+            if (ev_start) cudaEventDestroy(ev_start);
+        };
+        // the copy stream must not overtake earlier work on the main stream that still reads the buffers
+        if (cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventRecord(ev_start, st) != cudaSuccess || cudaStreamWaitEvent(cp, ev_start, 0) != cudaSuccess) {
+            cleanup();
+            return set_err(ctx, VLR_ERR_CUDA, "event setup failed");
+        }
+        int64_t p0 = 0;
+        int rc = VLR_OK;
+        for (int c = 0; c < n_chunks && rc == VLR_OK; ++c) {
+            const int64_t p1 = c + 1 == n_chunks ? n_pairs : n_pairs * (c + 1) / n_chunks;
+            if (p1 <= p0) continue;
+            // reads [ra, rb) are first needed by this chunk (earlier chunks brought everything below ra)
+            const int64_t ra = c == 0 ? 0 : (int64_t)pair_read[p0 - 1] + 1;
+            const int64_t rb = c + 1 == n_chunks ? n_reads : (int64_t)pair_read[p1 - 1] + 1;
+            bool ok = cudaEventCreateWithFlags(&evs[c], cudaEventDisableTiming) == cudaSuccess;
+            if (ok && rb > ra) {
+                const int64_t b0 = read_off[ra] - rd_lo, nb = read_off[rb] - read_off[ra];
+                ok = ok && cudaMemcpyAsync(d_rb + b0, read_bases + read_off[ra], (size_t)nb, cudaMemcpyHostToDevice, cp) == cudaSuccess;
+                ok = ok && cudaMemcpyAsync(d_rq + b0, read_quals + read_off[ra], (size_t)nb, cudaMemcpyHostToDevice, cp) == cudaSuccess;
+            }
+            ok = ok && cudaMemcpyAsync(d_ph + p0, pair_hap + p0, (size_t)(p1 - p0) * 4, cudaMemcpyHostToDevice, cp) == cudaSuccess;
+            ok = ok && cudaMemcpyAsync(d_pr + p0, pair_read + p0, (size_t)(p1 - p0) * 4, cudaMemcpyHostToDevice, cp) == cudaSuccess;
+            if (max_edit_dist)
+                ok = ok && cudaMemcpyAsync(d_med + p0, max_edit_dist + p0, (size_t)(p1 - p0) * 4, cudaMemcpyHostToDevice, cp) == cudaSuccess;
+            ok = ok && cudaEventRecord(evs[c], cp) == cudaSuccess && cudaStreamWaitEvent(st, evs[c], 0) == cudaSuccess;
+            if (!ok) { rc = set_err(ctx, VLR_ERR_CUDA, "chunk copy failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
+            rc = vlr_pairhmm_batch_dev(ctx, p1 - p0, d_hap - hap_lo, d_hoff, n_haps, d_rb - rd_lo, d_rq - rd_lo,
+                                       d_roff, n_reads, d_ph + p0, d_pr + p0, d_med ? d_med + p0 : nullptr, gap,
+                                       flags, d_ws, ws_bytes, d_out + p0);
+            if (rc == VLR_OK &&
+                cudaMemcpyAsync(out_lnprob + p0, d_out + p0, (size_t)(p1 - p0) * 8, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+                rc = set_err(ctx, VLR_ERR_CUDA, "D2H failed");
+            p0 = p1;
+        }
+        cudaStreamSynchronize(cp);
+        cudaError_t es = cudaStreamSynchronize(st);
+        cleanup();
+        if (rc != VLR_OK) return rc;
+        if (es != cudaSuccess) return set_err(ctx, VLR_ERR_CUDA, "pairhmm pipeline failed: %s", cudaGetErrorString(es));
+        return VLR_OK;
+    }
     VLR_CUDA(ctx, cudaMemcpyAsync(out_lnprob, d_out, (size_t)n_pairs * 8, cudaMemcpyDeviceToHost, st));
     VLR_CUDA(ctx, cudaStreamSynchronize(st));
     return VLR_OK;
