@@ -163,29 +163,40 @@ __global__ void __launch_bounds__(128) besthit_kernel(MyersArgs g) {
                 if (cur == 2) return prev == 2 ? g.reopen_y : (prev == 3 ? g.close_x + g.gap_y : g.gap_y);
                 return prev == 3 ? g.reopen_x : (prev == 2 ? g.close_y + g.gap_x : g.gap_x);
             };
+            // D[j][i] of the current cell is carried along; predecessors are evaluated on demand.
+            // Tie-breaking: diagonal first, then Ins, then Del -- calibrated against the reference's
+            // integration tests
+            int d = dms[e];
             while (j > 0) {
-                const int d = i > 0 ? dist_at(cols + (int64_t)i * (2 * kMyW), dms[i], j, m) : j;
-                const int dup = i > 0 ? dist_at(cols + (int64_t)i * (2 * kMyW), dms[i], j - 1, m) : j - 1;
                 int op;
-                if (d == dup + 1) {  // vertical delta +1: Ins
+                if (i > 0) {
+                    const int ddiag = i > 1 ? dist_at(cols + (int64_t)(i - 1) * (2 * kMyW), dms[i - 1], j - 1, m) : j - 1;
+                    const int cost = pat[j - 1] == up_char(txt[i - 1]) ? 0 : 1;
+                    if (ddiag + cost == d) {
+                        op = 0;
+                        d = ddiag;
+                    } else {
+                        const int dup = dist_at(cols + (int64_t)i * (2 * kMyW), dms[i], j - 1, m);
+                        if (d == dup + 1) { op = 3; d = dup; }
+                        else { op = 2; d -= 1; }  // D[j][i-1] + 1 == D[j][i]
+                    }
+                } else {
+                    op = 3;  // text exhausted: D[j][0] = j
+                    d -= 1;
+                }
+                if (op == 3) {
                     ops[nindel & (kMaxIndelOps - 1)] = 3;
                     nindel++; j--;
-                    op = 3;
                     if (want_path) path += (double)g.rqual[ro + j] * -0.23025850929940456;  // prob_emit_y
-                } else {
-                    const int dl = i > 1 ? dist_at(cols + (int64_t)(i - 1) * (2 * kMyW), dms[i - 1], j, m) : j;
-                    if (i > 0 && dl + 1 == d) {  // Del (prob_emit_x = ln 1)
-                        ops[nindel & (kMaxIndelOps - 1)] = 2;
-                        nindel++; i--;
-                        op = 2;
-                    } else {
-                        j--; i--;  // Match / Subst
-                        op = 0;
-                        if (want_path) {
-                            const int q = g.rqual[ro + j];
-                            path += pat[j] == up_char(txt[i]) ? g.qlut[q * kQlutStride + 3]
-                                                              : (double)q * -0.23025850929940456 + -1.098712293668443;
-                        }
+                } else if (op == 2) {  // Del (prob_emit_x = ln 1)
+                    ops[nindel & (kMaxIndelOps - 1)] = 2;
+                    nindel++; i--;
+                } else {               // Match / Subst
+                    j--; i--;
+                    if (want_path) {
+                        const int q = g.rqual[ro + j];
+                        path += pat[j] == up_char(txt[i]) ? g.qlut[q * kQlutStride + 3]
+                                                          : (double)q * -0.23025850929940456 + -1.098712293668443;
                     }
                 }
                 if (want_path && next >= 0) path += trans(op, next);

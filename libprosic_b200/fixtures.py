@@ -1,0 +1,652 @@
+"""Host glue of `varlociraptor preprocess` + `call` for the reference's bundled tumor/normal indel
+testcases: everything AROUND the hot path, so that the GPU kernels
+can be run on the testcases end to end and checked against the `expected:` blocks the reference's
+own integration tests assert (tests/lib.rs, tests/common/mod.rs:289-343).
+
+Restated from the reference (paths relative to /root/reference/src):
+  * record selection and pairing      variants/types/mod.rs:196-312, variants/sample.rs:211-216
+  * evidence validity                 variants/types/deletion.rs:163-203, insertion.rs:105-122
+  * candidate regions / windows       variants/evidence/realignment/mod.rs:61-162
+  * haplotypes                        realignment/pairhmm.rs:213-237, deletion.rs:129-152,300-312,
+                                      insertion.rs:47-74,200-222
+  * allele support per record / pair  realignment/mod.rs:164-335, types/mod.rs:41-83,
+                                      deletion.rs:63-96,216-256 (insert-size evidence)
+  * sampling bias                     variants/sampling_bias/{reads,fragments}.rs
+  * observation assembly              variants/evidence/observation.rs:229-275,379-418
+  * tumor/normal scenario             cli.rs:918-940; bias sets calling.rs:398-412
+BAM decoding follows the SAM/BAM specification; CigarStringView::read_pos and
+Record::read_pair_orientation are recollections of rust-htslib 0.36.
+
+The two compute stages are injected as callables, so the same glue runs on the GPU context
+(`GpuBackend`) and, in the CPU test-suite, on the oracle; this module never imports the oracle.
+Not restated (outside what the fixtures need): subsampling above max_depth (StdRng stream),
+aux-tag strand / orientation info, breakends, SNV/MNV evidence.
+"""
+import gzip
+import json
+import math
+import os
+import struct
+from collections import Counter
+
+import numpy as np
+import yaml
+
+from . import obs_codec, scenario
+
+SEQ_CODE = "=ACMGRSVTWYHKDBN"
+M, I, D, N, S, H, P, EQ, X = range(9)
+LN2 = math.log(2.0)
+
+
+# ------------------------------------------------------------------------------- BAM records
+def read_bam(path):
+    data = gzip.open(path, "rb").read()
+    assert data[:4] == b"BAM\1"
+    l_text = struct.unpack_from("<i", data, 4)[0]
+    pos = 8 + l_text
+    n_ref = struct.unpack_from("<i", data, pos)[0]
+    pos += 4
+    refs = []
+    for _ in range(n_ref):
+        l_name = struct.unpack_from("<i", data, pos)[0]
+        refs.append(data[pos + 4:pos + 4 + l_name - 1].decode())
+        pos += 4 + l_name + 4
+    recs = []
+    while pos < len(data):
+        bs = struct.unpack_from("<i", data, pos)[0]
+        (ref_id, p, l_rn, mapq, _bin, n_cig, flag, l_seq, nref, npos, _tl) = struct.unpack_from("<iiBBHHHiiii", data, pos + 4)
+        q = pos + 36
+        name = data[q:q + l_rn - 1]
+        q += l_rn
+        cigar = [(v & 15, v >> 4) for v in struct.unpack_from("<%dI" % n_cig, data, q)]
+        q += 4 * n_cig
+        raw = data[q:q + (l_seq + 1) // 2]
+        seq = "".join(SEQ_CODE[(raw[k >> 1] >> (4 if k % 2 == 0 else 0)) & 15] for k in range(l_seq)).encode()
+        q += (l_seq + 1) // 2
+        qual = bytes(data[q:q + l_seq])
+        recs.append(dict(name=name, tid=ref_id, contig=refs[ref_id] if ref_id >= 0 else None, pos=p, mapq=mapq,
+                         flag=flag, cigar=cigar, seq=seq, qual=qual, mtid=nref, mpos=npos))
+        pos += 4 + bs
+    return recs
+
+
+def end_pos(r):
+    return r["pos"] + sum(l for op, l in r["cigar"] if op in (M, D, N, EQ, X))
+
+
+def _clips(r, leading, kinds):
+    ops = r["cigar"] if leading else r["cigar"][::-1]
+    n = 0
+    for op, l in ops:
+        if op in kinds:
+            n += l
+        elif op not in (S, H):
+            break
+    return n
+
+
+def leading_softclips(r):
+    return _clips(r, True, (S,))
+
+
+def trailing_softclips(r):
+    return _clips(r, False, (S,))
+
+
+def is_valid_record(r):  # sample.rs:211-216
+    return not (r["flag"] & (0x100 | 0x400 | 0x4 | 0x200)) and bool(r["cigar"])
+
+
+def read_pos(rec, ref_pos, include_softclips, include_dels):
+    """CigarStringView::read_pos (recollected, appendix A.5)."""
+    rpos, qpos, j = rec["pos"], 0, 0
+    cig = rec["cigar"]
+    for i, (op, l) in enumerate(cig):
+        if op in (M, X, EQ, I):
+            j = i
+            break
+        if op == S:
+            j = i
+            if include_softclips:
+                rpos = max(0, rpos - l)
+            break
+        if op in (D, N):
+            return None
+        if op in (P, H) and i == len(cig) - 1:
+            return None
+    while rpos <= ref_pos and j < len(cig):
+        op, l = cig[j]
+        inside = rpos <= ref_pos < rpos + l
+        if op in (M, X, EQ) and inside:
+            return qpos + ref_pos - rpos
+        if op == S and include_softclips and inside:
+            return qpos + ref_pos - rpos
+        if op == D and include_dels and inside:
+            return qpos
+        if op in (M, X, EQ):
+            rpos += l
+            qpos += l
+        elif op == S:
+            qpos += l
+            if include_softclips:
+                rpos += l
+        elif op == I:
+            qpos += l
+        elif op in (D, N):
+            rpos += l
+        elif op == H and j == len(cig) - 1:
+            return None
+        j += 1
+    return None
+
+
+def overlap(locus, r, consider_clips):
+    """SingleLocus::overlap (types/mod.rs:333-361): 'enclosing', 'left', 'right', 'enclosed', None."""
+    pos, end = r["pos"], end_pos(r)
+    if consider_clips:
+        pos = max(0, pos - leading_softclips(r))
+        end += trailing_softclips(r)
+    l0, l1 = locus
+    if pos <= l0:
+        if end >= l1:
+            return "enclosing"
+        if end > l0:
+            return "left"
+    elif end >= l1 and pos < l1:
+        return "right"
+    elif pos >= l0 and end <= l1:
+        return "enclosed"
+    return None
+
+
+def read_orientation(r):
+    """Record::read_pair_orientation (rust-htslib, recollected) -> bio-types variant index."""
+    f = r["flag"]
+    if (f & 1) and not (f & 4) and not (f & 8) and r["tid"] == r["mtid"]:
+        if r["pos"] == r["mpos"]:
+            return 8
+        rev, mrev = bool(f & 0x10), bool(f & 0x20)
+        if f & 0x40:
+            p1, p2, f1, f2 = r["pos"], r["mpos"], not rev, not mrev
+        else:
+            p1, p2, f1, f2 = r["mpos"], r["pos"], not mrev, not rev
+        if p1 < p2:  # F1R2 F2R1 R1F2 R2F1 F1F2 R1R2 F2F1 R2R1 None
+            return {(True, True): 4, (True, False): 0, (False, True): 2, (False, False): 5}[(f1, f2)]
+        return {(True, True): 6, (True, False): 1, (False, True): 3, (False, False): 7}[(f2, f1)]
+    return 8
+
+
+# ------------------------------------------------------------------------------- testcases
+def load_testcase(path):
+    y = yaml.safe_load(open(os.path.join(path, "testcase.yaml")))
+    opts = json.loads(y["options"])["Call"]["kind"]["Variants"] if "options" in y else {}
+    rec = [l for l in open(os.path.join(path, y.get("candidate", "candidates.vcf")), encoding="latin-1")
+           if not l.startswith("#")][0].rstrip("\n").split("\t")
+    info = dict(kv.split("=", 1) for kv in rec[7].split(";") if "=" in kv)
+    samples = {}
+    for name, s in y["samples"].items():
+        props = json.loads(s["properties"])
+        props.setdefault("max_read_len", 100)  # version-0 testcases (tests/common/version0.rs:45-56)
+        sopt = json.loads(s["options"])["Preprocess"]["kind"]["Variants"] if s.get("options") else opts
+        samples[name] = dict(bam=os.path.join(path, s["path"]), props=props, opts=sopt)
+    purity = y.get("purity")
+    if purity is None and opts:
+        purity = opts["mode"]["TumorNormal"]["purity"]
+    if "seq" in y["reference"]:
+        ref_seq, contig = y["reference"]["seq"].encode(), y["reference"]["name"]
+    else:  # later testcase versions ship a FASTA file
+        fa = open(os.path.join(path, y["reference"]["path"])).read().split(">")[1]
+        contig = fa.split("\n", 1)[0].split()[0]
+        ref_seq = "".join(fa.split("\n")[1:]).encode()
+    return dict(name=os.path.basename(path), ref=ref_seq, contig=contig,
+                pos=int(rec[1]) - 1, ref_allele=rec[3], alt_allele=rec[4].split(",")[0], info=info,
+                samples=samples, purity=purity, expected=y.get("expected", {}),
+                omit={k: bool(y.get("omit_" + k, False)) for k in
+                      ("strand_bias", "read_orientation_bias", "read_position_bias", "softclip_bias", "divindel_bias")})
+
+
+def save_fixture(tc, path):
+    """Compact, self-contained form of a testcase (reference sequence, candidate, expectations and
+    the valid records of every sample) -- what the GPU box gets instead of /root/reference."""
+    out = {k: v for k, v in tc.items() if k not in ("ref", "samples")}
+    out["ref"] = tc["ref"].decode()
+    out["samples"] = {}
+    for name, s in tc["samples"].items():
+        props = dict(s["props"])
+        mw = int(s["opts"].get("realignment_window", s["opts"].get("indel_window", 64)))
+        evs = select_evidences(tc, name, make_variant(tc, int(mw * 1.5)), props)
+        recs = [r for ev in evs for r in ev if r is not None]
+        rank = {n: k for k, n in enumerate(sorted({r["name"] for r in recs}))}  # keeps the qname order
+        recs.sort(key=lambda r: r["pos"])
+        out["samples"][name] = dict(props=props, props_final=True, opts=s["opts"], records=[
+            ["%05d" % rank[r["name"]], r["flag"], r["pos"], r["mapq"], r["cigar"], r["seq"].decode(),
+             bytes(q + 33 for q in r["qual"]).decode(), r["tid"], r["mtid"], r["mpos"]] for r in recs])
+    with gzip.open(path, "wt") as f:
+        json.dump(out, f, separators=(",", ":"))
+
+
+def load_fixture(path):
+    with gzip.open(path, "rt") as f:
+        tc = json.load(f)
+    tc["ref"] = tc["ref"].encode()
+    for s in tc["samples"].values():
+        s["records"] = [dict(name=r[0].encode(), flag=r[1], pos=r[2], mapq=r[3], cigar=[tuple(c) for c in r[4]],
+                             seq=r[5].encode(), qual=bytes(ord(c) - 33 for c in r[6]), tid=r[7], mtid=r[8], mpos=r[9],
+                             contig=tc["contig"]) for r in s["records"]]
+    return tc
+
+
+def make_variant(tc, ref_window):
+    """Deletion / Insertion from the candidate record (preprocessing/mod.rs:318-356)."""
+    start, r, a, ref = tc["pos"], tc["ref_allele"], tc["alt_allele"], tc["ref"]
+    if a == "<DEL>" or (not a.startswith("<") and len(r) > len(a)):
+        dl = (int(tc["info"]["END"]) - 1 - start) if a == "<DEL>" and "END" in tc["info"] else len(r) - len(a)
+        if a == "<DEL>" and "SVLEN" in tc["info"]:
+            dl = abs(int(tc["info"]["SVLEN"]))
+        ro, re_ = max(0, start - ref_window), min(start + ref_window, len(ref) - dl)
+        alt = bytes(ref[i] if i <= start else ref[i + dl] for i in range(ro, re_))
+        center = start + int(math.floor(dl / 2.0 + 0.5))
+        return dict(kind="del", len=dl, locus=(start, start + dl), centerpoint=center, alt=alt, alt_extra=0,
+                    fetch_loci=[(start, start + 1), (center, center + 1), (start + dl - 1, start + dl)])
+    if not a.startswith("<") and len(a) > len(r):
+        ins = a[1:].encode()
+        il = len(ins)
+        ro, re_ = max(0, start - ref_window), min(start + il + ref_window, len(ref))
+        alt = bytes(ref[i] if i <= start else (ref[i - il] if i > start + il else ins[i - start - 1])
+                    for i in range(ro, re_ + il))
+        return dict(kind="ins", len=il, locus=(start, start + 1), alt=alt, alt_extra=il,
+                    fetch_loci=[(start, start + 1)])
+    raise NotImplementedError("variant type of %s %s>%s" % (tc["name"], r[:10], a[:10]))
+
+
+# ------------------------------------------------------------------------------- realignment glue
+def candidate_region(rec, locus, ref_len, max_window):
+    """Realigner::candidate_region (realignment/mod.rs:61-156)."""
+    ref_window = int(max_window * 1.5)
+    max_pattern = 128
+    seq_len = len(rec["seq"])
+    l0, l1 = locus
+
+    def ref_iv(bp):
+        return max(0, bp - ref_window), min(bp + ref_window, ref_len)
+    qs, qe = read_pos(rec, l0, True, True), read_pos(rec, l1, True, True)
+    if qs is not None and qe is not None:
+        mw = max(0, max_window - (qe - qs) // 2)
+        ro, re_ = max(0, qs - mw), min(qe + mw, seq_len)
+        exceed = max(0, (re_ - ro) - max_pattern)
+        if exceed > 0:
+            ro += exceed // 2
+            re_ -= (exceed + 1) // 2
+        return True, (ro, re_), ref_iv(l0)
+    if qs is not None:
+        return True, (max(0, qs - max_window), min(qs + max_window, seq_len)), ref_iv(l0)
+    if qe is not None:
+        return True, (max(0, qe - max_window), min(qe + max_window, seq_len)), ref_iv(l1)
+    m = seq_len // 2
+    enclosed = rec["pos"] >= l0 and end_pos(rec) <= l1
+    return enclosed, (max(0, m - max_window), min(m + max_window - 1, seq_len)), ref_iv(rec["pos"] + m)
+
+
+class RealignBatch:
+    """Collects (read window, ref window, alt window) jobs of many records; one backend call."""
+
+    def __init__(self, tc, variant, max_window):
+        self.tc, self.variant, self.max_window = tc, variant, max_window
+        self.jobs, self.by_record = [], {}
+
+    def add(self, rec):
+        key = id(rec)
+        if key in self.by_record:
+            return
+        ov, (q0, q1), (r0, r1) = candidate_region(rec, self.variant["locus"], len(self.tc["ref"]), self.max_window)
+        if not ov or q1 <= q0:
+            self.by_record[key] = None  # no overlap: (ln .5, ln .5, Strand::None), mod.rs:188-199
+            return
+        self.by_record[key] = len(self.jobs)
+        self.jobs.append(dict(ref=self.tc["ref"][r0:r1], alt=self.variant["alt"], alt_extra=self.variant["alt_extra"],
+                              bases=rec["seq"][q0:q1], quals=rec["qual"][q0:q1]))
+
+    def run(self, backend):
+        self.results = backend.allele_support(self.jobs) if self.jobs else []
+
+    def support(self, rec):
+        """AlleleSupport of one record: dict(prob_ref, prob_alt, strand, indel_ops)."""
+        j = self.by_record[id(rec)]
+        if j is None:
+            return dict(prob_ref=-LN2, prob_alt=-LN2, strand=3, indel_ops=())
+        r = self.results[j]
+        informative = r["prob_ref"] != r["prob_alt"]
+        strand = (1 if rec["flag"] & 0x10 else 0) if informative else 3  # Strand::from_record / None
+        return dict(prob_ref=r["prob_ref"], prob_alt=r["prob_alt"], strand=strand,
+                    indel_ops=tuple(r["indel_ops"]) if informative else ())
+
+
+def merge_support(a, b):
+    """AlleleSupport::merge (types/mod.rs:67-83)."""
+    out = dict(prob_ref=a["prob_ref"] + b["prob_ref"], prob_alt=a["prob_alt"] + b["prob_alt"],
+               strand=a["strand"], indel_ops=a["indel_ops"])
+    if a["strand"] == 3:
+        out["strand"], out["indel_ops"] = b["strand"], b["indel_ops"]
+    elif b["strand"] != 3:
+        if a["strand"] != b["strand"]:
+            out["strand"] = 2
+        out["indel_ops"] = a["indel_ops"] + b["indel_ops"]
+    return out
+
+
+# ------------------------------------------------------------------------------- sampling bias / insert size
+def _phi(x):  # GSL ugaussian_P
+    return 0.5 * math.erfc(-x / math.sqrt(2.0))
+
+
+def _ln(x):
+    return math.log(x) if x > 0 else -math.inf
+
+
+def isize_pmf(value, mean, sd):  # sampling_bias/fragments.rs:175-178
+    return _ln(_phi((value + 0.5 - mean) / sd) - _phi((value - 0.5 - mean) / sd))
+
+
+def ln_one_minus_exp(p):
+    if p == -math.inf:
+        return 0.0
+    if p >= 0.0:
+        return -math.inf
+    return math.log1p(-math.exp(p)) if p < -0.693 else math.log(-math.expm1(p))
+
+
+def ln_sum_exp(ps):
+    ps = [p for p in ps]
+    if not ps:
+        return -math.inf
+    mx = max(ps)
+    if mx == -math.inf:
+        return -math.inf
+    k = ps.index(mx)
+    return mx + math.log1p(sum(math.exp(p - mx) for i, p in enumerate(ps) if i != k and p != -math.inf))
+
+
+def feasible_bases(variant, read_len, props):  # deletion.rs:104-118, insertion.rs:78-92
+    maxlen = props["max_del_cigar_len"] if variant["kind"] == "del" else props["max_ins_cigar_len"]
+    if maxlen is not None and variant["len"] <= maxlen:
+        return read_len
+    if props["frac_max_softclip"] is not None:
+        return int(read_len * props["frac_max_softclip"])
+    return None
+
+
+def prob_sample_alt_read(variant, read_len, props):  # sampling_bias/reads.rs:21-40
+    feasible = feasible_bases(variant, read_len, props)
+    if feasible is None:
+        return 0.0
+    n_alt = min(variant["len"], read_len)
+    return math.log(min(n_alt, feasible)) - math.log(n_alt)
+
+
+def prob_sample_alt_fragment(variant, ll, rl, props):  # sampling_bias/fragments.rs:44-151
+    lf, rf = feasible_bases(variant, ll, props), feasible_bases(variant, rl, props)
+    if lf is None or rf is None:
+        return -math.inf
+    delta_ref, delta_alt = variant["len"], 0
+    infeasible_read_pos = max(0, ll - lf) + max(0, rl - rf)  # enclose_only = true
+    mean, sd = props["insert_size"]["mean"], props["insert_size"]["sd"]
+    m = int(math.floor(mean + 0.5))
+    s = int(math.ceil(sd)) * 6
+    terms = []
+    for x in range(max(0, m - s), m + s):
+        internal = max(0, max(0, x - ll) - rl)
+        infeasible_pos_alt = infeasible_read_pos + max(0, internal + 1 - delta_alt)
+        infeasible_pos_ref = max(0, internal + 1 - delta_ref)
+        valid_alt = max(0, max(0, x - delta_alt) - infeasible_pos_alt)
+        valid_ref = max(0, x - infeasible_pos_ref)
+        if x <= delta_alt or x <= delta_alt + infeasible_pos_alt or x <= infeasible_pos_ref:
+            continue
+        terms.append(isize_pmf(x, mean, sd) + _ln(valid_alt) - math.log(valid_ref))
+    p = ln_sum_exp(terms)
+    return 0.0 if 0.0 < p <= 1e-3 else p  # cap_numerical_overshoot
+
+
+def estimate_insert_size(left, right):  # variants/evidence/insert_size.rs:17-45
+    def aln(r):
+        return (max(0, r["pos"] - _clips(r, True, (S, H))), end_pos(r) + _clips(r, False, (S, H)))
+    (ls, le), (rs, re_) = aln(left), aln(right)
+    return (rs - le) + (le - ls) + (re_ - rs)
+
+
+# ------------------------------------------------------------------------------- observations
+def select_evidences(tc, sample_name, variant, props):
+    """Record fetching, pairing and validity (types/mod.rs:196-312): list of (left, right|None).
+    `props` (alignment properties) is updated as update_max_cigar_ops_len does, unless the fixture
+    already holds the updated values."""
+    smp = tc["samples"][sample_name]
+    records = smp.get("records")
+    if records is None:
+        records = [r for r in read_bam(smp["bam"]) if r["contig"] == tc["contig"]]
+    # ---- fetch windows around the loci (sample.rs:40-100): read-pair window on both sides, merged
+    w = int(props["insert_size"]["mean"] + props["insert_size"]["sd"] * 6.0) if props["insert_size"] else props["max_read_len"]
+    fetches = []
+    for l0, l1 in variant["fetch_loci"]:
+        if fetches and max(0, l0 - w) <= fetches[-1][1] + w:
+            fetches[-1][1] = l1
+        else:
+            fetches.append([l0, l1])
+    cands = {}
+    for f0, f1 in fetches:
+        lo, hi = max(0, f0 - w), f1 + w
+        for r in records:
+            if not is_valid_record(r) or r["pos"] >= hi or end_pos(r) < lo:
+                continue
+            if not smp.get("props_final"):
+                for op, l in r["cigar"]:  # AlignmentProperties::update_max_cigar_ops_len
+                    if op == S and props["frac_max_softclip"] is not None:
+                        props["frac_max_softclip"] = max(props["frac_max_softclip"], l / len(r["seq"]))
+                    elif op == D and props["max_del_cigar_len"] is not None:
+                        props["max_del_cigar_len"] = max(props["max_del_cigar_len"], l)
+                    elif op == I and props["max_ins_cigar_len"] is not None:
+                        props["max_ins_cigar_len"] = max(props["max_ins_cigar_len"], l)
+            c = cands.get(r["name"])
+            if c is None:
+                cands[r["name"]] = [r, None]
+            elif c[0] is not r and c[1] is not r:
+                c[1] = r
+    evidences = []
+    for name in sorted(cands):  # BTreeMap order
+        left, right = cands[name]
+        if right is not None:
+            if left["mapq"] == 0 or right["mapq"] == 0:
+                continue
+            ev = (left, right)
+        else:
+            ev = (left, None)
+        if _is_valid_evidence(variant, ev, props):
+            evidences.append(ev)
+    return evidences
+
+
+def extract_observations(tc, sample_name, backend, max_window=64):
+    """Observable<PairedEndEvidence>::extract_observations + Sample::extract_observations for the
+    testcase's candidate in one sample.  Returns (cols dict, cat) of the processed pileup,
+    quantised through the observation wire format as `call` would read it."""
+    smp = tc["samples"][sample_name]
+    props = dict(smp["props"])
+    max_window = int(smp["opts"].get("realignment_window", smp["opts"].get("indel_window", max_window)))
+    variant = make_variant(tc, int(max_window * 1.5))
+    evidences = select_evidences(tc, sample_name, variant, props)
+    if len(evidences) > int(smp["opts"].get("max_depth", 200)):
+        raise NotImplementedError("subsampling above max_depth (StdRng stream) is not restated")
+    batch = RealignBatch(tc, variant, max_window)
+    for left, right in evidences:
+        batch.add(left)
+        if right is not None:
+            batch.add(right)
+    batch.run(backend)
+    raw = []
+    for left, right in evidences:
+        sup = batch.support(left)
+        if right is not None:
+            sup = merge_support(sup, batch.support(right))
+            if variant["kind"] == "del" and props["insert_size"] is not None:
+                sup = merge_support(sup, _isize_support(variant, left, right, props))
+        if sup["strand"] == 3:
+            continue  # evidence_to_observation: unstranded support is dropped (observation.rs:384-388)
+        mis = [r["mapq"] * (-math.log(10.0) / 10.0) for r in (left, right) if r is not None]
+        if right is None:
+            psa = prob_sample_alt_read(variant, len(left["seq"]), props)
+            ln_len = len(left["seq"])
+            softclipped = leading_softclips(left) > 0 or trailing_softclips(left) > 0
+        else:
+            ll, rl = len(left["seq"]), len(right["seq"])
+            if variant["kind"] == "del" and props["insert_size"] is not None:
+                psa = prob_sample_alt_fragment(variant, ll, rl, props)
+            else:
+                psa = ln_one_minus_exp(ln_one_minus_exp(prob_sample_alt_read(variant, ll, props)) +
+                                       ln_one_minus_exp(prob_sample_alt_read(variant, rl, props)))
+            ln_len = ll + rl
+            softclipped = any(leading_softclips(r) > 0 or trailing_softclips(r) > 0 for r in (left, right))
+        raw.append(dict(prob_mapping=ln_one_minus_exp(max(mis)), prob_alt=sup["prob_alt"], prob_ref=sup["prob_ref"],
+                        prob_missed_allele=ln_sum_exp([sup["prob_ref"], sup["prob_alt"]]) - LN2,
+                        prob_sample_alt=psa, prob_double_overlap=0.0 if sup["strand"] == 2 else -math.inf,
+                        prob_hit_base=-math.log(ln_len), strand=sup["strand"], orientation=read_orientation(left),
+                        softclipped=softclipped, paired=bool(left["flag"] & 1), indel_ops=sup["indel_ops"]))
+    # ---- Observation::process: major indel operations (observation.rs:229-275, 339-359)
+    counter = Counter(o["indel_ops"] for o in raw if o["indel_ops"])
+    major = counter.most_common(1)[0][0] if counter else None
+    n = len(raw)
+    cols = {c: np.array([o[c] for o in raw], np.float64) for c in
+            ("prob_mapping", "prob_alt", "prob_ref", "prob_missed_allele", "prob_sample_alt", "prob_double_overlap",
+             "prob_hit_base")}
+    cat = np.zeros(n, np.uint16)
+    for k, o in enumerate(raw):
+        indel = 2 if not o["indel_ops"] else (0 if o["indel_ops"] == major else 1)
+        cat[k] = (o["strand"] | (o["orientation"] << 2) | (1 << 6) | (int(o["softclipped"]) << 7) | (indel << 8) |
+                  (int(o["paired"]) << 10))  # read_position: None -> ReadPosition::Some
+    # ---- through the wire format, as `call` reads what `preprocess` wrote
+    return obs_codec.decode_record(obs_codec.encode_record(cols, cat))
+
+
+def _is_valid_evidence(variant, ev, props):
+    left, right = ev
+    loc = variant["locus"]
+    if right is None:
+        return overlap(loc, left, True) is not None
+    any_ov = overlap(loc, left, True) is not None or overlap(loc, right, True) is not None
+    if variant["kind"] == "del" and props["insert_size"] is not None:
+        return left["pos"] < variant["centerpoint"] < end_pos(right) and any_ov
+    return any_ov
+
+
+def _isize_support(variant, left, right, props):  # deletion.rs:63-96
+    isz = estimate_insert_size(left, right)
+    mean, sd = props["insert_size"]["mean"], props["insert_size"]["sd"]
+    p_ref, p_alt = isize_pmf(isz, mean, sd), isize_pmf(isz, mean + variant["len"], sd)
+
+    def within(shift):
+        return abs(isz - (mean + shift)) <= sd
+    if (p_ref == -math.inf and not within(variant["len"])) or (p_alt == -math.inf and not within(0.0)):
+        return dict(prob_ref=0.0, prob_alt=0.0, strand=3, indel_ops=())
+    return dict(prob_ref=p_ref, prob_alt=p_alt, strand=3, indel_ops=())
+
+
+# ------------------------------------------------------------------------------- calling + expectations
+def tn_scenario(tc):
+    """Built-in tumor/normal scenario (cli.rs:918-940) with the indel bias set of calling.rs:398-412."""
+    scn = scenario.tumor_normal(purity=tc["purity"], indel=True)
+    arts = scenario.artifact_biases(not tc["omit"]["strand_bias"], False, False, False, not tc["omit"]["divindel_bias"])
+    b = scenario._Builder()
+    b.nodes = scn["nodes"]
+    named, seen = [], set()
+    for ev in scn["events"]:
+        if ev["name"] != "absent" and ev["name"] not in seen:
+            seen.add(ev["name"])
+            named.append((ev["name"], ev["roots"]))
+    absent = [ev for ev in scn["events"] if ev["name"] == "absent"][0]
+    events, biases = [dict(name="absent", roots=absent["roots"], biases=[0])], [scenario.bias()] + arts
+    for name, roots in named:
+        events.append(dict(name=name, roots=roots, biases=[0]))
+        if arts:
+            events.append(dict(name=name, roots=roots, biases=list(range(1, len(biases)))))
+    return dict(scn, events=events, biases=biases)
+
+
+def run_testcase(path, backend):
+    """preprocess (both samples) + call: dict(PROB_*: PHRED f32, af: {sample: f32}, n_obs).
+    path: a reference testcase directory or a compact fixture written by save_fixture."""
+    tc = load_fixture(path) if os.path.isfile(path) else load_testcase(path)
+    pile = {s: extract_observations(tc, s, backend) for s in ("normal", "tumor")}  # alphabetical (quirk Q12)
+    names = obs_codec.COLUMNS
+    cols = {c: np.concatenate([pile["normal"][0][c], pile["tumor"][0][c]]) for c in names}
+    cat = np.concatenate([pile["normal"][1], pile["tumor"][1]])
+    off = np.array([0, len(pile["normal"][1]), len(cat)], np.int64)
+    scn = tn_scenario(tc)
+    post = backend.posterior(scn, cols, cat, off)
+    rec = backend.call_records(scn, post, cols["prob_mapping"], off)
+    out = {"PROB_" + n.upper(): float(v) for n, v in zip(rec["names"], rec["prob"][0])}
+    out["af"] = {"normal": float(rec["af"][0][0]), "tumor": float(rec["af"][0][1])}
+    out["n_obs"] = {"normal": int(off[1]), "tumor": int(off[2] - off[1])}
+    out["expected"] = tc["expected"]
+    return out
+
+
+def check_expectations(result):
+    """tests/common/mod.rs:289-343: list of (expression, passed)."""
+    env = dict(result["af"])
+    env.update({k: v for k, v in result.items() if k.startswith("PROB_")})
+    env["inf"] = math.inf
+    verdicts = []
+    for group in ("allelefreqs", "posteriors"):
+        for expr in (result["expected"] or {}).get(group, []) or []:
+            py = expr.replace("&&", " and ").replace("||", " or ")
+            try:
+                ok = bool(eval(py, {"__builtins__": {}}, env))  # noqa: S307 -- fixture expressions
+            except Exception:
+                ok = False
+            verdicts.append((expr, ok))
+    return verdicts
+
+
+class GpuBackend:
+    """The two compute stages on the GPU context (C-ABI entry points)."""
+
+    def __init__(self, ctx, gap=None, flags=None):
+        from . import GapParams, HMM_DEFAULT
+        self.ctx, self.gap, self.flags = ctx, gap or GapParams(), HMM_DEFAULT if flags is None else flags
+
+    def allele_support(self, jobs):
+        haps, extra, reads, quals = [], [], [], []
+        rr, rh, rho, rnr = [], [], [0], []
+        cache = {}
+        for j in jobs:
+            ids = []
+            for key, ex in ((j["ref"], 0), (j["alt"], j["alt_extra"])):
+                if (key, ex) not in cache:
+                    cache[(key, ex)] = len(haps)
+                    haps.append(np.frombuffer(key, np.uint8))
+                    extra.append(ex)
+                ids.append(cache[(key, ex)])
+            rr.append(len(reads))
+            reads.append(np.frombuffer(j["bases"], np.uint8))
+            quals.append(np.frombuffer(j["quals"], np.uint8))
+            rh += ids
+            rho.append(len(rh))
+            rnr.append(1)
+        hap_off = np.concatenate([[0], np.cumsum([len(h) for h in haps])]).astype(np.int64)
+        read_off = np.concatenate([[0], np.cumsum([len(r) for r in reads])]).astype(np.int64)
+        got = self.ctx.allele_support_batch(np.array(rr, np.int32), np.array(rho, np.int32), np.array(rh, np.int32),
+                                            np.array(rnr, np.int32), np.concatenate(haps), hap_off,
+                                            np.concatenate(reads), np.concatenate(quals), read_off, self.gap,
+                                            shrink_extra=np.array(extra, np.int32), flags=self.flags)
+        out = []
+        for k in range(len(jobs)):
+            n = int(got["n_indel_ops"][k])
+            if n > got["indel_ops"].shape[1]:
+                raise NotImplementedError("more than %d indel operations in one alignment" % got["indel_ops"].shape[1])
+            out.append(dict(prob_ref=float(got["prob_ref"][k]), prob_alt=float(got["prob_alt"][k]),
+                            indel_ops=[int(x) for x in got["indel_ops"][k][:n]]))
+        return out
+
+    def posterior(self, scn, cols, cat, off):
+        return self.ctx.posterior_batch(scn, cols, cat, off)
+
+    def call_records(self, scn, post, prob_mapping, off):
+        return self.ctx.call_records(scn, post, prob_mapping, off)

@@ -328,6 +328,18 @@ double vlro_pairhmm_bruteforce(const uint8_t *hap, int len_x, const uint8_t *rea
  * (traceback tie-breaking is the recollected upstream rule -- unpinned, see header).
  * ops: 0=Match 1=Subst 2=Del 3=Ins, forward order.
  * ===================================================================================== */
+/* Traceback tie-breaking among equally good predecessors.  bio's rule is not in /root/reference; it
+ * is CALIBRATED against the reference's own integration tests: with the restated preprocess/call
+ * glue (libprosic_b200/fixtures.py) the `expected:` blocks of the 31 tumor/normal indel testcases
+ * pass 30/31 with "diagonal first" (rules 1, 2), 28/31 with "Ins, Del, diagonal" (rule 0, the
+ * first recollection), 4-5 of the 7 discriminating cases with the other orders (rules 3-6).
+ * The rule decides DivIndelBias classes (IndelOperations::{Major,Other}) through
+ * best_indel_operations, which is why the testcases see it.
+ * 0 = Ins, Del, diag; 1 = diag, Ins, Del (default); 2 = diag, Del, Ins; 3 = match, Ins, Del, subst;
+ * 4 = Ins, diag, Del; 5 = Del, diag, Ins; 6 = match, Del, Ins, subst */
+static int g_traceback_rule = 1;
+void vlro_set_traceback_rule(int rule) { g_traceback_rule = rule; }
+
 int vlro_best_hit(const uint8_t *hap, int len_x, const uint8_t *read, int len_y, vlro_hit_t *hit,
                   uint8_t *indel_ops, int indel_ops_cap, int32_t *aln_starts, int aln_cap,
                   uint8_t *aln_ops, int32_t *aln_ops_off, int aln_ops_cap) {
@@ -368,8 +380,20 @@ int vlro_best_hit(const uint8_t *hap, int len_x, const uint8_t *read, int len_y,
         if (DD(m, i) != best) continue;
         int j = m, ii = i, len = 0;
         while (j > 0) {
-            if (DD(j, ii) == DD(j - 1, ii) + 1) { tmp[len++] = 3; j--; }
-            else if (ii > 0 && DD(j, ii - 1) + 1 == DD(j, ii)) { tmp[len++] = 2; ii--; }
+            const int can_ins = DD(j, ii) == DD(j - 1, ii) + 1;
+            const int can_del = ii > 0 && DD(j, ii - 1) + 1 == DD(j, ii);
+            const int can_diag = ii > 0 && DD(j - 1, ii - 1) + (read[j - 1] == up(hap[ii - 1]) ? 0 : 1) == DD(j, ii);
+            int op; /* 0 diag, 2 del, 3 ins */
+            const int is_match = ii > 0 && read[j - 1] == up(hap[ii - 1]);
+            if (g_traceback_rule == 0) op = can_ins ? 3 : (can_del ? 2 : 0);
+            else if (g_traceback_rule == 1) op = can_diag ? 0 : (can_ins ? 3 : 2);
+            else if (g_traceback_rule == 2) op = can_diag ? 0 : (can_del ? 2 : 3);
+            else if (g_traceback_rule == 3) op = (can_diag && is_match) ? 0 : (can_ins ? 3 : (can_del ? 2 : 0));
+            else if (g_traceback_rule == 4) op = can_ins ? 3 : (can_diag ? 0 : 2);
+            else if (g_traceback_rule == 5) op = can_del ? 2 : (can_diag ? 0 : 3);
+            else op = (can_diag && is_match) ? 0 : (can_del ? 2 : (can_ins ? 3 : 0));
+            if (op == 3) { tmp[len++] = 3; j--; }
+            else if (op == 2) { tmp[len++] = 2; ii--; }
             else {
                 tmp[len++] = (DD(j - 1, ii - 1) == DD(j, ii)) ? 0 : 1;
                 j--; ii--;

