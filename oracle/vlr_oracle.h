@@ -4,13 +4,19 @@
  * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
  * may load it.  The product path (libprosic_b200) never links or calls this file.
  *
- * PARITY UNPINNED: the arithmetic of this path lives in the third-party crate
- * `bio 0.37.0` (Cargo.lock:181-184) whose source is not in /root/reference and there is
- * no Rust toolchain in the image, so the restatement follows the reference's call sites
- * plus the published algorithms (Durbin et al. pair-HMM forward recursion, Myers 1999
- * bit-vector edit distance, log-space Simpson) and cannot be checked against the real
- * binary.  What IS pinned: the reference's own likelihood identities
- * (src/variants/model/likelihood.rs:267-386) and a brute-force path enumeration.
+ * PARITY: the arithmetic of this path lives in the third-party crate `bio 0.37.0`
+ * (Cargo.lock:181-184) whose source is not in /root/reference and there is no Rust toolchain
+ * in the image, so the restatement follows the reference's call sites plus the published
+ * algorithms (Durbin et al. pair-HMM forward recursion, Myers 1999 bit-vector edit distance,
+ * log-space Simpson) and cannot be compared bit for bit with the real binary: PARITY UNPINNED
+ * in that sense.  What IS pinned: (i) the reference's own likelihood identities
+ * (src/variants/model/likelihood.rs:267-386) and a brute-force path enumeration; (ii) the
+ * reference's integration tests -- with the restated preprocess/call glue
+ * (libprosic_b200/fixtures.py) 31 of its 32 tumor/normal indel testcases satisfy their
+ * `expected:` blocks, four of them on thresholds that are floors of the reference's output
+ * (e.g. PROB_SOMATIC_TUMOR 590.2 vs >= 590.0), i.e. agreement to ~1e-3 relative end to end
+ * (tests/golden/tn_results.txt); (iii) the observation wire format, byte for byte, against
+ * records written by the reference (oracle/obs_codec.py).
  *
  * Every function cites the reference file:line it follows (paths relative to
  * /root/reference).
