@@ -381,6 +381,31 @@ def bench_allele_support(args, ctx, w, flags, rank, world, torch, dist, dev):
     return res
 
 
+def bench_c1(ctx):
+    """Config C1 (the reference's bundled tumor/normal testcases, tests/golden/tn): preprocess + call
+    end to end with both compute stages on the GPU; counts the testcases whose `expected:` block
+    (the reference's own integration-test assertions) holds."""
+    import glob
+    from libprosic_b200 import fixtures as F
+    paths = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "tn", "*.json.gz")))
+    be = F.GpuBackend(ctx)
+    t0 = time.perf_counter()
+    held, failed, n_obs = 0, [], 0
+    for p in paths:
+        r = F.run_testcase(p, be)
+        n_obs += r["n_obs"]["normal"] + r["n_obs"]["tumor"]
+        if all(v for _, v in F.check_expectations(r)):
+            held += 1
+        else:
+            failed.append(os.path.basename(p).split(".")[0])
+    return {"workload": "C1: %d tumor/normal indel testcases of the reference (real reads), preprocess + call "
+                        "through the restated host glue with K2/K1 and K3/K4 on the GPU" % len(paths),
+            "testcases": len(paths), "expectations_hold": held, "not_holding": failed,
+            "observations": n_obs, "seconds": time.perf_counter() - t0,
+            "note": "test21 is the documented exception (DESIGN.md section 5); all 32 testcases: "
+                    "tests/golden/tn_results.txt (31 hold)"}
+
+
 def bench_c4(args, ctx, torch, dist, dev, rank, world, timed):
     """Config C4 (long reads 15 kb x 20 kb haplotype windows), labelled SUBSAMPLE of the 1 M pairs:
     strip-wise K1 with per-strip renormalisation; gap parameters raised as in SURVEY 8(d)."""
@@ -549,6 +574,9 @@ def main():
     allele_support = None
     if not args.skip_part2:
         allele_support = bench_allele_support(args, ctx, w, flags, rank, world, torch, dist, dev)
+    c1 = None
+    if not args.skip_part2 and rank == 0 and not args.part2_only:
+        c1 = bench_c1(ctx)
     c4 = None
     if not args.skip_part2 and args.c4_pairs > 0:
         del d, d_hap, d_ws, d_out
@@ -616,6 +644,7 @@ def main():
                            "value": total_cells * args.steps / (ms_other * 1e-3) / 1e9, "unit": "GCUPS"},
             "parity_max_abs_ln": parity,
             "allele_support": allele_support,
+            "c1_testcases": c1,
             "c4_long_reads": c4,
             "sites_per_sec": part2,
             "clocks": clocks,
