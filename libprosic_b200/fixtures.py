@@ -191,7 +191,7 @@ def load_testcase(path):
         sopt = json.loads(s["options"])["Preprocess"]["kind"]["Variants"] if s.get("options") else opts
         samples[name] = dict(bam=os.path.join(path, s["path"]), props=props, opts=sopt)
     purity = y.get("purity")
-    if purity is None and opts:
+    if purity is None and opts and "TumorNormal" in opts.get("mode", {}):
         purity = opts["mode"]["TumorNormal"]["purity"]
     if "seq" in y["reference"]:
         ref_seq, contig = y["reference"]["seq"].encode(), y["reference"]["name"]
@@ -215,8 +215,13 @@ def save_fixture(tc, path):
     for name, s in tc["samples"].items():
         props = dict(s["props"])
         mw = int(s["opts"].get("realignment_window", s["opts"].get("indel_window", 64)))
-        evs = select_evidences(tc, name, make_variant(tc, int(mw * 1.5)), props)
-        recs = [r for ev in evs for r in ev if r is not None]
+        variant = make_variant(tc, int(mw * 1.5))
+        if variant["kind"] == "snv":  # SingleEndEvidence: records enclosing the locus
+            recs = [r for r in read_bam(s["bam"]) if r["contig"] == tc["contig"] and is_valid_record(r) and
+                    overlap(variant["locus"], r, False) == "enclosing"]
+        else:
+            evs = select_evidences(tc, name, variant, props)
+            recs = [r for ev in evs for r in ev if r is not None]
         rank = {n: k for k, n in enumerate(sorted({r["name"] for r in recs}))}  # keeps the qname order
         recs.sort(key=lambda r: r["pos"])
         out["samples"][name] = dict(props=props, props_final=True, opts=s["opts"], records=[
@@ -257,6 +262,11 @@ def make_variant(tc, ref_window):
                     for i in range(ro, re_ + il))
         return dict(kind="ins", len=il, locus=(start, start + 1), alt=alt, alt_extra=il,
                     fetch_loci=[(start, start + 1)])
+    if len(r) == 1 and len(a) == 1 and not a.startswith("<"):  # SNV (types/snv.rs:35-73, 175-186)
+        ro, re_ = max(0, start - ref_window), min(start + 1 + ref_window, len(ref))
+        alt = bytes(ord(a.upper()) if i == start else ref[i] for i in range(ro, re_))
+        return dict(kind="snv", len=1, locus=(start, start + 1), alt=alt, alt_extra=0, fetch_loci=[(start, start + 1)],
+                    ref_base=r.upper(), alt_base=a.upper())
     raise NotImplementedError("variant type of %s %s>%s" % (tc["name"], r[:10], a[:10]))
 
 
@@ -525,6 +535,166 @@ def extract_observations(tc, sample_name, backend, max_window=64):
     return obs_codec.decode_record(obs_codec.encode_record(cols, cat))
 
 
+def prob_read_base(read_base, ref_base, q):
+    """variants/evidence/bases.rs:13-21 with the LUTs of 33-48."""
+    ln_eps = q * (-math.log(10.0) / 10.0)
+    if chr(read_base).upper() == ref_base.upper():
+        return ln_one_minus_exp(ln_eps)
+    return ln_eps + math.log(0.3333)
+
+
+def extract_observations_snv(tc, sample_name, backend, omit_read_orientation_bias=False, max_window=64):
+    """Observable<SingleEndEvidence>::extract_observations (types/mod.rs:132-183) for an SNV
+    (types/snv.rs:75-165), Observation::process and the call-time removal of non-standard
+    alignments (calling.rs:423-441, observation.rs:303-322)."""
+    smp = tc["samples"][sample_name]
+    props = dict(smp["props"])
+    max_window = int(smp["opts"].get("realignment_window", smp["opts"].get("indel_window", max_window)))
+    variant = make_variant(tc, int(max_window * 1.5))
+    start = variant["locus"][0]
+    records = smp.get("records")
+    if records is None:
+        records = [r for r in read_bam(smp["bam"]) if r["contig"] == tc["contig"]]
+    lo, hi = max(0, start - props["max_read_len"]), start + 1  # RecordBuffer::fetch(locus, false)
+    evidences = []
+    for r in records:
+        if not is_valid_record(r) or r["pos"] >= hi or end_pos(r) < lo:
+            continue
+        if overlap(variant["locus"], r, False) == "enclosing":
+            evidences.append(r)
+    if len(evidences) > int(smp["opts"].get("max_depth", 200)):
+        raise NotImplementedError("subsampling above max_depth (StdRng stream) is not restated")
+    batch = RealignBatch(tc, variant, max_window)
+    for r in evidences:
+        if any(op in (I, D) for op, _ in r["cigar"]):
+            batch.add(r)
+    batch.run(backend)
+    raw = []
+    for r in evidences:
+        if any(op in (I, D) for op, _ in r["cigar"]):
+            sup = batch.support(r)
+            qpos = None
+        else:
+            qpos = read_pos(r, start, False, False)
+            if qpos is None:
+                continue
+            rb, q = r["seq"][qpos], r["qual"][qpos]
+            p_alt = prob_read_base(rb, variant["alt_base"], q)
+            non_alt = chr(rb) if chr(rb).upper() != variant["alt_base"] else variant["ref_base"]
+            p_ref = prob_read_base(rb, non_alt, q)
+            sup = dict(prob_ref=p_ref, prob_alt=p_alt, strand=(1 if r["flag"] & 0x10 else 0) if p_ref != p_alt else 3)
+        if sup["strand"] == 3:
+            continue
+        raw.append(dict(prob_mapping=ln_one_minus_exp(r["mapq"] * (-math.log(10.0) / 10.0)), prob_alt=sup["prob_alt"],
+                        prob_ref=sup["prob_ref"], prob_missed_allele=ln_sum_exp([sup["prob_ref"], sup["prob_alt"]]) - LN2,
+                        prob_sample_alt=0.0, prob_double_overlap=-math.inf, prob_hit_base=-math.log(len(r["seq"])),
+                        strand=sup["strand"], orientation=read_orientation(r),
+                        softclipped=leading_softclips(r) > 0 or trailing_softclips(r) > 0, paired=bool(r["flag"] & 1),
+                        read_position=qpos))
+    counter = Counter(o["read_position"] for o in raw if o["read_position"] is not None)
+    major = counter.most_common(1)[0][0] if counter else None
+    if not omit_read_orientation_bias:
+        raw = [o for o in raw if o["orientation"] in (0, 1, 8)]
+    cols = {c: np.array([o[c] for o in raw], np.float64) for c in
+            ("prob_mapping", "prob_alt", "prob_ref", "prob_missed_allele", "prob_sample_alt", "prob_double_overlap",
+             "prob_hit_base")}
+    cat = np.zeros(len(raw), np.uint16)
+    for k, o in enumerate(raw):
+        rp = 0 if (o["read_position"] is not None and o["read_position"] == major) else 1
+        cat[k] = (o["strand"] | (o["orientation"] << 2) | (rp << 6) | (int(o["softclipped"]) << 7) | (2 << 8) |
+                  (int(o["paired"]) << 10))  # SNVs do not report indel operations: IndelOperations::None
+    return obs_codec.decode_record(obs_codec.encode_record(cols, cat))
+
+
+def single_sample_scenario(tc, events, resolution=100, prior=None):
+    """One-sample Generic scenario, hand-flattened for the testcase's variant (grammar formulas with
+    variant-type atoms such as `C>T | G>A` are resolved against the candidate by the host).
+    events: list of (name, node spec) with node spec ('range', lo, hi, left_excl, right_excl),
+    ('set', [afs]) or None (formula false for this variant).  Bias sets: calling.rs:398-412."""
+    b = scenario._Builder()
+    snv = make_variant(tc, 96)["kind"] == "snv"
+    om = tc["omit"]
+    arts = scenario.artifact_biases(not om["strand_bias"], snv and not om["read_orientation_bias"],
+                                    snv and not om["read_position_bias"], snv and not om["softclip_bias"],
+                                    not om["divindel_bias"])
+    named = []
+    for name, spec in events:
+        if spec is None:
+            root = b.node(scenario.NODE_FALSE)
+        elif spec[0] == "range":
+            root = b.chain([(0, scenario.NODE_RANGE, [spec[1], spec[2], float(spec[3]), float(spec[4])])])
+        else:
+            root = b.chain([(0, scenario.NODE_SET, list(spec[1]))])
+        named.append((name, [root]))
+    ev, biases = scenario._with_events(b, named, 1, arts)
+    scn = dict(n_samples=1, resolution=[resolution], contaminated=[0], by=[0], purity=[1.0], nodes=b.nodes,
+               events=ev, biases=biases)
+    if prior is not None:
+        scn["prior_fn"] = prior
+    return scn
+
+
+def run_single_sample_testcase(path, backend, sample, events, prior=None):
+    """preprocess + call of a one-sample Generic testcase; same result layout as run_testcase."""
+    tc = load_fixture(path) if os.path.isfile(path) else load_testcase(path)
+    variant = make_variant(tc, 96)
+    if variant["kind"] == "snv":
+        cols, cat = extract_observations_snv(tc, sample, backend, tc["omit"]["read_orientation_bias"])
+    else:
+        cols, cat = extract_observations(tc, sample, backend)
+    off = np.array([0, len(cat)], np.int64)
+    scn = single_sample_scenario(tc, events, prior=prior)
+    if prior is not None:  # Prior::compute on the leaves the library reports (set-only universes)
+        _, afs = backend.model_leaves(scn)
+        scn["prior_ln"] = np.array([prior(list(a)) for a in afs])
+    post = backend.posterior(scn, cols, cat, off)
+    rec = backend.call_records(scn, post, cols["prob_mapping"], off)
+    out = {"PROB_" + n.upper(): float(v) for n, v in zip(rec["names"], rec["prob"][0])}
+    out["af"] = {sample: float(rec["af"][0][0])}
+    out["n_obs"] = {sample: int(off[1])}
+    out["expected"] = tc["expected"]
+    return out
+
+
+def _range(lo, hi, left_excl, right_excl):
+    return ("range", lo, hi, left_excl, right_excl)
+
+
+# One-sample Generic testcases of the reference, scenarios flattened by hand for the testcase's
+# candidate (scenario.yaml next to each testcase; `(C>T | G>A)`-style atoms resolved against REF>ALT):
+#   name -> (sample, [(event, VAF spec | None)], heterozygosity of the species prior | None)
+GENERIC_CASES = {
+    # present: "tumor:]0.0,1.0]"
+    "test41": ("tumor", [("present", _range(0.0, 1.0, True, False))], None),
+    # T>C matches "(T>C | G>A)": ffpe_artifact ]0.0,0.1[, present ]0.1,1.0]
+    "test40": ("tumor", [("ffpe_artifact", _range(0.0, 0.1, True, True)), ("present", _range(0.1, 1.0, True, False))], None),
+    # G>T does not match "(C>T | G>A)": ffpe_artifact is false, present ]0.0,1.0]
+    "test57": ("tumor", [("ffpe_artifact", None), ("present", _range(0.0, 1.0, True, False))], None),
+    # a deletion does not match either
+    "test59": ("tumor", [("ffpe_artifact", None), ("present", _range(0.0, 1.0, True, False))], None),
+    # present: "NA12878:0.5 | NA12878:1.0", species heterozygosity 0.001, ploidy 2
+    "test_giab_03": ("NA12878", [("present", ("set", [0.5, 1.0]))], 0.001),
+}
+
+
+def run_generic_case(path, backend):
+    name = os.path.basename(path).split(".")[0]
+    sample, events, het = GENERIC_CASES[name]
+    return run_single_sample_testcase(path, backend, sample, events, germline_prior(het) if het else None)
+
+
+def germline_prior(heterozygosity, ploidy=2):
+    """Prior::prob_population_germline for one diploid sample without inheritance or somatic terms
+    (variants/model/prior.rs:288-431, 628-656): m alt alleles -> ln(het) - ln(m); none ->
+    ln(1 - sum_k het/k)."""
+    def f(afs):
+        m = int(round(ploidy * afs[0]))
+        if m > 0:
+            return math.log(heterozygosity) - math.log(m)
+        return ln_one_minus_exp(ln_sum_exp([math.log(heterozygosity) - math.log(k) for k in range(1, ploidy + 1)]))
+    return f
+
+
 def _is_valid_evidence(variant, ev, props):
     left, right = ev
     loc = variant["locus"]
@@ -650,3 +820,6 @@ class GpuBackend:
 
     def call_records(self, scn, post, prob_mapping, off):
         return self.ctx.call_records(scn, post, prob_mapping, off)
+
+    def model_leaves(self, scn):
+        return self.ctx.model_leaves({k: v for k, v in scn.items() if k != "prior_fn"})

@@ -25,9 +25,13 @@ class OracleBackend:
                            scn["nodes"], scn["events"], [O.make_biases(**b) for b in scn["biases"]])
         ns = scn["n_samples"]
         res = [O.model_compute(spec, [O.PileupView(cols, cat, int(off[s * ns + k]), int(off[s * ns + k + 1]))
-                                      for k in range(ns)]) for s in range((len(off) - 1) // ns)]
+                                      for k in range(ns)], prior=scn.get("prior_fn"))
+               for s in range((len(off) - 1) // ns)]
         return dict(event_ln=np.array([r["event_ln"] for r in res]), marginal=np.array([r["marginal"] for r in res]),
                     map_af=np.array([r["map_af"] for r in res]))
+
+    def model_leaves(self, scn):
+        return None, np.zeros((0, scn["n_samples"]))  # the oracle takes the prior as a callback
 
     def call_records(self, scn, post, prob_mapping, off):
         from oracle import call_records as ocr

@@ -18,7 +18,14 @@ CASES = ["test02", "test03", "test04", "test08", "test10", "test12", "test15", "
 
 def main():
     os.makedirs(OUT, exist_ok=True)
+    gen = os.path.join(os.path.dirname(OUT), "gen")
+    os.makedirs(gen, exist_ok=True)
     total = 0
+    for c in F.GENERIC_CASES:  # one-sample Generic testcases (SNVs, prior table)
+        p = os.path.join(gen, c + ".json.gz")
+        F.save_fixture(F.load_testcase(os.path.join(REF, c)), p)
+        total += os.path.getsize(p)
+        print(c, os.path.getsize(p))
     for c in CASES:
         d = os.path.join(REF, c)
         if not os.path.isdir(d):

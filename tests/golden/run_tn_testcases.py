@@ -3,7 +3,7 @@
 on the CPU oracle and print which `expected:` blocks hold (needs /root/reference; the GPU suite
 runs the committed subset under tests/golden/tn/ through the CUDA kernels).
 
-    python tests/golden/run_tn_testcases.py [traceback_rule] > tests/golden/tn_results.txt
+    python tests/golden/run_tn_testcases.py [traceback_rule [fast]] > tests/golden/tn_results.txt
 """
 import os
 import sys
@@ -21,7 +21,7 @@ REF = "/root/reference/tests/resources/testcases"
 def main():
     if len(sys.argv) > 1:
         oracle.lib().vlro_set_traceback_rule(int(sys.argv[1]))
-    be = OracleBackend()
+    be = OracleBackend(fast=len(sys.argv) > 2 and sys.argv[2] == "fast")
     n_pass = n_tot = 0
     for c in ["test%02d" % k for k in range(2, 34)] + ["issue_154"]:
         d = os.path.join(REF, c)

@@ -3,11 +3,14 @@ SURVEY section 8f row 1): the restated preprocess/call glue (libprosic_b200/fixt
 hot path, evaluated against the `expected:` blocks that the reference's own integration tests
 assert (tests/lib.rs, tests/common/mod.rs:289-343).
 
-tests/golden/tn/*.json.gz are compact forms of 13 testcases (tests/golden/make_tn_fixtures.py);
-all 32 run in this container with tests/golden/run_tn_testcases.py (results: tn_results.txt,
-31 of 32 hold).  test21 is the known exception: its PROB_SOMATIC_TUMOR >= 200 depends on the
-Myers traceback tie-breaking, which is calibrated on these very testcases (oracle/vlr_oracle.c,
-g_traceback_rule)."""
+tests/golden/tn/*.json.gz are compact forms of 13 tumor/normal indel testcases and
+tests/golden/gen/*.json.gz of 5 one-sample Generic testcases (SNVs with all five bias types, a
+deletion, a ploidy universe with the species prior as a prior table); both are written by
+tests/golden/make_tn_fixtures.py.  All 32 tumor/normal testcases run in this container with
+tests/golden/run_tn_testcases.py (tn_results.txt: 31 of 32 hold, in exact and in fast realignment
+mode).  test21 is the one that does not -- and the reference itself has it commented out
+(tests/lib.rs:102); its PROB_SOMATIC_TUMOR >= 200 depends on the Myers traceback tie-breaking,
+which is calibrated on these very testcases (oracle/vlr_oracle.c, g_traceback_rule)."""
 import glob
 import os
 
@@ -18,7 +21,8 @@ from libprosic_b200 import fixtures as F
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 FIXTURES = sorted(glob.glob(os.path.join(HERE, "golden", "tn", "*.json.gz")))
-KNOWN_EXCEPTIONS = {"test21"}
+GENERIC = sorted(glob.glob(os.path.join(HERE, "golden", "gen", "*.json.gz")))
+KNOWN_EXCEPTIONS = {"test21"}  # disabled upstream as well (reference tests/lib.rs:102)
 
 
 def _name(p):
@@ -26,7 +30,54 @@ def _name(p):
 
 
 def test_fixture_set_is_complete():
-    assert len(FIXTURES) == 13
+    assert len(FIXTURES) == 13 and len(GENERIC) == 5
+
+
+@pytest.mark.parametrize("path", FIXTURES[::3], ids=_name)
+def test_reference_expectations_hold_in_fast_mode(path):
+    """`--pairhmm-mode fast` (PathHMMRealigner): the reference runs these testcases in both modes."""
+    from _oracle_backend import OracleBackend
+    r = F.run_testcase(path, OracleBackend(fast=True))
+    assert all(v for _, v in F.check_expectations(r)) or _name(path) in KNOWN_EXCEPTIONS
+
+
+@pytest.mark.parametrize("path", GENERIC, ids=_name)
+def test_generic_single_sample_expectations_hold_on_the_oracle(path):
+    from _oracle_backend import OracleBackend
+    r = F.run_generic_case(path, OracleBackend())
+    verdicts = F.check_expectations(r)
+    assert verdicts and all(v for _, v in verdicts), (verdicts, r)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", GENERIC, ids=_name)
+def test_generic_single_sample_expectations_hold_on_the_gpu(ctx, path):
+    """SNV evidence (strand, read orientation, read position, softclip biases), a deletion, and
+    the species prior through the prior table: GPU results hold the reference's expectations and
+    agree with the oracle run."""
+    from _oracle_backend import OracleBackend
+    got = F.run_generic_case(path, F.GpuBackend(ctx))
+    want = F.run_generic_case(path, OracleBackend())
+    assert got["n_obs"] == want["n_obs"] and got["af"] == want["af"], (got, want)
+    for k, w in want.items():
+        if k.startswith("PROB_"):
+            g = got[k]
+            assert (np.isinf(g) and np.isinf(w)) or abs(g - w) <= 2e-5 * max(1.0, abs(w)), (k, g, w)
+    assert all(v for _, v in F.check_expectations(got))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", FIXTURES[::3], ids=_name)
+def test_fast_mode_on_the_gpu(ctx, path):
+    import libprosic_b200 as P
+    from _oracle_backend import OracleBackend
+    got = F.run_testcase(path, F.GpuBackend(ctx, flags=P.HMM_DEFAULT | P.REALIGN_FAST))
+    want = F.run_testcase(path, OracleBackend(fast=True))
+    assert got["af"] == want["af"] and got["n_obs"] == want["n_obs"], (got["af"], want["af"])
+    for k, w in want.items():
+        if k.startswith("PROB_"):
+            g = got[k]
+            assert (np.isinf(g) and np.isinf(w)) or abs(g - w) <= 2e-5 * max(1.0, abs(w)), (k, g, w)
 
 
 @pytest.mark.parametrize("path", FIXTURES, ids=_name)
