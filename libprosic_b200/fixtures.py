@@ -683,6 +683,82 @@ def run_generic_case(path, backend):
     return run_single_sample_testcase(path, backend, sample, events, germline_prior(het) if het else None)
 
 
+# ------------------------------------------------------------------------------- pedigree (trio) testcases
+def _hypergeom_pmf(N, K, n, k):
+    """statrs Hypergeometric::new(N, K, n).pmf(k)."""
+    if k > K or n - k > N - K or k > n:
+        return 0.0
+    return math.comb(K, k) * math.comb(N - K, n - k) / math.comb(N, n)
+
+
+def mendelian_trio_prior(heterozygosity, germline_mutation_rate, child, parents, ploidy=2):
+    """Prior::calc_prob for a diploid trio without somatic terms (variants/model/prior.rs:288-431):
+    population prior of the parents (prob_population_germline, 628-656) and Mendelian inheritance of
+    the child (prob_mendelian_alt_counts / prob_mendelian_inheritance, 674-786).  child / parents are
+    sample indices in the scenario's (alphabetical) order."""
+    def f(afs):
+        n_alt = [int(round(ploidy * a)) for a in afs]
+        m = sum(n_alt[p] for p in parents)
+        if m > 0:
+            prob = math.log(heterozygosity) - math.log(m)
+        else:
+            n = ploidy * len(parents)
+            prob = ln_one_minus_exp(ln_sum_exp([math.log(heterozygosity) - math.log(k) for k in range(1, n + 1)]))
+        half = ploidy // 2  # even ploidies: one meiotic split case
+        terms = []
+        for a1 in range(0, min(n_alt[parents[0]], half) + 1):
+            for a2 in range(0, min(n_alt[parents[1]], half) + 1):
+                if a1 + a2 > n_alt[child]:
+                    continue
+                p = (_ln(_hypergeom_pmf(ploidy, n_alt[parents[0]], half, a1)) +
+                     _ln(_hypergeom_pmf(ploidy, n_alt[parents[1]], half, a2)))
+                terms.append(p + math.log(germline_mutation_rate) * (n_alt[child] - a1 - a2))
+        return prob + ln_sum_exp(terms)
+    return f
+
+
+def trio_scenario(tc):
+    """test61-63 (scenario.yaml): samples father = 0, index = 1, mother = 2 (alphabetical, quirk Q12),
+    universe {0, .5, 1} each (ploidy 2);
+      denovo:          "(index:0.5 | index:1.0) & father:0.0 & mother:0.0"
+      not_interesting: "!father:0.0 | !mother:0.0"   (disjoint cover: father != 0, or father = 0 & mother != 0)"""
+    b = scenario._Builder()
+    S, gt = scenario.NODE_SET, [0.0, 0.5, 1.0]
+    denovo = b.chain([(0, S, [0.0]), (1, S, [0.5, 1.0]), (2, S, [0.0])])
+    ni_a = b.chain([(0, S, [0.5, 1.0]), (1, S, gt), (2, S, gt)])
+    ni_b = b.chain([(0, S, [0.0]), (1, S, gt), (2, S, [0.5, 1.0])])
+    om = tc["omit"]
+    arts = scenario.artifact_biases(not om["strand_bias"], not om["read_orientation_bias"],
+                                    not om["read_position_bias"], not om["softclip_bias"], not om["divindel_bias"])
+    ev, biases = scenario._with_events(b, [("denovo", [denovo]), ("not_interesting", [ni_a, ni_b])], 3, arts)
+    return dict(n_samples=3, resolution=[100, 100, 100], contaminated=[0, 0, 0], by=[0, 0, 0], purity=[1.0] * 3,
+                nodes=b.nodes, events=ev, biases=biases,
+                prior_fn=mendelian_trio_prior(0.001, 0.1, child=1, parents=(2, 0)))
+
+
+def run_trio_testcase(path, backend):
+    """preprocess (father, index, mother) + call for the pedigree SNV testcases test61-63."""
+    tc = load_fixture(path) if os.path.isfile(path) else load_testcase(path)
+    order = ["father", "index", "mother"]
+    pile = [extract_observations_snv(tc, s_, backend, tc["omit"]["read_orientation_bias"]) for s_ in order]
+    cols = {c: np.concatenate([p_[0][c] for p_ in pile]) for c in obs_codec.COLUMNS}
+    cat = np.concatenate([p_[1] for p_ in pile])
+    off = np.concatenate([[0], np.cumsum([len(p_[1]) for p_ in pile])]).astype(np.int64)
+    scn = trio_scenario(tc)
+    _, afs = backend.model_leaves(scn)
+    scn["prior_ln"] = np.array([scn["prior_fn"](list(a)) for a in afs])
+    post = backend.posterior(scn, cols, cat, off)
+    rec = backend.call_records(scn, post, cols["prob_mapping"], off)
+    out = {"PROB_" + n.upper(): float(v) for n, v in zip(rec["names"], rec["prob"][0])}
+    out["af"] = {s_: float(rec["af"][0][k]) for k, s_ in enumerate(order)}
+    out["n_obs"] = {s_: int(off[k + 1] - off[k]) for k, s_ in enumerate(order)}
+    out["expected"] = tc["expected"]
+    return out
+
+
+TRIO_CASES = ("test61", "test62", "test63")
+
+
 def germline_prior(heterozygosity, ploidy=2):
     """Prior::prob_population_germline for one diploid sample without inheritance or somatic terms
     (variants/model/prior.rs:288-431, 628-656): m alt alleles -> ln(het) - ln(m); none ->

@@ -21,6 +21,13 @@ def main():
     gen = os.path.join(os.path.dirname(OUT), "gen")
     os.makedirs(gen, exist_ok=True)
     total = 0
+    trio = os.path.join(os.path.dirname(OUT), "trio")
+    os.makedirs(trio, exist_ok=True)
+    for c in F.TRIO_CASES:  # pedigree SNV testcases (Mendelian prior through the prior table)
+        p = os.path.join(trio, c + ".json.gz")
+        F.save_fixture(F.load_testcase(os.path.join(REF, c)), p)
+        total += os.path.getsize(p)
+        print(c, os.path.getsize(p))
     for c in F.GENERIC_CASES:  # one-sample Generic testcases (SNVs, prior table)
         p = os.path.join(gen, c + ".json.gz")
         F.save_fixture(F.load_testcase(os.path.join(REF, c)), p)

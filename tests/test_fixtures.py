@@ -5,7 +5,8 @@ assert (tests/lib.rs, tests/common/mod.rs:289-343).
 
 tests/golden/tn/*.json.gz are compact forms of 13 tumor/normal indel testcases and
 tests/golden/gen/*.json.gz of 5 one-sample Generic testcases (SNVs with all five bias types, a
-deletion, a ploidy universe with the species prior as a prior table); both are written by
+deletion, a ploidy universe with the species prior as a prior table), tests/golden/trio/*.json.gz
+of the three pedigree testcases test61-63 (Mendelian prior); all written by
 tests/golden/make_tn_fixtures.py.  All 32 tumor/normal testcases run in this container with
 tests/golden/run_tn_testcases.py (tn_results.txt: 31 of 32 hold, in exact and in fast realignment
 mode).  test21 is the one that does not -- and the reference itself has it commented out
@@ -22,6 +23,7 @@ from libprosic_b200 import fixtures as F
 HERE = os.path.dirname(os.path.abspath(__file__))
 FIXTURES = sorted(glob.glob(os.path.join(HERE, "golden", "tn", "*.json.gz")))
 GENERIC = sorted(glob.glob(os.path.join(HERE, "golden", "gen", "*.json.gz")))
+TRIO = sorted(glob.glob(os.path.join(HERE, "golden", "trio", "*.json.gz")))
 KNOWN_EXCEPTIONS = {"test21"}  # disabled upstream as well (reference tests/lib.rs:102)
 
 
@@ -30,7 +32,31 @@ def _name(p):
 
 
 def test_fixture_set_is_complete():
-    assert len(FIXTURES) == 13 and len(GENERIC) == 5
+    assert len(FIXTURES) == 13 and len(GENERIC) == 5 and len(TRIO) == 3
+
+
+@pytest.mark.parametrize("path", TRIO, ids=_name)
+def test_trio_expectations_hold_on_the_oracle(path):
+    """Pedigree testcases test61-63 (config C5's shape on real reads): three samples, genotype
+    universes, joint events, Mendelian-inheritance prior (prior.rs:288-431, 674-786)."""
+    from _oracle_backend import OracleBackend
+    r = F.run_trio_testcase(path, OracleBackend())
+    verdicts = F.check_expectations(r)
+    assert verdicts and all(v for _, v in verdicts), (verdicts, r)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", TRIO, ids=_name)
+def test_trio_expectations_hold_on_the_gpu(ctx, path):
+    from _oracle_backend import OracleBackend
+    got = F.run_trio_testcase(path, F.GpuBackend(ctx))
+    want = F.run_trio_testcase(path, OracleBackend())
+    assert got["n_obs"] == want["n_obs"] and got["af"] == want["af"], (got, want)
+    for k, w in want.items():
+        if k.startswith("PROB_"):
+            g = got[k]
+            assert (np.isinf(g) and np.isinf(w)) or abs(g - w) <= 2e-5 * max(1.0, abs(w)), (k, g, w)
+    assert all(v for _, v in F.check_expectations(got))
 
 
 @pytest.mark.parametrize("path", FIXTURES[::3], ids=_name)
