@@ -339,10 +339,20 @@ def bench_allele_support(args, ctx, w, flags, rank, world, torch, dist, dev):
     region_n_ref = np.ones(n_reads, dtype=np.int32)
     gap = P.GapParams()
 
+    # inputs and outputs in pinned host memory, as a host integration would hold its batch buffers
+    def pin(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    p_in = {k: pin(v) for k, v in dict(rr=region_read, rho=region_hap_off, rh=region_haps, rnr=region_n_ref,
+                                      hb=w["hap_bytes"], ho=w["hap_off"], rb=w["read_bases"][:int(w["read_off"][n_reads])],
+                                      rq=w["read_quals"][:int(w["read_off"][n_reads])], ro=w["read_off"][:n_reads + 1]).items()}
+    p_out = dict(prob_ref=pin(np.empty(n_reads)), prob_alt=pin(np.empty(n_reads)), raw_ref=pin(np.empty(n_reads)),
+                 raw_alt=pin(np.empty(n_reads)), ref_dist=pin(np.empty(n_reads, np.int32)),
+                 alt_dist=pin(np.empty(n_reads, np.int32)), n_indel_ops=pin(np.empty(n_reads, np.int32)),
+                 indel_ops=pin(np.zeros((n_reads, 32), np.uint8)))
+
     def run():
-        return ctx.allele_support_batch(region_read, region_hap_off, region_haps, region_n_ref,
-                                        w["hap_bytes"], w["hap_off"], w["read_bases"], w["read_quals"],
-                                        w["read_off"][:n_reads + 1], gap, flags=flags)
+        return ctx.allele_support_batch(p_in["rr"], p_in["rho"], p_in["rh"], p_in["rnr"], p_in["hb"], p_in["ho"],
+                                        p_in["rb"], p_in["rq"], p_in["ro"], gap, flags=flags, out=p_out)
     out = run()
     run()
     torch.cuda.synchronize(dev)

@@ -148,8 +148,9 @@ class Context:
 
     def allele_support_batch(self, region_read, region_hap_off, region_haps, region_n_ref, hap_bytes,
                              hap_off, read_bases, read_quals, read_off, gap, shrink_extra=None,
-                             flags=_ffi.HMM_DEFAULT):
-        """Fused Realigner::allele_support per merged region (see include/vlr_gpu.h)."""
+                             flags=_ffi.HMM_DEFAULT, out=None):
+        """Fused Realigner::allele_support per merged region (see include/vlr_gpu.h).
+        out: optional dict of preallocated (e.g. pinned) output arrays with the keys returned."""
         region_read = _arr(region_read, np.int32)
         region_hap_off = _arr(region_hap_off, np.int32)
         region_haps = _arr(region_haps, np.int32)
@@ -161,10 +162,11 @@ class Context:
         read_off = _arr(read_off, np.int64)
         shrink_extra = _arr(shrink_extra, np.int32)
         n = len(region_read)
-        out = dict(prob_ref=np.empty(n), prob_alt=np.empty(n), raw_ref=np.empty(n), raw_alt=np.empty(n),
-                   ref_dist=np.empty(n, np.int32), alt_dist=np.empty(n, np.int32),
-                   n_indel_ops=np.empty(n, np.int32),
-                   indel_ops=np.zeros((n, _ffi.MAX_INDEL_OPS), np.uint8))
+        if out is None:
+            out = dict(prob_ref=np.empty(n), prob_alt=np.empty(n), raw_ref=np.empty(n), raw_alt=np.empty(n),
+                       ref_dist=np.empty(n, np.int32), alt_dist=np.empty(n, np.int32),
+                       n_indel_ops=np.empty(n, np.int32),
+                       indel_ops=np.zeros((n, _ffi.MAX_INDEL_OPS), np.uint8))
         self._check(self.lib.vlr_allele_support_batch(
             self.h, n, _ptr(region_read), _ptr(region_hap_off), _ptr(region_haps), _ptr(region_n_ref),
             _ptr(hap_bytes), _ptr(hap_off), len(hap_off) - 1, _ptr(shrink_extra), _ptr(read_bases),

@@ -20,6 +20,8 @@
 
 #include <stdlib.h>
 
+#include <chrono>
+
 #include "pairhmm_host.cuh"
 
 namespace vlr {
@@ -523,6 +525,16 @@ int vlr_allele_support_batch(vlr_ctx *ctx, int64_t n_regions, const int32_t *reg
                              double *out_raw_ref, double *out_raw_alt, int32_t *out_ref_dist,
                              int32_t *out_alt_dist, int32_t *out_n_indel_ops, uint8_t *out_indel_ops) {
     if (!ctx) return VLR_ERR_INVALID;
+    const bool trace = getenv("VLR_TRACE") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_prev = now();
+    auto lap = [&](const char *what, bool sync) {
+        if (!trace) return;
+        if (sync) cudaStreamSynchronize(ctx->stream);
+        const double t = now();
+        fprintf(stderr, "[vlr trace] allele_support %-12s %8.3f ms\n", what, t - t_prev);
+        t_prev = t;
+    };
     if (n_regions < 0 || n_regions > 0x3fffffff) return set_err(ctx, VLR_ERR_INVALID, "n_regions out of range");
     if (n_regions == 0) return VLR_OK;
     if (!region_read || !region_hap_off || !region_haps || !region_n_ref || !hap_bytes || !hap_off ||
@@ -552,6 +564,7 @@ int vlr_allele_support_batch(vlr_ctx *ctx, int64_t n_regions, const int32_t *reg
     }
     for (int64_t s = 0; s < n_slots; ++s)
         if (region_haps[s] < 0 || region_haps[s] >= n_haps) return set_err(ctx, VLR_ERR_INVALID, "region_haps out of range");
+    lap("validate", false);
     enum { S_HAP = 40, S_HOFF, S_RB, S_ROFF, S_PH, S_PR, S_OUT, S_OPS, S_SCR, S_SCR2, S_SCR3,
            S_RQ, S_RR, S_RHO, S_RNR, S_SE, S_WS0, S_WL, S_MED, S_SP, S_SM, S_O1, S_O2, S_O3, S_O4, S_O5,
            S_O6, S_O7, S_O8, S_PWS, S_PATH = 75 };
@@ -583,6 +596,7 @@ int vlr_allele_support_batch(vlr_ctx *ctx, int64_t n_regions, const int32_t *reg
         (shrink_extra && !d_se) || !d_slot_read || !d_hits || !d_ops || !d_ws || !d_wl || !d_med ||
         !d_sp || !d_sm || !d_pref || !d_palt || !d_rref || !d_ralt || !d_rd || !d_ad || !d_ni || !d_io || !d_pws)
         return set_err(ctx, VLR_ERR_NOMEM, "scratch allocation failed");
+    lap("scratch", false);
     // slot -> read index (the Myers pairs)
     std::vector<int32_t> slot_read((size_t)n_slots);
     for (int64_t r = 0; r < n_regions; ++r)
@@ -602,6 +616,7 @@ int vlr_allele_support_batch(vlr_ctx *ctx, int64_t n_regions, const int32_t *reg
     VLR_CUDA(ctx, cudaStreamSynchronize(st));  // slot_read is a stack-owned staging vector
     VLR_CUDA(ctx, cudaMemsetAsync(d_ops, 0, (size_t)n_slots * kMaxIndelOps, st));
     VLR_CUDA(ctx, cudaMemsetAsync(d_io, 0, (size_t)n_regions * kMaxIndelOps, st));
+    lap("h2d", true);
     // 1. best hit of every (read window, haplotype) slot
     MyersArgs ma;
     memset(&ma, 0, sizeof(ma));
@@ -617,6 +632,7 @@ int vlr_allele_support_batch(vlr_ctx *ctx, int64_t n_regions, const int32_t *reg
     }
     int rc = launch_besthit(ctx, ma, max_lx, S_SCR);
     if (rc != VLR_OK) return rc;
+    lap("myers", true);
     // 2. minimal-distance selection, certainty short-circuit, HMM windows
     SupportArgs sa;
     memset(&sa, 0, sizeof(sa));
@@ -637,6 +653,7 @@ int vlr_allele_support_batch(vlr_ctx *ctx, int64_t n_regions, const int32_t *reg
                                  d_roff, d_slot_read, d_med, d_sm, gap, flags, d_pws, pws_bytes, d_sp);
         if (rc != VLR_OK) return rc;
     }
+    lap("select+hmm", true);
     // 4. max over haplotypes, normalisation, fallbacks
     support_epilogue_kernel<<<grid, 128, 0, st>>>(sa);
     VLR_LAUNCH_CHECK(ctx);
@@ -650,6 +667,7 @@ int vlr_allele_support_batch(vlr_ctx *ctx, int64_t n_regions, const int32_t *reg
     VLR_CUDA(ctx, D2H(out_n_indel_ops, d_ni, (size_t)n_regions * 4));
     if (out_indel_ops) VLR_CUDA(ctx, D2H(out_indel_ops, d_io, (size_t)n_regions * kMaxIndelOps));
     VLR_CUDA(ctx, cudaStreamSynchronize(st));
+    lap("epilogue+d2h", false);
     return VLR_OK;
 }
 
