@@ -62,24 +62,32 @@ __device__ __forceinline__ int sym_of(int c) {  // A C G T N -> 0..4, anything e
 
 // D[j][i] from the stored column state (i >= 1): bottom distance minus the vertical deltas of
 // rows j+1..m
-__device__ __forceinline__ int dist_at(const uint64_t *col, int dm, int j, int m) {
+// D[j][i] from a column record (W words of Pv, then W words of Mv) and the bottom distance
+__device__ __forceinline__ int dist_from(const uint64_t *rec, int dm, int j, int m, int W) {
     int d = dm;
 #pragma unroll
     for (int w = 0; w < kMyW; ++w) {
         const int lo = w * 64, hi = min(m, lo + 64);
-        if (hi <= lo || j >= hi) continue;
+        if (w >= W || j >= hi) continue;
         const int from = max(j, lo) - lo;  // bit index of row from+1
         uint64_t mask = (hi - lo == 64 ? ~0ull : ((1ull << (hi - lo)) - 1ull)) & (~0ull << from);
-        d -= __popcll(col[w] & mask);
-        d += __popcll(col[kMyW + w] & mask);
+        d -= __popcll(rec[w] & mask);
+        d += __popcll(rec[kMyW + w] & mask);
     }
     return d;
 }
 
 __global__ void __launch_bounds__(128) besthit_kernel(MyersArgs g) {
     const int64_t worker = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    uint64_t *cols = g.scratch + worker * g.scratch_stride * (2 * kMyW);
-    int32_t *dms = g.scratch_dm + worker * g.scratch_stride;
+    // Scratch is interleaved across the lanes of a warp: word pair w of column c of lane l sits at
+    // ((c * kMyW + w) * 32 + l) * 16 bytes, the bottom distance at (c * 32 + l) * 4.  The lanes of
+    // a warp walk the columns in lock step, so a column's stores are whole 512-byte rows instead
+    // of 32 scattered 48-byte pieces.
+    const int64_t warp_id = worker >> 5;
+    const int lane_id = (int)(worker & 31);
+    ulonglong2 *cols = reinterpret_cast<ulonglong2 *>(g.scratch) + warp_id * g.scratch_stride * (kMyW * 32) + lane_id;
+    int32_t *dms_base = g.scratch_dm + warp_id * g.scratch_stride * 32 + lane_id;
+    auto dms = [&](int c) -> int32_t & { return dms_base[(int64_t)c * 32]; };
     for (;;) {
         const int64_t k = (int64_t)atomicAdd(g.cursor, 1);
         if (k >= g.n_pairs) break;
@@ -110,8 +118,15 @@ __global__ void __launch_bounds__(128) besthit_kernel(MyersArgs g) {
         for (int w = 0; w < kMyW; ++w) { Pv[w] = ~0ull; Mv[w] = 0; }
         const int W = (m + 63) >> 6, lastbit = (m - 1) & 63;
         int score = m, best = 1 << 30, n_best = 0, first_best = 0, last_best = 0;
+        // text characters arrive in aligned 8-byte chunks, one chunk ahead of their use (the
+        // staged haplotype buffer carries slack on both sides of every window)
+        const int toff = (int)(reinterpret_cast<uintptr_t>(txt) & 7);
+        const uint64_t *t8 = reinterpret_cast<const uint64_t *>(txt - toff);
+        uint64_t tw = t8[0], tw_next = t8[1];
         for (int i = 0; i < n; ++i) {
-            const int c = up_char(txt[i]);
+            const int tq = i + toff;
+            if ((tq & 7) == 0 && i > 0) { tw = tw_next; tw_next = t8[(tq >> 3) + 1]; }
+            const int c = up_char((int)((tw >> ((tq & 7) * 8)) & 0xffu));
             const int s = sym_of(c);
             int hin = 0;
 #pragma unroll
@@ -139,10 +154,12 @@ __global__ void __launch_bounds__(128) besthit_kernel(MyersArgs g) {
                 hin = hout;
             }
             score += hin;
-            uint64_t *col = cols + (int64_t)(i + 1) * (2 * kMyW);
+            // column record: (Pv, Mv) of the words the pattern uses
+            ulonglong2 *col = cols + (int64_t)(i + 1) * (kMyW * 32);
 #pragma unroll
-            for (int w = 0; w < kMyW; ++w) { col[w] = Pv[w]; col[kMyW + w] = Mv[w]; }
-            dms[i + 1] = score;
+            for (int w = 0; w < kMyW; ++w)
+                if (w < W) col[w * 32] = make_ulonglong2(Pv[w], Mv[w]);
+            dms(i + 1) = score | (c << 16);  // bottom distance and the column's (upper-cased) text character
             if (score < best) { best = score; n_best = 1; first_best = i + 1; last_best = i + 1; }
             else if (score == best) { n_best++; last_best = i + 1; }
         }
@@ -153,7 +170,7 @@ __global__ void __launch_bounds__(128) besthit_kernel(MyersArgs g) {
         double best_path = -INFINITY;
         bool have_path = false;
         for (int e = first_best; e <= last_best; ++e) {
-            if (dms[e] != best) continue;
+            if ((dms(e) & 0xffff) != best) continue;
             int j = m, i = e, nindel = 0;
             uint8_t ops[kMaxIndelOps];  // ring of the indel ops in traceback (reverse) order
             // PathHMM: the walk runs backwards, so the transition INTO the operation found last
@@ -168,17 +185,48 @@ __global__ void __launch_bounds__(128) besthit_kernel(MyersArgs g) {
             // D[j][i] of the current cell is carried along; predecessors are evaluated on demand.
             // Tie-breaking: diagonal first, then Ins, then Del -- calibrated against the reference's
             // integration tests
-            int d = dms[e];
+            // The records of columns i, i-1 live in registers and column i-2 is prefetched while
+            // the current step is evaluated: the walk moves left by at most one column per step,
+            // so the scratch latency stays off the dependent chain.
+            // Only the words at or above the current row are ever looked at (dist_from counts the
+            // deltas of rows j+1..m), and every 16-byte word pair costs a 32-byte sector: skip the
+            // words below.  A record survives at most two column moves in registers, each taking j
+            // down by at most one; an insertion takes j down without moving, so it reloads.
+            auto load_rec = [&](uint64_t *rec, int c) {
+                const int wmin = max(j - 4, 0) >> 6;
+#pragma unroll
+                for (int w = 0; w < kMyW; ++w)
+                    if (w < W && w >= wmin) {
+                        const ulonglong2 v = cols[((int64_t)max(c, 1) * kMyW + w) * 32];
+                        rec[w] = v.x;
+                        rec[kMyW + w] = v.y;
+                    }
+            };
+            uint64_t r_cur[2 * kMyW], r_left[2 * kMyW], r_pre[2 * kMyW];
+            load_rec(r_cur, i);
+            load_rec(r_left, i - 1);
+            int dm_cur = dms(i), dm_left = dms(max(i - 1, 0));
+            int d = dm_cur & 0xffff;
+            const int poff = (int)(reinterpret_cast<uintptr_t>(pat) & 7);
+            const uint64_t *p8 = reinterpret_cast<const uint64_t *>(pat - poff);
+            int pchunk = -1;
+            uint64_t pw = 0;
             while (j > 0) {
+                load_rec(r_pre, i - 2);                       // prefetch
+                const int dm_pre = dms(max(i - 2, 0));
                 int op;
+                bool match = false;
                 if (i > 0) {
-                    const int ddiag = i > 1 ? dist_at(cols + (int64_t)(i - 1) * (2 * kMyW), dms[i - 1], j - 1, m) : j - 1;
-                    const int cost = pat[j - 1] == up_char(txt[i - 1]) ? 0 : 1;
+                    const int ddiag = i > 1 ? dist_from(r_left, dm_left & 0xffff, j - 1, m, W) : j - 1;
+                    const int pq = j - 1 + poff;  // pattern bytes in aligned 8-byte chunks, reloaded every 8 rows
+                    if ((pq >> 3) != pchunk) { pchunk = pq >> 3; pw = p8[pchunk]; }
+                    match = (int)((pw >> ((pq & 7) * 8)) & 0xffu) == (dm_cur >> 16);  // pat[j-1] == T[i-1]
+                    const int cost = match ? 0 : 1;
                     if (ddiag + cost == d) {
                         op = 0;
                         d = ddiag;
                     } else {
-                        const int dup = dist_at(cols + (int64_t)i * (2 * kMyW), dms[i], j - 1, m);
+                        const int dup = dist_from(r_cur, dm_cur & 0xffff, j - 1, m, W);
                         if (d == dup + 1) { op = 3; d = dup; }
                         else { op = 2; d -= 1; }  // D[j][i-1] + 1 == D[j][i]
                     }
@@ -186,9 +234,17 @@ __global__ void __launch_bounds__(128) besthit_kernel(MyersArgs g) {
                     op = 3;  // text exhausted: D[j][0] = j
                     d -= 1;
                 }
+                if (op != 3) {  // moved one column to the left
+#pragma unroll
+                    for (int w = 0; w < 2 * kMyW; ++w) { r_cur[w] = r_left[w]; r_left[w] = r_pre[w]; }
+                    dm_cur = dm_left;
+                    dm_left = dm_pre;
+                }
                 if (op == 3) {
                     ops[nindel & (kMaxIndelOps - 1)] = 3;
                     nindel++; j--;
+                    load_rec(r_cur, i);  // the rows in reach may now start one word lower
+                    load_rec(r_left, i - 1);
                     if (want_path) path += (double)g.rqual[ro + j] * -0.23025850929940456;  // prob_emit_y
                 } else if (op == 2) {  // Del (prob_emit_x = ln 1)
                     ops[nindel & (kMaxIndelOps - 1)] = 2;
@@ -197,7 +253,7 @@ __global__ void __launch_bounds__(128) besthit_kernel(MyersArgs g) {
                     j--; i--;
                     if (want_path) {
                         const int q = g.rqual[ro + j];
-                        path += pat[j] == up_char(txt[i]) ? g.qlut[q * kQlutStride + 3]
+                        path += match ? g.qlut[q * kQlutStride + 3]
                                                           : (double)q * -0.23025850929940456 + -1.098712293668443;
                     }
                 }
