@@ -333,10 +333,17 @@ int vlr_posterior_batch_dev(vlr_ctx *ctx, int64_t n_sites, const vlr_model *mode
         const int NS = model->n_samples;
         const int team = big ? 4 : 1;
         const int mb = big ? 3 : (minb >= 5 ? 5 : 3);
-        const int nsc = big ? (NS == 2 ? 2 : 0) : (NS <= 3 ? NS : 0);
+        bool any_cont = false;
+        for (int k = 0; k < NS; ++k) any_cont |= model->contaminated[k] != 0;
+        // instantiations: without contamination 1..3 samples; with contamination 2 samples or generic
+        int nsc, cont;
+        if (big) { cont = 1; nsc = NS == 2 ? 2 : 0; }
+        else if (!any_cont && NS <= 3) { cont = 0; nsc = NS; }
+        else { cont = 1; nsc = NS == 2 ? 2 : 0; }
         cudaError_t le = cudaErrorInvalidValue;
-#define VLR_POST_TRY(TEAM, MINB, NSC) \
-        if (team == TEAM && mb == MINB && nsc == NSC) le = VLR_POSTERIOR_LAUNCHER(TEAM, MINB, NSC)(grid, dyn_smem, st, a);
+#define VLR_POST_TRY(TEAM, MINB, NSC, CONT) \
+        if (team == TEAM && mb == MINB && nsc == NSC && cont == CONT)  \
+            le = VLR_POSTERIOR_LAUNCHER(TEAM, MINB, NSC, CONT)(grid, dyn_smem, st, a);
         VLR_POSTERIOR_FOR_ALL(VLR_POST_TRY)
 #undef VLR_POST_TRY
         if (le != cudaSuccess)

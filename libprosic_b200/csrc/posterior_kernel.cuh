@@ -387,8 +387,10 @@ __device__ __forceinline__ double s_eff(double af, double sigma) {
 
 // TEAM = warps per site; MINB = CTAs per SM the register allocation must allow; NSC = number of
 // samples when known at compile time (0: run-time) -- the per-sample loops of the integration then
-// unroll and their small index arrays stay in registers instead of local memory.
-template <int TEAM, int MINB, int NSC>
+// unroll and their small index arrays stay in registers instead of local memory; CONT = false
+// leaves out the contaminated-sample paths (scenarios without contamination) -- the kernel is
+// instruction-fetch sensitive, less code is measurably faster.
+template <int TEAM, int MINB, int NSC, bool CONT>
 __global__ void __launch_bounds__(kTeamThreadsMax, MINB) posterior_kernel(PostArgs g) {
     constexpr int NSA = NSC > 0 ? NSC : kMaxSamples;   // capacity of per-sample register arrays
     constexpr int NSU = NSC > 0 ? NSC : 1;              // unroll factor of per-sample loops
@@ -425,7 +427,8 @@ __global__ void __launch_bounds__(kTeamThreadsMax, MINB) posterior_kernel(PostAr
 
     #pragma unroll 1
     for (;;) {
-        // ---- next site (dynamic)
+        // ---- next site (dynamic; chunks of consecutive sites and a prefetch of the following
+        // site's rows were measured and lose 2-8 % on the C2 / C5 workloads)
         __shared__ int64_t s_site[kTeamsPerCta];
         team_sync<TEAM>();
         if (tt == 0) s_site[team_in_cta] = (int64_t)atomicAdd(g.cursor, 1);
@@ -529,7 +532,7 @@ __global__ void __launch_bounds__(kTeamThreadsMax, MINB) posterior_kernel(PostAr
             int64_t toff = 0;
             #pragma unroll 1
             for (int smp = 0; smp < NS; ++smp) {
-                const int64_t keys = m.contaminated[smp]
+                const int64_t keys = (CONT && m.contaminated[smp])
                                          ? (int64_t)S.sample_nv[smp] * S.sample_nv[m.by[smp]]
                                          : (int64_t)S.sample_nv[smp];
                 S.tab_off[smp] = toff;
@@ -643,7 +646,7 @@ __global__ void __launch_bounds__(kTeamThreadsMax, MINB) posterior_kernel(PostAr
         for (int smp = 0; smp < NS; ++smp) {
             const int64_t o0 = g.obs_off[site * NS + smp];
             const int n = S.n_obs[smp];
-            const bool cont = m.contaminated[smp] != 0;
+            const bool cont = CONT && m.contaminated[smp] != 0;
             const double rho = m.purity[smp];
             const int nv = S.sample_nv[smp], v0 = S.sample_voff[smp];
             const int byv0 = cont ? S.sample_voff[m.by[smp]] : 0;
@@ -939,8 +942,9 @@ __global__ void __launch_bounds__(kTeamThreadsMax, MINB) posterior_kernel(PostAr
             bool art = false;
             const double *prior = nullptr;
             const unsigned rounds = (NT + TT - 1) / TT;
+            // (one extra round in which every lane is past the last term flushes what is pending)
             #pragma unroll 1
-            for (unsigned r = 0; r < rounds; ++r) {
+            for (unsigned r = 0; r <= rounds; ++r) {
                 const unsigned t = r * TT + tt;
                 const bool valid = t < NT;
                 int e_t = NE;  // sentinel: beyond the last term
@@ -984,7 +988,7 @@ __global__ void __launch_bounds__(kTeamThreadsMax, MINB) posterior_kernel(PostAr
                 #pragma unroll NSU
                 for (int smp = 0; smp < NS; ++smp) {
                     int key = vidx[smp];
-                    if (m.contaminated[smp]) {
+                    if (CONT && m.contaminated[smp]) {
                         int vby = 0;
                         if (NSC > 0) {  // pick the source's digit without dynamic register indexing
                             #pragma unroll
@@ -1012,11 +1016,6 @@ __global__ void __launch_bounds__(kTeamThreadsMax, MINB) posterior_kernel(PostAr
                 if (isnan(tv)) { sum = NAN; }
                 else if (tv > mx) { sum = sum * exp_ni(mx - tv) + 1.0; mx = tv; }
                 else if (tv != -INFINITY) sum += exp_ni(tv - mx);
-            }
-            // whatever is still pending (cur_e == NE: nothing)
-            {
-                const bool pend = cur_e >= 0 && cur_e < NE;
-                if (__any_sync(0xffffffffu, pend)) flush(pend, pend ? cur_e : NE, mx, sum);
             }
             team_sync<TEAM>();
             #pragma unroll 1
@@ -1145,23 +1144,25 @@ __global__ void __launch_bounds__(kTeamThreadsMax, MINB) posterior_kernel(PostAr
 }
 
 // ---------------------------------------------------------------- instantiation (posterior_inst_*.cu)
-#define VLR_POSTERIOR_LAUNCHER(TEAM, MINB, NSC) launch_posterior_t##TEAM##_m##MINB##_n##NSC
-#define VLR_POSTERIOR_DECLARE(TEAM, MINB, NSC)                                                    \
-    cudaError_t VLR_POSTERIOR_LAUNCHER(TEAM, MINB, NSC)(int grid, size_t dyn_smem, cudaStream_t st, \
-                                                        const PostArgs &a);
-#define VLR_POSTERIOR_INSTANTIATE(TEAM, MINB, NSC)                                                \
-    cudaError_t VLR_POSTERIOR_LAUNCHER(TEAM, MINB, NSC)(int grid, size_t dyn_smem, cudaStream_t st, \
-                                                        const PostArgs &a) {                      \
-        cudaError_t e = cudaFuncSetAttribute(posterior_kernel<TEAM, MINB, NSC>,                   \
+#define VLR_POSTERIOR_LAUNCHER(TEAM, MINB, NSC, CONT) launch_posterior_t##TEAM##_m##MINB##_n##NSC##_c##CONT
+#define VLR_POSTERIOR_DECLARE(TEAM, MINB, NSC, CONT)                                              \
+    cudaError_t VLR_POSTERIOR_LAUNCHER(TEAM, MINB, NSC, CONT)(int grid, size_t dyn_smem,          \
+                                                              cudaStream_t st, const PostArgs &a);
+#define VLR_POSTERIOR_INSTANTIATE(TEAM, MINB, NSC, CONT)                                          \
+    cudaError_t VLR_POSTERIOR_LAUNCHER(TEAM, MINB, NSC, CONT)(int grid, size_t dyn_smem,          \
+                                                              cudaStream_t st, const PostArgs &a) { \
+        cudaError_t e = cudaFuncSetAttribute(posterior_kernel<TEAM, MINB, NSC, CONT != 0>,        \
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,         \
                                              (int)dyn_smem);                                      \
         if (e != cudaSuccess) return e;                                                           \
-        posterior_kernel<TEAM, MINB, NSC><<<grid, kTeamThreadsMax, dyn_smem, st>>>(a);            \
+        posterior_kernel<TEAM, MINB, NSC, CONT != 0><<<grid, kTeamThreadsMax, dyn_smem, st>>>(a); \
         return cudaGetLastError();                                                                \
     }
-// every (team, CTAs per SM, compile-time sample count) combination that is built
-#define VLR_POSTERIOR_FOR_ALL(X) \
-    X(1, 5, 0) X(1, 5, 1) X(1, 5, 2) X(1, 5, 3) X(1, 3, 0) X(1, 3, 1) X(1, 3, 2) X(1, 3, 3) X(4, 3, 0) X(4, 3, 2)
+// every (team, CTAs per SM, compile-time sample count, contamination) combination that is built
+#define VLR_POSTERIOR_FOR_ALL(X)                                                                  \
+    X(1, 5, 1, 0) X(1, 5, 2, 0) X(1, 5, 3, 0) X(1, 5, 2, 1) X(1, 5, 0, 1)                         \
+    X(1, 3, 1, 0) X(1, 3, 2, 0) X(1, 3, 3, 0) X(1, 3, 2, 1) X(1, 3, 0, 1)                         \
+    X(4, 3, 2, 1) X(4, 3, 0, 1)
 VLR_POSTERIOR_FOR_ALL(VLR_POSTERIOR_DECLARE)
 
 }  // namespace vlr

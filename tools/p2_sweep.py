@@ -57,10 +57,13 @@ def main():
         def step():
             ctx.posterior_batch_dev(scn, n_sites, ptrs, d_cat.data_ptr(), d_off.data_ptr(), max(wl["depths"]),
                                     d_ev.data_ptr(), d_marg.data_ptr(), d_af.data_ptr(), d_mb.data_ptr())
-        knob, vals = (a.env.split("=")[0], a.env.split("=")[1].split(",")) if a.env else (None, [None])
+        # --env "A=1,2;B=0,1" sweeps the cartesian product of the knobs
+        import itertools
+        knobs = [(kv.split("=")[0], kv.split("=")[1].split(",")) for kv in a.env.split(";")] if a.env else []
+        vals = list(itertools.product(*[v for _, v in knobs])) or [None]
         for val in vals:
-          if knob:
-              os.environ[knob] = val
+          for (k, _), v in zip(knobs, val or ()):
+              os.environ[k] = v
           for _ in range(3):
               step()
           torch.cuda.synchronize(dev)
