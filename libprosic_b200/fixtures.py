@@ -634,7 +634,23 @@ def single_sample_scenario(tc, events, resolution=100, prior=None):
     return scn
 
 
-def run_single_sample_testcase(path, backend, sample, events, prior=None):
+def scenario_from_yaml(tc, text):
+    """Scenario of a testcase derived from its scenario.yaml by the grammar front end
+    (libprosic_b200/grammar.py) for the testcase's contig, candidate and omit_* flags."""
+    from . import grammar
+    variant = make_variant(tc, 96)
+    snv = variant["kind"] == "snv"
+    om = tc["omit"]
+    g = grammar.Scenario(text)
+    return grammar.flatten(g, contig=tc["contig"],
+                           snv=(tc["ref_allele"].upper(), tc["alt_allele"].upper()) if snv else None,
+                           snv_or_mnv=snv, omit_strand_bias=om["strand_bias"],
+                           omit_read_orientation_bias=om["read_orientation_bias"],
+                           omit_read_position_bias=om["read_position_bias"],
+                           omit_softclip_bias=om["softclip_bias"], omit_divindel_bias=om["divindel_bias"])
+
+
+def run_single_sample_testcase(path, backend, sample, events, prior=None, scenario_yaml=None):
     """preprocess + call of a one-sample Generic testcase; same result layout as run_testcase."""
     tc = load_fixture(path) if os.path.isfile(path) else load_testcase(path)
     variant = make_variant(tc, 96)
@@ -644,6 +660,10 @@ def run_single_sample_testcase(path, backend, sample, events, prior=None):
         cols, cat = extract_observations(tc, sample, backend)
     off = np.array([0, len(cat)], np.int64)
     scn = single_sample_scenario(tc, events, prior=prior)
+    if scenario_yaml is not None:
+        scn = scenario_from_yaml(tc, scenario_yaml)
+        if prior is not None:
+            scn["prior_fn"] = prior
     if prior is not None:  # Prior::compute on the leaves the library reports (set-only universes)
         _, afs = backend.model_leaves(scn)
         scn["prior_ln"] = np.array([prior(list(a)) for a in afs])
@@ -677,10 +697,11 @@ GENERIC_CASES = {
 }
 
 
-def run_generic_case(path, backend):
+def run_generic_case(path, backend, scenario_yaml=None):
     name = os.path.basename(path).split(".")[0]
     sample, events, het = GENERIC_CASES[name]
-    return run_single_sample_testcase(path, backend, sample, events, germline_prior(het) if het else None)
+    return run_single_sample_testcase(path, backend, sample, events, germline_prior(het) if het else None,
+                                      scenario_yaml=scenario_yaml)
 
 
 # ------------------------------------------------------------------------------- pedigree (trio) testcases
@@ -736,7 +757,7 @@ def trio_scenario(tc):
                 prior_fn=mendelian_trio_prior(0.001, 0.1, child=1, parents=(2, 0)))
 
 
-def run_trio_testcase(path, backend):
+def run_trio_testcase(path, backend, scenario_yaml=None):
     """preprocess (father, index, mother) + call for the pedigree SNV testcases test61-63."""
     tc = load_fixture(path) if os.path.isfile(path) else load_testcase(path)
     order = ["father", "index", "mother"]
@@ -745,6 +766,11 @@ def run_trio_testcase(path, backend):
     cat = np.concatenate([p_[1] for p_ in pile])
     off = np.concatenate([[0], np.cumsum([len(p_[1]) for p_ in pile])]).astype(np.int64)
     scn = trio_scenario(tc)
+    if scenario_yaml is not None:
+        prior_fn = scn["prior_fn"]
+        scn = scenario_from_yaml(tc, scenario_yaml)
+        assert scn["sample_names"] == order
+        scn["prior_fn"] = prior_fn
     _, afs = backend.model_leaves(scn)
     scn["prior_ln"] = np.array([scn["prior_fn"](list(a)) for a in afs])
     post = backend.posterior(scn, cols, cat, off)
