@@ -212,8 +212,12 @@ int vlr_posterior_batch_dev(vlr_ctx *ctx, int64_t n_sites, const vlr_model *mode
             nvb[sp.sample] += c;
             nv_all += c;
         }
-        // allele-frequency values + ln weights of one site (sites above the cap fail loudly)
-        val_cap = (int)((std::min<int64_t>(nv_all, kMaxValues) + 3) & ~(int64_t)3);
+        // allele-frequency values + ln weights of one site: sized for the deepest pileup the kernel
+        // admits, so no site can exceed it (the shared-memory total is checked below)
+        if (nv_all > kMaxValues)
+            return set_err(ctx, VLR_ERR_UNSUPPORTED, "the model needs up to %lld allele-frequency values per site "
+                           "(limit %d)", (long long)nv_all, kMaxValues);
+        val_cap = (int)((nv_all + 3) & ~(int64_t)3);
         team_smem += (size_t)val_cap * 16;
         for (int smp = 0; smp < model->n_samples; ++smp)
             if (model->contaminated[smp])
@@ -491,6 +495,9 @@ static int posterior_pipeline(vlr_ctx *ctx, int64_t n_sites, const vlr_model *mo
     }
     // earlier work of this context may still read the buffers the copy stream is about to overwrite
     VLR_CUDA(ctx, cudaStreamSynchronize(st));
+    int32_t *h_status = (int32_t *)pin_scratch(ctx, 5, (size_t)n_chunks * 4 + 16);
+    if (!h_status) return set_err(ctx, VLR_ERR_NOMEM, "scratch allocation failed");
+    memset(h_status, 0, (size_t)n_chunks * 4);
     cudaStream_t cp = ctx->copy_stream;
     for (int c = 0; c <= n_chunks; ++c) {
         if (c < n_chunks) {  // H2D of chunk c
@@ -525,6 +532,9 @@ static int posterior_pipeline(vlr_ctx *ctx, int64_t n_sites, const vlr_model *mo
             rc = vlr_posterior_batch_dev(ctx, s1 - s0, model, &dc, d_off[b], (int32_t)max_obs, d_ev[b], d_marg[b],
                                          d_af[b], d_mb[b]);
             if (rc != VLR_OK) return rc;
+            // number of sites of this chunk that exceeded a kernel limit (their outputs are NaN)
+            VLR_CUDA(ctx, cudaMemcpyAsync(&h_status[c - 1], (const int32_t *)dev_scratch(ctx, 18, 256) + 1, 4,
+                                          cudaMemcpyDeviceToHost, st));
             const int64_t ns_ = s1 - s0;
             VLR_CUDA(ctx, cudaMemcpyAsync(out_event_ln + s0 * NE, d_ev[b], (size_t)ns_ * NE * 8, cudaMemcpyDeviceToHost, st));
             VLR_CUDA(ctx, cudaMemcpyAsync(out_marginal + s0, d_marg[b], (size_t)ns_ * 8, cudaMemcpyDeviceToHost, st));
@@ -534,6 +544,12 @@ static int posterior_pipeline(vlr_ctx *ctx, int64_t n_sites, const vlr_model *mo
         }
     }
     VLR_CUDA(ctx, cudaStreamSynchronize(st));
+    int64_t n_over = 0;
+    for (int c = 0; c < n_chunks; ++c) n_over += h_status[c];
+    if (n_over)
+        return set_err(ctx, VLR_ERR_UNSUPPORTED, "%lld site(s) exceeded a kernel limit (observations per pileup, "
+                       "allele-frequency values or likelihood-table entries per site); their outputs are NaN",
+                       (long long)n_over);
     return VLR_OK;
 }
 

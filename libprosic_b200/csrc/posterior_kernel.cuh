@@ -41,7 +41,7 @@ namespace vlr {
 
 constexpr int kMaxSamples = 8;
 constexpr int kMaxSpectra = 48;
-constexpr int kMaxValues = 384;   // distinct allele-frequency values per site (all samples)
+constexpr int kMaxValues = 4096;  // distinct allele-frequency values per site (all samples; dynamic shared memory)
 constexpr int kMaxCfg = 32;       // distinct bias configurations
 constexpr int kMaxEvents = 64;
 constexpr int kTeamThreadsMax = 128;

@@ -331,3 +331,57 @@ def test_chunked_pipeline_and_f32_entry(ctx, oracle):
     _close(got32["marginal"], got["marginal"], 1e-9)
     assert np.array_equal(got32["map_af"], got["map_af"], equal_nan=True)
     assert np.array_equal(got32["map_bias"], got["map_bias"])
+
+
+def _random_scenario(rng, n_samples):
+    """Random event universe: 2-6 events, each 1-3 tree roots; a root is a chain over the samples in
+    random order whose nodes are random Sets / Ranges (some chains end in a fan-out of two children,
+    some carry a FALSE or SKIP node); artifact events over a random subset of bias components."""
+    b = scenario._Builder()
+    grid = [0.0, 0.1, 0.25, 0.5, 0.75, 1.0]
+
+    def spectrum(s):
+        if rng.random() < 0.45:
+            lo, hi = sorted(rng.choice(len(grid), 2, replace=False))
+            return (s, scenario.NODE_RANGE, [grid[lo], grid[hi], float(rng.random() < 0.5), float(rng.random() < 0.5)])
+        k = int(rng.integers(1, 4))
+        return (s, scenario.NODE_SET, sorted(float(v) for v in rng.choice(grid, k, replace=False)))
+
+    def root():
+        order = list(rng.permutation(n_samples))
+        if n_samples >= 2 and rng.random() < 0.3:   # fan-out below the first sample
+            first = spectrum(order[0])
+            kids = [b.chain([spectrum(s) for s in order[1:]]) for _ in range(2)]
+            if rng.random() < 0.3:
+                kids.append(b.node(scenario.NODE_FALSE))
+            top = b.node(first[1], first[0], first[2], kids)
+            return b.node(scenario.NODE_SKIP, 0, [], [top]) if rng.random() < 0.3 else top
+        return b.chain([spectrum(s) for s in order])
+
+    named = [("e%d" % k, [root() for _ in range(int(rng.integers(1, 4)))]) for k in range(int(rng.integers(1, 6)))]
+    flags = [bool(rng.random() < 0.6) for _ in range(5)]
+    arts = scenario.artifact_biases(*flags) if any(flags) else []
+    events, biases = scenario._with_events(b, named, n_samples, arts)
+    cont = [0] * n_samples
+    by = [0] * n_samples
+    purity = [1.0] * n_samples
+    if n_samples >= 2 and rng.random() < 0.5:
+        c = int(rng.integers(0, n_samples))
+        cont[c], by[c], purity[c] = 1, int((c + 1 + rng.integers(0, n_samples - 1)) % n_samples), float(rng.choice([0.3, 0.75, 0.9]))
+    return dict(n_samples=n_samples, resolution=[int(rng.choice([5, 9, 20, 100])) for _ in range(n_samples)],
+                contaminated=cont, by=by, purity=purity, nodes=b.nodes, events=events, biases=biases)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_models(ctx, oracle, seed):
+    """Fuzz of the model flattening, the term-major integration with its segmented flush (events of
+    1 .. several hundred terms, several events per warp round, gated-out configurations, FALSE
+    branches), every kernel instantiation (1-4 samples, with and without contamination, one-warp
+    and CTA teams) and ragged / empty pileups."""
+    rng = np.random.default_rng(1000 + seed)
+    ns = int(rng.integers(1, 5))
+    scn = _random_scenario(rng, ns)
+    depths = [int(rng.choice([3, 12, 30, 70])) for _ in range(ns)]
+    cols, cat, off, _ = synth.make_pileups(40, depths, seed=seed, kind=str(rng.choice(["snv", "indel"])),
+                                           ragged=bool(rng.random() < 0.5), artifact_frac=0.2)
+    _check(ctx, oracle, scn, cols, cat, off)
