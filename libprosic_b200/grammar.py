@@ -789,7 +789,7 @@ def flatten(scn, contig="all", snv=None, snv_or_mnv=True, omit_strand_bias=False
         if c:
             if scn.idx(c["by"]) is None:
                 raise ValueError("invalid sample name %s" % c["by"])
-            contaminated.append(1); by.append(scn.idx(c["by"])); purity.append(1.0 - float(c["fraction"]))
+            contaminated.append(1); by.append(scn.idx(c["by"])); purity.append(1.0 - float(c["fraction"]))  # float(): PyYAML reads `1e-3` as str
         else:
             contaminated.append(0); by.append(0); purity.append(1.0)
     return dict(n_samples=len(names), resolution=[scn.samples[n].resolution for n in names],

@@ -33,6 +33,13 @@ def main():
         F.save_fixture(F.load_testcase(os.path.join(REF, c)), p)
         total += os.path.getsize(p)
         print(c, os.path.getsize(p))
+    scn = os.path.join(os.path.dirname(OUT), "scn")
+    os.makedirs(scn, exist_ok=True)
+    for c in F.SCENARIO_CASES:  # Generic testcases driven by their scenario.yaml (grammar front end)
+        p = os.path.join(scn, c + ".json.gz")
+        F.save_fixture(F.load_testcase(os.path.join(REF, c)), p)
+        total += os.path.getsize(p)
+        print(c, os.path.getsize(p))
     for c in CASES:
         d = os.path.join(REF, c)
         if not os.path.isdir(d):

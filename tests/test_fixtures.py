@@ -147,3 +147,39 @@ def test_reference_expectations_hold_on_the_gpu(ctx, path):
     if _name(path) not in KNOWN_EXCEPTIONS:
         verdicts = F.check_expectations(got)
         assert all(v for _, v in verdicts), verdicts
+
+
+# ---- Generic testcases driven by their scenario.yaml through the grammar front end
+SCN = sorted(glob.glob(os.path.join(HERE, "golden", "scn", "*.json.gz")))
+# the reference asserts nothing but "runs" for these (empty `expected:` block)
+NO_EXPECTATION = {"test37", "test_contig_universe"}
+
+
+def test_scenario_fixture_set_is_complete():
+    assert [_name(p) for p in SCN] == sorted(F.SCENARIO_CASES)
+
+
+@pytest.mark.parametrize("path", SCN, ids=_name)
+def test_scenario_testcases_hold_on_the_oracle(path):
+    """scenario.yaml -> grammar -> vlr_model, preprocess of every sample with a BAM file, call:
+    one to three samples, contamination (test34, test49, test58), contig-specific universes,
+    expressions, variant-type atoms, samples without observations."""
+    from _oracle_backend import OracleBackend
+    r = F.run_scenario_testcase(path, OracleBackend())
+    verdicts = F.check_expectations(r)
+    assert (verdicts or _name(path) in NO_EXPECTATION) and all(v for _, v in verdicts), (verdicts, r)
+    assert all(np.isfinite(v) or np.isinf(v) for k, v in r.items() if k.startswith("PROB_"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", SCN, ids=_name)
+def test_scenario_testcases_hold_on_the_gpu(ctx, path):
+    from _oracle_backend import OracleBackend
+    got = F.run_scenario_testcase(path, F.GpuBackend(ctx))
+    want = F.run_scenario_testcase(path, OracleBackend())
+    assert got["n_obs"] == want["n_obs"] and got["af"] == want["af"], (got, want)
+    for k, w in want.items():
+        if k.startswith("PROB_"):
+            g = got[k]
+            assert (np.isinf(g) and np.isinf(w)) or abs(g - w) <= 2e-5 * max(1.0, abs(w)), (k, g, w)
+    assert all(v for _, v in F.check_expectations(got))

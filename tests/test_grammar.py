@@ -423,3 +423,30 @@ def test_grammar_scenarios_on_the_gpu(ctx):
     for path in sorted(glob.glob(os.path.join(HERE, "golden", "trio", "*.json.gz"))):
         r = F.run_trio_testcase(path, F.GpuBackend(ctx), scenario_yaml=TRIO_YAML)
         assert all(v for _, v in F.check_expectations(r))
+
+
+def test_prior_module_matches_the_hand_written_priors():
+    """libprosic_b200/prior.py (general restatement of Prior::calc_prob without somatic terms) against
+    the two special cases fixtures.py carried before: diploid trio and one germline sample."""
+    import itertools
+    from libprosic_b200 import prior as PR
+    trio = G.Scenario(TRIO_YAML)          # father = 0, index = 1, mother = 2
+    f = PR.make_prior(trio, "1", "snv")
+    h = F.mendelian_trio_prior(0.001, 0.1, child=1, parents=(2, 0))
+    for afs in itertools.product([0.0, 0.5, 1.0], repeat=3):
+        a, b = f(list(afs)), h(list(afs))
+        assert (np.isinf(a) and np.isinf(b)) or abs(a - b) < 1e-12, (afs, a, b)
+    assert f([0.25, 0.0, 0.0]) == -np.inf          # not a germline VAF at ploidy 2
+    one = G.Scenario(GIAB03_YAML)
+    f1, h1 = PR.make_prior(one, "1", "snv"), F.germline_prior(0.001)
+    for af in (0.0, 0.5, 1.0):
+        assert abs(f1([af]) - h1([af])) < 1e-12
+    # indels: heterozygosity scaled by the variant-type fraction (default 0.0125)
+    fi = PR.make_prior(one, "1", "del")
+    assert abs(fi([0.5]) - np.log(0.001 * 0.0125)) < 1e-12
+    # ploidy 0 (female, Y): only AF 0 is possible
+    fy = PR.make_prior(one, "Y", "snv")
+    assert fy([0.5]) == -np.inf and fy([0.0]) == 0.0
+    with pytest.raises(NotImplementedError):
+        PR.make_prior(G.Scenario(TRIO_YAML.replace("  mother:\n    sex: female",
+                                                   "  mother:\n    sex: female\n    somatic-effective-mutation-rate: 1e-10")), "1")
