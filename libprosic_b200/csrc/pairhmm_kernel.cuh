@@ -689,7 +689,9 @@ __global__ void __launch_bounds__(kWarps * 32, 2) pairhmm_long_kernel(HmmArgs g)
             s.dX = s.dY = A::zero();
             s.acc = A::zero();
             s.acc2 = A::zero();
-            double bmax = A::zero();
+            // largest boundary value of the strip: only its exponent is needed, so the running maximum
+            // is kept on the high words (non-negative doubles order like their bit patterns)
+            int bmax_hi = 0;
             // prefetch registers for the incoming boundary chunk (columns t .. t+31)
             double pfM = A::zero(), pfX = A::zero(), pfY = A::zero();
             if (strip > 0 && lane < lx) {
@@ -781,7 +783,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) pairhmm_long_kernel(HmmArgs g)
                 } else if (lane == 30 && (unsigned)i < (unsigned)lx) {
                     // full strip: lane 30 holds its last row; hand it to the next strip
                     __stcg(&bout[i], s.bM); __stcg(&bout[g.long_stride + i], s.bX); __stcg(&bout[2 * g.long_stride + i], s.bY);
-                    if (!A::kLog) bmax = fmax(bmax, fmax(s.bM, fmax(s.bX, s.bY)));
+                    if (!A::kLog) bmax_hi = max(bmax_hi, max(__double2hiint(s.bM), max(__double2hiint(s.bX), __double2hiint(s.bY))));
                 }
             }
             if (last_strip) {
@@ -789,9 +791,12 @@ __global__ void __launch_bounds__(kWarps * 32, 2) pairhmm_long_kernel(HmmArgs g)
                 if (LUT) acc = fma(acc, c.inv_tmm, __shfl_sync(0xffffffffu, s.acc2, last_lane));
             } else if (!A::kLog) {
                 // renormalise: bring the largest boundary value back to 2^960
-                bmax = __shfl_sync(0xffffffffu, bmax, 30);
-                if (!(bmax > 0.0) || !(bmax < 1.0e307)) { dead = true; break; }
-                const int k = 960 - ilogb(bmax);
+                bmax_hi = __shfl_sync(0xffffffffu, bmax_hi, 30);
+                const int bexp = (bmax_hi >> 20) & 0x7ff;   // biased exponent of the maximum
+                // zero / subnormal, above 1e307 (2^1020), Inf or NaN (a NaN state has sign 0 here or
+                // shows up as a negative high word): the pair takes the log-space pass
+                if (bmax_hi < 0 || bexp == 0 || bexp >= 1023 + 1019) { dead = true; break; }
+                const int k = 960 - (bexp - 1023);
                 kshift = k;
                 e_total += k;
             }
