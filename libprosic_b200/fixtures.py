@@ -285,7 +285,7 @@ def save_fixture(tc, path):
         props = dict(s["props"])
         mw = int(s["opts"].get("realignment_window", s["opts"].get("indel_window", 64)))
         variant = make_variant(tc, int(mw * 1.5))
-        if variant["kind"] == "snv":  # SingleEndEvidence: records enclosing the locus
+        if variant["kind"] in ("snv", "mnv"):  # SingleEndEvidence: records enclosing the locus
             recs = [r for r in read_bam(s["bam"]) if r["contig"] == tc["contig"] and is_valid_record(r) and
                     overlap(variant["locus"], r, False) == "enclosing"]
         else:
@@ -341,6 +341,13 @@ def make_variant(tc, ref_window):
         ro, re_ = max(0, start - ref_window), min(start + 1 + ref_window, len(ref))
         alt = bytes(ord(a.upper()) if i == start else ref[i] for i in range(ro, re_))
         return dict(kind="snv", len=1, locus=(start, start + 1), alt=alt, alt_extra=0, fetch_loci=[(start, start + 1)],
+                    ref_base=r.upper(), alt_base=a.upper())
+    if len(r) == len(a) and len(r) > 1 and not a.startswith("<"):  # MNV (types/mnv.rs:30-82, 215-227)
+        n = len(a)
+        ro, re_ = max(0, start - ref_window), min(start + n + ref_window, len(ref))
+        au = a.upper().encode()
+        alt = bytes(au[i - start] if start <= i < start + n else ref[i] for i in range(ro, re_))
+        return dict(kind="mnv", len=n, locus=(start, start + n), alt=alt, alt_extra=0, fetch_loci=[(start, start + n)],
                     ref_base=r.upper(), alt_base=a.upper())
     raise NotImplementedError("variant type of %s %s>%s" % (tc["name"], r[:10], a[:10]))
 
@@ -630,7 +637,7 @@ def extract_observations_snv(tc, sample_name, backend, omit_read_orientation_bia
     records = smp.get("records")
     if records is None:
         records = [r for r in read_bam(smp["bam"]) if r["contig"] == tc["contig"]]
-    lo, hi = max(0, start - props["max_read_len"]), start + 1  # RecordBuffer::fetch(locus, false)
+    lo, hi = max(0, start - props["max_read_len"]), variant["locus"][1]  # RecordBuffer::fetch(locus, false)
     evidences = []
     for r in records:
         if not is_valid_record(r) or r["pos"] >= hi or end_pos(r) < lo:
@@ -650,13 +657,23 @@ def extract_observations_snv(tc, sample_name, backend, omit_read_orientation_bia
             sup = batch.support(r)
             qpos = None
         else:
-            qpos = read_pos(r, start, False, False)
-            if qpos is None:
+            # one base (snv.rs:109-151) or every base of the MNV (mnv.rs:116-197); the read position is
+            # the first base's
+            qpos, p_ref, p_alt, gone = None, 0.0, 0.0, False
+            for k in range(variant["len"]):
+                qp = read_pos(r, start + k, False, False)
+                if qp is None:   # position deleted / skipped in this read: no observation
+                    gone = True
+                    break
+                if qpos is None:
+                    qpos = qp
+                rb, q = r["seq"][qp], r["qual"][qp]
+                ab, fb = variant["alt_base"][k], variant["ref_base"][k]
+                p_alt += prob_read_base(rb, ab, q)
+                non_alt = chr(rb) if chr(rb).upper() != ab else fb
+                p_ref += prob_read_base(rb, non_alt, q)
+            if gone:
                 continue
-            rb, q = r["seq"][qpos], r["qual"][qpos]
-            p_alt = prob_read_base(rb, variant["alt_base"], q)
-            non_alt = chr(rb) if chr(rb).upper() != variant["alt_base"] else variant["ref_base"]
-            p_ref = prob_read_base(rb, non_alt, q)
             sup = dict(prob_ref=p_ref, prob_alt=p_alt, strand=(1 if r["flag"] & 0x10 else 0) if p_ref != p_alt else 3)
         if sup["strand"] == 3:
             continue
@@ -719,7 +736,7 @@ def scenario_from_yaml(tc, text):
     g = grammar.Scenario(text)
     return grammar.flatten(g, contig=tc["contig"],
                            snv=(tc["ref_allele"].upper(), tc["alt_allele"].upper()) if snv else None,
-                           snv_or_mnv=snv, omit_strand_bias=om["strand_bias"],
+                           snv_or_mnv=variant["kind"] in ("snv", "mnv"), omit_strand_bias=om["strand_bias"],
                            omit_read_orientation_bias=om["read_orientation_bias"],
                            omit_read_position_bias=om["read_position_bias"],
                            omit_softclip_bias=om["softclip_bias"], omit_divindel_bias=om["divindel_bias"])
@@ -960,7 +977,7 @@ def run_scenario_testcase(path, backend, scenario_yaml=None):
     for name in order:
         if name not in tc["samples"]:
             pile.append(({c: np.zeros(0) for c in obs_codec.COLUMNS}, np.zeros(0, np.uint16)))
-        elif variant["kind"] == "snv":
+        elif variant["kind"] in ("snv", "mnv"):
             pile.append(extract_observations_snv(tc, name, backend, tc["omit"]["read_orientation_bias"]))
         else:
             pile.append(extract_observations(tc, name, backend))
@@ -979,7 +996,7 @@ def run_scenario_testcase(path, backend, scenario_yaml=None):
 # Generic testcases of the reference with a scenario.yaml and a uniform prior that the suites run from
 # compact fixtures (all that run in the build container: tests/golden/scenario_results.txt)
 SCENARIO_CASES = ("omit_sb", "test34", "test37", "test40", "test49", "test52", "test58", "test57", "test70",
-                  "test_low_cov_vaf", "test_panel_overlap", "test_contig_universe")
+                  "test_low_cov_vaf", "test_panel_overlap", "test_contig_universe", "test_giab_02")
 
 
 def check_expectations(result):
