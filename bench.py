@@ -408,12 +408,28 @@ def bench_c1(ctx):
             held += 1
         else:
             failed.append(os.path.basename(p).split(".")[0])
-    return {"workload": "C1: %d tumor/normal indel testcases of the reference (real reads), preprocess + call "
-                        "through the restated host glue with K2/K1 and K3/K4 on the GPU" % len(paths),
+    # Generic-mode testcases driven by their own scenario.yaml through the grammar front end
+    spaths = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "scn", "*.json.gz")))
+    s_held, s_failed, s_asserted = 0, [], 0
+    for p in spaths:
+        r = F.run_scenario_testcase(p, be)
+        n_obs += sum(r["n_obs"].values())
+        v = F.check_expectations(r)
+        s_asserted += bool(v)
+        if all(x for _, x in v):
+            s_held += bool(v)
+        else:
+            s_failed.append(os.path.basename(p).split(".")[0])
+    return {"workload": "C1: %d tumor/normal indel testcases and %d Generic (scenario.yaml) testcases of the "
+                        "reference (real reads), preprocess + call through the restated host glue with K2/K1 and "
+                        "K3/K4 on the GPU" % (len(paths), len(spaths)),
             "testcases": len(paths), "expectations_hold": held, "not_holding": failed,
+            "scenario_testcases": len(spaths), "scenario_with_expectations": s_asserted,
+            "scenario_expectations_hold": s_held, "scenario_not_holding": s_failed,
             "observations": n_obs, "seconds": time.perf_counter() - t0,
-            "note": "test21 is the documented exception (DESIGN.md section 5); all 32 testcases: "
-                    "tests/golden/tn_results.txt (31 hold)"}
+            "note": "test21 is the documented exception (DESIGN.md section 5); all 32 tumor/normal testcases: "
+                    "tests/golden/tn_results.txt (31 hold); all runnable Generic testcases: "
+                    "tests/golden/scenario_results.txt (19 of 22 hold = all that upstream asserts)"}
 
 
 def bench_c4(args, ctx, torch, dist, dev, rank, world, timed):
