@@ -171,6 +171,15 @@ __global__ void __launch_bounds__(128) besthit_kernel(MyersArgs g) {
         bool have_path = false;
         for (int e = first_best; e <= last_best; ++e) {
             if ((dms(e) & 0xffff) != best) continue;
+            if (best == 0 && !want_path) {
+                // an exact occurrence: D[m][e] = 0 forces the diagonal at every step, so the alignment
+                // starts at e - m and has no indel operation -- no walk through the column records
+                // (41 % of the pairs of the C3 read set)
+                if (e == first_best) start_first = e - m;
+                start_last = e - m;
+                if (best_nindel > 0) { best_nindel = 0; best_nops = 0; }
+                continue;
+            }
             int j = m, i = e, nindel = 0;
             uint8_t ops[kMaxIndelOps];  // ring of the indel ops in traceback (reverse) order
             // PathHMM: the walk runs backwards, so the transition INTO the operation found last
