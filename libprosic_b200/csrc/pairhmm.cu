@@ -1,6 +1,7 @@
 // pairhmm.cu -- host side of K1 (pair classification, launches, C-ABI entry points).
 // The kernel itself is in pairhmm_kernel.cuh, instantiated in pairhmm_inst_*.cu.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -8,6 +9,7 @@
 
 #include "pairhmm_host.cuh"
 #include "pairhmm_kernel.cuh"
+#include "pairhmm_band.cuh"
 
 namespace vlr {
 
@@ -28,7 +30,7 @@ __host__ __device__ inline int class_of_len(int ly) {
 // [24..31] work cursors (one per class launch), [32] fallback count, [33] fallback work cursor
 constexpr int kCntCount = 0, kCntOff = 8, kCntScatter = 16, kCntWork = 24, kCntFb = 32,
               kCntFbWork = 33, kCntFbLong = 34, kCntFbLongWork = 35, kCntGen = 36, kCntGenWork = 37,
-              kCntTotal = 64;
+              kCntBand = 40 /* three work cursors of the band-only kernels */, kCntTotal = 64;
 constexpr int64_t kLongWarpsCap = 160 * kLongBlocksPerSm * kWarps;  // boundary-row slots (<= 160 SMs)
 
 __global__ void classify_kernel(int64_t n_pairs, const int64_t *read_off, const int32_t *pair_read,
@@ -224,6 +226,24 @@ static int pairhmm_core_dev(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *d_hap_
     // extension probabilities of exactly 0 (CLI default) select the 5-op specialisation
     const bool ext = !(gap->prob_gap_x_extend == -INFINITY && gap->prob_gap_y_extend == -INFINITY);
 
+    // Banded pairs on narrow windows (the allele-support path): the band-only kernel takes what it
+    // can and marks those list entries; the class kernels below skip them.  Needs gap-extension
+    // probabilities of 0 and small gap-open probabilities (its error bound, pairhmm_band.cuh).
+    {
+        const char *e = getenv("VLR_K1_BAND");
+        const double small = -9.210340371976182;  // ln 1e-4
+        if (banded && !ext && gap->prob_gap_x <= small && gap->prob_gap_y <= small && !(e && atoi(e) == 0)) {
+            HmmArgs ab = a;
+            ab.list = w.list;
+            cudaError_t ce = approx ? launch_pairhmm_band<true>(ab, w.list, w.counters + kCntOff + 7,
+                                                                w.counters + kCntBand, ctx->sm_count, st)
+                                    : launch_pairhmm_band<false>(ab, w.list, w.counters + kCntOff + 7,
+                                                                 w.counters + kCntBand, ctx->sm_count, st);
+            if (ce != cudaSuccess)
+                return set_err(ctx, VLR_ERR_CUDA, "pairhmm launch failed: %s", cudaGetErrorString(ce));
+            ctx->launches += 3;
+        }
+    }
     // Class sizes live on the device: every class kernel is launched as a persistent grid with a
     // dynamic work counter and exits at once when its list is empty, so the device entry point
     // never synchronises with the host.

@@ -433,6 +433,7 @@ __global__ void __launch_bounds__(kWarps * 32, Occ<R>::kMinBlocks) pairhmm_kerne
         p = __shfl_sync(0xffffffffu, p, 0);
         if (p >= n) break;
         const int pair = list ? list[p] : p;
+        if (pair < 0) continue;  // computed by the band-only kernel (pairhmm_band.cuh)
         const int64_t hidx = g.pair_hap ? (int64_t)g.pair_hap[pair] : (int64_t)pair;
         const int64_t rd = g.pair_read ? (int64_t)g.pair_read[pair] : (int64_t)pair;
         const int64_t ho = g.win_start ? g.win_start[pair] : g.hap_off[hidx];

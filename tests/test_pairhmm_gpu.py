@@ -184,3 +184,61 @@ def test_non_acgt_bases(ctx, oracle, flags):
     want = np.array([oracle.pairhmm_prob_related(haps[k], reads[k], quals[k], gap.as_ln_array(), -1, flags)
                      for k in range(96)])
     _compare(got, want)
+
+
+def _band_cases(rng, n, kind):
+    """(haplotype window, read, qualities, band) the way allele support produces them: the read is a
+    copy of a stretch of the window with a few edits, the window extends a little beyond the hit,
+    the band is a little more than the number of edits.  kind: 'random' sequence, 'homopolymer',
+    'repeat' (short tandem repeat) -- the low-complexity kinds keep many diagonals alive."""
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    haps, reads, quals, med = [], [], [], []
+    for _ in range(n):
+        ly = int(rng.integers(20, 200))
+        extra = int(rng.integers(0, 40))
+        lx = ly + extra
+        if kind == "random":
+            hap = acgt[rng.integers(0, 4, lx)]
+        elif kind == "homopolymer":
+            hap = np.full(lx, acgt[rng.integers(0, 4)], np.uint8)
+            hap[rng.random(lx) < 0.03] = acgt[rng.integers(0, 4)]
+        else:
+            unit = acgt[rng.integers(0, 4, int(rng.integers(2, 5)))]
+            hap = np.tile(unit, lx // len(unit) + 1)[:lx].copy()
+        start = int(rng.integers(0, extra + 1))
+        read = list(hap[start:start + ly])
+        n_edits = int(rng.integers(0, 9))
+        for _e in range(n_edits):
+            pos = int(rng.integers(0, len(read)))
+            op = rng.random()
+            if op < 0.5:
+                read[pos] = int(acgt[rng.integers(0, 4)])
+            elif op < 0.75 and len(read) > 10:
+                del read[pos]
+            else:
+                read.insert(pos, int(acgt[rng.integers(0, 4)]))
+        read = np.array(read[:248], np.uint8)
+        haps.append(hap)
+        reads.append(read)
+        quals.append(np.clip(np.rint(rng.normal(30, 8, len(read))), 2, 41).astype(np.uint8))
+        med.append(int(rng.integers(0, 14)))
+    hap_off = np.concatenate([[0], np.cumsum([len(h) for h in haps])]).astype(np.int64)
+    read_off = np.concatenate([[0], np.cumsum([len(r) for r in reads])]).astype(np.int64)
+    return (np.concatenate(haps), hap_off, np.concatenate(reads), np.concatenate(quals), read_off,
+            np.array(med, np.int32))
+
+
+@pytest.mark.parametrize("kind", ["random", "homopolymer", "repeat"])
+@pytest.mark.parametrize("flags", [P.HMM_DEFAULT, 0])
+def test_band_only_kernel(ctx, oracle, kind, flags):
+    """pairhmm_band.cuh (diagonals as lanes, only the band is computed) against the oracle's full
+    matrix with the reference's pruning rule: bands of 3 .. 96 diagonals (one to three diagonals
+    per lane), windows from len_y to len_y + 40, low-complexity sequence where most of the band
+    stays alive.  The kernel leaves out mass that needs k + 1 gaps in one direction: the observed
+    difference stays far below the 1e-6 bar."""
+    rng = np.random.default_rng({"random": 1, "homopolymer": 2, "repeat": 3}[kind] + (flags != 0))
+    hb, ho, rb, rq, ro, med = _band_cases(rng, 400, kind)
+    gap = P.GapParams()
+    got = ctx.pairhmm_batch(hb, ho, rb, rq, ro, gap, max_edit_dist=med, flags=flags)
+    want = oracle.pairhmm_batch(hb, ho, rb, rq, ro, gap.as_ln_array(), med, flags)
+    _compare(got, want, tol=1e-7)
