@@ -15,7 +15,10 @@
 //     X state (one shuffle of the finished M values) and the band bookkeeping depend on the left
 //     cell; the latter, L_i = min(A_i, L_{i-1} + 1 if L_{i-1} <= k), is a min-plus prefix scan over
 //     the lanes (five shuffle rounds of 32-bit integers).
-//   * read-row constants and haplotype base codes are staged in shared memory once per pair.
+//   * per pair only two bytes per read row (quality, base code) and one byte per haplotype base
+//     are staged in shared memory; the emission / Y-state factors come from a per-CTA table indexed
+//     by the quality (6 KB), so that 6 to 12 CTAs fit an SM -- the row loop is one dependent chain
+//     per warp (shuffles, the e^-10 rule, the scan) and needs the warps to hide its latency.
 //
 // What the band leaves out are paths (and liveness effects at the two edge diagonals) that need at
 // least k + 1 = dist + 3 gap openings in one direction; with the gap probabilities this kernel
@@ -33,24 +36,33 @@ constexpr int kBandMaxLy = 248;   // read rows staged per warp (same limit as pa
 constexpr int kBandPad = 128;     // codes before / after the window (cells outside are masked)
 constexpr int kBandInf = 1 << 28; // "no predecessor" in the min-plus scan (kMedMax + positions fit)
 constexpr int kBandMaxG = 3;      // diagonals per lane: bands of up to 96 diagonals
-constexpr int kBandBlocksPerSm = 6;  // 40-71 registers, 34.7 KB shared memory per CTA
+// CTAs per SM by diagonals per lane (40 / 56 / 71 registers; 11 KB shared memory per CTA)
+constexpr int band_blocks_per_sm(int G) { return G == 1 ? 12 : (G == 2 ? 8 : 6); }
 
-struct BandRow {  // per read row: emission factors (already times t_mm) and the Y-state factor
+struct BandQ {  // per base quality: emission factors (already times t_mm) and the Y-state factor
     double em, emm, cy;
-    int code, pad;
 };
 
 template <int G, bool APPROX>
-__global__ void __launch_bounds__(kWarps * 32, kBandBlocksPerSm) pairhmm_band_kernel(HmmArgs g, int32_t *list_rw,
-                                                                       const int32_t *n_total) {
+__global__ void __launch_bounds__(kWarps * 32, band_blocks_per_sm(G))
+pairhmm_band_kernel(HmmArgs g, int32_t *list_rw, const int32_t *n_total) {
     __shared__ __align__(16) uint8_t s_hap[kWarps][kBandPad + kBandMaxLx + kBandPad];
-    __shared__ __align__(16) BandRow s_row[kWarps][kBandMaxLy];
+    __shared__ __align__(4) uint16_t s_row[kWarps][kBandMaxLy];   // quality | base code << 8
+    __shared__ __align__(16) BandQ s_q[256];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     uint8_t *hap = s_hap[warp];
-    BandRow *rows = s_row[warp];
+    uint16_t *rows = s_row[warp];
     const HmmConsts c = g.lin;
     const int n = *n_total;
+    for (int q = threadIdx.x; q < 256; q += kWarps * 32) {
+        BandQ e;
+        e.em = g.qlut[q * kQlutStride + 1] * c.t_mm;
+        e.emm = g.qlut[q * kQlutStride + 2] * c.t_mm;
+        e.cy = g.qlut[q * kQlutStride + 0] * c.t_gx_s;
+        s_q[q] = e;
+    }
+    __syncthreads();
 
     for (;;) {
         int p = 0;
@@ -78,12 +90,7 @@ __global__ void __launch_bounds__(kWarps * 32, kBandBlocksPerSm) pairhmm_band_ke
             const int q = g.rqual[ro + j];
             const int code = base_code1(g.rbase[ro + j]);
             odd |= code == 4;
-            BandRow r;
-            r.em = g.qlut[q * kQlutStride + 1] * c.t_mm;
-            r.emm = g.qlut[q * kQlutStride + 2] * c.t_mm;
-            r.cy = g.qlut[q * kQlutStride + 0] * c.t_gx_s;
-            r.code = code; r.pad = 0;
-            rows[j] = r;
+            rows[j] = (uint16_t)(q | (code << 8));
         }
         if (__any_sync(0xffffffffu, odd)) continue;
         for (int i = lane; i < lx + 2 * kBandPad; i += 32) {
@@ -94,43 +101,55 @@ __global__ void __launch_bounds__(kWarps * 32, kBandBlocksPerSm) pairhmm_band_ke
         __syncwarp();
 
         const int dlo = -(k + 1);
+        // state of the previous row on my diagonals.  Row -1 is the free start: mass 1 and edit
+        // distance 0 on the diagonal predecessor of every cell (i, 0) of the matrix, nothing above it.
+        // Cells left of the matrix stay dead by themselves (all three predecessors are), cells right
+        // of it or beyond the band are masked by `i < ilim`.
         double Mp[G], Xp[G], Yp[G];
         int medp[G];
 #pragma unroll
-        for (int q = 0; q < G; ++q) { Mp[q] = c.one_s; Xp[q] = 0.0; Yp[q] = 0.0; medp[q] = 0; }
+        for (int q = 0; q < G; ++q) {
+            const int pos = lane * G + q, i0 = dlo + pos;
+            const bool in0 = pos < W && i0 >= 0 && i0 < lx;
+            Mp[q] = in0 ? c.one_s : 0.0; Xp[q] = 0.0; Yp[q] = 0.0; medp[q] = in0 ? 0 : kMedMax;
+        }
         double accM = 0.0, accXY = 0.0;
         bool any_alive = true;
-
-        #pragma unroll 1
-        for (int j = 0; j < ly && any_alive; ++j) {
-            const BandRow r = rows[j];
-            // row above = next diagonal of the previous row (row 0: the reset state of the column)
-            double upM_next = __shfl_down_sync(0xffffffffu, Mp[0], 1);
-            int upMed_next = __shfl_down_sync(0xffffffffu, medp[0], 1);
-            if (lane == 31) { upM_next = 0.0; upMed_next = kMedMax; }
-            double nM[G], nY[G];
-            int A[G], a_med[G];
+        // one read row; FIRST: the row above is the reset state of the column (no mass, no distance)
+        auto row = [&](int j, auto first_tag) {
+            constexpr bool FIRST = decltype(first_tag)::value;
+            const int rq = rows[j];
+            const BandQ qe = s_q[rq & 0xff];
+            const int rcode = rq >> 8;
+            double upM_next = 0.0;
+            int upMed_next = kMedMax;
+            if (!FIRST) {
+                upM_next = __shfl_down_sync(0xffffffffu, Mp[0], 1);
+                upMed_next = __shfl_down_sync(0xffffffffu, medp[0], 1);
+                if (lane == 31) { upM_next = 0.0; upMed_next = kMedMax; }
+            }
+            const int ibase = j + dlo + lane * G;
+            const int ilim = min(lx, j + dlo + W);
+            double sumv[G], ev[G], upMv[G];
+            int a_med[G], E[G];
             bool in[G], strong[G];
-            int vmin = kBandInf;          // min over my diagonals of A - position
-            int E[G];                     // exclusive prefix of that inside the lane
+            int vmin = kBandInf;          // min over my diagonals of (a - position)
 #pragma unroll
             for (int q = 0; q < G; ++q) {
-                const int pos = lane * G + q;
-                const int i = j + dlo + pos;
-                in[q] = pos < W && i >= 0 && i < lx;
-                const double upM = j == 0 ? 0.0 : (q + 1 < G ? Mp[q + 1 < G ? q + 1 : 0] : upM_next);
-                const int upMed = j == 0 ? kMedMax : (q + 1 < G ? medp[q + 1 < G ? q + 1 : 0] : upMed_next);
-                const bool match = hap[kBandPad + i] == r.code;
-                const double e = match ? r.em : r.emm;
-                nM[q] = e * Lin::sum3<APPROX, false, true>(c, Mp[q], Xp[q], Yp[q]);
-                nY[q] = r.cy * upM;
+                const int i = ibase + q;
+                in[q] = i < ilim;
+                upMv[q] = FIRST ? 0.0 : (q + 1 < G ? Mp[q + 1 < G ? q + 1 : 0] : upM_next);
+                const int upMed = FIRST ? kMedMax : (q + 1 < G ? medp[q + 1 < G ? q + 1 : 0] : upMed_next);
+                const bool match = hap[kBandPad + i] == rcode;
+                ev[q] = match ? qe.em : qe.emm;
+                sumv[q] = Lin::sum3<APPROX, false, true>(c, Mp[q], Xp[q], Yp[q]);
                 const int m_tl = medp[q];
-                const int pmin = min(m_tl, upMed);
-                a_med[q] = min(match ? m_tl : m_tl + 1, upMed + 1);
-                strong[q] = in[q] && pmin <= k;
-                A[q] = strong[q] ? a_med[q] : kBandInf;
-                E[q] = vmin;
-                vmin = min(vmin, A[q] - pos);
+                a_med[q] = min(m_tl + (match ? 0 : 1), upMed + 1);
+                strong[q] = min(m_tl, upMed) <= k;
+                E[q] = vmin;              // exclusive prefix inside the lane
+                // a cell without a predecessor within k has a >= k + 1 and can never start a chain
+                // (its candidate exceeds k + 1 one step later), so it enters the scan unmasked
+                vmin = min(vmin, a_med[q] - (lane * G + q));
             }
             // exclusive min-scan of the lanes' minima
             int S = vmin;
@@ -141,31 +160,36 @@ __global__ void __launch_bounds__(kWarps * 32, kBandBlocksPerSm) pairhmm_band_ke
             }
             S = __shfl_up_sync(0xffffffffu, S, 1);
             if (lane == 0) S = kBandInf;
-            // liveness, band bookkeeping of the row, X state from the finished M of the left cell
-            bool alive[G];
+            // liveness and band bookkeeping; dead cells are zeroed by a 0/1 factor on the fp64 pipe
+            // (the kernel is bound by the ALU pipe: selects and integer min/compare)
+            double nM[G], wv[G];
             bool row_alive = false;
 #pragma unroll
             for (int q = 0; q < G; ++q) {
                 const int pos = lane * G + q;
                 const int Pq = min(S, E[q]) + pos;       // best predecessor chain ending left of me
                 const bool chain = Pq <= k + 1;
-                alive[q] = in[q] && (strong[q] || chain);
-                const int L = min(A[q], chain ? Pq : kBandInf);
-                medp[q] = alive[q] ? min(L, kMedMax) : kMedMax;
-                if (!alive[q]) { nM[q] = 0.0; nY[q] = 0.0; }
-                row_alive |= alive[q];
+                const bool alive = in[q] && (strong[q] || chain);
+                const int L = chain ? min(a_med[q], Pq) : a_med[q];
+                medp[q] = alive ? L : kMedMax;
+                wv[q] = __hiloint2double(alive ? 0x3ff00000 : 0, 0);
+                nM[q] = (ev[q] * wv[q]) * sumv[q];
+                Yp[q] = (qe.cy * wv[q]) * upMv[q];
+                row_alive |= alive;
             }
             double leftM = __shfl_up_sync(0xffffffffu, nM[G - 1], 1);
             if (lane == 0) leftM = 0.0;
 #pragma unroll
             for (int q = 0; q < G; ++q) {
                 const double lm = q == 0 ? leftM : nM[q > 0 ? q - 1 : 0];
-                Xp[q] = alive[q] ? c.t_gy_s * lm : 0.0;
+                Xp[q] = (c.t_gy_s * wv[q]) * lm;
                 Mp[q] = nM[q];
-                Yp[q] = nY[q];
             }
             any_alive = __any_sync(0xffffffffu, row_alive);
-        }
+        };
+        row(0, std::true_type());
+        #pragma unroll 1
+        for (int j = 1; j < ly && any_alive; ++j) row(j, std::false_type());
         // ---- free end: the last read row of every column
         if (any_alive) {
 #pragma unroll
@@ -201,11 +225,11 @@ cudaError_t launch_pairhmm_band(const HmmArgs &a, int32_t *list_rw, const int32_
                                             int32_t *cursors, int sm_count, cudaStream_t st) {    \
         HmmArgs b = a;                                                                            \
         b.cursor = cursors + 0;                                                                   \
-        pairhmm_band_kernel<1, APPROX><<<sm_count * kBandBlocksPerSm, kWarps * 32, 0, st>>>(b, list_rw, n_total); \
+        pairhmm_band_kernel<1, APPROX><<<sm_count * band_blocks_per_sm(1), kWarps * 32, 0, st>>>(b, list_rw, n_total); \
         b.cursor = cursors + 1;                                                                   \
-        pairhmm_band_kernel<2, APPROX><<<sm_count * kBandBlocksPerSm, kWarps * 32, 0, st>>>(b, list_rw, n_total); \
+        pairhmm_band_kernel<2, APPROX><<<sm_count * band_blocks_per_sm(2), kWarps * 32, 0, st>>>(b, list_rw, n_total); \
         b.cursor = cursors + 2;                                                                   \
-        pairhmm_band_kernel<3, APPROX><<<sm_count * kBandBlocksPerSm, kWarps * 32, 0, st>>>(b, list_rw, n_total); \
+        pairhmm_band_kernel<3, APPROX><<<sm_count * band_blocks_per_sm(3), kWarps * 32, 0, st>>>(b, list_rw, n_total); \
         return cudaGetLastError();                                                                \
     }
 
