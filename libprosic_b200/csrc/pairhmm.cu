@@ -30,7 +30,7 @@ __host__ __device__ inline int class_of_len(int ly) {
 // [24..31] work cursors (one per class launch), [32] fallback count, [33] fallback work cursor
 constexpr int kCntCount = 0, kCntOff = 8, kCntScatter = 16, kCntWork = 24, kCntFb = 32,
               kCntFbWork = 33, kCntFbLong = 34, kCntFbLongWork = 35, kCntGen = 36, kCntGenWork = 37,
-              kCntBand = 40 /* three work cursors of the band-only kernels */, kCntTotal = 64;
+              kCntBand = 40 /* four work cursors of the band-only kernels */, kCntTotal = 64;
 constexpr int64_t kLongWarpsCap = 160 * kLongBlocksPerSm * kWarps;  // boundary-row slots (<= 160 SMs)
 
 __global__ void classify_kernel(int64_t n_pairs, const int64_t *read_off, const int32_t *pair_read,
@@ -241,7 +241,7 @@ static int pairhmm_core_dev(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *d_hap_
                                                                  w.counters + kCntBand, ctx->sm_count, st);
             if (ce != cudaSuccess)
                 return set_err(ctx, VLR_ERR_CUDA, "pairhmm launch failed: %s", cudaGetErrorString(ce));
-            ctx->launches += 3;
+            ctx->launches += 4;
         }
     }
     // Class sizes live on the device: every class kernel is launched as a persistent grid with a

@@ -35,9 +35,9 @@ constexpr int kBandMaxLx = 480;   // haplotype window bytes staged per warp
 constexpr int kBandMaxLy = 248;   // read rows staged per warp (same limit as pairhmm_kernel)
 constexpr int kBandPad = 128;     // codes before / after the window (cells outside are masked)
 constexpr int kBandInf = 1 << 28; // "no predecessor" in the min-plus scan (kMedMax + positions fit)
-constexpr int kBandMaxG = 3;      // diagonals per lane: bands of up to 96 diagonals
+constexpr int kBandMaxG = 4;      // diagonals per lane: bands of up to 128 diagonals
 // CTAs per SM by diagonals per lane (40 / 56 / 71 registers; 11 KB shared memory per CTA)
-constexpr int band_blocks_per_sm(int G) { return G == 1 ? 12 : (G == 2 ? 8 : 6); }
+constexpr int band_blocks_per_sm(int G) { return G == 1 ? 12 : (G == 2 ? 8 : (G == 3 ? 6 : 5)); }
 
 struct BandQ {  // per base quality: emission factors (already times t_mm) and the Y-state factor
     double em, emm, cy;
@@ -230,6 +230,8 @@ cudaError_t launch_pairhmm_band(const HmmArgs &a, int32_t *list_rw, const int32_
         pairhmm_band_kernel<2, APPROX><<<sm_count * band_blocks_per_sm(2), kWarps * 32, 0, st>>>(b, list_rw, n_total); \
         b.cursor = cursors + 2;                                                                   \
         pairhmm_band_kernel<3, APPROX><<<sm_count * band_blocks_per_sm(3), kWarps * 32, 0, st>>>(b, list_rw, n_total); \
+        b.cursor = cursors + 3;                                                                   \
+        pairhmm_band_kernel<4, APPROX><<<sm_count * band_blocks_per_sm(4), kWarps * 32, 0, st>>>(b, list_rw, n_total); \
         return cudaGetLastError();                                                                \
     }
 
