@@ -295,6 +295,13 @@ __global__ void __launch_bounds__(128) besthit_kernel(MyersArgs g) {
 }
 
 // ---------------------------------------------------------------- fused allele support
+// slot -> read index: every (region, haplotype) slot aligns the region's read window
+__global__ void slot_read_kernel(int64_t n_regions, const int32_t *region_hap_off, const int32_t *region_read,
+                                 int32_t *slot_read) {
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_regions; r += (int64_t)gridDim.x * blockDim.x)
+        for (int s = region_hap_off[r]; s < region_hap_off[r + 1]; ++s) slot_read[s] = region_read[r];
+}
+
 struct SupportArgs {
     int64_t n_regions;
     const int32_t *region_read, *region_hap_off, *region_haps, *region_n_ref;
@@ -610,30 +617,12 @@ int vlr_allele_support_batch(vlr_ctx *ctx, int64_t n_regions, const int32_t *reg
     cudaStream_t st = ctx->stream;
     const int64_t n_slots = region_hap_off[n_regions];
     if (n_slots <= 0 || n_slots > 0x7fffffff) return set_err(ctx, VLR_ERR_INVALID, "bad region_hap_off");
-    int64_t max_lx = 0, max_ly = 0;
-    for (int64_t h = 0; h < n_haps; ++h) {
-        if (hap_off[h + 1] < hap_off[h]) return set_err(ctx, VLR_ERR_INVALID, "hap_off not monotone");
-        max_lx = std::max(max_lx, hap_off[h + 1] - hap_off[h]);
-        if (shrink_extra && shrink_extra[h] > hap_off[h + 1] - hap_off[h])
-            return set_err(ctx, VLR_ERR_INVALID, "shrink_extra[%lld] exceeds the window", (long long)h);
-    }
-    for (int64_t r = 0; r < n_reads; ++r) {
-        if (read_off[r + 1] < read_off[r]) return set_err(ctx, VLR_ERR_INVALID, "read_off not monotone");
-        max_ly = std::max(max_ly, read_off[r + 1] - read_off[r]);
-    }
-    if (max_ly > 248) return set_err(ctx, VLR_ERR_UNSUPPORTED, "read window of %lld rows exceeds 248", (long long)max_ly);
-    for (int64_t r = 0; r < n_regions; ++r) {
-        const int s0 = region_hap_off[r], s1 = region_hap_off[r + 1];
-        if (s1 < s0 || region_n_ref[r] < 0 || region_n_ref[r] > s1 - s0 || region_read[r] < 0 || region_read[r] >= n_reads)
-            return set_err(ctx, VLR_ERR_INVALID, "region %lld is malformed", (long long)r);
-    }
-    for (int64_t s = 0; s < n_slots; ++s)
-        if (region_haps[s] < 0 || region_haps[s] >= n_haps) return set_err(ctx, VLR_ERR_INVALID, "region_haps out of range");
-    lap("validate", false);
     enum { S_HAP = 40, S_HOFF, S_RB, S_ROFF, S_PH, S_PR, S_OUT, S_OPS, S_SCR, S_SCR2, S_SCR3,
            S_RQ, S_RR, S_RHO, S_RNR, S_SE, S_WS0, S_WL, S_MED, S_SP, S_SM, S_O1, S_O2, S_O3, S_O4, S_O5,
            S_O6, S_O7, S_O8, S_PWS, S_PATH = 75 };
     const int64_t hap_lo = hap_off[0], rd_lo = read_off[0];
+    if (hap_off[n_haps] < hap_lo || read_off[n_reads] < rd_lo)
+        return set_err(ctx, VLR_ERR_INVALID, "offsets not monotone");
     const size_t hb = (size_t)(hap_off[n_haps] - hap_lo), rb = (size_t)(read_off[n_reads] - rd_lo);
     auto D = [&](int slot, size_t bytes) { return dev_scratch(ctx, slot, bytes ? bytes : 8); };
     uint8_t *d_hap = (uint8_t *)D(S_HAP, hb + 64);
@@ -662,26 +651,61 @@ int vlr_allele_support_batch(vlr_ctx *ctx, int64_t n_regions, const int32_t *reg
         !d_sp || !d_sm || !d_pref || !d_palt || !d_rref || !d_ralt || !d_rd || !d_ad || !d_ni || !d_io || !d_pws)
         return set_err(ctx, VLR_ERR_NOMEM, "scratch allocation failed");
     lap("scratch", false);
-    // slot -> read index (the Myers pairs)
-    std::vector<int32_t> slot_read((size_t)n_slots);
-    for (int64_t r = 0; r < n_regions; ++r)
-        for (int s = region_hap_off[r]; s < region_hap_off[r + 1]; ++s) slot_read[s] = region_read[r];
+    // Copies first, checks while they fly: everything the Myers kernel needs goes on the main stream,
+    // the base qualities (only used from the selection step on) on the copy stream, and the host
+    // validates the offset / index arrays meanwhile.  The byte counts below come from the first and
+    // last offsets only; a malformed array is rejected before any kernel reads the data.
+    int rc = ensure_copy_stream(ctx);
+    if (rc != VLR_OK) return rc;
+    cudaStream_t cp = ctx->copy_stream;
     auto H2D = [&](void *d, const void *h, size_t b) { return cudaMemcpyAsync(d, h, b, cudaMemcpyHostToDevice, st); };
+    VLR_CUDA(ctx, cudaMemcpyAsync(d_rq, read_quals + rd_lo, rb, cudaMemcpyHostToDevice, cp));
+    VLR_CUDA(ctx, cudaEventRecord(ctx->ev_h2d[0], cp));
     VLR_CUDA(ctx, H2D(d_hap, hap_bytes + hap_lo, hb));
     VLR_CUDA(ctx, H2D(d_hoff, hap_off, (size_t)(n_haps + 1) * 8));
     VLR_CUDA(ctx, H2D(d_rb, read_bases + rd_lo, rb));
-    VLR_CUDA(ctx, H2D(d_rq, read_quals + rd_lo, rb));
     VLR_CUDA(ctx, H2D(d_roff, read_off, (size_t)(n_reads + 1) * 8));
     VLR_CUDA(ctx, H2D(d_rr, region_read, (size_t)n_regions * 4));
     VLR_CUDA(ctx, H2D(d_rho, region_hap_off, (size_t)(n_regions + 1) * 4));
     VLR_CUDA(ctx, H2D(d_rh, region_haps, (size_t)n_slots * 4));
     VLR_CUDA(ctx, H2D(d_rnr, region_n_ref, (size_t)n_regions * 4));
     if (shrink_extra) VLR_CUDA(ctx, H2D(d_se, shrink_extra, (size_t)n_haps * 4));
-    VLR_CUDA(ctx, H2D(d_slot_read, slot_read.data(), (size_t)n_slots * 4));
-    VLR_CUDA(ctx, cudaStreamSynchronize(st));  // slot_read is a stack-owned staging vector
     VLR_CUDA(ctx, cudaMemsetAsync(d_ops, 0, (size_t)n_slots * kMaxIndelOps, st));
     VLR_CUDA(ctx, cudaMemsetAsync(d_io, 0, (size_t)n_regions * kMaxIndelOps, st));
-    lap("h2d", true);
+    // ---- validation (host), overlapped with the copies
+    int64_t max_lx = 0, max_ly = 0;
+    const char *bad = nullptr;
+    for (int64_t h = 0; h < n_haps && !bad; ++h) {
+        if (hap_off[h + 1] < hap_off[h]) bad = "hap_off not monotone";
+        max_lx = std::max(max_lx, hap_off[h + 1] - hap_off[h]);
+        if (shrink_extra && shrink_extra[h] > hap_off[h + 1] - hap_off[h]) bad = "shrink_extra exceeds the window";
+    }
+    for (int64_t r = 0; r < n_reads && !bad; ++r) {
+        if (read_off[r + 1] < read_off[r]) bad = "read_off not monotone";
+        max_ly = std::max(max_ly, read_off[r + 1] - read_off[r]);
+    }
+    for (int64_t r = 0; r < n_regions && !bad; ++r) {
+        const int s0 = region_hap_off[r], s1 = region_hap_off[r + 1];
+        if (s1 < s0 || s1 > n_slots || s0 < 0 || region_n_ref[r] < 0 || region_n_ref[r] > s1 - s0 || region_read[r] < 0 ||
+            region_read[r] >= n_reads)
+            bad = "a region is malformed";
+    }
+    for (int64_t k = 0; k < n_slots && !bad; ++k)
+        if (region_haps[k] < 0 || region_haps[k] >= n_haps) bad = "region_haps out of range";
+    if (bad || max_ly > 248) {
+        // the copies read caller memory: let them finish before the buffers go back to the caller
+        cudaStreamSynchronize(st);
+        cudaStreamSynchronize(cp);
+        if (bad) return set_err(ctx, VLR_ERR_INVALID, "%s", bad);
+        return set_err(ctx, VLR_ERR_UNSUPPORTED, "read window of %lld rows exceeds 248", (long long)max_ly);
+    }
+    // slot -> read index (the Myers pairs), on the device
+    {
+        const int sgrid = (int)std::min<int64_t>((n_regions + 255) / 256, (int64_t)ctx->sm_count * 8);
+        slot_read_kernel<<<sgrid, 256, 0, st>>>(n_regions, d_rho, d_rr, d_slot_read);
+        VLR_LAUNCH_CHECK(ctx);
+    }
+    lap("h2d+checks", true);
     // 1. best hit of every (read window, haplotype) slot
     MyersArgs ma;
     memset(&ma, 0, sizeof(ma));
@@ -689,16 +713,19 @@ int vlr_allele_support_batch(vlr_ctx *ctx, int64_t n_regions, const int32_t *reg
     ma.pair_hap = d_rh; ma.pair_read = d_slot_read; ma.n_pairs = n_slots; ma.out = d_hits; ma.out_ops = d_ops;
     const bool fast = (flags & VLR_REALIGN_FAST) != 0;
     double *d_path = nullptr;
+    if (fast) VLR_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_h2d[0], 0));  // the path probability reads the qualities
     if (fast) {
         d_path = (double *)D(S_PATH, (size_t)n_slots * 8);
         if (!d_path) return set_err(ctx, VLR_ERR_NOMEM, "scratch allocation failed");
         ma.rqual = d_rq - rd_lo; ma.qlut = ctx->d_qlut; ma.out_path = d_path;
         set_path_consts(ma, gap);
     }
-    int rc = launch_besthit(ctx, ma, max_lx, S_SCR);
+    rc = launch_besthit(ctx, ma, max_lx, S_SCR);
     if (rc != VLR_OK) return rc;
     lap("myers", true);
-    // 2. minimal-distance selection, certainty short-circuit, HMM windows
+    // 2. minimal-distance selection, certainty short-circuit, HMM windows (from here on the base
+    // qualities are read: join the copy stream)
+    VLR_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_h2d[0], 0));
     SupportArgs sa;
     memset(&sa, 0, sizeof(sa));
     sa.n_regions = n_regions; sa.region_read = d_rr; sa.region_hap_off = d_rho; sa.region_haps = d_rh;
