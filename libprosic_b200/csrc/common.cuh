@@ -27,6 +27,10 @@ struct vlr_ctx {
     // host-buffer entry points overlap H2D of chunk c+1 with the kernels of chunk c
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    // flattened model of the last posterior launch (host copy) and where it sits on the device:
+    // the same model is not uploaded again (the chunks of one batch, repeated calls of one scenario)
+    std::vector<uint8_t> model_copy;
+    const void *model_dev = nullptr;
 };
 
 namespace vlr {

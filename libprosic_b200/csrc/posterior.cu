@@ -276,22 +276,33 @@ int vlr_posterior_batch_dev(vlr_ctx *ctx, int64_t n_sites, const vlr_model *mode
     off[6] = align_up(off[5] + b_vaf, 16);
     off[7] = align_up(off[6] + b_seg, 16);
     off[8] = align_up(off[7] + b_pri, 16);
-    uint8_t *h_blob = (uint8_t *)pin_scratch(ctx, 4, off[8] + 16);
     uint8_t *d_blob = (uint8_t *)dev_scratch(ctx, S_MODEL, off[8] + 16);
     double *d_table = (double *)dev_scratch(ctx, S_TABLE, (size_t)((tab_cap ? 0 : n_teams * tbound) + 8) * sizeof(double));
     int32_t *d_cnt = (int32_t *)dev_scratch(ctx, S_CNT, 256);
-    if (!h_blob || !d_blob || !d_table || !d_cnt) return set_err(ctx, VLR_ERR_NOMEM, "scratch allocation failed");
-    // the pinned blob may still be in flight from a previous call on this stream
-    VLR_CUDA(ctx, cudaStreamSynchronize(st));
-    memcpy(h_blob + off[0], H.spectra.data(), b_spec);
-    memcpy(h_blob + off[1], H.paths.data(), b_path);
-    memcpy(h_blob + off[2], H.events.data(), b_ev);
-    memcpy(h_blob + off[3], H.eb.data(), b_eb);
-    memcpy(h_blob + off[4], H.cfg.data(), b_cfg);
-    memcpy(h_blob + off[5], H.vafs.data(), b_vaf);
-    memcpy(h_blob + off[6], H.segs.data(), b_seg);
-    if (has_prior) memcpy(h_blob + off[7], model->prior_ln, b_pri);
-    VLR_CUDA(ctx, cudaMemcpyAsync(d_blob, h_blob, off[8], cudaMemcpyHostToDevice, st));
+    if (!d_blob || !d_table || !d_cnt) return set_err(ctx, VLR_ERR_NOMEM, "scratch allocation failed");
+    {
+        std::vector<uint8_t> blob(off[8], 0);
+        memcpy(blob.data() + off[0], H.spectra.data(), b_spec);
+        memcpy(blob.data() + off[1], H.paths.data(), b_path);
+        memcpy(blob.data() + off[2], H.events.data(), b_ev);
+        memcpy(blob.data() + off[3], H.eb.data(), b_eb);
+        memcpy(blob.data() + off[4], H.cfg.data(), b_cfg);
+        memcpy(blob.data() + off[5], H.vafs.data(), b_vaf);
+        memcpy(blob.data() + off[6], H.segs.data(), b_seg);
+        if (has_prior) memcpy(blob.data() + off[7], model->prior_ln, b_pri);
+        // upload only when the model changed: the chunks of a batch and repeated calls of one
+        // scenario reuse the device copy, and the launch needs no synchronisation with the stream
+        if (ctx->model_dev != d_blob || ctx->model_copy != blob) {
+            uint8_t *h_blob = (uint8_t *)pin_scratch(ctx, 4, off[8] + 16);
+            if (!h_blob) return set_err(ctx, VLR_ERR_NOMEM, "scratch allocation failed");
+            // the pinned staging copy may still be in flight from a previous upload on this stream
+            VLR_CUDA(ctx, cudaStreamSynchronize(st));
+            memcpy(h_blob, blob.data(), off[8]);
+            VLR_CUDA(ctx, cudaMemcpyAsync(d_blob, h_blob, off[8], cudaMemcpyHostToDevice, st));
+            ctx->model_copy.swap(blob);
+            ctx->model_dev = d_blob;
+        }
+    }
     VLR_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, 256, st));
     PostArgs a;
     memset(&a, 0, sizeof(a));
