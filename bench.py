@@ -429,7 +429,7 @@ def bench_c1(ctx):
             "observations": n_obs, "seconds": time.perf_counter() - t0,
             "note": "test21 is the documented exception (DESIGN.md section 5); all 32 tumor/normal testcases: "
                     "tests/golden/tn_results.txt (31 hold); all runnable Generic testcases: "
-                    "tests/golden/scenario_results.txt (19 of 22 hold = all that upstream asserts)"}
+                    "tests/golden/scenario_results.txt (22 of 25 hold = all that upstream asserts)"}
 
 
 def bench_c4(args, ctx, torch, dist, dev, rank, world, timed):

@@ -999,6 +999,11 @@ SCENARIO_CASES = ("omit_sb", "test34", "test37", "test40", "test49", "test52", "
                   "test_low_cov_vaf", "test_panel_overlap", "test_contig_universe", "test_giab_02")
 
 
+# ... and with a prior over continuous allele frequencies (somatic mutation rates, clonal inheritance):
+# the GPU path takes a prior table for set-only universes only, so these run on the oracle
+SCENARIO_CASES_ORACLE_ONLY = ("test64", "test69")
+
+
 def check_expectations(result):
     """tests/common/mod.rs:289-343: list of (expression, passed)."""
     env = dict(result["af"])

@@ -40,6 +40,13 @@ def main():
         F.save_fixture(F.load_testcase(os.path.join(REF, c)), p)
         total += os.path.getsize(p)
         print(c, os.path.getsize(p))
+    scn_prior = os.path.join(os.path.dirname(OUT), "scn_prior")
+    os.makedirs(scn_prior, exist_ok=True)
+    for c in F.SCENARIO_CASES_ORACLE_ONLY:  # priors over continuous allele frequencies: oracle only
+        p = os.path.join(scn_prior, c + ".json.gz")
+        F.save_fixture(F.load_testcase(os.path.join(REF, c)), p)
+        total += os.path.getsize(p)
+        print(c, os.path.getsize(p))
     for c in CASES:
         d = os.path.join(REF, c)
         if not os.path.isdir(d):

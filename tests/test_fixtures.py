@@ -183,3 +183,20 @@ def test_scenario_testcases_hold_on_the_gpu(ctx, path):
             g = got[k]
             assert (np.isinf(g) and np.isinf(w)) or abs(g - w) <= 2e-5 * max(1.0, abs(w)), (k, g, w)
     assert all(v for _, v in F.check_expectations(got))
+
+
+SCN_PRIOR = sorted(glob.glob(os.path.join(HERE, "golden", "scn_prior", "*.json.gz")))
+
+
+@pytest.mark.parametrize("path", SCN_PRIOR, ids=_name)
+def test_scenario_testcases_with_somatic_priors_hold_on_the_oracle(path):
+    """Four-sample pedigrees with somatic mutation rates, Mendelian and clonal inheritance
+    (test64, test69): universes with continuous ranges AND a non-uniform prior
+    (libprosic_b200/prior.py restates prob_somatic_mutation / prob_clonal_inheritance).  The GPU path
+    takes prior tables for set-only universes, so these pin the
+    restated host glue, the grammar front end and the oracle only."""
+    assert len(SCN_PRIOR) == len(F.SCENARIO_CASES_ORACLE_ONLY)
+    from _oracle_backend import OracleBackend
+    r = F.run_scenario_testcase(path, OracleBackend())
+    verdicts = F.check_expectations(r)
+    assert verdicts and all(v for _, v in verdicts), (verdicts, r)

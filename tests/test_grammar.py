@@ -447,6 +447,17 @@ def test_prior_module_matches_the_hand_written_priors():
     # ploidy 0 (female, Y): only AF 0 is possible
     fy = PR.make_prior(one, "Y", "snv")
     assert fy([0.5]) == -np.inf and fy([0.0]) == 0.0
+    # somatic mutation rate (prior.rs:433-455): a non-germline VAF gets the density rate / (vaf^2 * genome size),
+    # summed over the possible germline genotypes; a germline VAF the complement of the integrated density
+    som = G.Scenario(TRIO_YAML.replace("  mother:\n    sex: female",
+                                       "  mother:\n    sex: female\n    somatic-effective-mutation-rate: 1e-6"))
+    fs = PR.make_prior(som, "1", "snv")
+    base = f([0.0, 0.0, 0.0])
+    want = np.log(1e-6) - (2 * np.log(0.25) + np.log(3.5e9))
+    got = fs([0.0, 0.0, 0.25])
+    assert np.isfinite(got) and abs((got - base) - want) < 1e-3     # germline 0 dominates the sum
+    assert abs(fs([0.0, 0.0, 0.0]) - base) < 1e-6                   # ln(1 - tiny)
     with pytest.raises(NotImplementedError):
         PR.make_prior(G.Scenario(TRIO_YAML.replace("  mother:\n    sex: female",
-                                                   "  mother:\n    sex: female\n    somatic-effective-mutation-rate: 1e-10")), "1")
+                                                   "  mother:\n    sex: female\n    inheritance:\n      subclonal:\n"
+                                                   "        from: father\n        origin: single-cell")), "1")
