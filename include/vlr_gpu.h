@@ -51,6 +51,12 @@ int vlr_ctx_synchronize(vlr_ctx *ctx);
 /* number of kernels launched through this context so far */
 int64_t vlr_ctx_launch_count(const vlr_ctx *ctx);
 
+/* The library's reference-arithmetic libm (csrc/detmath.cuh: exp, expm1, log, log1p as fixed
+ * sequences of correctly rounded binary64 operations, identical on host and device).  It backs
+ * every result that must be reproducible bit for bit (VLR_HMM_LITERAL below).  fn: 0 exp, 1 expm1,
+ * 2 log, 3 log1p over host arrays; ctx == NULL evaluates on the host, else on the device. */
+int vlr_ref_math(vlr_ctx *ctx, int fn, int64_t n, const double *x, double *out);
+
 /* ---- pair-HMM forward: replaces PairHMM::prob_related (realignment/mod.rs:439-443) ------
  * Gap parameters: GapParams, realignment/pairhmm.rs:73-101 (ln probabilities). */
 typedef struct {
@@ -60,11 +66,23 @@ typedef struct {
     double prob_gap_y_extend; /* prob_deletion_extend_artifact  (default 0 -> ln = -inf)        */
 } vlr_gap_params;
 
-/* flags */
-#define VLR_HMM_SUM3_APPROX 1u /* bio's ln_sum3_exp_approx in the M-state sum (reference behaviour) */
-#define VLR_HMM_PATH_CLOSE 2u  /* close-gap constants paired as PathHMMRealigner (mod.rs:469-470)   */
-#define VLR_REALIGN_FAST 4u    /* vlr_allele_support_batch: --pairhmm-mode fast (PathHMMRealigner)     */
-#define VLR_HMM_DEFAULT VLR_HMM_SUM3_APPROX
+/* flags.  The M-state sum of bio 0.37's pair-HMM is `ln_sum3_exp_approx`; the crate source is not in
+ * the reference checkout (un-vendored dependency), so both recollections of it are implemented and the
+ * choice is a flag (DESIGN.md section 5 has the measured sensitivity):
+ *   three-way (default): sorted p0 >= p1 >= p2;  p0 - p1 > 10 -> p0;  else p1 - p2 > 10 -> p0.ln_add_exp(p1);
+ *                        else the exact sum of three
+ *   two-way:             p0 - p1 > 10 -> p0, else the exact sum of three
+ *   neither flag:        always the exact sum */
+#define VLR_HMM_SUM3_APPROX 1u  /* two-way ln_sum3_exp_approx */
+#define VLR_HMM_PATH_CLOSE 2u   /* close-gap constants paired as PathHMMRealigner (mod.rs:469-470)   */
+#define VLR_REALIGN_FAST 4u     /* vlr_allele_support_batch: --pairhmm-mode fast (PathHMMRealigner)     */
+#define VLR_HMM_SUM3_APPROX3 8u /* three-way ln_sum3_exp_approx (wins over VLR_HMM_SUM3_APPROX) */
+/* vlr_pairhmm_batch only: evaluate every pair in natural-log space in the reference's literal
+ * operation order with the library's deterministic libm (bit-reproducible; ~50x slower).  The fused
+ * allele support uses this evaluation by itself for regions whose two allele probabilities are
+ * nearly tied, because the reference decides `prob_ref != prob_alt` exactly (mod.rs:303). */
+#define VLR_HMM_LITERAL 16u
+#define VLR_HMM_DEFAULT VLR_HMM_SUM3_APPROX3
 
 /*
  * Host-buffer entry point (H2D, kernels, D2H inside; synchronous).
@@ -114,9 +132,11 @@ int vlr_measure_fp64_peak(vlr_ctx *ctx, double *out_tflops);
  *      (edit_distance.rs:56-154); same haps/reads/pairs layout as above (host buffers).
  * out_dist = EditDistanceHit::dist (-1: no hit), out_start = alignments[0].start,
  * out_end = min(alignments.last().start + len_y + dist, len_x), out_n_best = number of best end
- * positions; best_indel_operations (131-144): count in out_n_indel_ops (nullable) and the first
- * VLR_MAX_INDEL_OPS of them in out_indel_ops[k*VLR_MAX_INDEL_OPS ..] (nullable; 2 = Del, 3 = Ins,
- * forward order).  Read windows up to 256 rows. ------ */
+ * positions; best_indel_operations (131-144): their count in out_n_indel_ops (nullable) and the
+ * operations RUN-LENGTH ENCODED in out_indel_ops[k*VLR_MAX_INDEL_OPS ..] (nullable): byte pairs
+ * (op, run length <= 255) in forward order, op 2 = Del, 3 = Ins, zero padded -- 16 runs per alignment,
+ * however long the runs (a 60-base insertion is one pair).  An alignment with more runs has its tail
+ * uncounted: sum of the run lengths < out_n_indel_ops tells.  Read windows up to 256 rows. ------ */
 #define VLR_MAX_INDEL_OPS 32
 int vlr_besthit_batch(vlr_ctx *ctx, int64_t n_pairs,
                       const uint8_t *hap_bytes, const int64_t *hap_off, int64_t n_haps,

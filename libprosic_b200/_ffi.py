@@ -10,10 +10,12 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libvlr_b200.so")
 
 VLR_OK = 0
-HMM_SUM3_APPROX = 1
+HMM_SUM3_APPROX = 1   # two-way ln_sum3_exp_approx
 HMM_PATH_CLOSE = 2
 REALIGN_FAST = 4  # vlr_allele_support_batch: --pairhmm-mode fast (PathHMMRealigner)
-HMM_DEFAULT = HMM_SUM3_APPROX
+HMM_SUM3_APPROX3 = 8  # three-way ln_sum3_exp_approx (default)
+HMM_LITERAL = 16      # vlr_pairhmm_batch: literal log-space evaluation, deterministic libm
+HMM_DEFAULT = HMM_SUM3_APPROX3
 MAX_INDEL_OPS = 32
 
 NODE_SET, NODE_RANGE, NODE_FALSE, NODE_SKIP = 0, 1, 2, 3
@@ -79,7 +81,7 @@ class Model(C.Structure):
 
 EXPORTS = [
     "vlr_version", "vlr_ctx_create", "vlr_ctx_destroy", "vlr_last_error", "vlr_ctx_set_stream",
-    "vlr_ctx_synchronize", "vlr_ctx_launch_count", "vlr_pairhmm_batch",
+    "vlr_ctx_synchronize", "vlr_ctx_launch_count", "vlr_ref_math", "vlr_pairhmm_batch",
     "vlr_pairhmm_workspace_bytes", "vlr_pairhmm_batch_dev", "vlr_measure_fp64_peak",
     "vlr_besthit_batch", "vlr_pathhmm_batch", "vlr_allele_support_batch", "vlr_likelihood_batch", "vlr_call_records", "vlr_model_leaves", "vlr_obs_decode", "vlr_obs_encode", "vlr_obs_encoded_bound", "vlr_posterior_batch", "vlr_posterior_batch_f32", "vlr_posterior_batch_dev",
 ]
@@ -108,6 +110,7 @@ def load():
     L.vlr_ctx_synchronize.argtypes = [vp]
     L.vlr_ctx_launch_count.argtypes = [vp]
     L.vlr_ctx_launch_count.restype = i64
+    L.vlr_ref_math.argtypes = [vp, C.c_int, i64, vp, vp]
     L.vlr_pairhmm_batch.argtypes = [vp, i64, vp, vp, i64, vp, vp, vp, i64, vp, vp, vp,
                                     C.POINTER(GapParams), u32, vp]
     L.vlr_pairhmm_workspace_bytes.argtypes = [i64, i64, i64]

@@ -11,7 +11,7 @@ OUT = os.path.join(HERE, "libvlr_b200.so")
 OBJ = os.path.join(HERE, "_build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-Xcompiler", "-fPIC,-O2", "--expt-relaxed-constexpr"]
+         "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "--expt-relaxed-constexpr"]
 
 
 def _sources():

@@ -38,6 +38,24 @@ def _arr(a, dt):
     return None if a is None else np.ascontiguousarray(a, dtype=dt)
 
 
+def expand_indel_runs(runs, n_ops):
+    """Decode the run-length encoded best_indel_operations of vlr_besthit_batch /
+    vlr_allele_support_batch (byte pairs (op, run length), include/vlr_gpu.h) into a zero padded
+    matrix [n, max(32, max n_ops)] of operations (2 = Del, 3 = Ins).  Raises if a record overflowed
+    its 16 runs."""
+    runs = np.asarray(runs, np.uint8).reshape(len(n_ops), -1, 2)
+    lens = runs[:, :, 1].astype(np.int64)
+    tot = lens.sum(axis=1)
+    if (tot != np.asarray(n_ops)).any():
+        k = int(np.argmax(tot != np.asarray(n_ops)))
+        raise NotImplementedError("record %d: more than %d indel runs in one alignment" % (k, runs.shape[1]))
+    width = max(32, int(tot.max()) if len(tot) else 0)
+    out = np.zeros((len(n_ops), width), np.uint8)
+    for k in np.nonzero(tot)[0]:
+        out[k, :tot[k]] = np.repeat(runs[k, :, 0], lens[k])
+    return out
+
+
 class Context:
     def __init__(self, device=0):
         self.lib = _ffi.load()
@@ -77,6 +95,13 @@ class Context:
         v = C.c_double()
         self._check(self.lib.vlr_measure_fp64_peak(self.h, C.byref(v)))
         return v.value
+
+    def ref_math(self, fn, x, on_device=True):
+        """The library's deterministic libm (csrc/detmath.cuh): fn 0 exp, 1 expm1, 2 log, 3 log1p."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.empty_like(x)
+        self._check(self.lib.vlr_ref_math(self.h if on_device else None, int(fn), x.size, _ptr(x), _ptr(out)))
+        return out
 
     # ---------------------------------------------------------------- pair-HMM
     def pairhmm_batch(self, hap_bytes, hap_off, read_bases, read_quals, read_off, gap,
@@ -123,7 +148,8 @@ class Context:
             self.h, n, _ptr(hap_bytes), _ptr(hap_off), n_haps, _ptr(read_bases), _ptr(read_off),
             n_reads, _ptr(pair_hap), _ptr(pair_read), _ptr(out["dist"]), _ptr(out["start"]),
             _ptr(out["end"]), _ptr(out["n_best"]), _ptr(out["n_indel_ops"]), _ptr(ops)))
-        out["indel_ops"] = ops
+        out["indel_runs"] = ops
+        out["indel_ops"] = expand_indel_runs(ops, out["n_indel_ops"])
         return out
 
     def pathhmm_batch(self, hap_bytes, hap_off, read_bases, read_quals, read_off, gap,
@@ -162,6 +188,7 @@ class Context:
         read_off = _arr(read_off, np.int64)
         shrink_extra = _arr(shrink_extra, np.int32)
         n = len(region_read)
+        decode = out is None
         if out is None:
             out = dict(prob_ref=np.empty(n), prob_alt=np.empty(n), raw_ref=np.empty(n), raw_alt=np.empty(n),
                        ref_dist=np.empty(n, np.int32), alt_dist=np.empty(n, np.int32),
@@ -174,6 +201,9 @@ class Context:
             _ptr(out["prob_ref"]), _ptr(out["prob_alt"]), _ptr(out["raw_ref"]), _ptr(out["raw_alt"]),
             _ptr(out["ref_dist"]), _ptr(out["alt_dist"]), _ptr(out["n_indel_ops"]),
             _ptr(out["indel_ops"])))
+        if decode:  # caller-provided (pinned) buffers keep the run-length encoded records
+            out["indel_runs"] = out["indel_ops"]
+            out["indel_ops"] = expand_indel_runs(out["indel_runs"], out["n_indel_ops"])
         return out
 
     def pairhmm_workspace_bytes(self, n_pairs, max_len_x=0, max_len_y=0):

@@ -3,6 +3,7 @@
 #include <stdarg.h>
 
 #include "common.cuh"
+#include "detmath.cuh"
 
 namespace vlr {
 
@@ -57,11 +58,42 @@ int ensure_copy_stream(vlr_ctx *ctx) {
     return VLR_OK;
 }
 
+__host__ __device__ static inline double ref_math_eval(int fn, double x) {
+    switch (fn) {
+    case 0: return dm::exp(x);
+    case 1: return dm::expm1(x);
+    case 2: return dm::log(x);
+    default: return dm::log1p(x);
+    }
+}
+__global__ void ref_math_kernel(int fn, int64_t n, const double *x, double *out) {
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+        out[k] = ref_math_eval(fn, x[k]);
+}
+
 }  // namespace vlr
 
 extern "C" {
 
-int vlr_version(void) { return 101; }
+int vlr_version(void) { return 200; }
+
+int vlr_ref_math(vlr_ctx *ctx, int fn, int64_t n, const double *x, double *out) {
+    if (fn < 0 || fn > 3 || n < 0 || (n > 0 && (!x || !out))) return ctx ? vlr::set_err(ctx, VLR_ERR_INVALID, "bad argument") : VLR_ERR_INVALID;
+    if (!ctx) {  // host evaluation
+        for (int64_t k = 0; k < n; ++k) out[k] = vlr::ref_math_eval(fn, x[k]);
+        return VLR_OK;
+    }
+    if (n == 0) return VLR_OK;
+    VLR_CUDA(ctx, cudaSetDevice(ctx->device));
+    double *d_x = (double *)vlr::dev_scratch(ctx, 92, (size_t)n * 8), *d_o = (double *)vlr::dev_scratch(ctx, 93, (size_t)n * 8);
+    if (!d_x || !d_o) return vlr::set_err(ctx, VLR_ERR_NOMEM, "scratch allocation failed");
+    VLR_CUDA(ctx, cudaMemcpyAsync(d_x, x, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    vlr::ref_math_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(fn, n, d_x, d_o);
+    VLR_LAUNCH_CHECK(ctx);
+    VLR_CUDA(ctx, cudaMemcpyAsync(out, d_o, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    VLR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VLR_OK;
+}
 
 int vlr_ctx_create(int device, vlr_ctx **out) {
     if (!out) return VLR_ERR_INVALID;
@@ -82,14 +114,17 @@ int vlr_ctx_create(int device, vlr_ctx **out) {
     ctx->stream = ctx->own_stream;
     // base-quality LUT, computed the way the reference does (bases.rs:23-48):
     // ln eps = q * (-ln10/10); ln(1-eps) = ln_one_minus_exp(ln eps); mismatch = ln eps + ln .3333
+    // (the library's deterministic libm, detmath.cuh: the literal log-space kernel and a host
+    // evaluation of the same formulas see identical table entries)
     std::vector<double> lut(256 * vlr::kQlutStride);
     const double f = -0.23025850929940456;
+    const double ln_conf = vlr::dm::log(0.3333);
     for (int q = 0; q < 256; ++q) {
         double ln_eps = (double)q * f;
-        double ln_call = ln_eps < -0.693 ? log1p(-exp(ln_eps)) : log(-expm1(ln_eps));
-        lut[q * 4 + 0] = exp(ln_eps);
-        lut[q * 4 + 1] = exp(ln_call);
-        lut[q * 4 + 2] = exp(ln_eps + log(0.3333));
+        double ln_call = vlr::dm::ln_one_minus_exp(ln_eps);
+        lut[q * 4 + 0] = vlr::dm::exp(ln_eps);
+        lut[q * 4 + 1] = vlr::dm::exp(ln_call);
+        lut[q * 4 + 2] = vlr::dm::exp(ln_eps + ln_conf);
         lut[q * 4 + 3] = ln_call;
     }
     if (cudaMalloc(&ctx->d_qlut, lut.size() * sizeof(double)) != cudaSuccess ||

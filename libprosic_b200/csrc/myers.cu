@@ -23,12 +23,13 @@
 #include <chrono>
 
 #include "pairhmm_host.cuh"
+#include "detmath.cuh"
 
 namespace vlr {
 
 constexpr int kMyW = 4;               // 64-bit words per column (pattern <= 256 rows)
-constexpr int kMaxIndelOps = VLR_MAX_INDEL_OPS;
-static_assert((kMaxIndelOps & (kMaxIndelOps - 1)) == 0, "ring size must be a power of two");
+constexpr int kMaxIndelOps = VLR_MAX_INDEL_OPS;   // bytes per output record: kMaxRuns (op, run length) pairs
+constexpr int kMaxRuns = kMaxIndelOps / 2;
 
 struct HitOut {
     int32_t dist, start, end, n_best, n_indel;
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(128) besthit_kernel(MyersArgs g) {
         }
         // tracebacks of every best end position (edit_distance.rs:88-97), in increasing position
         int start_first = 0, start_last = 0, best_nindel = 1 << 30, best_nops = 0;
-        uint8_t best_ops[kMaxIndelOps];
+        uint16_t best_runs[kMaxRuns];  // best_indel_operations, run-length encoded (op << 8 | length), forward order
         const bool want_path = g.out_path != nullptr;
         double best_path = -INFINITY;
         bool have_path = false;
@@ -181,7 +182,15 @@ __global__ void __launch_bounds__(128) besthit_kernel(MyersArgs g) {
                 continue;
             }
             int j = m, i = e, nindel = 0;
-            uint8_t ops[kMaxIndelOps];  // ring of the indel ops in traceback (reverse) order
+            // indel ops in traceback (reverse) order, run-length encoded: op << 8 | length (<= 255).  An
+            // alignment has a handful of indel runs however long they are (a 40-base insertion is one);
+            // more than kMaxRuns runs leave the tail uncounted, which the host reports as an error.
+            uint16_t runs[kMaxRuns];
+            int nruns = 0;
+            auto push_op = [&](int o) {
+                if (nruns > 0 && (runs[nruns - 1] >> 8) == o && (runs[nruns - 1] & 0xff) < 255) runs[nruns - 1]++;
+                else if (nruns < kMaxRuns) runs[nruns++] = (uint16_t)((o << 8) | 1);
+            };
             // PathHMM: the walk runs backwards, so the transition INTO the operation found last
             // step (`next`) is added once its predecessor is known; emissions as found
             double path = 0.0;
@@ -250,13 +259,13 @@ __global__ void __launch_bounds__(128) besthit_kernel(MyersArgs g) {
                     dm_left = dm_pre;
                 }
                 if (op == 3) {
-                    ops[nindel & (kMaxIndelOps - 1)] = 3;
+                    push_op(3);
                     nindel++; j--;
                     load_rec(r_cur, i);  // the rows in reach may now start one word lower
                     load_rec(r_left, i - 1);
                     if (want_path) path += (double)g.rqual[ro + j] * -0.23025850929940456;  // prob_emit_y
                 } else if (op == 2) {  // Del (prob_emit_x = ln 1)
-                    ops[nindel & (kMaxIndelOps - 1)] = 2;
+                    push_op(2);
                     nindel++; i--;
                 } else {               // Match / Subst
                     j--; i--;
@@ -277,9 +286,8 @@ __global__ void __launch_bounds__(128) besthit_kernel(MyersArgs g) {
             start_last = i;
             if (nindel < best_nindel) {  // fewest indel ops, first on ties (min_by_key)
                 best_nindel = nindel;
-                best_nops = min(nindel, kMaxIndelOps);
-                // forward order: op t is traceback entry nindel-1-t (the ring keeps the last 32 of those)
-                for (int t = 0; t < best_nops; ++t) best_ops[t] = ops[(nindel - 1 - t) & (kMaxIndelOps - 1)];
+                best_nops = nruns;
+                for (int t = 0; t < nruns; ++t) best_runs[t] = runs[nruns - 1 - t];  // forward order
             }
         }
         res.dist = best;
@@ -290,7 +298,10 @@ __global__ void __launch_bounds__(128) besthit_kernel(MyersArgs g) {
         g.out[k] = res;
         if (want_path) g.out_path[k] = best_path;
         if (g.out_ops)
-            for (int t = 0; t < best_nops; ++t) g.out_ops[k * kMaxIndelOps + t] = best_ops[t];
+            for (int t = 0; t < best_nops; ++t) {
+                g.out_ops[k * kMaxIndelOps + 2 * t] = (uint8_t)(best_runs[t] >> 8);
+                g.out_ops[k * kMaxIndelOps + 2 * t + 1] = (uint8_t)(best_runs[t] & 0xff);
+            }
     }
 }
 
@@ -321,6 +332,9 @@ struct SupportArgs {
     double *prob_ref, *prob_alt, *raw_ref, *raw_alt;
     int32_t *ref_dist, *alt_dist, *n_indel;
     uint8_t *indel_ops;
+    // near ties (first epilogue pass): pair-HMM slots to re-evaluate in literal log space
+    const uint8_t *hap_base;
+    int32_t *lit_list, *lit_count;
 };
 
 // prob_allele, first half (mod.rs:346-362): keep the haplotypes with minimal edit distance and
@@ -379,14 +393,16 @@ __global__ void support_select_kernel(SupportArgs g) {
     }
 }
 
-__device__ __forceinline__ double ln_add_exp_s(double a, double b) {
-    const double p0 = fmax(a, b), p1 = fmin(a, b);
-    if (p0 == -INFINITY) return -INFINITY;
-    if (p1 == -INFINITY) return p0;
-    return p0 + log1p(exp(p1 - p0));
-}
-
-// prob_allele second half (mod.rs:364-383) + the region epilogue of allele_support (283-301)
+// prob_allele second half (mod.rs:364-383) + the region epilogue of allele_support (283-301).
+// The reference keeps a read's strand / indel operations iff prob_ref != prob_alt EXACTLY (mod.rs:303)
+// and observation.rs:384-388 drops reads without strand information, so the last bit of the two
+// pair-HMM values decides a discrete output.  FIRST pass: regions whose raw values are nearly tied
+// (relative 1e-9; scaled-linear and log-space arithmetic agree to ~1e-11) put their pair-HMM slots on
+// the literal list -- unless both alleles are single windows with identical bytes and band, which
+// give identical bits in any deterministic arithmetic.  The literal kernel (LogLit) then replaces
+// those slot values by the reference's own operation order with the deterministic libm, and the
+// second pass redoes the epilogue on them.
+template <bool FIRST>
 __global__ void support_epilogue_kernel(SupportArgs g) {
     for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < g.n_regions;
          r += (int64_t)gridDim.x * blockDim.x) {
@@ -394,12 +410,14 @@ __global__ void support_epilogue_kernel(SupportArgs g) {
         const int nref = g.region_n_ref[r];
         double prob[2] = {-INFINITY, -INFINITY};
         int best_slot[2] = {-1, -1};
+        bool any_hmm = false;
         for (int allele = 0; allele < 2; ++allele) {
             const int a0 = allele == 0 ? s0 : s0 + nref, a1 = allele == 0 ? s0 + nref : s1;
             bool have = false;
             for (int s = a0; s < a1; ++s) {
                 const int mode = g.slot_mode[s];
                 if (mode == 0) continue;
+                any_hmm |= mode == 2;
                 const double p = g.slot_prob[s];
                 if (mode == 1) {  // perfect match: unconditional overwrite
                     prob[allele] = p; best_slot[allele] = s; have = true;
@@ -409,12 +427,28 @@ __global__ void support_epilogue_kernel(SupportArgs g) {
             }
         }
         double pr = prob[0], pa = prob[1];
+        if (FIRST && g.lit_list && any_hmm && pr != -INFINITY && pa != -INFINITY &&
+            fabs(pr - pa) <= 1e-9 * fmax(1.0, fabs(pr))) {
+            bool same = false;
+            if (nref == 1 && s1 - s0 == 2 && g.slot_mode[s0] == 2 && g.slot_mode[s0 + 1] == 2 &&
+                g.win_len[s0] == g.win_len[s0 + 1] && g.med[s0] == g.med[s0 + 1]) {
+                const uint8_t *x = g.hap_base + g.win_start[s0], *y = g.hap_base + g.win_start[s0 + 1];
+                same = true;
+                for (int k = 0; k < g.win_len[s0]; ++k) same &= x[k] == y[k];
+            }
+            if (!same)
+                for (int s = s0; s < s1; ++s)
+                    if (g.slot_mode[s] == 2) {
+                        g.slot_mode[s] = 4;  // literal value pending
+                        g.lit_list[atomicAdd(g.lit_count, 1)] = s;
+                    }
+        }
         if (g.raw_ref) g.raw_ref[r] = pr;
         if (g.raw_alt) g.raw_alt[r] = pa;
         if (pr != -INFINITY && pa != -INFINITY) {  // normalise only if both are non-zero
-            const double tot = ln_add_exp_s(pa, pr);
-            pr -= tot;
-            pa -= tot;
+            const double tot = dm::ln_add_exp(pa, pr);
+            pr = dm::sub(pr, tot);
+            pa = dm::sub(pa, tot);
         }
         if (pr == -INFINITY && pa == -INFINITY) pr = pa = -0.6931471805599453;  // Prob(0.5)
         g.prob_ref[r] = pr;
@@ -424,8 +458,8 @@ __global__ void support_epilogue_kernel(SupportArgs g) {
         int ni = 0;
         if (best_slot[1] >= 0) {
             ni = g.hits[best_slot[1]].n_indel;
-            if (g.indel_ops)
-                for (int t = 0; t < min(ni, kMaxIndelOps); ++t)
+            if (g.indel_ops && ni > 0)  // the run-length encoded record (zero padded)
+                for (int t = 0; t < kMaxIndelOps; ++t)
                     g.indel_ops[r * kMaxIndelOps + t] = g.hit_ops[(int64_t)best_slot[1] * kMaxIndelOps + t];
         }
         g.n_indel[r] = ni;
@@ -619,7 +653,7 @@ int vlr_allele_support_batch(vlr_ctx *ctx, int64_t n_regions, const int32_t *reg
     if (n_slots <= 0 || n_slots > 0x7fffffff) return set_err(ctx, VLR_ERR_INVALID, "bad region_hap_off");
     enum { S_HAP = 40, S_HOFF, S_RB, S_ROFF, S_PH, S_PR, S_OUT, S_OPS, S_SCR, S_SCR2, S_SCR3,
            S_RQ, S_RR, S_RHO, S_RNR, S_SE, S_WS0, S_WL, S_MED, S_SP, S_SM, S_O1, S_O2, S_O3, S_O4, S_O5,
-           S_O6, S_O7, S_O8, S_PWS, S_PATH = 75 };
+           S_O6, S_O7, S_O8, S_PWS, S_LIT, S_PATH = 75 };
     const int64_t hap_lo = hap_off[0], rd_lo = read_off[0];
     if (hap_off[n_haps] < hap_lo || read_off[n_reads] < rd_lo)
         return set_err(ctx, VLR_ERR_INVALID, "offsets not monotone");
@@ -746,8 +780,22 @@ int vlr_allele_support_batch(vlr_ctx *ctx, int64_t n_regions, const int32_t *reg
         if (rc != VLR_OK) return rc;
     }
     lap("select+hmm", true);
-    // 4. max over haplotypes, normalisation, fallbacks
-    support_epilogue_kernel<<<grid, 128, 0, st>>>(sa);
+    // 4. max over haplotypes, normalisation, fallbacks; near ties go through the literal log-space
+    // kernel and a second epilogue pass (no host round trip: the list length stays on the device)
+    if (!fast) {
+        int32_t *d_lit = (int32_t *)D(S_LIT, (size_t)n_slots * 4 + 64);
+        if (!d_lit) return set_err(ctx, VLR_ERR_NOMEM, "scratch allocation failed");
+        VLR_CUDA(ctx, cudaMemsetAsync(d_lit, 0, 64, st));
+        sa.hap_base = d_hap - hap_lo;
+        sa.lit_count = d_lit;
+        sa.lit_list = d_lit + 16;
+        support_epilogue_kernel<true><<<grid, 128, 0, st>>>(sa);
+        VLR_LAUNCH_CHECK(ctx);
+        rc = pairhmm_literal_dev(ctx, n_slots, d_hap - hap_lo, nullptr, d_ws, d_wl, d_rb - rd_lo, d_rq - rd_lo, d_roff,
+                                 nullptr, d_slot_read, d_med, sa.lit_list, sa.lit_count, gap, flags, max_lx, d_sp);
+        if (rc != VLR_OK) return rc;
+    }
+    support_epilogue_kernel<false><<<grid, 128, 0, st>>>(sa);
     VLR_LAUNCH_CHECK(ctx);
     auto D2H = [&](void *h, const void *d, size_t b) { return cudaMemcpyAsync(h, d, b, cudaMemcpyDeviceToHost, st); };
     VLR_CUDA(ctx, D2H(out_prob_ref, d_pref, (size_t)n_regions * 8));

@@ -87,55 +87,77 @@ __global__ void mark_unsupported_kernel(const int32_t *list, const int32_t *coun
         out[l[p]] = NAN;
 }
 
-static cudaError_t launch_lin(bool banded, bool approx, int cls, bool ext, const HmmArgs &a,
+// approx: 0 = exact sum, 1 = two-way, 2 = three-way ln_sum3_exp_approx
+#define VLR_APPROX_SWITCH(approx, CALL)                                                           \
+    switch (approx) {                                                                             \
+    case 0: return CALL(0);                                                                       \
+    case 1: return CALL(1);                                                                       \
+    default: return CALL(2);                                                                      \
+    }
+static cudaError_t launch_lin(bool banded, int approx, int cls, bool ext, const HmmArgs &a,
                               int sm_count, cudaStream_t st) {
-    if (banded)
-        return approx ? launch_pairhmm_lin<true, true>(cls, ext, a, sm_count, st)
-                      : launch_pairhmm_lin<true, false>(cls, ext, a, sm_count, st);
-    return approx ? launch_pairhmm_lin<false, true>(cls, ext, a, sm_count, st)
-                  : launch_pairhmm_lin<false, false>(cls, ext, a, sm_count, st);
+#define VLR_CALL_B(A) launch_pairhmm_lin<true, A>(cls, ext, a, sm_count, st)
+#define VLR_CALL_U(A) launch_pairhmm_lin<false, A>(cls, ext, a, sm_count, st)
+    if (banded) { VLR_APPROX_SWITCH(approx, VLR_CALL_B) }
+    VLR_APPROX_SWITCH(approx, VLR_CALL_U)
+#undef VLR_CALL_B
+#undef VLR_CALL_U
 }
-static cudaError_t launch_long(bool approx, bool ext, bool log_space, const HmmArgs &a, int sm_count,
+static cudaError_t launch_long(int approx, bool ext, bool log_space, const HmmArgs &a, int sm_count,
                                cudaStream_t st) {
-    return approx ? launch_pairhmm_long<true>(ext, log_space, a, sm_count, st)
-                  : launch_pairhmm_long<false>(ext, log_space, a, sm_count, st);
+#define VLR_CALL(A) launch_pairhmm_long<A>(ext, log_space, a, sm_count, st)
+    VLR_APPROX_SWITCH(approx, VLR_CALL)
+#undef VLR_CALL
 }
-static cudaError_t launch_generic(bool banded, bool approx, const HmmArgs &a, int sm_count,
+static cudaError_t launch_generic(bool banded, int approx, const HmmArgs &a, int sm_count,
                                   cudaStream_t st) {
-    if (banded)
-        return approx ? launch_pairhmm_generic<true, true>(a, sm_count, st)
-                      : launch_pairhmm_generic<true, false>(a, sm_count, st);
-    return approx ? launch_pairhmm_generic<false, true>(a, sm_count, st)
-                  : launch_pairhmm_generic<false, false>(a, sm_count, st);
+#define VLR_CALL_B(A) launch_pairhmm_generic<true, A>(a, sm_count, st)
+#define VLR_CALL_U(A) launch_pairhmm_generic<false, A>(a, sm_count, st)
+    if (banded) { VLR_APPROX_SWITCH(approx, VLR_CALL_B) }
+    VLR_APPROX_SWITCH(approx, VLR_CALL_U)
+#undef VLR_CALL_B
+#undef VLR_CALL_U
 }
-static cudaError_t launch_log(bool banded, bool approx, const HmmArgs &a, int sm_count,
+static cudaError_t launch_log(bool banded, int approx, const HmmArgs &a, int sm_count,
                               cudaStream_t st) {
-    if (banded)
-        return approx ? launch_pairhmm_log<true, true>(a, sm_count, st)
-                      : launch_pairhmm_log<true, false>(a, sm_count, st);
-    return approx ? launch_pairhmm_log<false, true>(a, sm_count, st)
-                  : launch_pairhmm_log<false, false>(a, sm_count, st);
+#define VLR_CALL_B(A) launch_pairhmm_log<true, A>(a, sm_count, st)
+#define VLR_CALL_U(A) launch_pairhmm_log<false, A>(a, sm_count, st)
+    if (banded) { VLR_APPROX_SWITCH(approx, VLR_CALL_B) }
+    VLR_APPROX_SWITCH(approx, VLR_CALL_U)
+#undef VLR_CALL_B
+#undef VLR_CALL_U
 }
+static cudaError_t launch_band(int approx, const HmmArgs &a, int32_t *list_rw, const int32_t *n_total,
+                               int32_t *cursors, int sm_count, cudaStream_t st) {
+#define VLR_CALL(A) launch_pairhmm_band<A>(a, list_rw, n_total, cursors, sm_count, st)
+    VLR_APPROX_SWITCH(approx, VLR_CALL)
+#undef VLR_CALL
+}
+static cudaError_t launch_literal(int approx, const HmmArgs &a, int sm_count, cudaStream_t st) {
+#define VLR_CALL(A) launch_pairhmm_literal<A>(a, sm_count, st)
+    VLR_APPROX_SWITCH(approx, VLR_CALL)
+#undef VLR_CALL
+}
+static int approx_of(uint32_t flags) {
+    return (flags & VLR_HMM_SUM3_APPROX3) ? 2 : ((flags & VLR_HMM_SUM3_APPROX) ? 1 : 0);
+}
+
+__global__ void set_int_kernel(int32_t *p, int32_t v) { *p = v; }
 
 // PairHMM::new (Appendix A.2): transition constants from the four gap parameters
 static void make_consts(const vlr_gap_params *gp, uint32_t flags, HmmConsts *lin, HmmConsts *ln) {
-    auto l1me = [](double p) -> double { return p < -0.693 ? log1p(-exp(p)) : log(-expm1(p)); };
-    auto lae = [](double a, double b) -> double {
-        double p0 = a > b ? a : b, p1 = a > b ? b : a;
-        if (p0 == -INFINITY) return -INFINITY;
-        if (p1 == -INFINITY) return p0;
-        return p0 + log1p(exp(p1 - p0));
-    };
+    // the library's deterministic libm (detmath.cuh): the literal log-space kernel must see the
+    // same constants as a host evaluation of the reference's formulas
     const double gx = gp->prob_gap_x, gy = gp->prob_gap_y, gxe = gp->prob_gap_x_extend,
                  gye = gp->prob_gap_y_extend;
-    const double no_gap = l1me(lae(gx, gy));
-    const double no_gxe = l1me(gxe), no_gye = l1me(gye);
+    const double no_gap = dm::ln_one_minus_exp(dm::ln_add_exp(gx, gy));
+    const double no_gxe = dm::ln_one_minus_exp(gxe), no_gye = dm::ln_one_minus_exp(gye);
     ln->t_mm = no_gap;
     if (flags & VLR_HMM_PATH_CLOSE) { ln->t_xm = no_gye; ln->t_ym = no_gxe; }
     else { ln->t_xm = no_gxe; ln->t_ym = no_gye; }
     ln->t_gy = gy; ln->t_gye = gye; ln->t_gx = gx; ln->t_gxe = gxe;
-    lin->t_mm = exp(ln->t_mm); lin->t_xm = exp(ln->t_xm); lin->t_ym = exp(ln->t_ym);
-    lin->t_gy = exp(gy); lin->t_gye = exp(gye); lin->t_gx = exp(gx); lin->t_gxe = exp(gxe);
+    lin->t_mm = dm::exp(ln->t_mm); lin->t_xm = dm::exp(ln->t_xm); lin->t_ym = dm::exp(ln->t_ym);
+    lin->t_gy = dm::exp(gy); lin->t_gye = dm::exp(gye); lin->t_gx = dm::exp(gx); lin->t_gxe = dm::exp(gxe);
     // scaled-state kernels keep M' = t_mm * M (pairhmm_kernel.cuh, hmm_step<..., LUT = true>)
     lin->t_gy_s = lin->t_gy / lin->t_mm;
     lin->t_gx_s = lin->t_gx / lin->t_mm;
@@ -222,7 +244,7 @@ static int pairhmm_core_dev(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *d_hap_
     a.long_ws = w.long_ws; a.long_stride = long_stride;
     make_consts(gap, flags, &a.lin, &a.ln);
     const bool banded = d_max_edit_dist != nullptr;
-    const bool approx = (flags & VLR_HMM_SUM3_APPROX) != 0;
+    const int approx = approx_of(flags);
     // extension probabilities of exactly 0 (CLI default) select the 5-op specialisation
     const bool ext = !(gap->prob_gap_x_extend == -INFINITY && gap->prob_gap_y_extend == -INFINITY);
 
@@ -235,10 +257,8 @@ static int pairhmm_core_dev(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *d_hap_
         if (banded && !ext && gap->prob_gap_x <= small && gap->prob_gap_y <= small && !(e && atoi(e) == 0)) {
             HmmArgs ab = a;
             ab.list = w.list;
-            cudaError_t ce = approx ? launch_pairhmm_band<true>(ab, w.list, w.counters + kCntOff + 7,
-                                                                w.counters + kCntBand, ctx->sm_count, st)
-                                    : launch_pairhmm_band<false>(ab, w.list, w.counters + kCntOff + 7,
-                                                                 w.counters + kCntBand, ctx->sm_count, st);
+            cudaError_t ce = launch_band(approx, ab, w.list, w.counters + kCntOff + 7, w.counters + kCntBand,
+                                         ctx->sm_count, st);
             if (ce != cudaSuccess)
                 return set_err(ctx, VLR_ERR_CUDA, "pairhmm launch failed: %s", cudaGetErrorString(ce));
             ctx->launches += 4;
@@ -310,6 +330,44 @@ static int pairhmm_core_dev(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *d_hap_
 
 
 namespace vlr {
+// Literal log-space evaluation (LogLit) of the pairs `d_list[0 .. *d_count)` (d_list == nullptr:
+// pairs 0 .. n_pairs_cap-1); windows as in pairhmm_core_dev.  max_lx sizes the per-warp prob_cols.
+int pairhmm_literal_dev(vlr_ctx *ctx, int64_t n_pairs_cap, const uint8_t *d_hap_bytes, const int64_t *d_hap_off,
+                        const int64_t *d_win_start, const int32_t *d_win_len, const uint8_t *d_read_bases,
+                        const uint8_t *d_read_quals, const int64_t *d_read_off, const int32_t *d_pair_hap,
+                        const int32_t *d_pair_read, const int32_t *d_med, const int32_t *d_list,
+                        const int32_t *d_count, const vlr_gap_params *gap, uint32_t flags, int64_t max_lx,
+                        double *d_out) {
+    enum { S_LIT = 90, S_LITCNT = 91 };
+    cudaStream_t st = ctx->stream;
+    const int64_t stride = (max_lx + 31) / 32 * 32;
+    const size_t warps = (size_t)ctx->sm_count * kLitBlocksPerSm * kWarps;
+    double *ws = (double *)dev_scratch(ctx, S_LIT, warps * 3 * (size_t)stride * sizeof(double));
+    int32_t *cnt = (int32_t *)dev_scratch(ctx, S_LITCNT, 64);
+    if (!ws || !cnt) return set_err(ctx, VLR_ERR_NOMEM, "scratch allocation failed");
+    VLR_CUDA(ctx, cudaMemsetAsync(cnt, 0, 64, st));
+    if (!d_count) {
+        set_int_kernel<<<1, 1, 0, st>>>(cnt + 1, (int32_t)n_pairs_cap);
+        VLR_LAUNCH_CHECK(ctx);
+    }
+    HmmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.hap = d_hap_bytes; a.hap_off = d_hap_off;
+    a.rbase = d_read_bases; a.rqual = d_read_quals; a.read_off = d_read_off;
+    a.pair_hap = d_pair_hap; a.pair_read = d_pair_read; a.med = d_med;
+    a.win_start = d_win_start; a.win_len = d_win_len;
+    a.list = d_list; a.list_off = nullptr;
+    a.count = d_count ? d_count : cnt + 1;
+    a.cursor = cnt;
+    a.out = d_out; a.qlut = ctx->d_qlut;
+    a.lit_ws = ws; a.lit_stride = stride;
+    make_consts(gap, flags, &a.lin, &a.ln);
+    cudaError_t e = launch_literal(approx_of(flags), a, ctx->sm_count, st);
+    if (e != cudaSuccess) return set_err(ctx, VLR_ERR_CUDA, "pairhmm launch failed: %s", cudaGetErrorString(e));
+    ctx->launches++;
+    return VLR_OK;
+}
+
 int pairhmm_windows_dev(vlr_ctx *ctx, int64_t n_slots, const uint8_t *d_hap_base,
                         const int64_t *d_win_start, const int32_t *d_win_len,
                         const uint8_t *d_read_bases, const uint8_t *d_read_quals,
@@ -337,6 +395,8 @@ int vlr_pairhmm_batch_dev(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *d_hap_by
                           const int32_t *d_pair_hap, const int32_t *d_pair_read,
                           const int32_t *d_max_edit_dist, const vlr_gap_params *gap, uint32_t flags,
                           void *d_workspace, size_t workspace_bytes, double *d_out_lnprob) {
+    if (ctx && (flags & VLR_HMM_LITERAL))
+        return set_err(ctx, VLR_ERR_UNSUPPORTED, "VLR_HMM_LITERAL needs the host-buffer entry (window lengths size its scratch)");
     return pairhmm_core_dev(ctx, n_pairs, d_hap_bytes, d_hap_off, n_haps, d_read_bases, d_read_quals,
                             d_read_off, n_reads, d_pair_hap, d_pair_read, d_max_edit_dist, nullptr,
                             nullptr, nullptr, gap, flags, d_workspace, workspace_bytes, d_out_lnprob);
@@ -406,6 +466,13 @@ int vlr_pairhmm_batch(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *hap_bytes,
     VLR_CUDA(ctx, cudaMemcpyAsync(d_roff, read_off, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
     const double stream_bytes = 2.0 * (double)rd_bytes_n + 12.0 * (double)n_pairs;
     int n_chunks = reads_in_pair_order ? (int)std::min<double>(32.0, floor(stream_bytes / (32.0 * 1048576.0))) : 1;
+    const bool literal = (flags & VLR_HMM_LITERAL) != 0;
+    if (literal) {
+        if (max_ly > 248)
+            return set_err(ctx, VLR_ERR_UNSUPPORTED, "literal evaluation of a read window of %lld rows (limit 248)",
+                           (long long)max_ly);
+        n_chunks = 1;
+    }
     if (n_chunks > 1 && ensure_copy_stream(ctx) != VLR_OK) n_chunks = 1;
     if (n_chunks <= 1) {
         VLR_CUDA(ctx, cudaMemcpyAsync(d_rb, read_bases + rd_lo, rd_bytes_n, cudaMemcpyHostToDevice, st));
@@ -415,9 +482,13 @@ int vlr_pairhmm_batch(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *hap_bytes,
         if (max_edit_dist)
             VLR_CUDA(ctx, cudaMemcpyAsync(d_med, max_edit_dist, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, st));
         // offsets are absolute into the caller's arrays: rebase the device pointers instead of the offsets
-        int rc = vlr_pairhmm_batch_dev(ctx, n_pairs, d_hap - hap_lo, d_hoff, n_haps, d_rb - rd_lo,
-                                       d_rq - rd_lo, d_roff, n_reads, d_ph, d_pr, d_med, gap, flags, d_ws,
-                                       ws_bytes, d_out);
+        int rc = literal
+                     ? pairhmm_literal_dev(ctx, n_pairs, d_hap - hap_lo, d_hoff, nullptr, nullptr, d_rb - rd_lo,
+                                           d_rq - rd_lo, d_roff, d_ph, d_pr, d_med, nullptr, nullptr, gap, flags,
+                                           max_lx, d_out)
+                     : vlr_pairhmm_batch_dev(ctx, n_pairs, d_hap - hap_lo, d_hoff, n_haps, d_rb - rd_lo,
+                                             d_rq - rd_lo, d_roff, n_reads, d_ph, d_pr, d_med, gap, flags, d_ws,
+                                             ws_bytes, d_out);
         if (rc != VLR_OK) return rc;
     } else {
         // Pairs reference their reads in non-decreasing order: stream reads and pair lists in

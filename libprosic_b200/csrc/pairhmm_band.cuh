@@ -43,7 +43,7 @@ struct BandQ {  // per base quality: emission factors (already times t_mm) and t
     double em, emm, cy;
 };
 
-template <int G, bool APPROX>
+template <int G, int APPROX>
 __global__ void __launch_bounds__(kWarps * 32, band_blocks_per_sm(G))
 pairhmm_band_kernel(HmmArgs g, int32_t *list_rw, const int32_t *n_total) {
     __shared__ __align__(16) uint8_t s_hap[kWarps][kBandPad + kBandMaxLx + kBandPad];
@@ -215,7 +215,7 @@ pairhmm_band_kernel(HmmArgs g, int32_t *list_rw, const int32_t *n_total) {
     }
 }
 
-template <bool APPROX>
+template <int APPROX>
 cudaError_t launch_pairhmm_band(const HmmArgs &a, int32_t *list_rw, const int32_t *n_total, int32_t *cursors,
                                 int sm_count, cudaStream_t st);
 

@@ -1,5 +1,5 @@
-// explicit instantiation of the pair-HMM kernels: BANDED=true, APPROX=true (see pairhmm_kernel.cuh)
+// explicit instantiation of the pair-HMM kernels: BANDED=true, APPROX=1 (see pairhmm_kernel.cuh)
 #include "pairhmm_kernel.cuh"
 namespace vlr {
-VLR_PAIRHMM_INSTANTIATE(true, true)
+VLR_PAIRHMM_INSTANTIATE(true, 1)
 }

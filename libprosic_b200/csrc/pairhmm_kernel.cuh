@@ -23,6 +23,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "detmath.cuh"
 
 namespace vlr {
 
@@ -31,6 +32,7 @@ constexpr int kChunk = 256;        // haplotype bytes per TMA bulk copy
 constexpr int kRing = 2 * kChunk;  // per-warp ring buffer (two chunks)
 constexpr int kMedMax = 1 << 20;   // "usize::MAX" of the band bookkeeping
 constexpr int kNumClasses = 8;     // R = 1,2,3,4,5,6,8 and "too long"
+constexpr double kLnConfusion = -1.098712293668443;  // LogProb::from(Prob(0.3333)), pairhmm.rs:21-23
 
 // 2^960 and its log; linear-space values are scaled by this (see header comment)
 #define VLR_SCALE 9.7453140114e288
@@ -64,6 +66,8 @@ struct HmmArgs {
     int32_t *gen_count;
     double *long_ws;       // long-read variant: per-warp boundary rows, 6 * long_stride doubles
     int64_t long_stride;   // columns per boundary row
+    double *lit_ws;        // literal log-space variant: per-warp prob_cols, 3 * lit_stride doubles
+    int64_t lit_stride;    // columns per warp
     double *out;
     const double *qlut;
     HmmConsts lin, ln;
@@ -119,6 +123,7 @@ __device__ __forceinline__ double ln_add_exp_d(double a, double b) {
 // default, cli.rs:219-230): then t_xm = t_ym = 1, t_gye = t_gxe = 0 and three products vanish.
 struct Lin {  // scaled linear space
     static constexpr bool kLog = false;
+    static constexpr bool kLit = false;
     __device__ static double zero() { return 0.0; }
     __device__ static double one() { return VLR_SCALE; }
     __device__ static double mul(double a, double b) { return a * b; }
@@ -128,11 +133,12 @@ struct Lin {  // scaled linear space
     __device__ static double dot2(double a, double b, double c, double d) {
         return EXT ? fma(a, b, c * d) : a * b;
     }
-    // sum over the three predecessors of the M state (SCALED: dM already carries t_mm)
-    template <bool APPROX, bool EXT, bool SCALED = false>
+    // sum over the three predecessors of the M state (SCALED: dM already carries t_mm).
+    // APPROX: 0 = exact sum, 1 = two-way, 2 = three-way ln_sum3_exp_approx (see vlr_gpu.h flags).
+    template <int APPROX, bool EXT, bool SCALED = false>
     __device__ static double sum3(const HmmConsts &k, double dM, double dX, double dY) {
-        if (APPROX) {
-            // bio pairhmm ln_sum3_exp_approx: return the maximum alone if the second largest term is
+        if (APPROX == 1) {
+            // two-way rule: return the maximum alone if the second largest term is
             // more than e^-10 below it, else the exact sum.  "second < max*e^-10" <=> exactly one of
             // the three terms reaches max*e^-10.  Written in PTX so that the three threshold
             // predicates feed one select (the C++ form compiles to nested 64-bit selects).
@@ -160,14 +166,28 @@ struct Lin {  // scaled linear space
                 "}" : "=d"(r) : "d"(a), "d"(b), "d"(c), "d"(s));
             return r;
         }
+        if (APPROX == 2) {
+            // three-way rule: sorted p0 >= p1 >= p2; p1 < p0*e^-10 -> p0; else p2 < p1*e^-10 ->
+            // p0 + p1; else all three.  Exact decisions on the fp64 values.
+            const double a = SCALED ? dM : k.t_mm * dM;
+            const double b = EXT ? k.t_xm * dX : dX;
+            const double c = EXT ? k.t_ym * dY : dY;
+            const double hi1 = fmax(b, c), lo1 = fmin(b, c);
+            const double p0 = fmax(a, hi1), m = fmin(a, hi1);
+            const double p1 = fmax(m, lo1), p2 = fmin(m, lo1);
+            const double kT = 4.5399929762484854e-05;  // e^-10 (0x3F07CD79B5647C9B)
+            const double t2 = p2 >= p1 * kT ? p1 + p2 : p1;
+            return p1 >= p0 * kT ? p0 + t2 : p0;
+        }
         if (SCALED) return EXT ? fma(k.t_ym, dY, fma(k.t_xm, dX, dM)) : dM + (dX + dY);
         if (EXT) return fma(k.t_ym, dY, fma(k.t_xm, dX, k.t_mm * dM));
         return fma(k.t_mm, dM, dX + dY);
     }
 };
 
-struct Log {  // natural-log space, the literal arithmetic of the reference
+struct Log {  // natural-log space, the arithmetic of the reference (CUDA libm)
     static constexpr bool kLog = true;
+    static constexpr bool kLit = false;
     __device__ static double zero() { return -INFINITY; }
     __device__ static double one() { return 0.0; }
     __device__ static double mul(double a, double b) { return a + b; }
@@ -176,19 +196,62 @@ struct Log {  // natural-log space, the literal arithmetic of the reference
     __device__ static double dot2(double a, double b, double c, double d) {
         return ln_add_exp_d(a + b, c + d);
     }
-    template <bool APPROX, bool EXT, bool SCALED = false>
+    template <int APPROX, bool EXT, bool SCALED = false>
     __device__ static double sum3(const HmmConsts &k, double dM, double dX, double dY) {
         double p0 = k.t_mm + dM, p1 = k.t_xm + dX, p2 = k.t_ym + dY, t;
-        if (p1 < p2) { t = p1; p1 = p2; p2 = t; }
-        if (p1 > p0) { t = p1; p1 = p0; p0 = t; }
-        if (p2 > p0) { t = p2; p2 = p0; p0 = t; }
-        const double second = fmax(p1, p2);
-        if (APPROX && (p0 - second > 10.0)) return p0;
+        if (APPROX) {
+            if (p1 < p2) { t = p1; p1 = p2; p2 = t; }
+            if (p1 > p0) { t = p1; p1 = p0; p0 = t; }
+            if (p2 > p1) { t = p2; p2 = p1; p1 = t; }
+            if (p0 - p1 > 10.0) return p0;
+            if (APPROX == 2 && p1 - p2 > 10.0) return ln_add_exp_d(p0, p1);
+        } else {
+            // ln_sum_exp over the slice (M, X, Y): the first maximum leads, the others follow in order
+            if (p2 > p0 && p2 > p1) { t = p2; p2 = p1; p1 = p0; p0 = t; }
+            else if (p1 > p0) { t = p1; p1 = p0; p0 = t; }
+        }
         if (p0 == -INFINITY) return -INFINITY;
         double s = 0.0;
         if (p1 != -INFINITY) s += exp(p1 - p0);
         if (p2 != -INFINITY) s += exp(p2 - p0);
         return p0 + log1p(s);
+    }
+};
+
+// Natural-log space in the LITERAL operation order of the reference with the library's
+// deterministic libm (detmath.cuh): every value is bit-identical to a host evaluation of the same
+// formulas (bio::stats::pairhmm::PairHMM::prob_related as restated in SURVEY Appendix A.2).  Slow;
+// used for the pairs whose result decides an exact comparison (allele-support near ties).
+struct LogLit {
+    static constexpr bool kLog = true;
+    static constexpr bool kLit = true;
+    __device__ static double zero() { return -INFINITY; }
+    __device__ static double one() { return 0.0; }
+    __device__ static double mul(double a, double b) { return dm::add(a, b); }
+    __device__ static double add(double a, double b) { return dm::ln_add_exp(a, b); }
+    template <bool EXT>
+    __device__ static double dot2(double a, double b, double c, double d) {
+        return dm::ln_add_exp(dm::add(a, b), dm::add(c, d));
+    }
+    template <int APPROX, bool EXT, bool SCALED = false>
+    __device__ static double sum3(const HmmConsts &k, double dM, double dX, double dY) {
+        double p0 = dm::add(k.t_mm, dM), p1 = dm::add(k.t_xm, dX), p2 = dm::add(k.t_ym, dY), t;
+        if (APPROX) {
+            if (p1 < p2) { t = p1; p1 = p2; p2 = t; }
+            if (p1 > p0) { t = p1; p1 = p0; p0 = t; }
+            if (p2 > p1) { t = p2; p2 = p1; p1 = t; }
+            if (dm::sub(p0, p1) > 10.0) return p0;
+            if (APPROX == 2 && dm::sub(p1, p2) > 10.0) return dm::ln_add_exp(p0, p1);
+        } else {
+            if (p2 > p0 && p2 > p1) { t = p2; p2 = p1; p1 = p0; p0 = t; }
+            else if (p1 > p0) { t = p1; p1 = p0; p0 = t; }
+        }
+        if (p0 == -INFINITY) return -INFINITY;
+        if (p0 == INFINITY) return INFINITY;
+        double s = 0.0;
+        if (p1 != -INFINITY) s = dm::add(s, dm::exp(dm::sub(p1, p0)));
+        if (p2 != -INFINITY) s = dm::add(s, dm::exp(dm::sub(p2, p0)));
+        return dm::add(p0, dm::log1p(s));
     }
 };
 
@@ -208,6 +271,7 @@ struct PairState {
     double bM, bX, bY, dM, dX, dY;         // bottom row of last column; diagonal inputs of row 0
     int bMed, dMed;
     double acc, acc2;                      // free-end sums (scaled state: M' and X + Y apart)
+    double acc3;                           // literal variant: (acc, acc2, acc3) = last row (M, X, Y) of this column
     double one0;                           // lane 0: start mass of the row-0 boundary; else 0
 };
 
@@ -220,6 +284,8 @@ struct HapRing {
     int lxs;              // window length + shift
     int n_chunks;
     uint32_t parity0, parity1;
+    double *cols;         // literal variant: prob_cols of this warp (3 doubles per column)
+    int last_lane;
 };
 
 // LUT kernels keep base CODES in the ring (A, C, G, T -> 0..3, anything else -> 4, case folded as
@@ -251,7 +317,7 @@ constexpr int kLutCols = 5;  // emission LUT: [row][code][lane]
 // from the per-warp shared-memory table lut[(r*5 + code)*32] (already multiplied by t_mm: the M
 // state carries that factor, which removes one multiplication per cell), and the row-0 start mass
 // is added instead of selected.
-template <int R, int LR, bool BANDED, bool APPROX, bool EXT, bool LUT, typename A>
+template <int R, int LR, bool BANDED, int APPROX, bool EXT, bool LUT, typename A>
 __device__ __forceinline__ void hmm_step(PairState<R> &s, const HmmConsts &c, const uint8_t *ring,
                                          const double *lut, int t, int lane, int shift, int band,
                                          int last_r) {
@@ -289,7 +355,11 @@ __device__ __forceinline__ void hmm_step(PairState<R> &s, const HmmConsts &c, co
         }
         double nM = A::mul(e, A::template sum3<APPROX, EXT, LUT>(c, diagM, diagX, diagY));
         double nX = A::template dot2<EXT>(LUT ? c.t_gy_s : c.t_gy, s.M[r], c.t_gye, s.X[r]);
-        double nY = A::template dot2<EXT>(s.cyo[r], upM, s.cye[r], upY);
+        double nY;
+        if (A::kLit)  // emit_y + ln_add_exp(gap_x + fm[curr][j], gap_x_ext + fy[curr][j]); cyo = ln eps
+            nY = A::mul(s.cyo[r], A::add(A::mul(c.t_gx, upM), A::mul(c.t_gxe, upY)));
+        else
+            nY = A::template dot2<EXT>(s.cyo[r], upM, s.cye[r], upY);
         if (BANDED) {
             // PairHMM band: skip the cell if all three predecessors exceed max_edit_dist
             const int leftMed = s.med[r];
@@ -327,6 +397,11 @@ __device__ __forceinline__ void hmm_step(PairState<R> &s, const HmmConsts &c, co
             s.acc = A::add(s.acc, A::add(A::add(s.M[LR >= 0 ? LR : 0], s.X[LR >= 0 ? LR : 0]),
                                          s.Y[LR >= 0 ? LR : 0]));
         }
+    } else if (A::kLit) {
+        // prob_cols keeps the three values apart: the final ln_sum_exp runs over all of them
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (r == last_r) { s.acc = s.M[r]; s.acc2 = s.X[r]; s.acc3 = s.Y[r]; }
     } else {
         double tsum = A::zero(), tm = A::zero();
 #pragma unroll
@@ -342,7 +417,7 @@ __device__ __forceinline__ void hmm_step(PairState<R> &s, const HmmConsts &c, co
 
 // Sweep all columns of one pair.  Ring maintenance happens only at segment boundaries
 // (ring position == 0 or 32 mod 256), the inner loop is branch-free.
-template <int R, int LR, bool BANDED, bool APPROX, bool EXT, bool LUT, typename A>
+template <int R, int LR, bool BANDED, int APPROX, bool EXT, bool LUT, typename A>
 __device__ __forceinline__ void hmm_sweep(PairState<R> &s, const HmmConsts &c, HapRing &h,
                                           const double *lut, int T, int lane, int shift, int band,
                                           int last_r) {
@@ -372,12 +447,17 @@ __device__ __forceinline__ void hmm_sweep(PairState<R> &s, const HmmConsts &c, H
         const int next_ts = ph < 32 ? (ts & ~(kChunk - 1)) + 32 : (ts & ~(kChunk - 1)) + kChunk;
         const int t_end = min(T, next_ts - shift);
 #pragma unroll 2
-        for (; t < t_end; ++t)
+        for (; t < t_end; ++t) {
             hmm_step<R, LR, BANDED, APPROX, EXT, LUT, A>(s, c, h.ring, lut, t, lane, shift, band, last_r);
+            if (A::kLit && lane == h.last_lane && t >= lane) {
+                double *col = h.cols + 3 * (int64_t)(t - lane);
+                col[0] = s.acc; col[1] = s.acc2; col[2] = s.acc3;
+            }
+        }
     }
 }
 
-template <int R, int LR, bool BANDED, bool APPROX, bool EXT, bool LUT, typename A>
+template <int R, int LR, bool BANDED, int APPROX, bool EXT, bool LUT, typename A>
 struct SweepDispatch {
     __device__ __forceinline__ static void run(PairState<R> &s, const HmmConsts &c, HapRing &h,
                                                const double *lut, int T, int lane, int shift,
@@ -389,7 +469,7 @@ struct SweepDispatch {
                                                                        band, last_r);
     }
 };
-template <int R, bool BANDED, bool APPROX, bool EXT, bool LUT, typename A>
+template <int R, bool BANDED, int APPROX, bool EXT, bool LUT, typename A>
 struct SweepDispatch<R, -1, BANDED, APPROX, EXT, LUT, A> {
     __device__ __forceinline__ static void run(PairState<R> &s, const HmmConsts &c, HapRing &h,
                                                const double *lut, int T, int lane, int shift,
@@ -398,7 +478,7 @@ struct SweepDispatch<R, -1, BANDED, APPROX, EXT, LUT, A> {
     }
 };
 
-template <int R, bool BANDED, bool APPROX, bool EXT, bool LUT, typename A>
+template <int R, bool BANDED, int APPROX, bool EXT, bool LUT, typename A>
 __global__ void __launch_bounds__(kWarps * 32, Occ<R>::kMinBlocks) pairhmm_kernel(HmmArgs g) {
     static_assert(!LUT || !A::kLog, "the emission LUT exists in scaled linear space only");
     __shared__ __align__(128) uint8_t s_hap[kWarps][kRing];
@@ -462,10 +542,16 @@ __global__ void __launch_bounds__(kWarps * 32, Occ<R>::kMinBlocks) pairhmm_kerne
                 const int b = g.rbase[ro + j];
                 s.rb[r] = LUT ? base_code1(b) : b;
                 if (LUT) odd_base |= s.rb[r] == 4;
-                if (A::kLog) {
+                if (A::kLit) {
+                    const double ln_eps = dm::mul((double)q, -0.23025850929940456);
+                    s.pm[r] = g.qlut[q * kQlutStride + 3];
+                    s.pmm[r] = dm::add(ln_eps, kLnConfusion);
+                    s.cyo[r] = ln_eps;   // emit_y; the transition is added in hmm_step
+                    s.cye[r] = ln_eps;
+                } else if (A::kLog) {
                     const double ln_eps = (double)q * -0.23025850929940456;
                     s.pm[r] = g.qlut[q * kQlutStride + 3];
-                    s.pmm[r] = ln_eps + -1.098712293668443;  // ln(0.3333), pairhmm.rs:21-23
+                    s.pmm[r] = ln_eps + kLnConfusion;  // ln(0.3333), pairhmm.rs:21-23
                     s.cyo[r] = ln_eps + c.t_gx;
                     s.cye[r] = ln_eps + c.t_gxe;
                 } else {
@@ -518,6 +604,17 @@ __global__ void __launch_bounds__(kWarps * 32, Occ<R>::kMinBlocks) pairhmm_kerne
         s.dMed = lane == 0 ? 0 : kMedMax;
         s.acc = A::zero();
         s.acc2 = A::zero();
+        s.acc3 = A::zero();
+        h.last_lane = last_lane;
+        if (A::kLit) {
+            if (lx > g.lit_stride) {  // the caller sized the workspace for shorter windows
+                if (lane == 0) g.out[pair] = NAN;
+                mbar_wait(&h.bar[0], h.parity0);
+                h.parity0 ^= 1;
+                continue;
+            }
+            h.cols = g.lit_ws + ((int64_t)blockIdx.x * kWarps + warp) * 3 * g.lit_stride;
+        }
 
         mbar_wait(&h.bar[0], h.parity0);
         h.parity0 ^= 1;
@@ -529,6 +626,40 @@ __global__ void __launch_bounds__(kWarps * 32, Occ<R>::kMinBlocks) pairhmm_kerne
         SweepDispatch<R, A::kLog ? -1 : R - 1, BANDED, APPROX, EXT, LUT, A>::run(s, c, h, lut, T, lane,
                                                                                  shift, band, last_r);
 
+        if (A::kLit) {
+            // LogProb::ln_sum_exp(prob_cols): first maximum, then the sum of exp(p - max) over the
+            // other finite entries in slice order, accumulated by ONE lane in that order
+            __syncwarp();
+            const int nc = 3 * lx;
+            double pmax = -INFINITY;
+            for (int k = lane; k < nc; k += 32) pmax = fmax(pmax, h.cols[k]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) pmax = fmax(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
+            int imax = nc;
+            for (int k = lane; k < nc; k += 32)
+                if (h.cols[k] == pmax) { imax = k; break; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) imax = min(imax, __shfl_xor_sync(0xffffffffu, imax, o));
+            double res = pmax;
+            if (pmax != -INFINITY && pmax != INFINITY) {
+                for (int k = lane; k < nc; k += 32) {
+                    const double v = h.cols[k];
+                    h.cols[k] = (k == imax || v == -INFINITY) ? 0.0 : dm::exp(dm::sub(v, pmax));
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    double sum = 0.0;
+                    for (int k = 0; k < nc; ++k) sum = dm::add(sum, h.cols[k]);  // + 0.0 is exact
+                    res = dm::add(pmax, dm::log1p(sum));
+                }
+            }
+            if (lane == 0) {
+                if (res > 0.0) res = 0.0;
+                g.out[pair] = res;
+            }
+            __syncwarp();
+            continue;
+        }
         // ---- result lives in lane last_lane
         double acc = __shfl_sync(0xffffffffu, s.acc, last_lane);
         if (LUT) acc = fma(acc, c.inv_tmm, __shfl_sync(0xffffffffu, s.acc2, last_lane));
@@ -564,7 +695,7 @@ __global__ void __launch_bounds__(kWarps * 32, Occ<R>::kMinBlocks) pairhmm_kerne
 constexpr int kLongR = 8;
 constexpr int kStripRows = 31 * kLongR;
 
-template <bool APPROX, bool EXT, bool LUT, typename A>
+template <int APPROX, bool EXT, bool LUT, typename A>
 __global__ void __launch_bounds__(kWarps * 32, 2) pairhmm_long_kernel(HmmArgs g) {
     static_assert(!LUT || !A::kLog, "the emission LUT exists in scaled linear space only");
     constexpr int R = kLongR;
@@ -822,17 +953,21 @@ __global__ void __launch_bounds__(kWarps * 32, 2) pairhmm_long_kernel(HmmArgs g)
 
 // ---------------------------------------------------------------- launch table (pairhmm_inst_*.cu)
 // cls: 0..6 -> R = 1,2,3,4,5,6,8
-template <bool BANDED, bool APPROX>
+template <bool BANDED, int APPROX>
 cudaError_t launch_pairhmm_lin(int cls, bool ext, const HmmArgs &a, int sm_count, cudaStream_t st);
-template <bool BANDED, bool APPROX>
+template <bool BANDED, int APPROX>
 cudaError_t launch_pairhmm_log(const HmmArgs &a, int sm_count, cudaStream_t st);
 // scaled linear space without the emission LUT (any byte alphabet), R = 8, gap extension on
-template <bool BANDED, bool APPROX>
+template <bool BANDED, int APPROX>
 cudaError_t launch_pairhmm_generic(const HmmArgs &a, int sm_count, cudaStream_t st);
 // long reads (unbanded only): linear pass and its log-space fallback
-template <bool APPROX>
+template <int APPROX>
 cudaError_t launch_pairhmm_long(bool ext, bool log_space, const HmmArgs &a, int sm_count, cudaStream_t st);
 constexpr int kLongBlocksPerSm = 2;
+// literal log-space variant (LogLit): banded or not (a negative band entry = unbanded), any alphabet
+template <int APPROX>
+cudaError_t launch_pairhmm_literal(const HmmArgs &a, int sm_count, cudaStream_t st);
+constexpr int kLitBlocksPerSm = 2;
 // persistent-grid size per SM; VLR_K1_BLOCKS_PER_SM overrides it (tuning aid)
 inline int blocks_per_sm(int dflt) {
     const char *e = getenv("VLR_K1_BLOCKS_PER_SM");
@@ -848,6 +983,14 @@ inline int blocks_per_sm(int dflt) {
         if (log_space) pairhmm_long_kernel<APPROX, true, false, Log><<<grid, kWarps * 32, 0, st>>>(a); \
         else if (ext) pairhmm_long_kernel<APPROX, true, true, Lin><<<grid, kWarps * 32, 0, st>>>(a);   \
         else pairhmm_long_kernel<APPROX, false, true, Lin><<<grid, kWarps * 32, 0, st>>>(a);           \
+        return cudaGetLastError();                                                                \
+    }
+
+#define VLR_PAIRHMM_LITERAL_INSTANTIATE(APPROX)                                                   \
+    template <>                                                                                   \
+    cudaError_t launch_pairhmm_literal<APPROX>(const HmmArgs &a, int sm_count, cudaStream_t st) { \
+        pairhmm_kernel<8, true, APPROX, true, false, LogLit>                                      \
+            <<<sm_count * kLitBlocksPerSm, kWarps * 32, 0, st>>>(a);                              \
         return cudaGetLastError();                                                                \
     }
 

@@ -1,5 +1,5 @@
-// explicit instantiation of the long-read pair-HMM kernels: APPROX=true (see pairhmm_kernel.cuh)
+// explicit instantiation of the long-read pair-HMM kernels: APPROX=1 (see pairhmm_kernel.cuh)
 #include "pairhmm_kernel.cuh"
 namespace vlr {
-VLR_PAIRHMM_LONG_INSTANTIATE(true)
+VLR_PAIRHMM_LONG_INSTANTIATE(1)
 }

@@ -1,0 +1,5 @@
+// explicit instantiation of the long-read pair-HMM kernels: APPROX=2 (see pairhmm_kernel.cuh)
+#include "pairhmm_kernel.cuh"
+namespace vlr {
+VLR_PAIRHMM_LONG_INSTANTIATE(2)
+}

@@ -556,7 +556,7 @@ def select_evidences(tc, sample_name, variant, props):
     return evidences
 
 
-def extract_observations(tc, sample_name, backend, max_window=64):
+def extract_observations(tc, sample_name, backend, max_window=64, trace=None):
     """Observable<PairedEndEvidence>::extract_observations + Sample::extract_observations for the
     testcase's candidate in one sample.  Returns (cols dict, cat) of the processed pileup,
     quantised through the observation wire format as `call` would read it."""
@@ -580,6 +580,9 @@ def extract_observations(tc, sample_name, backend, max_window=64):
             sup = merge_support(sup, batch.support(right))
             if variant["kind"] == "del" and props["insert_size"] is not None:
                 sup = merge_support(sup, _isize_support(variant, left, right, props))
+        if trace is not None:  # per evidence: what the realigner said and whether the observation is kept
+            trace.append(dict(name=left["name"], kept=sup["strand"] != 3, strand=sup["strand"],
+                              indel_ops=sup["indel_ops"], prob_ref=sup["prob_ref"], prob_alt=sup["prob_alt"]))
         if sup["strand"] == 3:
             continue  # evidence_to_observation: unstranded support is dropped (observation.rs:384-388)
         mis = [r["mapq"] * (-math.log(10.0) / 10.0) for r in (left, right) if r is not None]
@@ -1055,8 +1058,6 @@ class GpuBackend:
         out = []
         for k in range(len(jobs)):
             n = int(got["n_indel_ops"][k])
-            if n > got["indel_ops"].shape[1]:
-                raise NotImplementedError("more than %d indel operations in one alignment" % got["indel_ops"].shape[1])
             out.append(dict(prob_ref=float(got["prob_ref"][k]), prob_alt=float(got["prob_alt"][k]),
                             indel_ops=[int(x) for x in got["indel_ops"][k][:n]]))
         return out

@@ -13,8 +13,11 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libvlr_oracle.so")
 
-HMM_SUM3_APPROX = 1
+HMM_SUM3_APPROX = 1      # two-way ln_sum3_exp_approx (round-1 recollection)
 HMM_PATH_CLOSE = 2
+HMM_SUM3_APPROX3 = 8     # three-way ln_sum3_exp_approx (default)
+HMM_RESET_FM_ONLY = 16   # oracle only: reset fm[curr] alone after a column swap
+HMM_DEFAULT = HMM_SUM3_APPROX3
 
 NODE_SET, NODE_RANGE, NODE_FALSE, NODE_SKIP = 0, 1, 2, 3
 
@@ -22,8 +25,9 @@ NODE_SET, NODE_RANGE, NODE_FALSE, NODE_SKIP = 0, 1, 2, 3
 def build(force=False):
     src = os.path.join(_HERE, "vlr_oracle.c")
     hdr = os.path.join(_HERE, "vlr_oracle.h")
+    dmh = os.path.join(_HERE, "detmath.h")
     if (not force and os.path.exists(_SO)
-            and os.path.getmtime(_SO) >= max(os.path.getmtime(src), os.path.getmtime(hdr))):
+            and os.path.getmtime(_SO) >= max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(dmh))):
         return _SO
     subprocess.check_call(["make", "-C", _HERE, "-B", "libvlr_oracle.so"],
                           stdout=subprocess.DEVNULL)
@@ -88,6 +92,8 @@ def lib():
     build()
     L = C.CDLL(_SO)
     d = C.c_double
+    L.vlro_ref_math.restype = None
+    L.vlro_ref_math.argtypes = [C.c_int, C.c_long, _DP, _DP]
     L.vlro_ln_add_exp.restype = d
     L.vlro_ln_add_exp.argtypes = [d, d]
     L.vlro_ln_sum_exp.restype = d
@@ -161,7 +167,15 @@ def _i32(a):
     return a, a.ctypes.data_as(_I32P)
 
 
-def pairhmm_prob_related(hap, read, qual, gap_ln, max_edit_dist=-1, flags=HMM_SUM3_APPROX):
+def ref_math(fn, x):
+    """The oracle's libm (oracle/detmath.h): fn 0 exp, 1 expm1, 2 log, 3 log1p."""
+    a, ap = _f64(x)
+    out = np.empty_like(a)
+    lib().vlro_ref_math(int(fn), a.size, ap, out.ctypes.data_as(_DP))
+    return out
+
+
+def pairhmm_prob_related(hap, read, qual, gap_ln, max_edit_dist=-1, flags=HMM_DEFAULT):
     h, hp = _u8(hap)
     r, rp = _u8(read)
     q, qp = _u8(qual)
@@ -179,7 +193,7 @@ def pairhmm_bruteforce(hap, read, qual, gap_ln, flags=0):
 
 
 def pairhmm_batch(haps, hap_off, reads, quals, read_off, gap_ln, max_edit_dist=None,
-                  flags=HMM_SUM3_APPROX):
+                  flags=HMM_DEFAULT):
     """Loop the scalar oracle over a CSR batch (same layout as vlr_pairhmm_batch)."""
     n = len(hap_off) - 1
     out = np.empty(n, dtype=np.float64)
@@ -234,7 +248,7 @@ def pathhmm_prob(hap, read, qual, gap_ln):
 
 
 def allele_support_region(ref_haps, alt_haps, read, qual, gap_ln, shrink_extra=None,
-                          flags=HMM_SUM3_APPROX, fast_mode=False):
+                          flags=HMM_DEFAULT, fast_mode=False):
     """ref_haps / alt_haps: lists of uint8 arrays.  shrink_extra: list (ref haps then alt haps)."""
     allh = list(ref_haps) + list(alt_haps)
     off = np.zeros(len(allh) + 1, dtype=np.int32)

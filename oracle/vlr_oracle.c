@@ -5,6 +5,7 @@
  * the arithmetic is plain IEEE fp64 in the order written here.
  */
 #include "vlr_oracle.h"
+#include "detmath.h"
 
 #include <math.h>
 #include <stdlib.h>
@@ -16,6 +17,12 @@
  * bio::stats::probs
  * ===================================================================================== */
 
+/* the oracle's libm (detmath.h), exported for tests/test_detmath.py: 0 exp, 1 expm1, 2 log, 3 log1p */
+void vlro_ref_math(int fn, long n, const double *x, double *out) {
+    for (long k = 0; k < n; ++k)
+        out[k] = fn == 0 ? vlro_exp(x[k]) : (fn == 1 ? vlro_expm1(x[k]) : (fn == 2 ? vlro_log(x[k]) : vlro_log1p(x[k])));
+}
+
 /* LogProb::ln_add_exp */
 double vlro_ln_add_exp(double a, double b) {
     double p0 = a, p1 = b;
@@ -23,7 +30,7 @@ double vlro_ln_add_exp(double a, double b) {
     if (p0 == NEG_INF) return NEG_INF;
     if (p0 == INFINITY) return INFINITY;
     if (p1 == NEG_INF) return p0;
-    return p0 + log1p(exp(p1 - p0));
+    return p0 + vlro_log1p(vlro_exp(p1 - p0));
 }
 
 /* LogProb::ln_sum_exp: first max on ties, inner sum in slice order */
@@ -38,15 +45,15 @@ double vlro_ln_sum_exp(const double *p, size_t n) {
     double s = 0.0;
     for (size_t i = 0; i < n; ++i) {
         if (i == imax || p[i] == NEG_INF) continue;
-        s += exp(p[i] - pmax);
+        s += vlro_exp(p[i] - pmax);
     }
-    return pmax + log1p(s);
+    return pmax + vlro_log1p(s);
 }
 
 /* LogProb::ln_one_minus_exp */
 double vlro_ln_one_minus_exp(double p) {
-    if (p < -0.693) return log1p(-exp(p));
-    return log(-expm1(p));
+    if (p < -0.693) return vlro_log1p(-vlro_exp(p));
+    return vlro_log(-vlro_expm1(p));
 }
 
 /* LogProb::cap_numerical_overshoot; NaN marks the reference's panic */
@@ -66,7 +73,7 @@ double vlro_ln_prob_miscall(uint8_t qual) { return (double)qual * PHRED_TO_LOG_F
 double vlro_ln_prob_call(uint8_t qual) { return vlro_ln_one_minus_exp(vlro_ln_prob_miscall(qual)); }
 
 /* ln(0.3333): pairhmm.rs:21-23, bases.rs:8-10 (quirk Q5: 0.3333, not 1/3) */
-static double ln_confusion(void) { return log(0.3333); }
+static double ln_confusion(void) { return vlro_log(0.3333); }
 
 /* =====================================================================================
  * MiniLogProb (src/utils/mod.rs:381-407): f16 if p < -10 and floor(f16(p)) == floor(p), else f32.
@@ -167,16 +174,20 @@ static void hmm_consts(const double gap_ln[4], unsigned flags, hmm_consts_t *c) 
     }
 }
 
-/* bio pairhmm ln_sum3_exp_approx: sort descending; if p0 - p1 > 10 return p0, else exact sum */
+/* bio pairhmm ln_sum3_exp_approx.  The crate source is not in /root/reference; two recollections
+ * exist and both are implemented (flag, measured sensitivity in DESIGN.md section 5):
+ *   VLRO_HMM_SUM3_APPROX3 (default of the library): sort descending; p0 - p1 > 10 -> p0;
+ *       else p1 - p2 > 10 -> p0.ln_add_exp(p1); else the exact sum of three
+ *   VLRO_HMM_SUM3_APPROX  (round-1 recollection): p0 - p1 > 10 -> p0, else the exact sum of three */
 static double ln_sum3(double a, double b, double c, unsigned flags) {
-    if (flags & VLRO_HMM_SUM3_APPROX) {
+    if (flags & (VLRO_HMM_SUM3_APPROX | VLRO_HMM_SUM3_APPROX3)) {
         double p0 = a, p1 = b, p2 = c, t;
         if (p1 < p2) { t = p1; p1 = p2; p2 = t; }
         if (p1 > p0) { t = p1; p1 = p0; p0 = t; }
-        if (p2 > p0) { t = p2; p2 = p0; p0 = t; }
-        /* now p0 is the max; second largest is max(p1,p2) */
-        double second = p1 > p2 ? p1 : p2;
-        if (p0 - second > 10.0) return p0;
+        if (p2 > p1) { t = p2; p2 = p1; p1 = t; }
+        /* p0 >= p1 >= p2 */
+        if (p0 - p1 > 10.0) return p0;
+        if ((flags & VLRO_HMM_SUM3_APPROX3) && p1 - p2 > 10.0) return vlro_ln_add_exp(p0, p1);
         double v[3] = {p0, p1, p2};
         return vlro_ln_sum_exp(v, 3);
     }
@@ -257,9 +268,15 @@ double vlro_pairhmm_prob_related(const uint8_t *hap, int len_x, const uint8_t *r
         prob_cols[ncols++] = fy[curr][len_y];
         /* swap and reset the new curr column (oracle choice: reset all four arrays) */
         int t = prev; prev = curr; curr = t;
-        for (size_t j = 0; j < n; ++j) {
-            fm[curr][j] = fx[curr][j] = fy[curr][j] = NEG_INF;
-            md[curr][j] = MED_MAX;
+        if (flags & VLRO_HMM_RESET_FM_ONLY) {
+            /* the other recollection of upstream ("reset next column to zeros": fm only); skipped
+             * band cells then keep fx / fy / min_edit_dist from two columns back */
+            for (size_t j = 0; j < n; ++j) fm[curr][j] = NEG_INF;
+        } else {
+            for (size_t j = 0; j < n; ++j) {
+                fm[curr][j] = fx[curr][j] = fy[curr][j] = NEG_INF;
+                md[curr][j] = MED_MAX;
+            }
         }
     }
     double p = vlro_ln_sum_exp(prob_cols, ncols);
@@ -279,7 +296,7 @@ typedef struct {
 
 /* state: 0=M 1=X(del, consumes hap) 2=Y(ins, consumes read); i,j = consumed counts */
 static void bf_rec(bf_t *b, int i, int j, int state, double lp) {
-    if (j == b->len_y && state >= 0) b->total += exp(lp); /* free end: any column, last row */
+    if (j == b->len_y && state >= 0) b->total += vlro_exp(lp); /* free end: any column, last row */
     /* extend by M */
     if (i < b->len_x && j < b->len_y) {
         double tr = state < 0 ? b->c.no_gap : (state == 0 ? b->c.no_gap
@@ -311,7 +328,7 @@ double vlro_pairhmm_bruteforce(const uint8_t *hap, int len_x, const uint8_t *rea
     /* free start: the path may begin (state -1 = start, transition no_gap from fm[prev][0]=1)
      * at any hap offset */
     for (int s = 0; s < len_x; ++s) bf_rec(&b, s, 0, -1, 0.0);
-    double p = log(b.total);
+    double p = vlro_log(b.total);
     if (p > 0.0) p = 0.0;
     return p;
 }
@@ -576,7 +593,7 @@ int vlro_allele_support_region(const uint8_t *haps, const int32_t *hap_off, cons
         pr -= tot;
         pa -= tot;
     }
-    if (pr == NEG_INF && pa == NEG_INF) pr = pa = log(0.5);
+    if (pr == NEG_INF && pa == NEG_INF) pr = pa = vlro_log(0.5);
     out->prob_ref = pr;
     out->prob_alt = pa;
     out->informative = pr != pa;
@@ -624,7 +641,7 @@ static double bias_divindel(const vlro_biases_t *b, const vlro_pileup_t *p, int 
     int other = VLRO_CAT_INDEL(p->cat[i]) == 1; /* divindel_bias.rs:37-59 */
     if (b->divindel == 0) return other ? NEG_INF : 0.0;
     if (b->other_rate == 0.0) return NEG_INF;
-    return other ? log(b->other_rate) : log(1.0 - b->other_rate);
+    return other ? vlro_log(b->other_rate) : vlro_log(1.0 - b->other_rate);
 }
 
 /* Biases::prob (bias/mod.rs:225-232): left-to-right sum */
@@ -645,7 +662,7 @@ int vlro_biases_is_artifact(const vlro_biases_t *b) {
  * i.e. exp(prob_alt - prob_ref) > 20 (Appendix A.4) */
 int vlro_is_strong_obs(const vlro_pileup_t *p, int i) {
     static const double LN_095 = -0.05129329438755058;
-    return p->prob_mapping[i] >= LN_095 && exp(p->prob_alt[i] - p->prob_ref[i]) > 20.0;
+    return p->prob_mapping[i] >= LN_095 && vlro_exp(p->prob_alt[i] - p->prob_ref[i]) > 20.0;
 }
 
 typedef double (*comp_fn)(const vlro_biases_t *, const vlro_pileup_t *, int);
@@ -757,7 +774,7 @@ double vlro_likelihood_mapping(double ln_af, const vlro_biases_t *b, const vlro_
 
 /* SampleLikelihoodModel::likelihood_observation (165-187) folded over the pileup (220-244) */
 double vlro_likelihood_single(const vlro_pileup_t *p, double af, const vlro_biases_t *b) {
-    double ln_af = log(af);
+    double ln_af = vlro_log(af);
     double lh = 0.0;
     for (int i = 0; i < p->n_obs; ++i) {
         double prob = vlro_likelihood_mapping(ln_af, b, p, i);
@@ -773,9 +790,9 @@ double vlro_likelihood_single(const vlro_pileup_t *p, double af, const vlro_bias
 double vlro_likelihood_contaminated(const vlro_pileup_t *p, double purity, double af_primary,
                                     const vlro_biases_t *b_primary, double af_secondary,
                                     const vlro_biases_t *b_secondary) {
-    double ln_purity = log(purity);
+    double ln_purity = vlro_log(purity);
     double ln_impurity = vlro_ln_one_minus_exp(ln_purity);
-    double ln_af_p = log(af_primary), ln_af_s = log(af_secondary);
+    double ln_af_p = vlro_log(af_primary), ln_af_s = vlro_log(af_secondary);
     double lh = 0.0;
     for (int i = 0; i < p->n_obs; ++i) {
         double prob_primary = ln_purity + vlro_likelihood_mapping(ln_af_p, b_primary, p, i);
@@ -989,13 +1006,13 @@ static double density(post_ctx_t *c, int node) {
             double x = a + step * (double)i;
             c->cur_af[nd->sample] = x;
             double w = (double)(2 + (i % 2) * 2);
-            probs[k++] = subdensity(c, nd) + log(w);
+            probs[k++] = subdensity(c, nd) + vlro_log(w);
         }
         c->cur_af[nd->sample] = a;
         probs[k++] = subdensity(c, nd);
         c->cur_af[nd->sample] = b;
         probs[k++] = subdensity(c, nd);
-        double res = vlro_ln_sum_exp(probs, (size_t)k) + log(b - a) - log((double)(n - 1)) - log(3.0);
+        double res = vlro_ln_sum_exp(probs, (size_t)k) + vlro_log(b - a) - vlro_log((double)(n - 1)) - vlro_log(3.0);
         free(probs);
         return res;
     }
@@ -1029,7 +1046,7 @@ int vlro_model_compute(const vlro_model_t *m, const vlro_pileup_t *pileups, doub
         int is_art = 0;
         for (int k = 0; k < E->n_biases; ++k) is_art |= vlro_biases_is_artifact(&biases[E->bias_off + k]);
         /* generic.rs:251-255: |biases| counted before gating */
-        double bias_prior = is_art ? LN_05 + log(1.0 / (double)E->n_biases) : LN_05;
+        double bias_prior = is_art ? LN_05 + vlro_log(1.0 / (double)E->n_biases) : LN_05;
         size_t cap = (size_t)E->n_biases * (size_t)E->n_roots;
         double *terms = (double *)malloc(sizeof(double) * (cap ? cap : 1));
         size_t nt = 0;

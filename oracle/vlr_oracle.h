@@ -31,6 +31,10 @@
 extern "C" {
 #endif
 
+/* ---- the oracle's libm (detmath.h: msun exp / expm1 / log / log1p, every operation a single
+ *      rounded binary64 operation); fn: 0 exp, 1 expm1, 2 log, 3 log1p ---- */
+void vlro_ref_math(int fn, long n, const double *x, double *out);
+
 /* ---- bio::stats::probs::LogProb helpers ---- */
 double vlro_ln_add_exp(double a, double b);
 double vlro_ln_sum_exp(const double *p, size_t n);
@@ -56,6 +60,8 @@ double vlro_f16_bits_to_f64(uint16_t h);
  * flags: VLRO_HMM_* below. */
 #define VLRO_HMM_SUM3_APPROX 1u  /* M-state sum uses bio's ln_sum3_exp_approx (drop terms e^-10 below max) */
 #define VLRO_HMM_PATH_CLOSE  2u  /* close-gap pairing as PathHMMRealigner (realignment/mod.rs:469-470) */
+#define VLRO_HMM_SUM3_APPROX3 8u /* three-way ln_sum3_exp_approx (p0; p0+p1; all three), the default */
+#define VLRO_HMM_RESET_FM_ONLY 16u /* only fm[curr] is reset after a column swap (oracle only; sensitivity study) */
 double vlro_pairhmm_prob_related(const uint8_t *hap, int len_x, const uint8_t *read,
                                  const uint8_t *qual, int len_y, const double gap_ln[4],
                                  int max_edit_dist, unsigned flags);

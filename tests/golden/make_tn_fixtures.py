@@ -11,9 +11,8 @@ from libprosic_b200 import fixtures as F  # noqa: E402
 
 REF = "/root/reference/tests/resources/testcases"
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tn")
-# a subset keeps the fixtures small; `python tests/golden/run_tn_testcases.py` runs all of them here
-CASES = ["test02", "test03", "test04", "test08", "test10", "test12", "test15", "test16", "test20", "test21",
-         "test24", "test25", "issue_154"]
+# every tumor/normal indel testcase of the reference (tests/lib.rs:80-110) plus issue_154
+CASES = ["test%02d" % k for k in range(2, 34)] + ["issue_154"]
 
 
 def main():

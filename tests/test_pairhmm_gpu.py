@@ -26,7 +26,7 @@ def _compare(got, want, tol=TOL):
         np.nanmax(diff), int(np.nanargmax(diff)), got[np.nanargmax(diff)], want[np.nanargmax(diff)])
 
 
-@pytest.mark.parametrize("flags", [P.HMM_DEFAULT, 0])
+@pytest.mark.parametrize("flags", [P.HMM_DEFAULT, P.HMM_SUM3_APPROX, 0])
 def test_c3_shape_unbanded(ctx, oracle, flags):
     w = synth.make_pairhmm_workload(n_sites=6, reads_per_site=16, seed=synth.SEED_C3)
     gap = P.GapParams()
@@ -242,3 +242,48 @@ def test_band_only_kernel(ctx, oracle, kind, flags):
     got = ctx.pairhmm_batch(hb, ho, rb, rq, ro, gap, max_edit_dist=med, flags=flags)
     want = oracle.pairhmm_batch(hb, ho, rb, rq, ro, gap.as_ln_array(), med, flags)
     _compare(got, want, tol=1e-7)
+
+
+@pytest.mark.parametrize("gi,flags", [(0, P.HMM_SUM3_APPROX3), (0, P.HMM_SUM3_APPROX), (0, 0),
+                                      (1, P.HMM_SUM3_APPROX3), (2, P.HMM_SUM3_APPROX | P.HMM_PATH_CLOSE),
+                                      (1, P.HMM_SUM3_APPROX3 | P.HMM_PATH_CLOSE)])
+def test_literal_kernel_is_bit_identical_to_the_oracle(ctx, oracle, gi, flags):
+    """VLR_HMM_LITERAL: natural-log space in the reference's operation order with the deterministic
+    libm -- every result equals the oracle's BIT FOR BIT (banded with the reference's cell set,
+    unbanded, gap extension, any alphabet, Q0 bases).  This is the evaluation the fused allele
+    support falls back to when prob_ref and prob_alt are nearly tied (mod.rs:303)."""
+    gap = _gap_sets()[gi]
+    w = synth.make_ragged_pairs(240, seed=700 + gi, max_ly=248, max_lx=420)
+    n = len(w["hap_off"]) - 1
+    med = np.full(n, -1, dtype=np.int32)
+    for k in range(0, n, 2):  # every other pair banded as the reference does (dist + 2)
+        hit = oracle.best_hit(w["hap_bytes"][w["hap_off"][k]:w["hap_off"][k + 1]],
+                              w["read_bases"][w["read_off"][k]:w["read_off"][k + 1]])
+        med[k] = hit["dist"] + 2
+    got = ctx.pairhmm_batch(w["hap_bytes"], w["hap_off"], w["read_bases"], w["read_quals"],
+                            w["read_off"], gap, max_edit_dist=med, flags=flags | P.HMM_LITERAL)
+    want = oracle.pairhmm_batch(w["hap_bytes"], w["hap_off"], w["read_bases"], w["read_quals"],
+                                w["read_off"], gap.as_ln_array(), med, flags)
+    assert np.array_equal(got.view(np.int64), want.view(np.int64)), \
+        "first difference at %d: %r vs %r" % (int(np.argmax(got != want)), got[np.argmax(got != want)],
+                                              want[np.argmax(got != want)])
+
+
+def test_three_way_and_two_way_rules_differ_where_expected(ctx, oracle):
+    """The two recollections of ln_sum3_exp_approx: results differ by at most ~e^-10 per cell
+    (<= 1e-3 in ln on these reads) and both match their oracle variants."""
+    w = synth.make_pairhmm_workload(n_sites=4, reads_per_site=16, seed=77)
+    gap = P.GapParams()
+    res = {}
+    for flags in (P.HMM_SUM3_APPROX3, P.HMM_SUM3_APPROX, 0):
+        got = ctx.pairhmm_batch(w["hap_bytes"], w["hap_off"], w["read_bases"], w["read_quals"],
+                                w["read_off"], gap, w["pair_hap"], w["pair_read"], flags=flags)
+        want = np.array([oracle.pairhmm_prob_related(
+            w["hap_bytes"][w["hap_off"][h]:w["hap_off"][h + 1]],
+            w["read_bases"][w["read_off"][r]:w["read_off"][r + 1]],
+            w["read_quals"][w["read_off"][r]:w["read_off"][r + 1]], gap.as_ln_array(), -1, flags)
+            for h, r in zip(w["pair_hap"], w["pair_read"])])
+        _compare(got, want)
+        res[flags] = got
+    assert np.max(np.abs(res[P.HMM_SUM3_APPROX3] - res[0])) <= 1e-3
+    assert np.max(np.abs(res[P.HMM_SUM3_APPROX] - res[0])) <= 1e-3
