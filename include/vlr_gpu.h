@@ -259,6 +259,40 @@ typedef struct {
     int32_t bias_off;   /* into biases[] */
     int32_t n_biases;
 } vlr_event;
+/* Prior over allele-frequency vectors as a small program (Prior::calc_prob, prior.rs:288-431): used
+ * when tree paths bind Ranges, whose grid points depend on the site's depth so that no table over the
+ * leaves exists.  The recursion of calc_prob sums over the germline alt-allele counts of the samples
+ * with a somatic mutation rate; everything that does not depend on the allele frequencies themselves
+ * (population prior 628-656, Mendelian alt-count terms 658-786, the germline equality of clonal
+ * inheritance 465-467) is tabulated by the host per germline count vector, and the device adds the
+ * somatic terms (prob_somatic_mutation, 433-455: ln rate - (2 ln |vaf| + ln genome size), a constant
+ * for |vaf| <= 1e-4) at every leaf. */
+#define VLR_PRIOR_UNIFORM 0        /* sample with an explicit universe: ln 1 inside it, germline VAF 0 */
+#define VLR_PRIOR_SOMATIC 1        /* ploidy + somatic rate: sum over germline alt counts 0..ploidy */
+#define VLR_PRIOR_GERMLINE 2       /* ploidy, no somatic rate: the VAF must be a germline VAF k/ploidy */
+#define VLR_SOM_NONE 0
+#define VLR_SOM_PLAIN 1            /* prob_somatic_mutation(rate, af - germline) */
+#define VLR_SOM_CLONAL_DENOVO 2    /* (rate, af - germline - (af_parent - germline_parent)), prior.rs:474-480 */
+#define VLR_SOM_CLONAL_SAME 3      /* effective somatic VAF must equal the parent's, prior.rs:481-492 */
+typedef struct {
+    int32_t kind[8];               /* VLR_PRIOR_* per sample */
+    int32_t ploidy[8];             /* -1: none (UNIFORM samples only) */
+    int32_t som_kind[8];           /* VLR_SOM_* per sample */
+    int32_t parent[8];             /* clonal parent, else -1 */
+    double ln_rate[8];             /* ln(somatic effective mutation rate x variant-type fraction) */
+    double som_zero[8];            /* prob_somatic_mutation(rate, 0): ln(1 - Simpson integral), host-evaluated */
+    double ln_genome_size;
+    /* universes of the UNIFORM samples (VAFUniverse::contains): entries uni_off[s] .. uni_off[s+1] of
+     * uni_spec, five doubles each: kind (0 single value, 1 range), start, end, left_excl, right_excl */
+    int32_t uni_off[9];
+    int32_t _pad;
+    const double *uni_spec;
+    /* ln of the allele-frequency independent factor per germline alt-count vector: mixed radix over
+     * the samples, sample 0 slowest, radix ploidy + 1 (1 for UNIFORM samples and ploidy 0) */
+    const double *germ_ln;
+    int64_t n_germ;
+} vlr_prior_prog;
+
 typedef struct {
     int32_t n_samples;          /* <= 8 */
     int32_t n_events;
@@ -279,9 +313,12 @@ typedef struct {
      * vlr_model_leaves, or NULL = flat (ln 1).  The prior is data-independent, so the host
      * evaluates its unchanged Prior once per event universe.  Only for models whose tree paths
      * bind VAF sets (ploidy-derived universes, e.g. pedigrees): the grid points of a Range depend
-     * on the site's depth (generic.rs:109-122). */
+     * on the site's depth (generic.rs:109-122) -- such models pass `prior_prog` below. */
     const double *prior_ln;
     int64_t n_prior;
+    /* ... or the prior as a program (any universe; required when a tree path binds a Range and the
+     * prior is not flat).  NULL = none.  prior_ln wins when both are given and applicable. */
+    const vlr_prior_prog *prior_prog;
 } vlr_model;
 
 /* Leaves (event, tree path, value combination; last sample fastest) of a set-only model:

@@ -70,13 +70,21 @@ class ObsColumnsF32(C.Structure):
                                           "prob_sample_alt", "prob_double_overlap", "prob_hit_base", "cat")]
 
 
+class PriorProg(C.Structure):
+    """vlr_prior_prog (include/vlr_gpu.h)."""
+    _fields_ = [("kind", C.c_int32 * 8), ("ploidy", C.c_int32 * 8), ("som_kind", C.c_int32 * 8),
+                ("parent", C.c_int32 * 8), ("ln_rate", C.c_double * 8), ("som_zero", C.c_double * 8),
+                ("ln_genome_size", C.c_double), ("uni_off", C.c_int32 * 9), ("_pad", C.c_int32),
+                ("uni_spec", C.c_void_p), ("germ_ln", C.c_void_p), ("n_germ", C.c_int64)]
+
+
 class Model(C.Structure):
     _fields_ = [("n_samples", C.c_int32), ("n_events", C.c_int32), ("n_nodes", C.c_int32),
                 ("n_biases", C.c_int32), ("resolution", C.c_void_p), ("contaminated", C.c_void_p),
                 ("by", C.c_void_p), ("purity", C.c_void_p), ("nodes", C.c_void_p),
                 ("children", C.c_void_p), ("vafs", C.c_void_p), ("roots", C.c_void_p),
                 ("events", C.c_void_p), ("biases", C.c_void_p), ("prior_ln", C.c_void_p),
-                ("n_prior", C.c_int64)]
+                ("n_prior", C.c_int64), ("prior_prog", C.c_void_p)]
 
 
 EXPORTS = [

@@ -263,12 +263,34 @@ class Context:
         if prior is not None:
             prior = np.ascontiguousarray(prior, dtype=np.float64)
             keep.append(prior)
+        prog_ptr = None
+        pp = scn.get("prior_prog")  # dict form of vlr_prior_prog (libprosic_b200.prior.make_prior)
+        if pp is not None:
+            from ._ffi import PriorProg
+            ns = scn["n_samples"]
+            prog = PriorProg()
+            for k in range(ns):
+                prog.kind[k], prog.ploidy[k] = pp["kind"][k], pp["ploidy"][k]
+                prog.som_kind[k], prog.parent[k] = pp["som_kind"][k], pp["parent"][k]
+                prog.ln_rate[k], prog.som_zero[k] = pp["ln_rate"][k], pp["som_zero"][k]
+            prog.ln_genome_size = pp["ln_genome_size"]
+            uni, uoff = [], [0]
+            for k in range(ns):
+                uni.extend(pp["uni"][k])
+                uoff.append(len(uni))
+            for k in range(9):
+                prog.uni_off[k] = uoff[min(k, ns)]
+            us = np.asarray(uni if uni else [(0.0,) * 5], np.float64).reshape(-1, 5)
+            gl = np.asarray(pp["germ_ln"], np.float64)
+            prog.uni_spec, prog.germ_ln, prog.n_germ = us.ctypes.data, gl.ctypes.data, len(gl)
+            keep.extend([prog, us, gl])
+            prog_ptr = C.addressof(prog)
         return Model(scn["n_samples"], len(scn["events"]), len(scn["nodes"]), len(flat),
                      res.ctypes.data, cont.ctypes.data, by.ctypes.data, pur.ctypes.data,
                      C.addressof(nodes), ch.ctypes.data, vf.ctypes.data, rt.ctypes.data,
                      C.addressof(events), C.addressof(biases),
                      prior.ctypes.data if prior is not None else None,
-                     len(prior) if prior is not None else 0)
+                     len(prior) if prior is not None else 0, prog_ptr)
 
     def call_records(self, scn, post, prob_mapping, obs_off):
         """BCF values of the call records: dict(prob[n_sites, n_named + 1] f32 PHRED, af f32, dp i32,
@@ -345,15 +367,29 @@ class Context:
                                                      _ptr(obs_off), _ptr(ev), _ptr(marg), _ptr(maf), _ptr(mb)))
         return dict(event_ln=ev, marginal=marg, map_af=maf, map_bias=mb)
 
-    def posterior_batch_dev(self, scn, n_sites, d_cols, d_cat, d_obs_off, max_obs, d_ev, d_marg, d_maf,
-                            d_mb, _cache={}):
+    def _cached_model(self, scn):
+        """vlr_model of a scenario dict, rebuilt when the dict changed.  The cache belongs to this
+        context, holds the dict itself (its id cannot be reused while cached) and compares a
+        fingerprint of the fields callers mutate in place (prior, resolutions, purities)."""
+        import json
+        cache = self.__dict__.setdefault("_model_cache", {})
+        fp = json.dumps([scn["n_samples"], list(map(int, scn["resolution"])), list(map(float, scn["purity"])),
+                         list(map(int, scn["contaminated"])), list(map(int, scn["by"])), scn["nodes"], scn["events"],
+                         scn["biases"]], sort_keys=True, default=str) + \
+            "|%d|%d" % (id(scn.get("prior_ln")), id(scn.get("prior_prog")))
+        ent = cache.get(id(scn))
+        if ent is None or ent[0] is not scn or ent[1] != fp:
+            keep = []
+            ent = (scn, fp, self.build_model(scn, keep), keep, scn.get("prior_ln"), scn.get("prior_prog"))
+            if len(cache) >= 8:
+                cache.pop(next(iter(cache)))
+            cache[id(scn)] = ent
+        return ent[2]
+
+    def posterior_batch_dev(self, scn, n_sites, d_cols, d_cat, d_obs_off, max_obs, d_ev, d_marg, d_maf, d_mb):
         """Device-pointer variant (ints).  d_cols: dict name -> device pointer."""
         from ._ffi import ObsColumns
-        key = id(scn)
-        if key not in _cache:
-            keep = []
-            _cache[key] = (self.build_model(scn, keep), keep)
-        model = _cache[key][0]
+        model = self._cached_model(scn)
         names = ("prob_mapping", "prob_mismapping", "prob_alt", "prob_ref", "prob_missed_allele",
                  "prob_sample_alt", "prob_double_overlap", "prob_single_overlap", "prob_hit_base")
         oc = ObsColumns(*[d_cols[n] for n in names], d_cat)

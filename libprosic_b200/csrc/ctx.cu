@@ -160,7 +160,9 @@ const char *vlr_last_error(const vlr_ctx *ctx) { return ctx ? ctx->err.c_str() :
 
 int vlr_ctx_set_stream(vlr_ctx *ctx, void *cuda_stream) {
     if (!ctx) return VLR_ERR_INVALID;
-    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    cudaStream_t ns = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    if (ns != ctx->stream) ctx->model_dev = nullptr;  // the cached model upload was ordered on the old stream
+    ctx->stream = ns;
     return VLR_OK;
 }
 

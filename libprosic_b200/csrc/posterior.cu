@@ -251,21 +251,56 @@ int vlr_posterior_batch_dev(vlr_ctx *ctx, int64_t n_sites, const vlr_model *mode
     const int64_t n_teams = (int64_t)grid * teams_per_cta;
     if (tbound > ((int64_t)1 << 24))
         return set_err(ctx, VLR_ERR_UNSUPPORTED, "likelihood table of %lld entries per site is too large", (long long)tbound);
-    const bool has_prior = model->prior_ln != nullptr;
+    // the kernel enumerates a site's terms (event, bias cfg, path, grid combination) with 32-bit
+    // counters: bound their number for the deepest pileup the kernel admits
+    {
+        double terms = 0.0;
+        for (const DevSeg &sg : H.segs) {
+            double c = 1.0;
+            for (int smp = 0; smp < model->n_samples; ++smp)
+                c *= sg.nv[smp] < 0 ? (double)grid_bound(model, smp, obs_cap) : (double)sg.nv[smp];
+            terms += c;
+        }
+        if (terms > 2147483647.0)
+            return set_err(ctx, VLR_ERR_UNSUPPORTED, "up to %.3g integration terms per site (limit 2^31 - 1): lower the "
+                                                     "resolutions of the samples bound by Ranges", terms);
+    }
+    // prior: a table over the leaves (set-only universes) or a program evaluated at every leaf
+    const bool has_prior = model->prior_ln != nullptr && !(H.any_range_path && model->prior_prog);
+    const vlr_prior_prog *prog = has_prior ? nullptr : model->prior_prog;
     if (has_prior) {
         if (H.any_range_path)
             return set_err(ctx, VLR_ERR_UNSUPPORTED, "a prior table needs every tree path to bind VAF sets only "
-                                                     "(grid points of a Range depend on the site's depth)");
+                                                     "(grid points of a Range depend on the site's depth): pass prior_prog");
         if (model->n_prior != H.n_leaves)
             return set_err(ctx, VLR_ERR_INVALID, "prior table has %lld entries, the model has %lld leaves",
                            (long long)model->n_prior, (long long)H.n_leaves);
+    }
+    int64_t n_uni = 0;
+    if (prog) {
+        int64_t want = 1;
+        for (int s = 0; s < model->n_samples; ++s) {
+            const int k = prog->kind[s];
+            if (k < VLR_PRIOR_UNIFORM || k > VLR_PRIOR_GERMLINE || prog->som_kind[s] < VLR_SOM_NONE ||
+                prog->som_kind[s] > VLR_SOM_CLONAL_SAME || (k != VLR_PRIOR_UNIFORM && (prog->ploidy[s] < 0 || prog->ploidy[s] > 16)) ||
+                (prog->som_kind[s] >= VLR_SOM_CLONAL_DENOVO && (prog->parent[s] < 0 || prog->parent[s] >= model->n_samples)) ||
+                prog->uni_off[s + 1] < prog->uni_off[s] || prog->uni_off[0] != 0)
+                return set_err(ctx, VLR_ERR_INVALID, "prior program: bad entry for sample %d", s);
+            want *= (k == VLR_PRIOR_UNIFORM || prog->ploidy[s] <= 0) ? 1 : prog->ploidy[s] + 1;
+        }
+        n_uni = prog->uni_off[model->n_samples];
+        if (want != prog->n_germ || !prog->germ_ln || (n_uni > 0 && !prog->uni_spec) || want > (1 << 20))
+            return set_err(ctx, VLR_ERR_INVALID, "prior program: germline table has %lld entries, expected %lld",
+                           (long long)prog->n_germ, (long long)want);
     }
     enum { S_MODEL = 16, S_TABLE, S_CNT };
     // model blob
     const size_t b_spec = H.spectra.size() * sizeof(DevSpectrum), b_path = H.paths.size() * sizeof(DevPath),
                  b_ev = H.events.size() * sizeof(DevEvent), b_eb = H.eb.size() * sizeof(DevEventBias),
                  b_cfg = H.cfg.size() * sizeof(vlr_biases), b_vaf = H.vafs.size() * sizeof(double),
-                 b_seg = H.segs.size() * sizeof(DevSeg), b_pri = has_prior ? (size_t)H.n_leaves * 8 : 0;
+                 b_seg = H.segs.size() * sizeof(DevSeg),
+                 b_pri = has_prior ? (size_t)H.n_leaves * 8
+                                   : (prog ? (size_t)(prog->n_germ + 5 * n_uni) * 8 + align_up(sizeof(vlr_prior_prog), 16) : 0);
     size_t off[9];
     off[0] = 0;
     off[1] = align_up(off[0] + b_spec, 16);
@@ -290,6 +325,15 @@ int vlr_posterior_batch_dev(vlr_ctx *ctx, int64_t n_sites, const vlr_model *mode
         memcpy(blob.data() + off[5], H.vafs.data(), b_vaf);
         memcpy(blob.data() + off[6], H.segs.data(), b_seg);
         if (has_prior) memcpy(blob.data() + off[7], model->prior_ln, b_pri);
+        if (prog) {  // the program with device pointers, the germline table, the universes of the uniform samples
+            const size_t hdr = align_up(sizeof(vlr_prior_prog), 16);
+            vlr_prior_prog dp = *prog;
+            dp.germ_ln = (const double *)(d_blob + off[7] + hdr);
+            dp.uni_spec = dp.germ_ln + prog->n_germ;
+            memcpy(blob.data() + off[7], &dp, sizeof(dp));
+            memcpy(blob.data() + off[7] + hdr, prog->germ_ln, (size_t)prog->n_germ * 8);
+            if (n_uni > 0) memcpy(blob.data() + off[7] + hdr + (size_t)prog->n_germ * 8, prog->uni_spec, (size_t)n_uni * 40);
+        }
         // upload only when the model changed: the chunks of a batch and repeated calls of one
         // scenario reuse the device copy, and the launch needs no synchronisation with the stream
         if (ctx->model_dev != d_blob || ctx->model_copy != blob) {
@@ -328,6 +372,7 @@ int vlr_posterior_batch_dev(vlr_ctx *ctx, int64_t n_sites, const vlr_model *mode
     a.m.segs = (const DevSeg *)(d_blob + off[6]);
     a.m.n_segs = (int)H.segs.size();
     a.m.prior = has_prior ? (const double *)(d_blob + off[7]) : nullptr;
+    a.m.prog = prog ? (const vlr_prior_prog *)(d_blob + off[7]) : nullptr;
     a.obs = *d_obs;
     a.obs_off = d_obs_off;
     a.n_sites = n_sites;

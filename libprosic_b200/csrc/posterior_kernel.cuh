@@ -84,6 +84,9 @@ struct DevModel {
     const double *vafs;
     const DevSeg *segs;
     const double *prior;  // ln prior per leaf (event, path, combination), nullptr = flat
+    // prior as a program (vlr_prior_prog in device memory, its arrays patched to device copies),
+    // used when prior == nullptr
+    const vlr_prior_prog *prog;
 };
 
 struct PostArgs {
@@ -204,6 +207,77 @@ static __device__ __noinline__ double ln_T_exact(const vlr_obs_columns &o, int64
     const double t1 = o.prob_mismapping[row] + o.prob_missed_allele[row] + pab;
     if (isnan(t0) || isnan(t1)) return NAN;
     return ln_add_exp2(t0, t1);
+}
+
+// Prior::compute as a program (vlr_prior_prog, include/vlr_gpu.h): Prior::calc_prob (prior.rs:288-431)
+// at one allele-frequency vector.  The nested ln_sum_exp of the recursion is a flat sum here.
+static __device__ __noinline__ double prior_prog_eval(const vlr_prior_prog *Pp, int NS, const double *af) {
+    const vlr_prior_prog &P = *Pp;
+    int stride[kMaxSamples], radix[kMaxSamples], bs[kMaxSamples];
+    double germ[kMaxSamples];
+    int nb = 0, total = 1;
+    for (int s = NS - 1, st = 1; s >= 0; --s) {
+        radix[s] = (P.kind[s] == VLR_PRIOR_UNIFORM || P.ploidy[s] <= 0) ? 1 : P.ploidy[s] + 1;
+        stride[s] = st;
+        st *= radix[s];
+    }
+    int fixed = 0;
+    for (int s = 0; s < NS; ++s) {
+        germ[s] = 0.0;
+        if (P.ploidy[s] == 0 && af[s] != 0.0) return -INFINITY;  // chromosome absent from the sample
+        if (P.kind[s] == VLR_PRIOR_UNIFORM) {
+            bool in = false;
+            for (int u = P.uni_off[s]; u < P.uni_off[s + 1] && !in; ++u) {
+                const double *e = P.uni_spec + 5 * u;
+                if (e[0] == 0.0) in = af[s] == e[1];
+                else in = (e[3] != 0.0 ? af[s] > e[1] : af[s] >= e[1]) && (e[4] != 0.0 ? af[s] < e[2] : af[s] <= e[2]);
+            }
+            if (!in) return -INFINITY;
+        } else if (P.kind[s] == VLR_PRIOR_GERMLINE) {
+            const double x = (double)P.ploidy[s] * af[s], r = rint(x);
+            if (fabs(x - r) > fmax(1e-9 * fmax(fabs(x), fabs(r)), 1e-9)) return -INFINITY;  // is_valid_germline_vaf
+            fixed += (int)r * stride[s];
+            germ[s] = af[s];
+        } else if (radix[s] > 1) {
+            bs[nb++] = s;
+            total *= radix[s];
+        }
+    }
+    double mx = -INFINITY, sum = 0.0;
+    for (int combo = 0; combo < total; ++combo) {
+        int idx = fixed, rem = combo;
+        for (int b = nb - 1; b >= 0; --b) {
+            const int s = bs[b], k = rem % radix[s];
+            rem /= radix[s];
+            idx += k * stride[s];
+            germ[s] = (double)k / (double)P.ploidy[s];
+        }
+        double t = P.germ_ln[idx];
+        if (t == -INFINITY) continue;
+        for (int s = 0; s < NS && t != -INFINITY; ++s) {
+            const int sk = P.som_kind[s];
+            if (sk == VLR_SOM_NONE) continue;
+            const double eff = af[s] - germ[s];
+            double v = eff;
+            if (sk != VLR_SOM_PLAIN) {
+                const double effp = af[P.parent[s]] - germ[P.parent[s]];
+                if (sk == VLR_SOM_CLONAL_SAME) {  // approx::relative_eq! with the crate's defaults
+                    const double d = fabs(eff - effp);
+                    if (!(eff == effp || d <= 2.220446049250313e-16 ||
+                          d <= fmax(fabs(eff), fabs(effp)) * 2.220446049250313e-16))
+                        t = -INFINITY;
+                    continue;
+                }
+                v = af[s] - germ[s] - effp;
+            }
+            v = fabs(v);
+            t += v <= 0.0001 ? P.som_zero[s] : P.ln_rate[s] - (2.0 * log_ni(v) + P.ln_genome_size);
+        }
+        if (t == -INFINITY) continue;
+        if (t > mx) { sum = sum * exp_ni(mx - t) + 1.0; mx = t; }
+        else sum += exp_ni(t - mx);
+    }
+    return mx == -INFINITY ? -INFINITY : mx + log_ni(sum);
 }
 
 // Bias::is_strong_obs (bias/mod.rs:79-83)
@@ -985,6 +1059,12 @@ __global__ void __launch_bounds__(kTeamThreadsMax, MINB) posterior_kernel(PostAr
                     lw += S.lnw[S.sample_voff[smp] + vidx[smp]];
                 }
                 double J = prior ? prior[combo] : 0.0;  // Prior::compute (prior.rs:788-805) via the host's table
+                if (!prior && m.prog) {                  // ... or evaluated here (universes with Ranges)
+                    double afv[NSA];
+                    #pragma unroll NSU
+                    for (int smp = 0; smp < NS; ++smp) afv[smp] = S.val[S.sample_voff[smp] + vidx[smp]];
+                    J = prior_prog_eval(m.prog, NS, afv);
+                }
                 #pragma unroll NSU
                 for (int smp = 0; smp < NS; ++smp) {
                     int key = vidx[smp];

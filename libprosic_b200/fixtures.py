@@ -973,9 +973,14 @@ def run_scenario_testcase(path, backend, scenario_yaml=None):
     if any(smp.universe is None for smp in g.samples.values()):
         # Prior::compute on the host (libprosic_b200/prior.py): callback for the oracle, table over the
         # leaves the library reports for the GPU
-        scn["prior_fn"] = prior_mod.make_prior(g, tc["contig"], variant["kind"])
-        _, afs = backend.model_leaves(scn)
-        scn["prior_ln"] = np.array([scn["prior_fn"](list(a)) for a in afs])
+        scn["prior_fn"], prog = prior_mod.make_prior(g, tc["contig"], variant["kind"], want_program=True)
+        leaves = backend.model_leaves(scn)
+        if leaves is None:
+            # a tree path binds a Range: its grid points depend on the site's depth, no table over
+            # the leaves exists -- the device evaluates the prior program at every leaf
+            scn["prior_prog"] = prog
+        else:
+            scn["prior_ln"] = np.array([scn["prior_fn"](list(a)) for a in leaves[1]])
     pile = []
     for name in order:
         if name not in tc["samples"]:
@@ -1002,9 +1007,9 @@ SCENARIO_CASES = ("omit_sb", "test34", "test37", "test40", "test49", "test52", "
                   "test_low_cov_vaf", "test_panel_overlap", "test_contig_universe", "test_giab_02")
 
 
-# ... and with a prior over continuous allele frequencies (somatic mutation rates, clonal inheritance):
-# the GPU path takes a prior table for set-only universes only, so these run on the oracle
-SCENARIO_CASES_ORACLE_ONLY = ("test64", "test69")
+# ... and with a prior over continuous allele frequencies (somatic mutation rates, Mendelian and clonal
+# inheritance): the device evaluates the prior as a program (vlr_prior_prog) at every leaf
+SCENARIO_CASES_PRIOR = ("test64", "test69", "test71")
 
 
 def check_expectations(result):
@@ -1069,4 +1074,10 @@ class GpuBackend:
         return self.ctx.call_records(scn, post, prob_mapping, off)
 
     def model_leaves(self, scn):
-        return self.ctx.model_leaves({k: v for k, v in scn.items() if k != "prior_fn"})
+        from . import VlrError
+        try:
+            return self.ctx.model_leaves({k: v for k, v in scn.items() if k not in ("prior_fn", "prior_prog")})
+        except VlrError as e:
+            if e.code == -4:  # VLR_ERR_UNSUPPORTED: leaves are enumerable only for set-only tree paths
+                return None
+            raise

@@ -57,8 +57,9 @@ def variant_type_fraction(species, kind):
     return {"ins": f["indel"], "del": f["indel"], "mnv": f["mnv"], "sv": f["sv"]}.get(kind, 1.0)
 
 
-def make_prior(scn, contig, kind="snv"):
-    """ln prior of an allele-frequency vector (sample order of the scenario), Prior::compute."""
+def _setup(scn, contig, kind):
+    """Everything Prior::new + set_universe_and_ploidies + set_variant_type fix for one contig and
+    variant type: per-sample ploidies, universes, rates (times the variant-type fraction), inheritance."""
     sp = scn.species or {}
     names = scn.sample_names
     frac = variant_type_fraction(sp, kind)
@@ -87,6 +88,15 @@ def make_prior(scn, contig, kind="snv"):
             inherit.append(("clonal", scn.idx(inh["clonal"]["from"]), bool(inh["clonal"]["somatic"])))
         else:
             raise NotImplementedError("inheritance pattern %s" % list(inh))
+    return names, het, ln_het, uniform, ploidy, universe, genome_size, germ_rate, som_rate, inherit
+
+
+def make_prior(scn, contig, kind="snv", want_program=False):
+    """ln prior of an allele-frequency vector (sample order of the scenario), Prior::compute.
+    want_program: return (f, program) where program is the dict form of vlr_prior_prog
+    (include/vlr_gpu.h) that lets the device evaluate the same prior at every leaf."""
+    names, het, ln_het, uniform, ploidy, universe, genome_size, germ_rate, som_rate, inherit = \
+        _setup(scn, contig, kind)
 
     def mendelian_alt_counts(sp_, tp, sa, ta, rate):  # prob_mendelian_alt_counts
         def cases(p):
@@ -193,4 +203,154 @@ def make_prior(scn, contig, kind="snv"):
         if key not in cache:
             cache[key] = rec(list(afs), [])
         return cache[key]
-    return f
+    if not want_program:
+        return f
+
+    # ---- the same prior as a program for the device (vlr_prior_prog).  The allele-frequency
+    # independent part of the recursion end is tabulated per germline alt-count vector.
+    ns = len(names)
+    pkind, som_kind, parent, ln_rate, som_zero = [], [], [], [], []
+    for s_ in range(ns):
+        if uniform[s_]:
+            pkind.append(0)
+        elif som_rate[s_] is not None:
+            if ploidy[s_] is None:
+                raise ValueError("sample %s with a somatic mutation rate but no ploidy" % names[s_])
+            pkind.append(1)
+        elif ploidy[s_] is not None and het is not None:
+            pkind.append(2)
+        else:
+            raise ValueError("not enough information for the prior of sample %s" % names[s_])
+        inh, sk, par = inherit[s_], 0, -1
+        if not uniform[s_]:
+            if inh is None or inh[0] == "mendelian":
+                sk = 1 if som_rate[s_] is not None else 0
+            else:
+                par = inh[1]
+                if inh[2] and som_rate[s_] is not None:
+                    sk = 2
+                elif inh[2]:
+                    sk = 3
+                elif som_rate[s_] is not None:
+                    sk = 1
+        som_kind.append(sk)
+        parent.append(par)
+        ln_rate.append(math.log(som_rate[s_]) if som_rate[s_] is not None else 0.0)
+        som_zero.append(somatic_mutation(som_rate[s_], 0.0) if sk in (1, 2) else 0.0)
+    radix = [1 if (pkind[s_] == 0 or not ploidy[s_]) else ploidy[s_] + 1 for s_ in range(ns)]
+    n_germ = 1
+    for r in radix:
+        n_germ *= r
+    germ_ln = []
+    for idx in range(n_germ):
+        rem, counts = idx, [0] * ns
+        for s_ in range(ns - 1, -1, -1):
+            counts[s_] = rem % radix[s_]
+            rem //= radix[s_]
+        germ = [(counts[s_] / ploidy[s_]) if radix[s_] > 1 else 0.0 for s_ in range(ns)]
+        prob = 0.0
+        if ln_het is not None:
+            pop = [s_ for s_ in range(ns) if inherit[s_] is None and ploidy[s_] is not None and not uniform[s_]]
+            m = sum(int(round(ploidy[s_] * germ[s_])) for s_ in pop)
+            if m > 0:
+                prob = ln_het - math.log(m)
+            else:
+                n = sum(ploidy[s_] for s_ in pop)
+                prob = _ln_one_minus_exp(_ln_sum_exp([ln_het - math.log(k) for k in range(1, n + 1)]))
+        for s_, inh in enumerate(inherit):
+            if uniform[s_] or inh is None:
+                continue
+            if inh[0] == "mendelian":
+                if germ_rate[s_] is None:
+                    raise ValueError("no germline mutation rate for child %s" % names[s_])
+                prob += mendelian_alt_counts((ploidy[inh[1]], ploidy[inh[2]]), ploidy[s_],
+                                             (int(round(germ[inh[1]] * ploidy[inh[1]])),
+                                              int(round(germ[inh[2]] * ploidy[inh[2]]))),
+                                             int(round(germ[s_] * ploidy[s_])), germ_rate[s_])
+            elif not close(germ[s_], germ[inh[1]]):
+                prob = LN_ZERO
+            if prob == LN_ZERO:
+                break
+        germ_ln.append(prob)
+    uni = []
+    for s_ in range(ns):
+        ent = []
+        for spc in (universe[s_] or []):
+            if spc[0] == "set":
+                ent += [(0.0, float(v), float(v), 0.0, 0.0) for v in sorted(spc[1])]
+            else:
+                ent.append((1.0, float(spc[1]), float(spc[2]), float(bool(spc[3])), float(bool(spc[4]))))
+        uni.append(ent)
+    program = dict(kind=pkind, ploidy=[-1 if p_ is None else int(p_) for p_ in ploidy], som_kind=som_kind,
+                   parent=parent, ln_rate=ln_rate, som_zero=som_zero,
+                   ln_genome_size=math.log(genome_size) if genome_size else 0.0, uni=uni, germ_ln=germ_ln)
+    return f, program
+
+
+def eval_program(prog, afs):
+    """Host evaluation of a prior program (the dict form of vlr_prior_prog), operation for operation
+    what the device does (csrc/posterior_kernel.cuh: prior_prog_eval).  Used by the tests as the
+    callback of the oracle for random programs and to check make_prior's program against its closure."""
+    ns = len(afs)
+    radix = [1 if (prog["kind"][s] == 0 or prog["ploidy"][s] <= 0) else prog["ploidy"][s] + 1 for s in range(ns)]
+    stride, st = [0] * ns, 1
+    for s in range(ns - 1, -1, -1):
+        stride[s] = st
+        st *= radix[s]
+    germ, fixed, branch = [0.0] * ns, 0, []
+    for s in range(ns):
+        af = afs[s]
+        if prog["ploidy"][s] == 0 and af != 0.0:
+            return LN_ZERO
+        if prog["kind"][s] == 0:
+            ok = False
+            for k, a, b, lex, rex in prog["uni"][s]:
+                if k == 0.0:
+                    ok = ok or af == a
+                else:
+                    ok = ok or ((af > a if lex else af >= a) and (af < b if rex else af <= b))
+            if not ok:
+                return LN_ZERO
+        elif prog["kind"][s] == 2:
+            x = prog["ploidy"][s] * af
+            r = float(round(x))
+            if abs(x - r) > max(1e-9 * max(abs(x), abs(r)), 1e-9):
+                return LN_ZERO
+            fixed += int(r) * stride[s]
+            germ[s] = af
+        elif radix[s] > 1:
+            branch.append(s)
+    total = 1
+    for s in branch:
+        total *= radix[s]
+    terms = []
+    for combo in range(total):
+        idx, rem = fixed, combo
+        for s in reversed(branch):
+            k = rem % radix[s]
+            rem //= radix[s]
+            idx += k * stride[s]
+            germ[s] = k / prog["ploidy"][s]
+        t = prog["germ_ln"][idx]
+        if t == LN_ZERO:
+            continue
+        for s in range(ns):
+            sk = prog["som_kind"][s]
+            if sk == 0 or t == LN_ZERO:
+                continue
+            eff = afs[s] - germ[s]
+            v = eff
+            if sk != 1:
+                par = prog["parent"][s]
+                effp = afs[par] - germ[par]
+                if sk == 3:
+                    d = abs(eff - effp)
+                    if not (eff == effp or d <= 2.220446049250313e-16 or d <= max(abs(eff), abs(effp)) * 2.220446049250313e-16):
+                        t = LN_ZERO
+                    continue
+                v = afs[s] - germ[s] - effp
+            v = abs(v)
+            t += prog["som_zero"][s] if v <= SOMATIC_EPSILON else prog["ln_rate"][s] - (2.0 * math.log(v) + prog["ln_genome_size"])
+        if t != LN_ZERO:
+            terms.append(t)
+    return _ln_sum_exp(terms)

@@ -41,7 +41,7 @@ def main():
         print(c, os.path.getsize(p))
     scn_prior = os.path.join(os.path.dirname(OUT), "scn_prior")
     os.makedirs(scn_prior, exist_ok=True)
-    for c in F.SCENARIO_CASES_ORACLE_ONLY:  # priors over continuous allele frequencies: oracle only
+    for c in F.SCENARIO_CASES_PRIOR:  # priors over continuous allele frequencies (prior program)
         p = os.path.join(scn_prior, c + ".json.gz")
         F.save_fixture(F.load_testcase(os.path.join(REF, c)), p)
         total += os.path.getsize(p)

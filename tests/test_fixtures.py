@@ -210,12 +210,46 @@ SCN_PRIOR = sorted(glob.glob(os.path.join(HERE, "golden", "scn_prior", "*.json.g
 @pytest.mark.parametrize("path", SCN_PRIOR, ids=_name)
 def test_scenario_testcases_with_somatic_priors_hold_on_the_oracle(path):
     """Four-sample pedigrees with somatic mutation rates, Mendelian and clonal inheritance
-    (test64, test69): universes with continuous ranges AND a non-uniform prior
-    (libprosic_b200/prior.py restates prob_somatic_mutation / prob_clonal_inheritance).  The GPU path
-    takes prior tables for set-only universes, so these pin the
-    restated host glue, the grammar front end and the oracle only."""
-    assert len(SCN_PRIOR) == len(F.SCENARIO_CASES_ORACLE_ONLY)
+    (test64, test69, test71): universes with continuous ranges AND a non-uniform prior
+    (libprosic_b200/prior.py restates prob_somatic_mutation / prob_clonal_inheritance)."""
+    assert len(SCN_PRIOR) == len(F.SCENARIO_CASES_PRIOR)
     from _oracle_backend import OracleBackend
     r = F.run_scenario_testcase(path, OracleBackend())
     verdicts = F.check_expectations(r)
     assert verdicts and all(v for _, v in verdicts), (verdicts, r)
+
+
+@pytest.mark.parametrize("path", SCN_PRIOR, ids=_name)
+def test_prior_program_equals_the_prior_closure(path):
+    """make_prior's program (what the device evaluates, vlr_prior_prog) against its closure (the
+    restated Prior::calc_prob recursion the oracle calls) on random allele-frequency vectors."""
+    from libprosic_b200 import grammar, prior as prior_mod
+    tc = F.load_fixture(path)
+    g = grammar.Scenario(tc["scenario_yaml"])
+    variant = F.make_variant(tc, 96)
+    f, prog = prior_mod.make_prior(g, tc["contig"], variant["kind"], want_program=True)
+    rng = np.random.default_rng(3)
+    ns = len(prog["kind"])
+    n_finite = 0
+    for _ in range(4000):
+        afs = [float(rng.choice([0.0, 0.5, 1.0, rng.random(), 0.00005, 0.25]))for _ in range(ns)]
+        a, b = f(afs), prior_mod.eval_program(prog, afs)
+        assert (a == b) or abs(a - b) <= 1e-9 * max(1.0, abs(a)), (afs, a, b)
+        n_finite += np.isfinite(a)
+    assert n_finite > 3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", SCN_PRIOR, ids=_name)
+def test_scenario_testcases_with_somatic_priors_hold_on_the_gpu(ctx, path):
+    """The same testcases through the CUDA kernels: the prior is evaluated on the device as a program
+    at every leaf (tree paths bind Ranges, so no table over the leaves exists)."""
+    from _oracle_backend import OracleBackend
+    got = F.run_scenario_testcase(path, F.GpuBackend(ctx))
+    want = F.run_scenario_testcase(path, OracleBackend())
+    assert got["n_obs"] == want["n_obs"] and got["af"] == want["af"], (got, want)
+    for k, w in want.items():
+        if k.startswith("PROB_"):
+            g = got[k]
+            assert (np.isinf(g) and np.isinf(w)) or abs(g - w) <= 2e-5 * max(1.0, abs(w)), (k, g, w)
+    assert all(v for _, v in F.check_expectations(got))

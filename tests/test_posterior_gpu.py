@@ -27,7 +27,7 @@ def _oracle_run(oracle, scn, cols, cat, off, sites):
     for s in sites:
         pv = [oracle.PileupView(cols, cat, int(off[s * ns + k]), int(off[s * ns + k + 1]))
               for k in range(ns)]
-        r = oracle.model_compute(spec, pv)
+        r = oracle.model_compute(spec, pv, prior=scn.get("prior_fn"))
         r["map_bias_cfg"] = np.array([spec.flat_bias_idx[b] if b >= 0 else -1 for b in r["map_bias"]])
         out.append(r)
     return out
@@ -383,5 +383,51 @@ def test_random_models(ctx, oracle, seed):
     scn = _random_scenario(rng, ns)
     depths = [int(rng.choice([3, 12, 30, 70])) for _ in range(ns)]
     cols, cat, off, _ = synth.make_pileups(40, depths, seed=seed, kind=str(rng.choice(["snv", "indel"])),
+                                           ragged=bool(rng.random() < 0.5), artifact_frac=0.2)
+    _check(ctx, oracle, scn, cols, cat, off)
+
+
+def _random_prior_program(rng, ns):
+    """A random vlr_prior_prog (dict form): uniform / somatic / germline samples, somatic terms of
+    every kind, a random germline table with some impossible count vectors."""
+    kind, ploidy, som_kind, parent, ln_rate, som_zero, uni = [], [], [], [], [], [], []
+    for s in range(ns):
+        k = int(rng.choice([0, 1, 1, 2]))
+        kind.append(k)
+        ploidy.append(-1 if k == 0 and rng.random() < 0.5 else int(rng.choice([1, 2, 2, 3])))
+        uni.append([(1.0, 0.0, 1.0, float(rng.random() < 0.3), 0.0)] if k == 0 else [])
+        sk = 0 if k == 2 else int(rng.choice([0, 1, 1, 2, 3])) if ns > 1 else int(rng.choice([0, 1]))
+        if k == 0:
+            sk = 0
+        som_kind.append(sk)
+        parent.append(int((s + 1 + rng.integers(0, max(1, ns - 1))) % ns) if sk >= 2 else -1)
+        ln_rate.append(float(np.log(rng.choice([1e-10, 1e-7, 1e-4]))))
+        som_zero.append(float(-rng.random() * 1e-3))
+    n_germ = 1
+    for s in range(ns):
+        n_germ *= 1 if (kind[s] == 0 or ploidy[s] <= 0) else ploidy[s] + 1
+    germ_ln = (-20.0 * rng.random(n_germ)).tolist()
+    for k in rng.choice(n_germ, n_germ // 4, replace=False):
+        germ_ln[int(k)] = -np.inf
+    return dict(kind=kind, ploidy=ploidy, som_kind=som_kind, parent=parent, ln_rate=ln_rate, som_zero=som_zero,
+                ln_genome_size=float(np.log(3.5e9)), uni=uni, germ_ln=germ_ln)
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_models_with_prior_programs_on_ranges(ctx, oracle, seed):
+    """Prior::compute on the device for universes with Ranges (vlr_prior_prog): random models whose
+    tree paths bind Ranges and Sets, random prior programs (somatic mutation terms of every kind,
+    germline tables, uniform samples); the oracle takes the host evaluation of the same program as
+    its prior callback (prior.rs:288-431 restated in libprosic_b200/prior.py)."""
+    from libprosic_b200 import prior as prior_mod
+    rng = np.random.default_rng(5000 + seed)
+    ns = int(rng.integers(1, 5))
+    scn = _random_scenario(rng, ns)
+    scn["resolution"] = [int(rng.choice([5, 9, 20])) for _ in range(ns)]
+    prog = _random_prior_program(rng, ns)
+    scn["prior_prog"] = prog
+    scn["prior_fn"] = lambda afs: prior_mod.eval_program(prog, list(afs))
+    depths = [int(rng.choice([3, 12, 30])) for _ in range(ns)]
+    cols, cat, off, _ = synth.make_pileups(12, depths, seed=seed, kind=str(rng.choice(["snv", "indel"])),
                                            ragged=bool(rng.random() < 0.5), artifact_frac=0.2)
     _check(ctx, oracle, scn, cols, cat, off)
