@@ -794,6 +794,7 @@ int vlr_allele_support_batch(vlr_ctx *ctx, int64_t n_regions, const int32_t *reg
         rc = pairhmm_literal_dev(ctx, n_slots, d_hap - hap_lo, nullptr, d_ws, d_wl, d_rb - rd_lo, d_rq - rd_lo, d_roff,
                                  nullptr, d_slot_read, d_med, sa.lit_list, sa.lit_count, gap, flags, max_lx, d_sp);
         if (rc != VLR_OK) return rc;
+        lap("near ties", true);
     }
     support_epilogue_kernel<false><<<grid, 128, 0, st>>>(sa);
     VLR_LAUNCH_CHECK(ctx);
@@ -808,6 +809,11 @@ int vlr_allele_support_batch(vlr_ctx *ctx, int64_t n_regions, const int32_t *reg
     if (out_indel_ops) VLR_CUDA(ctx, D2H(out_indel_ops, d_io, (size_t)n_regions * kMaxIndelOps));
     VLR_CUDA(ctx, cudaStreamSynchronize(st));
     lap("epilogue+d2h", false);
+    if (trace && !fast) {
+        int32_t n_lit = 0;
+        cudaMemcpy(&n_lit, (const int32_t *)D(S_LIT, 64), 4, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[vlr trace] allele_support literal log-space slots: %d of %lld\n", n_lit, (long long)n_slots);
+    }
     return VLR_OK;
 }
 

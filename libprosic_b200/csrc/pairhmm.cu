@@ -544,6 +544,12 @@ int vlr_pairhmm_batch(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *hap_bytes,
     }
     VLR_CUDA(ctx, cudaMemcpyAsync(out_lnprob, d_out, (size_t)n_pairs * 8, cudaMemcpyDeviceToHost, st));
     VLR_CUDA(ctx, cudaStreamSynchronize(st));
+    if (getenv("VLR_TRACE") && !literal) {  // how many pairs took the slower kernels
+        int32_t cnt[kCntTotal];
+        if (cudaMemcpy(cnt, d_ws, sizeof(cnt), cudaMemcpyDeviceToHost) == cudaSuccess)
+            fprintf(stderr, "[vlr trace] pairhmm %lld pairs: exact-decision / generic kernel %d, log-space pass %d, long %d\n",
+                    (long long)n_pairs, cnt[kCntGen], cnt[kCntFb], cnt[kCntCount + 7]);
+    }
     return VLR_OK;
 }
 

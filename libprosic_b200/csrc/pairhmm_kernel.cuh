@@ -135,8 +135,19 @@ struct Lin {  // scaled linear space
     }
     // sum over the three predecessors of the M state (SCALED: dM already carries t_mm).
     // APPROX: 0 = exact sum, 1 = two-way, 2 = three-way ln_sum3_exp_approx (see vlr_gpu.h flags).
+    __device__ static double sum3_exact3(double a, double b, double c) {
+        const double kT = 4.5399929762484854e-05;
+        const bool bc = b >= c;
+        const double hi1 = bc ? b : c, lo1 = bc ? c : b;
+        const bool ah = a >= hi1;
+        const double p0 = ah ? a : hi1, m = ah ? hi1 : a;
+        const bool ml = m >= lo1;
+        const double p1 = ml ? m : lo1, p2 = ml ? lo1 : m;
+        const double t2 = p2 >= p1 * kT ? p1 + p2 : p1;
+        return p1 >= p0 * kT ? p0 + t2 : p0;
+    }
     template <int APPROX, bool EXT, bool SCALED = false>
-    __device__ static double sum3(const HmmConsts &k, double dM, double dX, double dY) {
+    __device__ static double sum3(const HmmConsts &k, double dM, double dX, double dY, unsigned &trk) {
         if (APPROX == 1) {
             // two-way rule: return the maximum alone if the second largest term is
             // more than e^-10 below it, else the exact sum.  "second < max*e^-10" <=> exactly one of
@@ -166,18 +177,54 @@ struct Lin {  // scaled linear space
                 "}" : "=d"(r) : "d"(a), "d"(b), "d"(c), "d"(s));
             return r;
         }
-        if (APPROX == 2) {
-            // three-way rule: sorted p0 >= p1 >= p2; p1 < p0*e^-10 -> p0; else p2 < p1*e^-10 ->
-            // p0 + p1; else all three.  Exact decisions on the fp64 values.
+        if (APPROX == 3) {
+            // three-way rule, exact decisions on the fp64 values: sorted p0 >= p1 >= p2;
+            // p1 < p0*e^-10 -> p0; else p2 < p1*e^-10 -> p0 + p1; else all three
             const double a = SCALED ? dM : k.t_mm * dM;
             const double b = EXT ? k.t_xm * dX : dX;
             const double c = EXT ? k.t_ym * dY : dY;
-            const double hi1 = fmax(b, c), lo1 = fmin(b, c);
-            const double p0 = fmax(a, hi1), m = fmin(a, hi1);
-            const double p1 = fmax(m, lo1), p2 = fmin(m, lo1);
-            const double kT = 4.5399929762484854e-05;  // e^-10 (0x3F07CD79B5647C9B)
-            const double t2 = p2 >= p1 * kT ? p1 + p2 : p1;
-            return p1 >= p0 * kT ? p0 + t2 : p0;
+            return sum3_exact3(a, b, c);
+        }
+        if (APPROX == 2 || APPROX == 4) {
+            // three-way rule, decided on the HIGH WORDS of the terms (non-negative doubles order like
+            // their bit patterns; the ALU pipe is idle next to the fp64 pipe): every term whose high
+            // word reaches hi(e^-10 * max) is "in level 1", the smallest of those sets the second
+            // threshold.  A high word within 3 units of a threshold cannot be decided without the
+            // low words: `trk` keeps the closest approach, and the caller re-evaluates with the
+            // exact rule -- the whole pair (APPROX == 2: pairs are short, the fallback kernel is the
+            // exact APPROX == 3 instantiation) or this cell after a warp vote (APPROX == 4).
+            const double a = SCALED ? dM : k.t_mm * dM;
+            const double b = EXT ? k.t_xm * dX : dX;
+            const double c = EXT ? k.t_ym * dY : dY;
+            const int ha = __double2hiint(a), hb = __double2hiint(b), hc = __double2hiint(c);
+            const double kT = 4.5399929762484854e-05;               // e^-10 (0x3F07CD79B5647C9B)
+            // Cells whose largest term is below 2^-960 of the scale cannot move the result (a pair is
+            // only valid above 2^-940, a cell contributes at most its own value, and a wrong decision
+            // changes it by e^-10 relative): they never raise the flag.  Every pair has a zone where
+            // values decay through the tiny and subnormal range towards zero; there the high words
+            // are too coarse to decide anything.
+            const int kLive = 0x03F00000;                           // high word of 2^-960
+            const int k0 = max(ha, max(hb, hc));
+            const int t0 = __double2hiint(__hiloint2double(k0, 0) * kT);
+            const unsigned ua = (unsigned)(ha - t0), ub = (unsigned)(hb - t0), uc = (unsigned)(hc - t0);
+            const unsigned um = min(ua, min(ub, uc));
+            const int t1 = __double2hiint(__hiloint2double((int)um + t0, 0) * kT);
+            const int va = ha - t1, vb = hb - t1, vc = hc - t1;
+            const unsigned vm = min((unsigned)va, min((unsigned)vb, (unsigned)vc));
+            // excluded terms are cleared by zeroing their HIGH word (what is left of the low word is a
+            // subnormal below 2^-1042, far under every threshold of this kernel).  The mask arithmetic
+            // (sign of v by a high multiply, then hi + hi * sign) runs on the FMA pipe, which idles
+            // next to the fp64 and ALU pipes that bound this kernel.
+            const double a2 = __hiloint2double(ha + ha * __mulhi(va, 2), __double2loint(a));
+            const double b2 = __hiloint2double(hb + hb * __mulhi(vb, 2), __double2loint(b));
+            const double c2 = __hiloint2double(hc + hc * __mulhi(vc, 2), __double2loint(c));
+            double r = a2 + (b2 + c2);
+            if (APPROX == 4) {
+                if (__any_sync(0xffffffffu, k0 >= kLive && min(um, vm) <= 3u)) r = sum3_exact3(a, b, c);
+            } else {
+                if (k0 >= kLive) trk = min(trk, min(um, vm));
+            }
+            return r;
         }
         if (SCALED) return EXT ? fma(k.t_ym, dY, fma(k.t_xm, dX, dM)) : dM + (dX + dY);
         if (EXT) return fma(k.t_ym, dY, fma(k.t_xm, dX, k.t_mm * dM));
@@ -197,14 +244,14 @@ struct Log {  // natural-log space, the arithmetic of the reference (CUDA libm)
         return ln_add_exp_d(a + b, c + d);
     }
     template <int APPROX, bool EXT, bool SCALED = false>
-    __device__ static double sum3(const HmmConsts &k, double dM, double dX, double dY) {
+    __device__ static double sum3(const HmmConsts &k, double dM, double dX, double dY, unsigned &) {
         double p0 = k.t_mm + dM, p1 = k.t_xm + dX, p2 = k.t_ym + dY, t;
         if (APPROX) {
             if (p1 < p2) { t = p1; p1 = p2; p2 = t; }
             if (p1 > p0) { t = p1; p1 = p0; p0 = t; }
             if (p2 > p1) { t = p2; p2 = p1; p1 = t; }
             if (p0 - p1 > 10.0) return p0;
-            if (APPROX == 2 && p1 - p2 > 10.0) return ln_add_exp_d(p0, p1);
+            if (APPROX >= 2 && p1 - p2 > 10.0) return ln_add_exp_d(p0, p1);
         } else {
             // ln_sum_exp over the slice (M, X, Y): the first maximum leads, the others follow in order
             if (p2 > p0 && p2 > p1) { t = p2; p2 = p1; p1 = p0; p0 = t; }
@@ -234,14 +281,14 @@ struct LogLit {
         return dm::ln_add_exp(dm::add(a, b), dm::add(c, d));
     }
     template <int APPROX, bool EXT, bool SCALED = false>
-    __device__ static double sum3(const HmmConsts &k, double dM, double dX, double dY) {
+    __device__ static double sum3(const HmmConsts &k, double dM, double dX, double dY, unsigned &) {
         double p0 = dm::add(k.t_mm, dM), p1 = dm::add(k.t_xm, dX), p2 = dm::add(k.t_ym, dY), t;
         if (APPROX) {
             if (p1 < p2) { t = p1; p1 = p2; p2 = t; }
             if (p1 > p0) { t = p1; p1 = p0; p0 = t; }
             if (p2 > p1) { t = p2; p2 = p1; p1 = t; }
             if (dm::sub(p0, p1) > 10.0) return p0;
-            if (APPROX == 2 && dm::sub(p1, p2) > 10.0) return dm::ln_add_exp(p0, p1);
+            if (APPROX >= 2 && dm::sub(p1, p2) > 10.0) return dm::ln_add_exp(p0, p1);
         } else {
             if (p2 > p0 && p2 > p1) { t = p2; p2 = p1; p1 = p0; p0 = t; }
             else if (p1 > p0) { t = p1; p1 = p0; p0 = t; }
@@ -273,6 +320,7 @@ struct PairState {
     double acc, acc2;                      // free-end sums (scaled state: M' and X + Y apart)
     double acc3;                           // literal variant: (acc, acc2, acc3) = last row (M, X, Y) of this column
     double one0;                           // lane 0: start mass of the row-0 boundary; else 0
+    unsigned trk;                          // closest approach of a high word to a threshold (sum3, APPROX == 2)
 };
 
 // Ring of haplotype bytes: two 256-byte slots filled by TMA; `pos` is the ring position
@@ -353,7 +401,7 @@ __device__ __forceinline__ void hmm_step(PairState<R> &s, const HmmConsts &c, co
             match = xb == s.rb[r];
             e = match ? s.pm[r] : s.pmm[r];
         }
-        double nM = A::mul(e, A::template sum3<APPROX, EXT, LUT>(c, diagM, diagX, diagY));
+        double nM = A::mul(e, A::template sum3<APPROX, EXT, LUT>(c, diagM, diagX, diagY, s.trk));
         double nX = A::template dot2<EXT>(LUT ? c.t_gy_s : c.t_gy, s.M[r], c.t_gye, s.X[r]);
         double nY;
         if (A::kLit)  // emit_y + ln_add_exp(gap_x + fm[curr][j], gap_x_ext + fy[curr][j]); cyo = ln eps
@@ -605,6 +653,7 @@ __global__ void __launch_bounds__(kWarps * 32, Occ<R>::kMinBlocks) pairhmm_kerne
         s.acc = A::zero();
         s.acc2 = A::zero();
         s.acc3 = A::zero();
+        s.trk = 0xffffffffu;
         h.last_lane = last_lane;
         if (A::kLit) {
             if (lx > g.lit_stride) {  // the caller sized the workspace for shorter windows
@@ -659,6 +708,14 @@ __global__ void __launch_bounds__(kWarps * 32, Occ<R>::kMinBlocks) pairhmm_kerne
             }
             __syncwarp();
             continue;
+        }
+        if (APPROX == 2 && !A::kLog) {
+            // a decision of the three-way rule came within reach of its threshold: the pair is
+            // re-evaluated by the exact-decision kernel (generic list)
+            if (__reduce_min_sync(0xffffffffu, s.trk) <= 3u) {
+                if (lane == 0) g.gen_list[atomicAdd(g.gen_count, 1)] = pair;
+                continue;
+            }
         }
         // ---- result lives in lane last_lane
         double acc = __shfl_sync(0xffffffffu, s.acc, last_lane);
@@ -885,12 +942,15 @@ __global__ void __launch_bounds__(kWarps * 32, 2) pairhmm_long_kernel(HmmArgs g)
                     uY = in ? s_bnd[warp][2][t & 31] : A::zero();
                 }
                 double diagM = s.dM, diagX = s.dX, diagY = s.dY, upM = uM, upY = uY;
+                unsigned trk_unused = 0;
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     double e;
                     if (LUT) e = lcol[r * (kLutCols * 32)];
                     else e = xb == s.rb[r] ? s.pm[r] : s.pmm[r];
-                    const double nM = A::mul(e, A::template sum3<APPROX, EXT, LUT>(c, diagM, diagX, diagY));
+                    // (three-way rule: a long pair has ~1e8 cells, so a doubtful decision is settled cell by
+                    // cell after a warp vote instead of re-evaluating the pair)
+                    const double nM = A::mul(e, A::template sum3<APPROX == 2 ? 4 : APPROX, EXT, LUT>(c, diagM, diagX, diagY, trk_unused));
                     const double nX = A::template dot2<EXT>(LUT ? c.t_gy_s : c.t_gy, s.M[r], c.t_gye, s.X[r]);
                     const double nY = A::template dot2<EXT>(s.cyo[r], upM, s.cye[r], upY);
                     diagM = s.M[r]; diagX = s.X[r]; diagY = s.Y[r];
@@ -1018,7 +1078,7 @@ inline int blocks_per_sm(int dflt) {
     template <>                                                                                   \
     cudaError_t launch_pairhmm_generic<BANDED, APPROX>(const HmmArgs &a, int sm_count,            \
                                                        cudaStream_t st) {                         \
-        pairhmm_kernel<8, BANDED, APPROX, true, false, Lin>                                       \
+        pairhmm_kernel<8, BANDED, (APPROX == 2 ? 3 : APPROX), true, false, Lin>                   \
             <<<sm_count * Occ<8>::kMinBlocks, kWarps * 32, 0, st>>>(a);                           \
         return cudaGetLastError();                                                                \
     }                                                                                             \
