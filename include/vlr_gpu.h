@@ -383,6 +383,22 @@ int vlr_call_records(vlr_ctx *ctx, int64_t n_sites, int32_t n_events, int32_t n_
                      const double *marginal, const double *map_af, const double *prob_mapping,
                      const int64_t *obs_off, float *out_prob, float *out_af, int32_t *out_dp);
 
+/* OBS / SOBS FORMAT strings and bias flag characters of the call record (calling/variants/mod.rs:
+ * 147-260, 335-392; utils/mod.rs:101-146).  vlr_obs_codes derives, on the device, the packed
+ * 7-character code of every observation row (host arrays in, host array out):
+ *   bits 0-2 Kass-Raftery letter of exp(prob_alt - prob_ref) (0 N, 1 E, 2 B, 3 P, 4 S, 5 V), bit 3 lower
+ *   case (prob_mapping < ln 0.95), bit 4 paired (p|s), bits 5-6 strand (0 *, 1 -, 2 +), bits 7-8 read
+ *   orientation (0 >, 1 <, 2 *, 3 !), bit 9 read position (0 ^, 1 *), bit 10 softclip ($|.), bits 11-12
+ *   indel operations (0 *, 1 #, 2 .)
+ * vlr_obs_cigar (host, no context) formats the generalized CIGAR of one (site, sample) pileup from its
+ * codes: simple = 0 -> OBS, 1 -> SOBS; returns the length (out is NUL terminated; "." for no rows) or a
+ * negative error.  Most common first, E.. after the others, N.. last; equal counts in code order (the
+ * reference's order among equal counts is a HashMap's).  vlr_bias_chars: SB ROB RPB SCB DIB. */
+int vlr_obs_codes(vlr_ctx *ctx, int64_t n_rows, const double *prob_alt, const double *prob_ref,
+                  const double *prob_mapping, const uint16_t *cat, uint16_t *out_code);
+int64_t vlr_obs_cigar(const uint16_t *codes, int64_t n, int simple, char *out, int64_t capacity);
+int vlr_bias_chars(const vlr_biases *biases, char out[5]);
+
 /* ---- observation wire format: the INFO fields between `preprocess` and `call` -------------
  * Replaces read_observations / write_observations (src/calling/variants/preprocessing/mod.rs:
  * 452-598, OBSERVATION_FORMAT_VERSION "8"; format 7 = the same without INDEL_OPERATIONS) and

@@ -91,7 +91,8 @@ EXPORTS = [
     "vlr_version", "vlr_ctx_create", "vlr_ctx_destroy", "vlr_last_error", "vlr_ctx_set_stream",
     "vlr_ctx_synchronize", "vlr_ctx_launch_count", "vlr_ref_math", "vlr_pairhmm_batch",
     "vlr_pairhmm_workspace_bytes", "vlr_pairhmm_batch_dev", "vlr_measure_fp64_peak",
-    "vlr_besthit_batch", "vlr_pathhmm_batch", "vlr_allele_support_batch", "vlr_likelihood_batch", "vlr_call_records", "vlr_model_leaves", "vlr_obs_decode", "vlr_obs_encode", "vlr_obs_encoded_bound", "vlr_posterior_batch", "vlr_posterior_batch_f32", "vlr_posterior_batch_dev",
+    "vlr_besthit_batch", "vlr_pathhmm_batch", "vlr_allele_support_batch", "vlr_likelihood_batch", "vlr_call_records",
+    "vlr_obs_codes", "vlr_obs_cigar", "vlr_bias_chars", "vlr_model_leaves", "vlr_obs_decode", "vlr_obs_encode", "vlr_obs_encoded_bound", "vlr_posterior_batch", "vlr_posterior_batch_f32", "vlr_posterior_batch_dev",
 ]
 
 _lib = None
@@ -132,6 +133,10 @@ def load():
                                            C.POINTER(GapParams), u32, vp, vp, vp, vp, vp, vp, vp, vp]
     L.vlr_likelihood_batch.argtypes = [vp, i64, i32, C.POINTER(ObsColumns), vp, vp, i32, vp, i64, vp]
     L.vlr_call_records.argtypes = [vp, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.vlr_obs_codes.argtypes = [vp, i64, vp, vp, vp, vp, vp]
+    L.vlr_obs_cigar.argtypes = [vp, i64, C.c_int, vp, i64]
+    L.vlr_obs_cigar.restype = i64
+    L.vlr_bias_chars.argtypes = [vp, vp]
     L.vlr_obs_decode.argtypes = [vp, vp, i64, vp, vp, vp]
     L.vlr_obs_encode.argtypes = [i64, vp, vp, vp, i64, vp]
     L.vlr_obs_encoded_bound.argtypes = [i64]

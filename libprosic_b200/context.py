@@ -314,6 +314,35 @@ class Context:
         names = [e["name"] for e, a in zip(scn["events"], is_art) if not a] + ["artifact"]
         return dict(prob=prob, af=af, dp=dp, names=names)
 
+    def call_obs_strings(self, cols, cat, obs_off):
+        """OBS and SOBS strings of every (site, sample) pileup: list of (obs, sobs) in obs_off order."""
+        pa = np.ascontiguousarray(cols["prob_alt"], np.float64)
+        pr = np.ascontiguousarray(cols["prob_ref"], np.float64)
+        pm = np.ascontiguousarray(cols["prob_mapping"], np.float64)
+        ct = np.ascontiguousarray(cat, np.uint16)
+        codes = np.empty(len(ct), np.uint16)
+        self._check(self.lib.vlr_obs_codes(self.h, len(ct), _ptr(pa), _ptr(pr), _ptr(pm), _ptr(ct), _ptr(codes)))
+        out = []
+        buf = C.create_string_buffer(1 << 16)
+        for k in range(len(obs_off) - 1):
+            seg = np.ascontiguousarray(codes[int(obs_off[k]):int(obs_off[k + 1])])
+            pair = []
+            for simple in (0, 1):
+                n = self.lib.vlr_obs_cigar(_ptr(seg) if len(seg) else None, len(seg), simple, buf, len(buf))
+                if n < 0:
+                    raise _ffi.VlrError(int(n), "vlr_obs_cigar")
+                pair.append(buf.value.decode())
+            out.append(tuple(pair))
+        return out
+
+    def bias_chars(self, b):
+        """SB ROB RPB SCB DIB flag characters of a scenario bias dict."""
+        from ._ffi import Biases
+        bb = Biases(b["strand"], b["orientation"], b["read_position"], b["softclip"], b["divindel"], 0, b["min_other_rate"])
+        out = C.create_string_buffer(5)
+        self._check(self.lib.vlr_bias_chars(C.byref(bb), out))
+        return out.raw.decode()
+
     def model_leaves(self, scn):
         """Leaf AF vectors of a set-only scenario: (event index per leaf, afs[n_leaves, n_samples])."""
         keep = []

@@ -7,6 +7,10 @@
 //   AF            = MAP allele frequency as f32 (mod.rs:185)
 //   DP            = round(exp(ln_sum_exp(prob_mapping))) per sample (observation.rs:31-36, mod.rs:187)
 #include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <utility>
 
 #include "common.cuh"
 
@@ -138,5 +142,132 @@ extern "C" int vlr_call_records(vlr_ctx *ctx, int64_t n_sites, int32_t n_events,
     VLR_CUDA(ctx, cudaMemcpyAsync(out_af, d_oaf, (size_t)n_sites * n_samples * 4, cudaMemcpyDeviceToHost, st));
     VLR_CUDA(ctx, cudaMemcpyAsync(out_dp, d_odp, (size_t)n_sites * n_samples * 4, cudaMemcpyDeviceToHost, st));
     VLR_CUDA(ctx, cudaStreamSynchronize(st));
+    return VLR_OK;
+}
+
+// ---------------------------------------------------------------- OBS / SOBS strings, bias flags
+// The per-sample OBS and SOBS FORMAT strings of the call record (src/calling/variants/mod.rs:186-260)
+// are "generalized CIGAR" strings over a 7-character code per observation (utils/mod.rs:101-146):
+//   Kass-Raftery letter of the alt-vs-ref Bayes factor (N E B P S V; lower case if
+//   prob_mapping < ln 0.95), p|s (paired), strand * - +, read orientation > < * !, read position ^ *,
+//   softclip $ ., indel operations * # .
+// The device derives the packed code of every observation (one exp per row, fused with nothing else
+// worth a kernel: it is one pass over three columns); counting and formatting is host work.
+namespace vlr {
+
+// packed code: letter (0 N, 1 E, 2 B, 3 P, 4 S, 5 V) | lower << 3 | paired << 4 | strand (0 *, 1 -, 2 +,
+// 3 invalid) << 5 | orientation (0 >, 1 <, 2 *, 3 !) << 7 | read position (0 ^, 1 *) << 9 |
+// softclip << 10 | indel (0 *, 1 #, 2 .) << 11
+__host__ __device__ static inline uint16_t obs_code_of(double prob_alt, double prob_ref, double prob_mapping,
+                                                        unsigned cat, double bf) {
+    // BayesFactor::evidence_kass_raftery (bio 0.37) + bayes_factor_to_letter
+    int letter;
+    if (bf <= 1.0) {
+        const double d = fabs(bf - 1.0);  // approx::relative_eq!(bf, 1.0)
+        letter = (bf == 1.0 || d <= 2.220446049250313e-16 || d <= fmax(fabs(bf), 1.0) * 2.220446049250313e-16) ? 1 : 0;
+    } else if (bf <= 3.0) letter = 2;
+    else if (bf <= 20.0) letter = 3;
+    else if (bf <= 150.0) letter = 4;
+    else letter = 5;
+    (void)prob_alt; (void)prob_ref;
+    const unsigned lower = prob_mapping < -0.05129329438755058 ? 1u : 0u;  // ln 0.95
+    const unsigned st = VLR_CAT_STRAND(cat), orr = VLR_CAT_ORIENT(cat);
+    const unsigned strand = st == 2 ? 0u : (st == 1 ? 1u : (st == 0 ? 2u : 3u));
+    const unsigned orient = orr == 0 ? 0u : (orr == 1 ? 1u : (orr == 8 ? 2u : 3u));
+    return (uint16_t)(letter | (lower << 3) | (VLR_CAT_PAIRED(cat) << 4) | (strand << 5) | (orient << 7) |
+                      (VLR_CAT_READPOS(cat) << 9) | (VLR_CAT_SOFTCLIP(cat) << 10) | (VLR_CAT_INDEL(cat) << 11));
+}
+
+__global__ void obs_codes_kernel(int64_t n, const double *prob_alt, const double *prob_ref, const double *prob_mapping,
+                                 const uint16_t *cat, uint16_t *out) {
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+        out[k] = obs_code_of(prob_alt[k], prob_ref[k], prob_mapping[k], cat[k], exp(prob_alt[k] - prob_ref[k]));
+}
+
+static int code_text(uint16_t c, int simple, char *o) {
+    const char L[6] = {'N', 'E', 'B', 'P', 'S', 'V'};
+    char l = L[(c & 7) < 6 ? (c & 7) : 0];
+    if ((c >> 3) & 1) l = (char)(l + 32);
+    o[0] = l;
+    if (simple) return 1;
+    o[1] = ((c >> 4) & 1) ? 'p' : 's';
+    o[2] = "*-+?"[(c >> 5) & 3];
+    o[3] = "><*!"[(c >> 7) & 3];
+    o[4] = ((c >> 9) & 1) ? '*' : '^';
+    o[5] = ((c >> 10) & 1) ? '$' : '.';
+    o[6] = "*#.?"[(c >> 11) & 3];
+    return 7;
+}
+
+}  // namespace vlr
+
+extern "C" int vlr_obs_codes(vlr_ctx *ctx, int64_t n_rows, const double *prob_alt, const double *prob_ref,
+                             const double *prob_mapping, const uint16_t *cat, uint16_t *out_code) {
+    if (!ctx) return VLR_ERR_INVALID;
+    if (n_rows < 0 || (n_rows > 0 && (!prob_alt || !prob_ref || !prob_mapping || !cat || !out_code)))
+        return set_err(ctx, VLR_ERR_INVALID, "bad argument");
+    if (n_rows == 0) return VLR_OK;
+    VLR_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    enum { S_A = 94, S_R, S_M, S_C, S_O };
+    double *d_a = (double *)dev_scratch(ctx, S_A, (size_t)n_rows * 8), *d_r = (double *)dev_scratch(ctx, S_R, (size_t)n_rows * 8);
+    double *d_m = (double *)dev_scratch(ctx, S_M, (size_t)n_rows * 8);
+    uint16_t *d_c = (uint16_t *)dev_scratch(ctx, S_C, (size_t)n_rows * 2), *d_o = (uint16_t *)dev_scratch(ctx, S_O, (size_t)n_rows * 2);
+    if (!d_a || !d_r || !d_m || !d_c || !d_o) return set_err(ctx, VLR_ERR_NOMEM, "scratch allocation failed");
+    VLR_CUDA(ctx, cudaMemcpyAsync(d_a, prob_alt, (size_t)n_rows * 8, cudaMemcpyHostToDevice, st));
+    VLR_CUDA(ctx, cudaMemcpyAsync(d_r, prob_ref, (size_t)n_rows * 8, cudaMemcpyHostToDevice, st));
+    VLR_CUDA(ctx, cudaMemcpyAsync(d_m, prob_mapping, (size_t)n_rows * 8, cudaMemcpyHostToDevice, st));
+    VLR_CUDA(ctx, cudaMemcpyAsync(d_c, cat, (size_t)n_rows * 2, cudaMemcpyHostToDevice, st));
+    const int grid = (int)std::min<int64_t>((n_rows + 255) / 256, (int64_t)ctx->sm_count * 8);
+    obs_codes_kernel<<<grid, 256, 0, st>>>(n_rows, d_a, d_r, d_m, d_c, d_o);
+    VLR_LAUNCH_CHECK(ctx);
+    VLR_CUDA(ctx, cudaMemcpyAsync(out_code, d_o, (size_t)n_rows * 2, cudaMemcpyDeviceToHost, st));
+    VLR_CUDA(ctx, cudaStreamSynchronize(st));
+    return VLR_OK;
+}
+
+// generalized_cigar(items, keep_order = false, aux_sort): "<count><code>" per distinct code, most
+// common first, codes starting with E after the others and with N last (stable).  The reference's
+// order among equal counts is a HashMap's; this library breaks ties by the packed code.
+extern "C" int64_t vlr_obs_cigar(const uint16_t *codes, int64_t n, int simple, char *out, int64_t capacity) {
+    if (n < 0 || (n > 0 && !codes) || !out || capacity < 2) return VLR_ERR_INVALID;
+    std::vector<std::pair<uint16_t, int64_t>> cnt;  // (code or letter class, count)
+    {
+        std::vector<int64_t> hist(1 << 13, 0);
+        for (int64_t k = 0; k < n; ++k) hist[(simple ? (codes[k] & 15) : codes[k]) & 0x1fff]++;
+        for (int c = 0; c < (1 << 13); ++c) if (hist[c]) cnt.emplace_back((uint16_t)c, hist[c]);
+    }
+    auto klass = [](uint16_t c) { return (c & 7) == 0 && !((c >> 3) & 1) ? 2 : (((c & 7) == 1 && !((c >> 3) & 1)) ? 1 : 0); };
+    std::stable_sort(cnt.begin(), cnt.end(), [](const std::pair<uint16_t, int64_t> &a, const std::pair<uint16_t, int64_t> &b) {
+        return a.second != b.second ? a.second > b.second : a.first < b.first;
+    });
+    std::stable_sort(cnt.begin(), cnt.end(), [&](const std::pair<uint16_t, int64_t> &a, const std::pair<uint16_t, int64_t> &b) {
+        return klass(a.first) < klass(b.first);
+    });
+    int64_t len = 0;
+    if (cnt.empty()) {  // an empty observation list is written as "."
+        out[0] = '.'; out[1] = 0;
+        return 1;
+    }
+    for (const auto &e : cnt) {
+        char buf[40];
+        int m = snprintf(buf, sizeof(buf), "%lld", (long long)e.second);
+        m += vlr::code_text(e.first, simple, buf + m);
+        if (len + m + 1 > capacity) return VLR_ERR_INVALID;
+        memcpy(out + len, buf, (size_t)m);
+        len += m;
+    }
+    out[len] = 0;
+    return len;
+}
+
+// SB ROB RPB SCB DIB flag characters of a bias configuration (calling/variants/mod.rs:147-183)
+extern "C" int vlr_bias_chars(const vlr_biases *b, char out[5]) {
+    if (!b || !out) return VLR_ERR_INVALID;
+    out[0] = b->strand == 1 ? '+' : (b->strand == 2 ? '-' : '.');
+    out[1] = b->orientation == 1 ? '>' : (b->orientation == 2 ? '<' : '.');
+    out[2] = b->read_position ? '^' : '.';
+    out[3] = b->softclip ? '$' : '.';
+    out[4] = b->divindel ? '#' : '.';
     return VLR_OK;
 }
