@@ -133,10 +133,11 @@ int vlr_measure_fp64_peak(vlr_ctx *ctx, double *out_tflops);
  * out_dist = EditDistanceHit::dist (-1: no hit), out_start = alignments[0].start,
  * out_end = min(alignments.last().start + len_y + dist, len_x), out_n_best = number of best end
  * positions; best_indel_operations (131-144): their count in out_n_indel_ops (nullable) and the
- * operations RUN-LENGTH ENCODED in out_indel_ops[k*VLR_MAX_INDEL_OPS ..] (nullable): byte pairs
- * (op, run length <= 255) in forward order, op 2 = Del, 3 = Ins, zero padded -- 16 runs per alignment,
- * however long the runs (a 60-base insertion is one pair).  An alignment with more runs has its tail
- * uncounted: sum of the run lengths < out_n_indel_ops tells.  Read windows up to 256 rows. ------ */
+ * operations RUN-LENGTH ENCODED in out_indel_ops[k*VLR_MAX_INDEL_OPS ..] (nullable): one byte per run in
+ * forward order, bit 7 = Ins (else Del), bits 0-6 = run length (1..127; a longer run continues in the next
+ * byte), zero padded -- 32 runs per alignment, however long the runs (a 60-base insertion is one byte).
+ * An alignment with more runs (an unrelated read) has its tail uncounted: the sum of the run lengths is
+ * then below out_n_indel_ops.  Read windows up to 256 rows. ------ */
 #define VLR_MAX_INDEL_OPS 32
 int vlr_besthit_batch(vlr_ctx *ctx, int64_t n_pairs,
                       const uint8_t *hap_bytes, const int64_t *hap_off, int64_t n_haps,

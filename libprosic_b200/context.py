@@ -40,20 +40,19 @@ def _arr(a, dt):
 
 def expand_indel_runs(runs, n_ops):
     """Decode the run-length encoded best_indel_operations of vlr_besthit_batch /
-    vlr_allele_support_batch (byte pairs (op, run length), include/vlr_gpu.h) into a zero padded
-    matrix [n, max(32, max n_ops)] of operations (2 = Del, 3 = Ins).  Raises if a record overflowed
-    its 16 runs."""
-    runs = np.asarray(runs, np.uint8).reshape(len(n_ops), -1, 2)
-    lens = runs[:, :, 1].astype(np.int64)
+    vlr_allele_support_batch (one byte per run: bit 7 = Ins, bits 0-6 = length; include/vlr_gpu.h)
+    into a zero padded matrix [n, max(32, max n_ops)] of operations (2 = Del, 3 = Ins).  Returns
+    (ops, overflow): overflow[k] marks records whose alignment had more than 32 runs (their decoded
+    prefix is shorter than n_ops[k])."""
+    runs = np.asarray(runs, np.uint8).reshape(len(n_ops), -1)
+    lens = (runs & 0x7f).astype(np.int64)
     tot = lens.sum(axis=1)
-    if (tot != np.asarray(n_ops)).any():
-        k = int(np.argmax(tot != np.asarray(n_ops)))
-        raise NotImplementedError("record %d: more than %d indel runs in one alignment" % (k, runs.shape[1]))
+    n_ops = np.asarray(n_ops)
     width = max(32, int(tot.max()) if len(tot) else 0)
     out = np.zeros((len(n_ops), width), np.uint8)
     for k in np.nonzero(tot)[0]:
-        out[k, :tot[k]] = np.repeat(runs[k, :, 0], lens[k])
-    return out
+        out[k, :tot[k]] = np.repeat(np.where(runs[k] & 0x80, 3, 2).astype(np.uint8), lens[k])
+    return out, tot != n_ops
 
 
 class Context:
@@ -149,7 +148,7 @@ class Context:
             n_reads, _ptr(pair_hap), _ptr(pair_read), _ptr(out["dist"]), _ptr(out["start"]),
             _ptr(out["end"]), _ptr(out["n_best"]), _ptr(out["n_indel_ops"]), _ptr(ops)))
         out["indel_runs"] = ops
-        out["indel_ops"] = expand_indel_runs(ops, out["n_indel_ops"])
+        out["indel_ops"], out["indel_overflow"] = expand_indel_runs(ops, out["n_indel_ops"])
         return out
 
     def pathhmm_batch(self, hap_bytes, hap_off, read_bases, read_quals, read_off, gap,
@@ -203,7 +202,7 @@ class Context:
             _ptr(out["indel_ops"])))
         if decode:  # caller-provided (pinned) buffers keep the run-length encoded records
             out["indel_runs"] = out["indel_ops"]
-            out["indel_ops"] = expand_indel_runs(out["indel_runs"], out["n_indel_ops"])
+            out["indel_ops"], out["indel_overflow"] = expand_indel_runs(out["indel_runs"], out["n_indel_ops"])
         return out
 
     def pairhmm_workspace_bytes(self, n_pairs, max_len_x=0, max_len_y=0):

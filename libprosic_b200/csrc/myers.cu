@@ -28,8 +28,9 @@
 namespace vlr {
 
 constexpr int kMyW = 4;               // 64-bit words per column (pattern <= 256 rows)
-constexpr int kMaxIndelOps = VLR_MAX_INDEL_OPS;   // bytes per output record: kMaxRuns (op, run length) pairs
-constexpr int kMaxRuns = kMaxIndelOps / 2;
+constexpr int kMaxIndelOps = VLR_MAX_INDEL_OPS;   // bytes per output record: one byte per run
+constexpr int kMaxRuns = kMaxIndelOps;
+constexpr int kMaxRunLen = 127;
 
 struct HitOut {
     int32_t dist, start, end, n_best, n_indel;
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(128) besthit_kernel(MyersArgs g) {
         }
         // tracebacks of every best end position (edit_distance.rs:88-97), in increasing position
         int start_first = 0, start_last = 0, best_nindel = 1 << 30, best_nops = 0;
-        uint16_t best_runs[kMaxRuns];  // best_indel_operations, run-length encoded (op << 8 | length), forward order
+        uint8_t best_runs[kMaxRuns];  // best_indel_operations, run-length encoded (Ins << 7 | length), forward order
         const bool want_path = g.out_path != nullptr;
         double best_path = -INFINITY;
         bool have_path = false;
@@ -182,14 +183,16 @@ __global__ void __launch_bounds__(128) besthit_kernel(MyersArgs g) {
                 continue;
             }
             int j = m, i = e, nindel = 0;
-            // indel ops in traceback (reverse) order, run-length encoded: op << 8 | length (<= 255).  An
+            // indel ops in traceback (reverse) order, run-length encoded in one byte per run: bit 7 = Ins
+            // (else Del), bits 0-6 = length (<= 127, longer runs continue in the next byte).  An
             // alignment has a handful of indel runs however long they are (a 40-base insertion is one);
-            // more than kMaxRuns runs leave the tail uncounted, which the host reports as an error.
-            uint16_t runs[kMaxRuns];
+            // more than kMaxRuns runs leave the tail uncounted, which the host can tell from the count.
+            uint8_t runs[kMaxRuns];
             int nruns = 0;
             auto push_op = [&](int o) {
-                if (nruns > 0 && (runs[nruns - 1] >> 8) == o && (runs[nruns - 1] & 0xff) < 255) runs[nruns - 1]++;
-                else if (nruns < kMaxRuns) runs[nruns++] = (uint16_t)((o << 8) | 1);
+                const int tag = o == 3 ? 0x80 : 0;
+                if (nruns > 0 && (runs[nruns - 1] & 0x80) == tag && (runs[nruns - 1] & 0x7f) < kMaxRunLen) runs[nruns - 1]++;
+                else if (nruns < kMaxRuns) runs[nruns++] = (uint8_t)(tag | 1);
             };
             // PathHMM: the walk runs backwards, so the transition INTO the operation found last
             // step (`next`) is added once its predecessor is known; emissions as found
@@ -201,8 +204,9 @@ __global__ void __launch_bounds__(128) besthit_kernel(MyersArgs g) {
                 return prev == 3 ? g.reopen_x : (prev == 2 ? g.close_y + g.gap_x : g.gap_x);
             };
             // D[j][i] of the current cell is carried along; predecessors are evaluated on demand.
-            // Tie-breaking: diagonal first, then Ins, then Del -- calibrated against the reference's
-            // integration tests
+            // Tie-breaking among equally good predecessors (bio's Myers traceback, recollected and
+            // confirmed by the reference's integration tests): a substitution
+            // first, then Ins, then Del, a match last
             // The records of columns i, i-1 live in registers and column i-2 is prefetched while
             // the current step is evaluated: the walk moves left by at most one column per step,
             // so the scratch latency stays off the dependent chain.
@@ -239,14 +243,17 @@ __global__ void __launch_bounds__(128) besthit_kernel(MyersArgs g) {
                     const int pq = j - 1 + poff;  // pattern bytes in aligned 8-byte chunks, reloaded every 8 rows
                     if ((pq >> 3) != pchunk) { pchunk = pq >> 3; pw = p8[pchunk]; }
                     match = (int)((pw >> ((pq & 7) * 8)) & 0xffu) == (dm_cur >> 16);  // pat[j-1] == T[i-1]
-                    const int cost = match ? 0 : 1;
-                    if (ddiag + cost == d) {
+                    if (!match && ddiag + 1 == d) {   // substitution
                         op = 0;
                         d = ddiag;
                     } else {
                         const int dup = dist_from(r_cur, dm_cur & 0xffff, j - 1, m, W);
-                        if (d == dup + 1) { op = 3; d = dup; }
-                        else { op = 2; d -= 1; }  // D[j][i-1] + 1 == D[j][i]
+                        if (d == dup + 1) { op = 3; d = dup; }   // Ins: vertical delta +1
+                        else {
+                            const int dleft = i > 1 ? dist_from(r_left, dm_left & 0xffff, j, m, W) : j;  // D[j][i-1]
+                            if (dleft + 1 == d) { op = 2; d = dleft; }   // Del
+                            else { op = 0; d = ddiag; }                    // match
+                        }
                     }
                 } else {
                     op = 3;  // text exhausted: D[j][0] = j
@@ -298,10 +305,7 @@ __global__ void __launch_bounds__(128) besthit_kernel(MyersArgs g) {
         g.out[k] = res;
         if (want_path) g.out_path[k] = best_path;
         if (g.out_ops)
-            for (int t = 0; t < best_nops; ++t) {
-                g.out_ops[k * kMaxIndelOps + 2 * t] = (uint8_t)(best_runs[t] >> 8);
-                g.out_ops[k * kMaxIndelOps + 2 * t + 1] = (uint8_t)(best_runs[t] & 0xff);
-            }
+            for (int t = 0; t < best_nops; ++t) g.out_ops[k * kMaxIndelOps + t] = best_runs[t];
     }
 }
 

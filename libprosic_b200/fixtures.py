@@ -19,8 +19,8 @@ Record::read_pair_orientation are recollections of rust-htslib 0.36 (SURVEY appe
 
 The two compute stages are injected as callables, so the same glue runs on the GPU context
 (`GpuBackend`) and, in the CPU test-suite, on the oracle; this module never imports the oracle.
-Not restated (outside what the fixtures need): subsampling above max_depth (StdRng stream),
-aux-tag strand / orientation info, breakends, SNV/MNV evidence.
+Breakend groups (replacements, duplications, inversions, BND events) are restated in
+libprosic_b200/breakends.py.  Not restated: aux-tag strand / orientation info, events across contigs.
 """
 import gzip
 import json
@@ -32,7 +32,7 @@ from collections import Counter
 import numpy as np
 import yaml
 
-from . import obs_codec, scenario
+from . import breakends as B, obs_codec, scenario
 
 SEQ_CODE = "=ACMGRSVTWYHKDBN"
 M, I, D, N, S, H, P, EQ, X = range(9)
@@ -65,8 +65,29 @@ def read_bam(path):
         seq = "".join(SEQ_CODE[(raw[k >> 1] >> (4 if k % 2 == 0 else 0)) & 15] for k in range(l_seq)).encode()
         q += (l_seq + 1) // 2
         qual = bytes(data[q:q + l_seq])
+        q += l_seq
+        # aux fields: per-base strand info "SI" and read orientation "RO" of consensus reads
+        # (utils/mod.rs:42-48, observation.rs:142-170); everything else is skipped
+        aux, end = {}, pos + 4 + bs
+        size = {"A": 1, "c": 1, "C": 1, "s": 2, "S": 2, "i": 4, "I": 4, "f": 4}
+        while q + 3 <= end:
+            tag, ty = data[q:q + 2].decode("latin-1"), chr(data[q + 2])
+            q += 3
+            if ty in size:
+                q += size[ty]
+            elif ty in ("Z", "H"):
+                z = data.index(b"\0", q)
+                if ty == "Z" and tag in ("SI", "RO"):
+                    aux[tag] = bytes(data[q:z])
+                q = z + 1
+            elif ty == "B":
+                sub, cnt = chr(data[q]), struct.unpack_from("<i", data, q + 1)[0]
+                q += 5 + cnt * size[sub]
+            else:
+                break
         recs.append(dict(name=name, tid=ref_id, contig=refs[ref_id] if ref_id >= 0 else None, pos=p, mapq=mapq,
-                         flag=flag, cigar=cigar, seq=seq, qual=qual, mtid=nref, mpos=npos))
+                         flag=flag, cigar=cigar, seq=seq, qual=qual, mtid=nref, mpos=npos,
+                         si=aux.get("SI"), ro=aux.get("RO")))
         pos += 4 + bs
     return recs
 
@@ -160,8 +181,32 @@ def overlap(locus, r, consider_clips):
     return None
 
 
+_RO_CODES = {b"F1R2": 0, b"F2R1": 1, b"F1F2": 2, b"F2F1": 3, b"R1R2": 4, b"R2R1": 5, b"R1F2": 6, b"R2F1": 7, b"None": 8}
+
+
+def strand_or(a, b):
+    """Strand |= (observation.rs:105-118): 0 Forward, 1 Reverse, 2 Both, 3 None."""
+    if a == 3:
+        return b
+    if b == 3 or a == b:
+        return a
+    return 2
+
+
+def strand_from_aux(si):
+    """Strand::from_aux (observation.rs:72-92) over a slice of the SI tag."""
+    st = 3
+    for c in si:
+        st = strand_or(st, {43: 0, 45: 1, 42: 2}[c])
+    return st
+
+
 def read_orientation(r):
-    """Record::read_pair_orientation (rust-htslib, recollected) -> bio-types variant index."""
+    """observation.rs:142-170: the RO aux tag of consensus reads, else
+    Record::read_pair_orientation (rust-htslib, recollected) -> bio-types variant index."""
+    if r.get("ro") is not None:
+        parts = r["ro"].split(b",")
+        return 8 if len(parts) != 1 else _RO_CODES[parts[0]]
     f = r["flag"]
     if (f & 1) and not (f & 4) and not (f & 8) and r["tid"] == r["mtid"]:
         if r["pos"] == r["mpos"]:
@@ -247,9 +292,18 @@ def load_testcase(path):
             rec = read_first_bcf_record(cand)
         except AssertionError:   # bgzipped VCF text
             cand = gzip.decompress(cand)
+    all_recs = [rec] if rec is not None else None
     if rec is None:
-        rec = [l for l in cand.decode("latin-1").split("\n") if l and not l.startswith("#")][0].split("\t")
+        all_recs = [l.split("\t") for l in cand.decode("latin-1").split("\n") if l and not l.startswith("#")]
+        rec = all_recs[0]
     info = dict(kv.split("=", 1) for kv in rec[7].split(";") if "=" in kv)
+    # every record of the first record's breakend event (SVTYPE=BND records share an EVENT)
+    event_records = []
+    if info.get("SVTYPE") == "BND" and "EVENT" in info:
+        for r_ in all_recs:
+            i_ = dict(kv.split("=", 1) for kv in r_[7].split(";") if "=" in kv)
+            if i_.get("SVTYPE") == "BND" and i_.get("EVENT") == info["EVENT"]:
+                event_records.append([int(r_[1]) - 1, r_[2], r_[3], r_[4].split(",")[0]])
     samples = {}
     for name, s in y["samples"].items():
         props = json.loads(s["properties"])
@@ -270,7 +324,7 @@ def load_testcase(path):
         scenario_yaml = open(os.path.join(path, y["scenario"])).read()
     return dict(name=os.path.basename(path), ref=ref_seq, contig=contig, scenario_yaml=scenario_yaml,
                 pos=int(rec[1]) - 1, ref_allele=rec[3], alt_allele=rec[4].split(",")[0], info=info,
-                samples=samples, purity=purity, expected=y.get("expected", {}),
+                event_records=event_records, samples=samples, purity=purity, expected=y.get("expected", {}),
                 omit={k: bool(y.get("omit_" + k, False)) for k in
                       ("strand_bias", "read_orientation_bias", "read_position_bias", "softclip_bias", "divindel_bias")})
 
@@ -295,7 +349,9 @@ def save_fixture(tc, path):
         recs.sort(key=lambda r: r["pos"])
         out["samples"][name] = dict(props=props, props_final=True, opts=s["opts"], records=[
             ["%05d" % rank[r["name"]], r["flag"], r["pos"], r["mapq"], r["cigar"], r["seq"].decode(),
-             bytes(q + 33 for q in r["qual"]).decode(), r["tid"], r["mtid"], r["mpos"]] for r in recs])
+             bytes(q + 33 for q in r["qual"]).decode(), r["tid"], r["mtid"], r["mpos"]] +
+            ([r["si"].decode() if r.get("si") is not None else None, r["ro"].decode() if r.get("ro") is not None else None]
+             if (r.get("si") is not None or r.get("ro") is not None) else []) for r in recs])
     with gzip.open(path, "wt") as f:
         json.dump(out, f, separators=(",", ":"))
 
@@ -307,6 +363,8 @@ def load_fixture(path):
     for s in tc["samples"].values():
         s["records"] = [dict(name=r[0].encode(), flag=r[1], pos=r[2], mapq=r[3], cigar=[tuple(c) for c in r[4]],
                              seq=r[5].encode(), qual=bytes(ord(c) - 33 for c in r[6]), tid=r[7], mtid=r[8], mpos=r[9],
+                             si=r[10].encode() if len(r) > 10 and r[10] is not None else None,
+                             ro=r[11].encode() if len(r) > 11 and r[11] is not None else None,
                              contig=tc["contig"]) for r in s["records"]]
     return tc
 
@@ -314,12 +372,33 @@ def load_fixture(path):
 def make_variant(tc, ref_window):
     """Deletion / Insertion from the candidate record (preprocessing/mod.rs:318-356)."""
     start, r, a, ref = tc["pos"], tc["ref_allele"], tc["alt_allele"], tc["ref"]
-    if "[" in a or "]" in a:
-        raise NotImplementedError("variant type of %s: breakend %s" % (tc["name"], a[:16]))
-    if not a.startswith("<") and len(r) != len(a) and (min(len(r), len(a)) != 1 or r[0].upper() != a[0].upper()):
-        # neither a deletion nor an insertion after one anchor base (utils/collect_variants.rs:80-90,
-        # 203-219): a Replacement (types/replacement.rs) or a multi-base anchor -- not restated
-        raise NotImplementedError("variant type of %s: replacement %s>%s" % (tc["name"], r[:10], a[:10]))
+    svtype = tc["info"].get("SVTYPE")
+
+    def bnd_variant(group, vtype, length):
+        return dict(kind="bnd", vtype=vtype, len=length, group=group, loci=group.loci, fetch_loci=group.loci,
+                    alts=group.alt_alleles(ref, ref_window), alt_extra=-1, locus=None)
+    # utils/collect_variants.rs:93-214: SVTYPE first, then the allele shapes
+    if svtype == "INV":
+        length = int(tc["info"]["END"]) - 1 + 1 - start
+        return bnd_variant(B.inversion_group(ref, start, length), "inv", length)
+    if svtype == "DUP":
+        length = int(tc["info"]["END"]) - 1 + 1 - start
+        return bnd_variant(B.duplication_group(ref, start, length), "dup", length)
+    if svtype == "BND":
+        recs = tc.get("event_records") or []
+        if not recs:
+            raise NotImplementedError("breakend without EVENT")
+        bnds = [B.parse_breakend(tc["contig"], p_, r_, a_, id_) for p_, id_, r_, a_ in recs]
+        return bnd_variant(B.BreakendGroup([b for b in bnds if b is not None]), "bnd", 1)
+    is_del = a == "<DEL>" or (len(r) > len(a) and r[:len(a)].upper() == a.upper())
+    is_ins = len(r) < len(a) and a[:len(r)].upper() == r.upper()
+    if svtype is None and not a.startswith("<") and len(r) != len(a) and not is_del and not is_ins:
+        # neither a deletion nor an insertion (collect_variants.rs:196-214): arbitrary replacement
+        return bnd_variant(B.replacement_group(ref, start, r, a), "rep", len(a))
+    if not a.startswith("<") and len(r) != len(a) and (min(len(r), len(a)) != 1):
+        # deletion / insertion behind a multi-base anchor: the reference keeps the record position
+        # ("TODO fix position", collect_variants.rs:199) -- not met in the testcases
+        raise NotImplementedError("variant type of %s: multi-base anchor %s>%s" % (tc["name"], r[:10], a[:10]))
     if a == "<DEL>" or (not a.startswith("<") and len(r) > len(a)):
         dl = (int(tc["info"]["END"]) - 1 - start) if a == "<DEL>" and "END" in tc["info"] else len(r) - len(a)
         if a == "<DEL>" and "SVLEN" in tc["info"]:
@@ -381,37 +460,64 @@ def candidate_region(rec, locus, ref_len, max_window):
 
 
 class RealignBatch:
-    """Collects (read window, ref window, alt window) jobs of many records; one backend call."""
+    """Collects the realignment jobs of many records (Realigner::allele_support, realignment/mod.rs:
+    164-335): per record the candidate regions of every locus, overlapping ones merged, one job per
+    merged region = (read window, ref window, alt haplotypes); one backend call for all of them."""
 
     def __init__(self, tc, variant, max_window):
         self.tc, self.variant, self.max_window = tc, variant, max_window
         self.jobs, self.by_record = [], {}
+        if variant["kind"] == "bnd":
+            self.loci = variant["loci"]
+            self.alts = [(a, -1) for a in variant["alts"]]       # not shrinkable (breakends.rs:649-664)
+        else:
+            self.loci = [variant["locus"]]
+            self.alts = [(variant["alt"], variant["alt_extra"])]
 
     def add(self, rec):
         key = id(rec)
         if key in self.by_record:
             return
-        ov, (q0, q1), (r0, r1) = candidate_region(rec, self.variant["locus"], len(self.tc["ref"]), self.max_window)
-        if not ov or q1 <= q0:
+        regions = [candidate_region(rec, l, len(self.tc["ref"]), self.max_window) for l in self.loci]
+        regions = [(q, r) for ov, q, r in regions if ov and q[1] > q[0]]
+        if not regions:
             self.by_record[key] = None  # no overlap: (ln .5, ln .5, Strand::None), mod.rs:188-199
             return
-        self.by_record[key] = len(self.jobs)
-        self.jobs.append(dict(ref=self.tc["ref"][r0:r1], alt=self.variant["alt"], alt_extra=self.variant["alt_extra"],
-                              bases=rec["seq"][q0:q1], quals=rec["qual"][q0:q1]))
+        merged = []
+        for (q0, q1), (r0, r1) in regions:                       # mod.rs:201-223
+            if merged and r0 <= merged[-1][1][1]:
+                (mq0, mq1), (mr0, _) = merged[-1]
+                merged[-1] = ((min(mq0, q0), max(mq1, q1)), (mr0, r1))
+            else:
+                merged.append(((q0, q1), (r0, r1)))
+        self.by_record[key] = []
+        for (q0, q1), (r0, r1) in merged:
+            self.by_record[key].append(len(self.jobs))
+            self.jobs.append(dict(ref=self.tc["ref"][r0:r1], alts=self.alts,
+                                  bases=rec["seq"][q0:q1], quals=rec["qual"][q0:q1], read_iv=(q0, q1)))
 
     def run(self, backend):
         self.results = backend.allele_support(self.jobs) if self.jobs else []
 
     def support(self, rec):
         """AlleleSupport of one record: dict(prob_ref, prob_alt, strand, indel_ops)."""
-        j = self.by_record[id(rec)]
-        if j is None:
+        js = self.by_record[id(rec)]
+        if js is None:
             return dict(prob_ref=-LN2, prob_alt=-LN2, strand=3, indel_ops=())
-        r = self.results[j]
-        informative = r["prob_ref"] != r["prob_alt"]
-        strand = (1 if rec["flag"] & 0x10 else 0) if informative else 3  # Strand::from_record / None
-        return dict(prob_ref=r["prob_ref"], prob_alt=r["prob_alt"], strand=strand,
-                    indel_ops=tuple(r["indel_ops"]) if informative else ())
+        pr = pa = 0.0
+        ops, strand = (), 3
+        for j in js:
+            r = self.results[j]
+            if r["prob_ref"] != r["prob_alt"]:   # uninformative regions keep nothing (mod.rs:303-315)
+                if rec.get("si") is not None:    # per-base strand info of consensus reads
+                    q0, q1 = self.jobs[j]["read_iv"]
+                    strand = strand_or(strand, strand_from_aux(rec["si"][q0:q1]))
+                ops += tuple(r["indel_ops"])
+            pr += r["prob_ref"]
+            pa += r["prob_alt"]
+        if rec.get("si") is None and pr != pa:
+            strand = 1 if rec["flag"] & 0x10 else 0  # Strand::from_record (mod.rs:321-325)
+        return dict(prob_ref=pr, prob_alt=pa, strand=strand, indel_ops=ops)
 
 
 def merge_support(a, b):
@@ -459,7 +565,9 @@ def ln_sum_exp(ps):
     return mx + math.log1p(sum(math.exp(p - mx) for i, p in enumerate(ps) if i != k and p != -math.inf))
 
 
-def feasible_bases(variant, read_len, props):  # deletion.rs:104-118, insertion.rs:78-92
+def feasible_bases(variant, read_len, props):  # deletion.rs:104-118, insertion.rs:78-92, breakends.rs:352-380
+    if variant["kind"] == "bnd":
+        return variant["group"].feasible_bases(read_len, props)
     maxlen = props["max_del_cigar_len"] if variant["kind"] == "del" else props["max_ins_cigar_len"]
     if maxlen is not None and variant["len"] <= maxlen:
         return read_len
@@ -472,8 +580,12 @@ def prob_sample_alt_read(variant, read_len, props):  # sampling_bias/reads.rs:21
     feasible = feasible_bases(variant, read_len, props)
     if feasible is None:
         return 0.0
-    n_alt = min(variant["len"], read_len)
-    return math.log(min(n_alt, feasible)) - math.log(n_alt)
+    if variant["kind"] == "bnd":   # enclosable_len(): None unless the group is a plain deletion / insertion
+        el = variant["group"].enclosable_len()
+        n_alt = read_len if el is None else min(el, read_len)
+    else:
+        n_alt = min(variant["len"], read_len)
+    return _ln(min(n_alt, feasible)) - math.log(n_alt)
 
 
 def prob_sample_alt_fragment(variant, ll, rl, props):  # sampling_bias/fragments.rs:44-151
@@ -504,6 +616,53 @@ def estimate_insert_size(left, right):  # variants/evidence/insert_size.rs:17-45
         return (max(0, r["pos"] - _clips(r, True, (S, H))), end_pos(r) + _clips(r, False, (S, H)))
     (ls, le), (rs, re_) = aln(left), aln(right)
     return (rs - le) + (le - ls) + (re_ - rs)
+
+
+# ------------------------------------------------------------------------------- subsampling
+class Subsampler:
+    """SubsampleCandidates (sample.rs:132-160): `StdRng::seed_from_u64(48074578)` of rand 0.7.3
+    (Cargo.lock) = ChaCha20 (rand_chacha 0.2: 64-bit block counter, stream 0) keyed by the PCG32
+    expansion of the seed (rand_core 0.5 SeedableRng::seed_from_u64); keep() draws
+    Uniform::new(0.0, 1.0): (next_u64 >> 12) as the mantissa of a float in [1, 2), minus 1."""
+
+    def __init__(self, max_depth, depth):
+        self.needed = depth > max_depth
+        self.prob = max_depth / depth if depth else 1.0
+        if self.needed:
+            state, key = 48074578, []
+            for _ in range(8):
+                state = (state * 6364136223846793005 + 11634580027462260723) & 0xFFFFFFFFFFFFFFFF
+                x = (((state >> 18) ^ state) >> 27) & 0xFFFFFFFF
+                rot = state >> 59
+                key.append(((x >> rot) | (x << ((32 - rot) & 31))) & 0xFFFFFFFF)
+            self.key, self.counter, self.buf = key, 0, []
+
+    def _block(self):
+        c = [0x61707865, 0x3320646E, 0x79622D32, 0x6B206574] + self.key + \
+            [self.counter & 0xFFFFFFFF, self.counter >> 32, 0, 0]
+        x = list(c)
+
+        def qr(a, b, cc, d):
+            x[a] = (x[a] + x[b]) & 0xFFFFFFFF; x[d] ^= x[a]; x[d] = ((x[d] << 16) | (x[d] >> 16)) & 0xFFFFFFFF
+            x[cc] = (x[cc] + x[d]) & 0xFFFFFFFF; x[b] ^= x[cc]; x[b] = ((x[b] << 12) | (x[b] >> 20)) & 0xFFFFFFFF
+            x[a] = (x[a] + x[b]) & 0xFFFFFFFF; x[d] ^= x[a]; x[d] = ((x[d] << 8) | (x[d] >> 24)) & 0xFFFFFFFF
+            x[cc] = (x[cc] + x[d]) & 0xFFFFFFFF; x[b] ^= x[cc]; x[b] = ((x[b] << 7) | (x[b] >> 25)) & 0xFFFFFFFF
+        for _ in range(10):
+            qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15)
+            qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14)
+        self.counter += 1
+        return [(a + b) & 0xFFFFFFFF for a, b in zip(x, c)]
+
+    def keep(self):
+        if not self.needed:
+            return True
+        if len(self.buf) < 2:
+            self.buf += self._block()
+        lo, hi = self.buf[0], self.buf[1]
+        del self.buf[:2]
+        u = ((hi << 32) | lo) >> 12
+        value = struct.unpack("<d", struct.pack("<Q", (1023 << 52) | u))[0] - 1.0
+        return value <= self.prob
 
 
 # ------------------------------------------------------------------------------- observations
@@ -565,8 +724,19 @@ def extract_observations(tc, sample_name, backend, max_window=64, trace=None):
     max_window = int(smp["opts"].get("realignment_window", smp["opts"].get("indel_window", max_window)))
     variant = make_variant(tc, int(max_window * 1.5))
     evidences = select_evidences(tc, sample_name, variant, props)
-    if len(evidences) > int(smp["opts"].get("max_depth", 200)):
-        raise NotImplementedError("subsampling above max_depth (StdRng stream) is not restated")
+    # METHOD (types/mod.rs:289-303): if ALL loci exceed the maximum depth, the evidences are subsampled
+    max_depth = int(smp["opts"].get("max_depth", 200))
+    if variant["kind"] == "bnd":
+        depth = [0] * len(variant["loci"])
+        for ev in evidences:
+            for i in variant["group"].is_valid_evidence(ev, overlap, end_pos):
+                depth[i] += 1
+    else:
+        depth = [len(evidences)]
+    if evidences and all(d > max_depth for d in depth):
+        sub = Subsampler(max_depth, len(evidences))
+        evidences = [ev for ev in evidences if sub.keep()]
+    report_ops = variant["kind"] in ("del", "ins") or variant.get("vtype") == "rep"
     batch = RealignBatch(tc, variant, max_window)
     for left, right in evidences:
         batch.add(left)
@@ -603,7 +773,9 @@ def extract_observations(tc, sample_name, backend, max_window=64, trace=None):
                         prob_missed_allele=ln_sum_exp([sup["prob_ref"], sup["prob_alt"]]) - LN2,
                         prob_sample_alt=psa, prob_double_overlap=0.0 if sup["strand"] == 2 else -math.inf,
                         prob_hit_base=-math.log(ln_len), strand=sup["strand"], orientation=read_orientation(left),
-                        softclipped=softclipped, paired=bool(left["flag"] & 1), indel_ops=sup["indel_ops"]))
+                        softclipped=softclipped, paired=bool(left["flag"] & 1),
+                        # Variant::report_indel_operations (deletion.rs:158, insertion.rs:105, replacement.rs:81)
+                        indel_ops=sup["indel_ops"] if report_ops else ()))
     # ---- Observation::process: major indel operations (observation.rs:229-275, 339-359)
     counter = Counter(o["indel_ops"] for o in raw if o["indel_ops"])
     major = counter.most_common(1)[0][0] if counter else None
@@ -647,8 +819,8 @@ def extract_observations_snv(tc, sample_name, backend, omit_read_orientation_bia
             continue
         if overlap(variant["locus"], r, False) == "enclosing":
             evidences.append(r)
-    if len(evidences) > int(smp["opts"].get("max_depth", 200)):
-        raise NotImplementedError("subsampling above max_depth (StdRng stream) is not restated")
+    sub = Subsampler(int(smp["opts"].get("max_depth", 200)), len(evidences))  # types/mod.rs:166-172
+    evidences = [r for r in evidences if sub.keep()]
     batch = RealignBatch(tc, variant, max_window)
     for r in evidences:
         if any(op in (I, D) for op, _ in r["cigar"]):
@@ -662,7 +834,7 @@ def extract_observations_snv(tc, sample_name, backend, omit_read_orientation_bia
         else:
             # one base (snv.rs:109-151) or every base of the MNV (mnv.rs:116-197); the read position is
             # the first base's
-            qpos, p_ref, p_alt, gone = None, 0.0, 0.0, False
+            qpos, p_ref, p_alt, gone, st_aux = None, 0.0, 0.0, False, 3
             for k in range(variant["len"]):
                 qp = read_pos(r, start + k, False, False)
                 if qp is None:   # position deleted / skipped in this read: no observation
@@ -672,17 +844,25 @@ def extract_observations_snv(tc, sample_name, backend, omit_read_orientation_bia
                     qpos = qp
                 rb, q = r["seq"][qp], r["qual"][qp]
                 ab, fb = variant["alt_base"][k], variant["ref_base"][k]
-                p_alt += prob_read_base(rb, ab, q)
                 non_alt = chr(rb) if chr(rb).upper() != ab else fb
-                p_ref += prob_read_base(rb, non_alt, q)
+                b_alt, b_ref = prob_read_base(rb, ab, q), prob_read_base(rb, non_alt, q)
+                if b_alt != b_ref and r.get("si") is not None:   # per-base strand of consensus reads (SI tag)
+                    st_aux = strand_or(st_aux, strand_from_aux(r["si"][qp:qp + 1]))
+                p_alt += b_alt
+                p_ref += b_ref
             if gone:
                 continue
-            sup = dict(prob_ref=p_ref, prob_alt=p_alt, strand=(1 if r["flag"] & 0x10 else 0) if p_ref != p_alt else 3)
+            if r.get("si") is not None:   # snv.rs:136-143 / mnv.rs:160-183
+                strand = st_aux
+            else:
+                strand = (1 if r["flag"] & 0x10 else 0) if p_ref != p_alt else 3
+            sup = dict(prob_ref=p_ref, prob_alt=p_alt, strand=strand)
         if sup["strand"] == 3:
             continue
         raw.append(dict(prob_mapping=ln_one_minus_exp(r["mapq"] * (-math.log(10.0) / 10.0)), prob_alt=sup["prob_alt"],
                         prob_ref=sup["prob_ref"], prob_missed_allele=ln_sum_exp([sup["prob_ref"], sup["prob_alt"]]) - LN2,
-                        prob_sample_alt=0.0, prob_double_overlap=-math.inf, prob_hit_base=-math.log(len(r["seq"])),
+                        prob_sample_alt=0.0, prob_double_overlap=0.0 if sup["strand"] == 2 else -math.inf,
+                        prob_hit_base=-math.log(len(r["seq"])),
                         strand=sup["strand"], orientation=read_orientation(r),
                         softclipped=leading_softclips(r) > 0 or trailing_softclips(r) > 0, paired=bool(r["flag"] & 1),
                         read_position=qpos))
@@ -894,6 +1074,8 @@ def germline_prior(heterozygosity, ploidy=2):
 
 def _is_valid_evidence(variant, ev, props):
     left, right = ev
+    if variant["kind"] == "bnd":
+        return variant["group"].is_valid_evidence(ev, overlap, end_pos) is not None
     loc = variant["locus"]
     if right is None:
         return overlap(loc, left, True) is not None
@@ -973,7 +1155,10 @@ def run_scenario_testcase(path, backend, scenario_yaml=None):
     if any(smp.universe is None for smp in g.samples.values()):
         # Prior::compute on the host (libprosic_b200/prior.py): callback for the oracle, table over the
         # leaves the library reports for the GPU
-        scn["prior_fn"], prog = prior_mod.make_prior(g, tc["contig"], variant["kind"], want_program=True)
+        # VariantTypeFraction::get (grammar/mod.rs:399-409): replacements count as indels, the other
+        # breakend groups as structural variants
+        pk = variant["kind"] if variant["kind"] != "bnd" else ("del" if variant["vtype"] == "rep" else "sv")
+        scn["prior_fn"], prog = prior_mod.make_prior(g, tc["contig"], pk, want_program=True)
         leaves = backend.model_leaves(scn)
         if leaves is None:
             # a tree path binds a Range: its grid points depend on the site's depth, no table over
@@ -1004,7 +1189,16 @@ def run_scenario_testcase(path, backend, scenario_yaml=None):
 # Generic testcases of the reference with a scenario.yaml and a uniform prior that the suites run from
 # compact fixtures (all that run in the build container: tests/golden/scenario_results.txt)
 SCENARIO_CASES = ("omit_sb", "test34", "test37", "test40", "test49", "test52", "test58", "test57", "test70",
-                  "test_low_cov_vaf", "test_panel_overlap", "test_contig_universe", "test_giab_02")
+                  "test_low_cov_vaf", "test_panel_overlap", "test_contig_universe", "test_giab_02",
+                  # breakend groups (libprosic_b200/breakends.py): inversion, duplication, a BND event of four
+                  # records, replacements (PCR homopolymer errors called as DivIndel artifacts)
+                  "test43", "test44", "test45", "test51", "test60", "test_giab_05", "test_pcr_homopolymer_error1",
+                  "test_pcr_homopolymer_error2", "test_pcr_homopolymer_error3",
+                  # deep amplicon / consensus-read data: subsampling above max_depth (Subsampler) and the
+                  # per-base strand (SI) / read orientation (RO) aux tags
+                  "test55", "test_panel_unknown_orientation_bias", "pattern_too_long")
+# tumor/normal testcases whose candidate is a breakend event (an insertion written as two BND records)
+TN_BND_CASES = ("test42", "test47")
 
 
 # ... and with a prior over continuous allele frequencies (somatic mutation rates, Mendelian and clonal
@@ -1042,7 +1236,7 @@ class GpuBackend:
         cache = {}
         for j in jobs:
             ids = []
-            for key, ex in ((j["ref"], 0), (j["alt"], j["alt_extra"])):
+            for key, ex in [(j["ref"], 0)] + list(j["alts"]):
                 if (key, ex) not in cache:
                     cache[(key, ex)] = len(haps)
                     haps.append(np.frombuffer(key, np.uint8))
@@ -1063,6 +1257,8 @@ class GpuBackend:
         out = []
         for k in range(len(jobs)):
             n = int(got["n_indel_ops"][k])
+            if got["indel_overflow"][k]:
+                raise NotImplementedError("job %d: more than 32 indel runs in the alt hit's alignment" % k)
             out.append(dict(prob_ref=float(got["prob_ref"][k]), prob_alt=float(got["prob_alt"][k]),
                             indel_ops=[int(x) for x in got["indel_ops"][k][:n]]))
         return out

@@ -46,6 +46,13 @@ def main():
         F.save_fixture(F.load_testcase(os.path.join(REF, c)), p)
         total += os.path.getsize(p)
         print(c, os.path.getsize(p))
+    tn_bnd = os.path.join(os.path.dirname(OUT), "tn_bnd")
+    os.makedirs(tn_bnd, exist_ok=True)
+    for c in F.TN_BND_CASES:  # tumor/normal mode, candidate = breakend event
+        p = os.path.join(tn_bnd, c + ".json.gz")
+        F.save_fixture(F.load_testcase(os.path.join(REF, c)), p)
+        total += os.path.getsize(p)
+        print(c, os.path.getsize(p))
     for c in CASES:
         d = os.path.join(REF, c)
         if not os.path.isdir(d):

@@ -53,8 +53,8 @@ def main():
             "/".join("%.3f" % x for x in r["af"].values()), probs,
             "" if ok else "violated: " + "; ".join(e for e, o in v if not o)))
     print("%d of %d testcases with an `expected:` block satisfy it.  Not asserted upstream either: test38 "
-          "(commented out, tests/lib.rs:121), test_giab_01 (commented out, 158-160), test_overlapping_events "
-          "(`testcase_should_panic!`, 184)" % (n_pass, n_tot))
+          "(commented out, tests/lib.rs:121), test_giab_01 (commented out, 158-160), test_giab_04 (commented out, "
+          "163-166), test_overlapping_events (`testcase_should_panic!`, 184)" % (n_pass, n_tot))
 
 
 if __name__ == "__main__":

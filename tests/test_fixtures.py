@@ -8,8 +8,7 @@ tests/golden/gen/*.json.gz of 5 one-sample Generic testcases (SNVs with all five
 deletion, a ploidy universe with the species prior as a prior table), tests/golden/trio/*.json.gz
 of the three pedigree testcases test61-63 (Mendelian prior); all written by
 tests/golden/make_tn_fixtures.py.  tests/golden/run_tn_testcases.py prints the table of all of them
-(tn_results.txt: 31 of 32 hold, in exact and in fast realignment mode; test31 needs the
-subsampling RNG stream and is skipped).  test21 is the one that does not -- and the reference itself has it commented out
+(tn_results.txt: 32 of 33 hold, in exact and in fast realignment mode).  test21 is the one that does not -- and the reference itself has it commented out
 (tests/lib.rs:102); its PROB_SOMATIC_TUMOR >= 200 depends on the Myers traceback tie-breaking,
 which is calibrated on these very testcases (oracle/vlr_oracle.c, g_traceback_rule)."""
 import glob
@@ -25,7 +24,7 @@ FIXTURES = sorted(glob.glob(os.path.join(HERE, "golden", "tn", "*.json.gz")))
 GENERIC = sorted(glob.glob(os.path.join(HERE, "golden", "gen", "*.json.gz")))
 TRIO = sorted(glob.glob(os.path.join(HERE, "golden", "trio", "*.json.gz")))
 KNOWN_EXCEPTIONS = {"test21"}  # disabled upstream as well (reference tests/lib.rs:102)
-NOT_RESTATED = {"test31"}      # subsampling above max_depth (StdRng stream, sample.rs:138-151)
+NOT_RESTATED = set()
 RUNS_ONLY = {"test11"}         # "nothing, just don't crash": an empty `expected:` block
 FIXTURES = [p for p in FIXTURES if os.path.basename(p).split(".")[0] not in NOT_RESTATED]
 
@@ -35,7 +34,7 @@ def _name(p):
 
 
 def test_fixture_set_is_complete():
-    assert len(FIXTURES) == 32 and len(GENERIC) == 5 and len(TRIO) == 3
+    assert len(FIXTURES) == 33 and len(GENERIC) == 5 and len(TRIO) == 3
 
 
 @pytest.mark.parametrize("path", TRIO, ids=_name)
@@ -171,7 +170,7 @@ def test_kept_observation_sets_are_identical_on_the_gpu(ctx, path):
 # ---- Generic testcases driven by their scenario.yaml through the grammar front end
 SCN = sorted(glob.glob(os.path.join(HERE, "golden", "scn", "*.json.gz")))
 # the reference asserts nothing but "runs" for these (empty `expected:` block)
-NO_EXPECTATION = {"test37", "test_contig_universe"}
+NO_EXPECTATION = {"test37", "test_contig_universe", "pattern_too_long"}
 
 
 def test_scenario_fixture_set_is_complete():
@@ -196,6 +195,34 @@ def test_scenario_testcases_hold_on_the_gpu(ctx, path):
     from _oracle_backend import OracleBackend
     got = F.run_scenario_testcase(path, F.GpuBackend(ctx))
     want = F.run_scenario_testcase(path, OracleBackend())
+    assert got["n_obs"] == want["n_obs"] and got["af"] == want["af"], (got, want)
+    for k, w in want.items():
+        if k.startswith("PROB_"):
+            g = got[k]
+            assert (np.isinf(g) and np.isinf(w)) or abs(g - w) <= 2e-5 * max(1.0, abs(w)), (k, g, w)
+    assert all(v for _, v in F.check_expectations(got))
+
+
+TN_BND = sorted(glob.glob(os.path.join(HERE, "golden", "tn_bnd", "*.json.gz")))
+
+
+@pytest.mark.parametrize("path", TN_BND, ids=_name)
+def test_tumor_normal_breakend_events_hold_on_the_oracle(path):
+    """test42 / test47: an insertion written as a breakend EVENT of two BND records (SURVEY row R-7:
+    types/breakends.rs alt-allele assembly, multi-locus candidate regions, unshrinkable windows)."""
+    assert len(TN_BND) == len(F.TN_BND_CASES)
+    from _oracle_backend import OracleBackend
+    r = F.run_testcase(path, OracleBackend())
+    verdicts = F.check_expectations(r)
+    assert verdicts and all(v for _, v in verdicts), (verdicts, r)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", TN_BND, ids=_name)
+def test_tumor_normal_breakend_events_hold_on_the_gpu(ctx, path):
+    from _oracle_backend import OracleBackend
+    got = F.run_testcase(path, F.GpuBackend(ctx))
+    want = F.run_testcase(path, OracleBackend())
     assert got["n_obs"] == want["n_obs"] and got["af"] == want["af"], (got, want)
     for k, w in want.items():
         if k.startswith("PROB_"):

@@ -49,9 +49,9 @@ class Recorder:
     def allele_support(self, jobs):
         out = []
         for j in jobs:
-            w = O.allele_support_region([np.frombuffer(j["ref"], np.uint8)], [np.frombuffer(j["alt"], np.uint8)],
+            w = O.allele_support_region([np.frombuffer(j["ref"], np.uint8)], [np.frombuffer(a, np.uint8) for a, _ in j["alts"]],
                                         np.frombuffer(j["bases"], np.uint8), np.frombuffer(j["quals"], np.uint8),
-                                        self.be.gap, shrink_extra=[0, j["alt_extra"]], flags=self.be.flags)
+                                        self.be.gap, shrink_extra=[0] + [e for _, e in j["alts"]], flags=self.be.flags)
             self.raw.append((w["raw_ref"], w["raw_alt"], w["prob_ref"] != w["prob_alt"]))
             out.append(dict(prob_ref=w["prob_ref"], prob_alt=w["prob_alt"], indel_ops=[int(x) for x in w["indel_ops"]]))
         return out
