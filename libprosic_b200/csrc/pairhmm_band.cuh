@@ -116,6 +116,7 @@ pairhmm_band_kernel(HmmArgs g, int32_t *list_rw, const int32_t *n_total) {
         double accM = 0.0, accXY = 0.0;
         bool any_alive = true;
         unsigned trk = 0xffffffffu;  // three-way rule: closest approach of a high word to a threshold
+        double wj = 0.0;
         // one read row; FIRST: the row above is the reset state of the column (no mass, no distance)
         auto row = [&](int j, auto first_tag) {
             constexpr bool FIRST = decltype(first_tag)::value;
@@ -143,7 +144,7 @@ pairhmm_band_kernel(HmmArgs g, int32_t *list_rw, const int32_t *n_total) {
                 const int upMed = FIRST ? kMedMax : (q + 1 < G ? medp[q + 1 < G ? q + 1 : 0] : upMed_next);
                 const bool match = hap[kBandPad + i] == rcode;
                 ev[q] = match ? qe.em : qe.emm;
-                sumv[q] = Lin::sum3<APPROX, false, true>(c, Mp[q], Xp[q], Yp[q], trk);
+                sumv[q] = Lin::sum3<APPROX, false, true>(c, Mp[q], Xp[q], Yp[q], trk, wj);
                 const int m_tl = medp[q];
                 a_med[q] = min(m_tl + (match ? 0 : 1), upMed + 1);
                 strong[q] = min(m_tl, upMed) <= k;
@@ -201,7 +202,7 @@ pairhmm_band_kernel(HmmArgs g, int32_t *list_rw, const int32_t *n_total) {
             accM += __shfl_xor_sync(0xffffffffu, accM, o);
             accXY += __shfl_xor_sync(0xffffffffu, accXY, o);
         }
-        if (APPROX == 2 && __reduce_min_sync(0xffffffffu, trk) <= 3u) {
+        if (APPROX == 2 && __reduce_min_sync(0xffffffffu, trk) <= 8u) {
             // a doubtful decision of the three-way rule: the exact-decision kernel takes the pair
             if (lane == 0) g.gen_list[atomicAdd(g.gen_count, 1)] = pair;
             continue;

@@ -147,7 +147,7 @@ struct Lin {  // scaled linear space
         return p1 >= p0 * kT ? p0 + t2 : p0;
     }
     template <int APPROX, bool EXT, bool SCALED = false>
-    __device__ static double sum3(const HmmConsts &k, double dM, double dX, double dY, unsigned &trk) {
+    __device__ static double sum3(const HmmConsts &k, double dM, double dX, double dY, unsigned &trk, double &wjunk) {
         if (APPROX == 1) {
             // two-way rule: return the maximum alone if the second largest term is
             // more than e^-10 below it, else the exact sum.  "second < max*e^-10" <=> exactly one of
@@ -187,42 +187,58 @@ struct Lin {  // scaled linear space
         }
         if (APPROX == 2 || APPROX == 4) {
             // three-way rule, decided on the HIGH WORDS of the terms (non-negative doubles order like
-            // their bit patterns; the ALU pipe is idle next to the fp64 pipe): every term whose high
-            // word reaches hi(e^-10 * max) is "in level 1", the smallest of those sets the second
-            // threshold.  A high word within 3 units of a threshold cannot be decided without the
-            // low words: `trk` keeps the closest approach, and the caller re-evaluates with the
-            // exact rule -- the whole pair (APPROX == 2: pairs are short, the fallback kernel is the
-            // exact APPROX == 3 instantiation) or this cell after a warp vote (APPROX == 4).
+            // their bit patterns).  Sorted p0 >= p1 >= p2: p1 < p0*e^-10 -> p0; else p2 < p1*e^-10 ->
+            // p0 + p1; else all three.  Equivalent without a sort: level 1 = the terms that reach
+            // e^-10 * max; the SMALLEST level-1 term sets the second threshold; every term that reaches
+            // it is summed (one level-1 term: the maximum alone; two: p2 is tested against p1; three:
+            // everything passes).
+            //   t = hi(fma((h, *), kTb, kF)) is the high word of the threshold that belongs to a term with
+            // high word h.  The low word of the factor is left as it is (whatever the register pair holds),
+            // kTb = e^-10 * (1 - 2.5 * 2^-20): the computed threshold lies 0.5 .. 6 units below the high
+            // word of the exact one, so a term whose high word is below t is certainly excluded, one more
+            // than 8 units above certainly included, and only [t, t + 8] needs the low words: `trk` keeps
+            // the closest approach, and the caller re-evaluates with the exact rule -- the whole pair
+            // (APPROX == 2: the fallback kernel is the exact APPROX == 3 instantiation) or this cell after
+            // a warp vote (APPROX == 4).
+            //   kF = 2^-1018 floors the thresholds: cells whose largest term is below ~2^-982 (the pair
+            // is only valid above 2^-940 and a cell contributes at most its own value) get inflated
+            // thresholds or are flushed to zero, and all-zero cells never look like ties.
             const double a = SCALED ? dM : k.t_mm * dM;
             const double b = EXT ? k.t_xm * dX : dX;
             const double c = EXT ? k.t_ym * dY : dY;
             const int ha = __double2hiint(a), hb = __double2hiint(b), hc = __double2hiint(c);
-            const double kT = 4.5399929762484854e-05;               // e^-10 (0x3F07CD79B5647C9B)
-            // Cells whose largest term is below 2^-960 of the scale cannot move the result (a pair is
-            // only valid above 2^-940, a cell contributes at most its own value, and a wrong decision
-            // changes it by e^-10 relative): they never raise the flag.  Every pair has a zone where
-            // values decay through the tiny and subnormal range towards zero; there the high words
-            // are too coarse to decide anything.
-            const int kLive = 0x03F00000;                           // high word of 2^-960
-            const int k0 = max(ha, max(hb, hc));
-            const int t0 = __double2hiint(__hiloint2double(k0, 0) * kT);
-            const unsigned ua = (unsigned)(ha - t0), ub = (unsigned)(hb - t0), uc = (unsigned)(hc - t0);
-            const unsigned um = min(ua, min(ub, uc));
-            const int t1 = __double2hiint(__hiloint2double((int)um + t0, 0) * kT);
+            const double kTb = 4.53998215206174e-05;                 // e^-10 * (1 - 2.5 * 2^-20)
+            const double kF = 3.5601181736115222e-307;               // 2^-1018
+            // w = (don't care, max(ha, hb, hc)): the maximum is written straight into the high half of a
+            // register pair whose low half is whatever the last cell left there (`wjunk`, one pair per row)
+            double w = wjunk;
+            asm("{\n\t.reg .b32 lo, hi;\n\tmov.b64 {lo, hi}, %0;\n\tmax.s32 hi, %1, %2;\n\tmax.s32 hi, hi, %3;\n\t"
+                "mov.b64 %0, {lo, hi};\n\t}" : "+d"(w) : "r"(ha), "r"(hb), "r"(hc));
+            w = fma(w, kTb, kF);
+            const int t0 = __double2hiint(w);
+            const unsigned um = __vimin3_u32((unsigned)(ha - t0), (unsigned)(hb - t0), (unsigned)(hc - t0));
+            // high word += um, in place (the register pair keeps whatever low word it has)
+            asm("{\n\t.reg .b32 lo, hi;\n\tmov.b64 {lo, hi}, %0;\n\tadd.s32 hi, hi, %1;\n\tmov.b64 %0, {lo, hi};\n\t}"
+                : "+d"(w) : "r"(um));
+            w = fma(w, kTb, kF);
+            const int t1 = __double2hiint(w);
+            wjunk = w;
             const int va = ha - t1, vb = hb - t1, vc = hc - t1;
-            const unsigned vm = min((unsigned)va, min((unsigned)vb, (unsigned)vc));
+            const unsigned near = __vimin3_u32(um, (unsigned)va, (unsigned)vb);
             // excluded terms are cleared by zeroing their HIGH word (what is left of the low word is a
-            // subnormal below 2^-1042, far under every threshold of this kernel).  The mask arithmetic
-            // (sign of v by a high multiply, then hi + hi * sign) runs on the FMA pipe, which idles
-            // next to the fp64 and ALU pipes that bound this kernel.
-            const double a2 = __hiloint2double(ha + ha * __mulhi(va, 2), __double2loint(a));
-            const double b2 = __hiloint2double(hb + hb * __mulhi(vb, 2), __double2loint(b));
-            const double c2 = __hiloint2double(hc + hc * __mulhi(vc, 2), __double2loint(c));
+            // subnormal below 2^-1042, far under every threshold of this kernel)
+            double a2 = a, b2 = b, c2 = c;
+            asm("{\n\t.reg .b32 lo, hi;\n\t.reg .pred p;\n\tmov.b64 {lo, hi}, %0;\n\tsetp.lt.s32 p, %1, 0;\n\t"
+                "@p mov.b32 hi, 0;\n\tmov.b64 %0, {lo, hi};\n\t}" : "+d"(a2) : "r"(va));
+            asm("{\n\t.reg .b32 lo, hi;\n\t.reg .pred p;\n\tmov.b64 {lo, hi}, %0;\n\tsetp.lt.s32 p, %1, 0;\n\t"
+                "@p mov.b32 hi, 0;\n\tmov.b64 %0, {lo, hi};\n\t}" : "+d"(b2) : "r"(vb));
+            asm("{\n\t.reg .b32 lo, hi;\n\t.reg .pred p;\n\tmov.b64 {lo, hi}, %0;\n\tsetp.lt.s32 p, %1, 0;\n\t"
+                "@p mov.b32 hi, 0;\n\tmov.b64 %0, {lo, hi};\n\t}" : "+d"(c2) : "r"(vc));
             double r = a2 + (b2 + c2);
             if (APPROX == 4) {
-                if (__any_sync(0xffffffffu, k0 >= kLive && min(um, vm) <= 3u)) r = sum3_exact3(a, b, c);
+                if (__any_sync(0xffffffffu, min(near, (unsigned)vc) <= 8u)) r = sum3_exact3(a, b, c);
             } else {
-                if (k0 >= kLive) trk = min(trk, min(um, vm));
+                trk = __vimin3_u32(trk, near, (unsigned)vc);
             }
             return r;
         }
@@ -244,7 +260,7 @@ struct Log {  // natural-log space, the arithmetic of the reference (CUDA libm)
         return ln_add_exp_d(a + b, c + d);
     }
     template <int APPROX, bool EXT, bool SCALED = false>
-    __device__ static double sum3(const HmmConsts &k, double dM, double dX, double dY, unsigned &) {
+    __device__ static double sum3(const HmmConsts &k, double dM, double dX, double dY, unsigned &, double &) {
         double p0 = k.t_mm + dM, p1 = k.t_xm + dX, p2 = k.t_ym + dY, t;
         if (APPROX) {
             if (p1 < p2) { t = p1; p1 = p2; p2 = t; }
@@ -281,7 +297,7 @@ struct LogLit {
         return dm::ln_add_exp(dm::add(a, b), dm::add(c, d));
     }
     template <int APPROX, bool EXT, bool SCALED = false>
-    __device__ static double sum3(const HmmConsts &k, double dM, double dX, double dY, unsigned &) {
+    __device__ static double sum3(const HmmConsts &k, double dM, double dX, double dY, unsigned &, double &) {
         double p0 = dm::add(k.t_mm, dM), p1 = dm::add(k.t_xm, dX), p2 = dm::add(k.t_ym, dY), t;
         if (APPROX) {
             if (p1 < p2) { t = p1; p1 = p2; p2 = t; }
@@ -321,6 +337,7 @@ struct PairState {
     double acc3;                           // literal variant: (acc, acc2, acc3) = last row (M, X, Y) of this column
     double one0;                           // lane 0: start mass of the row-0 boundary; else 0
     unsigned trk;                          // closest approach of a high word to a threshold (sum3, APPROX == 2)
+    double wj[R];                          // scratch register pairs of the threshold products (low word: don't care)
 };
 
 // Ring of haplotype bytes: two 256-byte slots filled by TMA; `pos` is the ring position
@@ -401,7 +418,7 @@ __device__ __forceinline__ void hmm_step(PairState<R> &s, const HmmConsts &c, co
             match = xb == s.rb[r];
             e = match ? s.pm[r] : s.pmm[r];
         }
-        double nM = A::mul(e, A::template sum3<APPROX, EXT, LUT>(c, diagM, diagX, diagY, s.trk));
+        double nM = A::mul(e, A::template sum3<APPROX, EXT, LUT>(c, diagM, diagX, diagY, s.trk, s.wj[r]));
         double nX = A::template dot2<EXT>(LUT ? c.t_gy_s : c.t_gy, s.M[r], c.t_gye, s.X[r]);
         double nY;
         if (A::kLit)  // emit_y + ln_add_exp(gap_x + fm[curr][j], gap_x_ext + fy[curr][j]); cyo = ln eps
@@ -654,6 +671,8 @@ __global__ void __launch_bounds__(kWarps * 32, Occ<R>::kMinBlocks) pairhmm_kerne
         s.acc2 = A::zero();
         s.acc3 = A::zero();
         s.trk = 0xffffffffu;
+#pragma unroll
+        for (int r = 0; r < R; ++r) s.wj[r] = 0.0;
         h.last_lane = last_lane;
         if (A::kLit) {
             if (lx > g.lit_stride) {  // the caller sized the workspace for shorter windows
@@ -712,7 +731,7 @@ __global__ void __launch_bounds__(kWarps * 32, Occ<R>::kMinBlocks) pairhmm_kerne
         if (APPROX == 2 && !A::kLog) {
             // a decision of the three-way rule came within reach of its threshold: the pair is
             // re-evaluated by the exact-decision kernel (generic list)
-            if (__reduce_min_sync(0xffffffffu, s.trk) <= 3u) {
+            if (__reduce_min_sync(0xffffffffu, s.trk) <= 8u) {
                 if (lane == 0) g.gen_list[atomicAdd(g.gen_count, 1)] = pair;
                 continue;
             }
@@ -943,6 +962,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) pairhmm_long_kernel(HmmArgs g)
                 }
                 double diagM = s.dM, diagX = s.dX, diagY = s.dY, upM = uM, upY = uY;
                 unsigned trk_unused = 0;
+                double wj_unused = 0.0;
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     double e;
@@ -950,7 +970,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) pairhmm_long_kernel(HmmArgs g)
                     else e = xb == s.rb[r] ? s.pm[r] : s.pmm[r];
                     // (three-way rule: a long pair has ~1e8 cells, so a doubtful decision is settled cell by
                     // cell after a warp vote instead of re-evaluating the pair)
-                    const double nM = A::mul(e, A::template sum3<APPROX == 2 ? 4 : APPROX, EXT, LUT>(c, diagM, diagX, diagY, trk_unused));
+                    const double nM = A::mul(e, A::template sum3<APPROX == 2 ? 4 : APPROX, EXT, LUT>(c, diagM, diagX, diagY, trk_unused, wj_unused));
                     const double nX = A::template dot2<EXT>(LUT ? c.t_gy_s : c.t_gy, s.M[r], c.t_gye, s.X[r]);
                     const double nY = A::template dot2<EXT>(s.cyo[r], upM, s.cye[r], upY);
                     diagM = s.M[r]; diagX = s.X[r]; diagY = s.Y[r];
