@@ -39,6 +39,9 @@ typedef struct vlr_ctx vlr_ctx;
 
 /* ---- context ------------------------------------------------------------------------ */
 int vlr_version(void);
+/* SHA-1 (hex) of the sources and compiler flags this library was built from; the host mirror compares it
+ * with the stamp of the source tree next to it and refuses a stale binary (libprosic_b200/build.py). */
+const char *vlr_build_stamp(void);
 /* One context per GPU.  Fails with VLR_ERR_CUDA if `device` is not a CUDA device: there is no
  * CPU fallback anywhere in this library. */
 int vlr_ctx_create(int device, vlr_ctx **out);

@@ -88,7 +88,7 @@ class Model(C.Structure):
 
 
 EXPORTS = [
-    "vlr_version", "vlr_ctx_create", "vlr_ctx_destroy", "vlr_last_error", "vlr_ctx_set_stream",
+    "vlr_version", "vlr_build_stamp", "vlr_ctx_create", "vlr_ctx_destroy", "vlr_last_error", "vlr_ctx_set_stream",
     "vlr_ctx_synchronize", "vlr_ctx_launch_count", "vlr_ref_math", "vlr_pairhmm_batch",
     "vlr_pairhmm_workspace_bytes", "vlr_pairhmm_batch_dev", "vlr_measure_fp64_peak",
     "vlr_besthit_batch", "vlr_pathhmm_batch", "vlr_allele_support_batch", "vlr_likelihood_batch", "vlr_call_records",
@@ -110,6 +110,13 @@ def load():
     L = C.CDLL(SO_PATH)
     vp, i32, i64, u32, d = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_double
     L.vlr_version.restype = C.c_int
+    L.vlr_build_stamp.restype = C.c_char_p
+    # a binary that was not built from the sources next to it is refused (a GPU box has no nvcc: the
+    # library travels prebuilt, and a stale one would otherwise pass silently)
+    have, want = L.vlr_build_stamp().decode(), _build.source_stamp()
+    if have != want:
+        raise ImportError("libvlr_b200.so is stale: built from sources %s, tree has %s -- run "
+                          "`python -m libprosic_b200.build -f`" % (have[:12], want[:12]))
     L.vlr_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
     L.vlr_ctx_destroy.argtypes = [vp]
     L.vlr_ctx_destroy.restype = None

@@ -18,7 +18,9 @@ def _sources():
     return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
-def _stamp():
+def source_stamp():
+    """SHA-1 over csrc/*, include/vlr_gpu.h and the compiler flags: compiled into the library
+    (vlr_build_stamp) and compared at load time."""
     h = hashlib.sha1()
     for f in sorted(os.listdir(CSRC)) + ["../../include/vlr_gpu.h"]:
         p = os.path.join(CSRC, f)
@@ -31,19 +33,20 @@ def _stamp():
 
 def build(force=False, verbose=False):
     stamp_file = os.path.join(OBJ, "stamp")
-    stamp = _stamp()
+    stamp = source_stamp()
     if (not force and os.path.exists(OUT) and os.path.exists(stamp_file)
             and open(stamp_file).read() == stamp):
         return OUT
     if not os.path.exists(NVCC):
         if os.path.exists(OUT):
-            return OUT  # GPU box without nvcc: use the prebuilt library shipped with the repo
+            return OUT  # GPU box without nvcc: the prebuilt library; _ffi.load() checks its build stamp
         raise RuntimeError("nvcc not found and no prebuilt libvlr_b200.so")
     os.makedirs(OBJ, exist_ok=True)
 
     def cc(src):
         obj = os.path.join(OBJ, src[:-3] + ".o")
         cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+              (['-DVLR_BUILD_STAMP="%s"' % stamp] if src == "ctx.cu" else []) + \
               ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

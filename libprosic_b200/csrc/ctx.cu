@@ -76,6 +76,10 @@ __global__ void ref_math_kernel(int fn, int64_t n, const double *x, double *out)
 extern "C" {
 
 int vlr_version(void) { return 200; }
+#ifndef VLR_BUILD_STAMP
+#define VLR_BUILD_STAMP "unstamped"
+#endif
+const char *vlr_build_stamp(void) { return VLR_BUILD_STAMP; }
 
 int vlr_ref_math(vlr_ctx *ctx, int fn, int64_t n, const double *x, double *out) {
     if (fn < 0 || fn > 3 || n < 0 || (n > 0 && (!x || !out))) return ctx ? vlr::set_err(ctx, VLR_ERR_INVALID, "bad argument") : VLR_ERR_INVALID;

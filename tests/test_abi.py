@@ -26,6 +26,19 @@ def test_library_exports_every_declared_symbol():
     assert lib.vlr_version() >= 100
 
 
+def test_build_stamp_matches_the_sources(monkeypatch):
+    """The library carries the hash of the sources it was built from; a binary that does not match
+    the tree next to it is refused at load time (a GPU box has no nvcc and uses the shipped .so)."""
+    from libprosic_b200 import _ffi, build
+    lib = _ffi.load()
+    assert lib.vlr_build_stamp().decode() == build.source_stamp()
+    monkeypatch.setattr(_ffi, "_lib", None)
+    monkeypatch.setattr(build, "build", lambda *a, **k: build.OUT)          # "no nvcc here"
+    monkeypatch.setattr(build, "source_stamp", lambda: "0" * 40)            # the tree has moved on
+    with pytest.raises(ImportError, match="stale"):
+        _ffi.load()
+
+
 def test_no_gpu_no_fallback():
     import torch
     if torch.cuda.is_available():
