@@ -201,21 +201,20 @@ def part2_workloads(args):
     }
 
 
-def oracle_part2(wl, cols, cat, off, n_sample):
-    """Oracle (1 thread) on the first n_sample sites: sites/s and distinct evaluations per site."""
+def oracle_part2(wl, cols, cat, off, n_sample, threads=1):
+    """Oracle on the first n_sample sites with `threads` host threads (POSIX threads inside the C
+    oracle, sites dealt round-robin): results, sites/s, seconds."""
     import oracle as O
     scn = wl["scn"]
     spec = O.ModelSpec(scn["n_samples"], scn["resolution"], scn["contaminated"], scn["by"],
                        scn["purity"], scn["nodes"], scn["events"],
                        [O.make_biases(**b) for b in scn["biases"]])
-    ns = scn["n_samples"]
-    res, evals = [], 0.0
+    O.model_compute_batch(spec, cols, cat, off, min(n_sample, 8), 1)  # load / warm
     t0 = time.perf_counter()
-    for s in range(n_sample):
-        pv = [O.PileupView(cols, cat, int(off[s * ns + k]), int(off[s * ns + k + 1])) for k in range(ns)]
-        r = O.model_compute(spec, pv)
-        res.append(r)
+    r = O.model_compute_batch(spec, cols, cat, off, n_sample, threads)
     dt = time.perf_counter() - t0
+    res = [dict(event_ln=r["event_ln"][s], map_af=r["map_af"][s], n_evals=int(r["n_evals"][s]))
+           for s in range(n_sample)]
     return res, n_sample / dt, dt
 
 
@@ -322,6 +321,11 @@ def bench_part2(args, ctx, torch, dist, dev, stream, rank, world, name, wl, time
                            "hbm": {"achieved": sps_gpu * n_obs_site * BYTES_PER_OBS / 1e9, "unit": "GB/s"}}
         res["cpu_baseline"] = {"value": cpu_sps, "unit": "sites/s", "cores": 1, "kind": "port",
                                "sample": "%d sites of this workload, 1 thread, %.1f s" % (n_cpu, cpu_dt)}
+        cores = os.cpu_count() or 1
+        n_all = min(n_sites, n_cpu * min(cores, 8))
+        _, all_sps, all_dt = oracle_part2(wl, cols, cat, off, n_all, cores)
+        res["cpu_baseline_all_cores"] = {"value": all_sps, "unit": "sites/s", "cores": cores, "kind": "port",
+                                         "sample": "%d sites of this workload, %d threads, %.1f s" % (n_all, cores, all_dt)}
     return res
 
 
@@ -388,6 +392,23 @@ def bench_allele_support(args, ctx, w, flags, rank, world, torch, dist, dev):
         res["parity_max_abs_ln"] = worst
         res["cpu_baseline"] = {"value": n_cpu / cdt, "unit": "reads/s", "cores": 1, "kind": "port",
                                "sample": "%d reads, 1 thread, %.1f s (oracle: DP-matrix edit distance + log-space banded HMM)" % (n_cpu, cdt)}
+        # all host cores (ctypes releases the GIL around the C oracle; ~0.5 ms of C per call)
+        from concurrent.futures import ThreadPoolExecutor
+        cores = os.cpu_count() or 1
+        n_all = min(n_reads, n_cpu * min(cores, 8))
+        gl = gap.as_ln_array()
+
+        def one(r):
+            ids = region_haps[2 * r:2 * r + 2]
+            hp = [w["hap_bytes"][w["hap_off"][h]:w["hap_off"][h + 1]] for h in ids]
+            O.allele_support_region([hp[0]], [hp[1]], w["read_bases"][w["read_off"][r]:w["read_off"][r + 1]],
+                                    w["read_quals"][w["read_off"][r]:w["read_off"][r + 1]], gl, flags=flags)
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=cores) as ex:
+            list(ex.map(one, range(n_all), chunksize=16))
+        adt = time.perf_counter() - t0
+        res["cpu_baseline_all_cores"] = {"value": n_all / adt, "unit": "reads/s", "cores": cores, "kind": "port",
+                                         "sample": "%d reads, %d threads, %.1f s" % (n_all, cores, adt)}
     return res
 
 

@@ -360,6 +360,30 @@ class ModelSpec:
 PRIOR_FN = C.CFUNCTYPE(C.c_double, C.POINTER(C.c_double), C.c_int, C.c_void_p)
 
 
+def model_compute_batch(spec, cols, cat, obs_off, n_sites, n_threads=1):
+    """Model::compute over the first n_sites sites of a struct-of-arrays batch on n_threads host
+    threads (flat prior).  Returns dict(event_ln [n, E], marginal, map_af [n, S], map_bias, n_evals)."""
+    L = lib()
+    ns, ne = spec.n_samples, len(spec.events_py)
+    keep = [np.ascontiguousarray(cols[n], dtype=np.float64) for n in OBS_COLUMNS]
+    catc = np.ascontiguousarray(cat, dtype=np.uint16)
+    off = np.ascontiguousarray(obs_off, dtype=np.int64)
+    base = Pileup(*[a.ctypes.data_as(_DP) for a in keep], catc.ctypes.data_as(_U16P), 0)
+    ev = np.zeros((n_sites, ne), np.float64)
+    marg = np.zeros(n_sites, np.float64)
+    maf = np.zeros((n_sites, ns), np.float64)
+    mb = np.zeros((n_sites, ns), np.int32)
+    nev = np.zeros(n_sites, np.int64)
+    L.vlro_model_compute_batch.restype = C.c_int
+    L.vlro_model_compute_batch.argtypes = [C.POINTER(Model), C.POINTER(Pileup), C.POINTER(C.c_int64), C.c_int64,
+                                           C.c_int, _DP, _DP, _DP, _I32P, C.POINTER(C.c_int64)]
+    st = L.vlro_model_compute_batch(C.byref(spec.c), C.byref(base), off.ctypes.data_as(C.POINTER(C.c_int64)),
+                                    n_sites, int(n_threads), ev.ctypes.data_as(_DP), marg.ctypes.data_as(_DP),
+                                    maf.ctypes.data_as(_DP), mb.ctypes.data_as(_I32P),
+                                    nev.ctypes.data_as(C.POINTER(C.c_int64)))
+    return dict(event_ln=ev, marginal=marg, map_af=maf, map_bias=mb, n_evals=nev, status=st)
+
+
 def model_compute(spec, pileup_views, prior=None):
     """Returns dict(event_ln, marginal, map_af, map_bias, n_evals, status).
     prior: optional callable(list of allele frequencies) -> ln prior (Prior::compute)."""

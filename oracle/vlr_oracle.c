@@ -1104,3 +1104,72 @@ int vlro_model_compute(const vlro_model_t *m, const vlro_pileup_t *pileups, doub
     free(biases);
     return c.nan_flag ? 1 : 0;
 }
+
+
+/* =====================================================================================
+ * All-cores driver for the CPU legs of bench.py: the per-site Model::compute above over a batch of
+ * sites given as struct-of-arrays columns (rows obs_off[s*n_samples + m] .. obs_off[s*n_samples + m + 1]),
+ * sites dealt round-robin to n_threads POSIX threads (the reference's `call` processes records
+ * independently, calling.rs:283-330).  Flat prior only (the bench workloads).
+ * ===================================================================================== */
+#include <pthread.h>
+typedef struct {
+    const vlro_model_t *m;
+    const vlro_pileup_t *cols;   /* column base pointers (n_obs unused) */
+    const int64_t *obs_off;
+    int64_t n_sites;
+    int t, n_threads;
+    double *event_ln, *marginal, *map_af;
+    int32_t *map_bias;
+    int64_t *n_evals;
+    int status;
+} batch_job_t;
+
+static void *batch_worker(void *arg) {
+    batch_job_t *j = (batch_job_t *)arg;
+    const int ns = j->m->n_samples, ne = j->m->n_events;
+    vlro_pileup_t pv[8];
+    for (int64_t s = j->t; s < j->n_sites; s += j->n_threads) {
+        for (int k = 0; k < ns; ++k) {
+            const int64_t lo = j->obs_off[s * ns + k], hi = j->obs_off[s * ns + k + 1];
+            pv[k].prob_mapping = j->cols->prob_mapping + lo;
+            pv[k].prob_mismapping = j->cols->prob_mismapping + lo;
+            pv[k].prob_alt = j->cols->prob_alt + lo;
+            pv[k].prob_ref = j->cols->prob_ref + lo;
+            pv[k].prob_missed_allele = j->cols->prob_missed_allele + lo;
+            pv[k].prob_sample_alt = j->cols->prob_sample_alt + lo;
+            pv[k].prob_double_overlap = j->cols->prob_double_overlap + lo;
+            pv[k].prob_single_overlap = j->cols->prob_single_overlap + lo;
+            pv[k].prob_hit_base = j->cols->prob_hit_base + lo;
+            pv[k].cat = j->cols->cat + lo;
+            pv[k].n_obs = (int32_t)(hi - lo);
+        }
+        int64_t nev = 0;
+        const int st = vlro_model_compute(j->m, pv, j->event_ln + s * ne, j->marginal + s, j->map_af + s * ns,
+                                          j->map_bias ? j->map_bias + s * ns : NULL, &nev, NULL, NULL);
+        if (j->n_evals) j->n_evals[s] = nev;
+        if (st < 0) j->status = st;
+    }
+    return NULL;
+}
+
+int vlro_model_compute_batch(const vlro_model_t *m, const vlro_pileup_t *cols, const int64_t *obs_off,
+                             int64_t n_sites, int n_threads, double *out_event_ln, double *out_marginal,
+                             double *out_map_af, int32_t *out_map_bias, int64_t *out_n_evals) {
+    if (m->n_samples > 8 || n_threads < 1) return -1;
+    if (n_threads > 256) n_threads = 256;
+    pthread_t th[256];
+    batch_job_t jobs[256];
+    for (int t = 0; t < n_threads; ++t) {
+        jobs[t] = (batch_job_t){m, cols, obs_off, n_sites, t, n_threads, out_event_ln, out_marginal,
+                                out_map_af, out_map_bias, out_n_evals, 0};
+        if (n_threads == 1) batch_worker(&jobs[t]);
+        else if (pthread_create(&th[t], NULL, batch_worker, &jobs[t]) != 0) return -2;
+    }
+    int status = 0;
+    for (int t = 0; t < n_threads; ++t) {
+        if (n_threads > 1) pthread_join(th[t], NULL);
+        if (jobs[t].status) status = jobs[t].status;
+    }
+    return status;
+}

@@ -218,6 +218,11 @@ typedef double (*vlro_prior_fn)(const double *afs, int n_samples, void *user);
 int vlro_model_compute(const vlro_model_t *m, const vlro_pileup_t *pileups, double *out_event_ln,
                        double *out_marginal, double *out_map_af, int32_t *out_map_bias,
                        int64_t *out_n_evals, vlro_prior_fn prior_cb, void *prior_user);
+/* the same over a batch of sites (struct-of-arrays columns, rows obs_off[s*n_samples+m] ..), sites dealt
+ * round-robin to n_threads threads; flat prior.  Used by the all-cores CPU legs of bench.py. */
+int vlro_model_compute_batch(const vlro_model_t *m, const vlro_pileup_t *cols, const int64_t *obs_off,
+                             int64_t n_sites, int n_threads, double *out_event_ln, double *out_marginal,
+                             double *out_map_af, int32_t *out_map_bias, int64_t *out_n_evals);
 
 #ifdef __cplusplus
 }
