@@ -279,6 +279,25 @@ def bench_part2(args, ctx, torch, dist, dev, stream, rank, world, name, wl, time
         t = torch.tensor([ms_e2e32], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e2e32 = float(t.item())
+    # the records as `preprocess` stores them (bincode words per field), decoded on the device
+    from libprosic_b200 import obs_codec as lc
+    wire = lc.encode_batch(cols, cat, off, pin=True)
+    wire_out = dict(event_ln=torch.empty((n_sites, ne), dtype=torch.float64).pin_memory().numpy(),
+                    marginal=torch.empty(n_sites, dtype=torch.float64).pin_memory().numpy(),
+                    map_af=torch.empty((n_sites, ns), dtype=torch.float64).pin_memory().numpy(),
+                    map_bias=torch.empty((n_sites, ns), dtype=torch.int32).pin_memory().numpy())
+
+    def step_e2e_wire():
+        return ctx.posterior_batch_wire(scn, wire, wire_out)
+
+    out_wire = {k: v.copy() for k, v in step_e2e_wire().items()}
+    t0 = time.perf_counter()
+    timed(step_e2e_wire, args.steps)
+    ms_e2ew = (time.perf_counter() - t0) * 1e3
+    if world > 1:
+        t = torch.tensor([ms_e2ew], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2ew = float(t.item())
     in_bytes32 = sum(int(v.numel() * 4) for v in h_cols32.values()) + int(h_cat.numel() * 2 + h_off.numel() * 8)
     in_bytes = sum(int(v.numel() * v.element_size()) for v in h_cols.values()) + \
         int(h_cat.numel() * 2 + h_off.numel() * 8)
@@ -291,8 +310,22 @@ def bench_part2(args, ctx, torch, dist, dev, stream, rank, world, name, wl, time
            "e2e_f32": {"value": n_sites * world * args.steps / (ms_e2e32 * 1e-3), "unit": "sites/s",
                        "h2d_bytes_per_step": in_bytes32, "d2h_bytes_per_step": out_bytes,
                        "ms_per_step": ms_e2e32 / args.steps,
-                       "note": "vlr_posterior_batch_f32: stored fields as f32, derived columns on the device"}}
+                       "note": "vlr_posterior_batch_f32: stored fields as f32, derived columns on the device"},
+           "e2e_wire": {"value": n_sites * world * args.steps / (ms_e2ew * 1e-3), "unit": "sites/s",
+                        "h2d_bytes_per_step": int(wire.nbytes), "d2h_bytes_per_step": out_bytes,
+                        "ms_per_step": ms_e2ew / args.steps,
+                        "wire_bytes_per_observation": float(wire.nbytes) / max(1, len(cat)),
+                        "host_gb_per_s": float(wire.nbytes + out_bytes) / (ms_e2ew / args.steps * 1e-3) / 1e9,
+                        "note": "vlr_posterior_batch_wire: the records as `preprocess` stores them (bincode "
+                                "words per field, format 8) uploaded as they are and decoded by a kernel"}}
     if rank == 0:
+        # the derived columns (prob_mismapping, prob_single_overlap) come from the device's libm here and
+        # from numpy in the f64 entry's inputs: last-bit differences in ln space, identical MAP calls
+        res["e2e_wire"]["max_abs_ln_vs_f64_entry"] = float(np.nanmax(np.abs(np.where(
+            np.isfinite(out_wire["event_ln"]) & np.isfinite(out_e2e["event_ln"]),
+            out_wire["event_ln"] - out_e2e["event_ln"], 0.0))))
+        res["e2e_wire"]["map_af_identical_to_f64_entry"] = bool(
+            np.array_equal(out_wire["map_af"], out_e2e["map_af"], equal_nan=True))
         res["e2e_f32"]["max_abs_ln_vs_f64_entry"] = float(np.nanmax(np.abs(np.where(
             np.isfinite(out32["event_ln"]) & np.isfinite(out_e2e["event_ln"]),
             out32["event_ln"] - out_e2e["event_ln"], 0.0))))

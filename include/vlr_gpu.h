@@ -438,6 +438,34 @@ int64_t vlr_obs_encoded_bound(int64_t n_obs);
 int vlr_obs_encode(int64_t n_obs, const double *const *cols, const uint16_t *cat,
                    int32_t *const *out_fields, int64_t capacity, int32_t *out_n_values);
 
+/* ---- the wire format on the device -------------------------------------------------------
+ * A batch of observation records AS STORED (what read_observations would parse, mod.rs:455-527): per
+ * field the u16 words of all records back to back (the BCF INFO integer values narrowed to u16, as
+ * mod.rs:473-479 does), record r = site * n_samples + sample occupying words[f][word_off[f][r] ..
+ * word_off[f][r+1]).  words[VLR_OBS_INDEL_OPERATIONS] == NULL: format 7 (IndelOperations::None). */
+typedef struct {
+    const uint16_t *words[VLR_OBS_N_FIELDS];
+    const int64_t *word_off[VLR_OBS_N_FIELDS];   /* n_records + 1 entries each */
+} vlr_obs_wire;
+/* Device-side read_observations: uploads the records, decodes them in one kernel (one thread per
+ * record and field walks the variable-length MiniLogProb vector; prob_mismapping /
+ * prob_single_overlap derived as ObservationBuilder does) and returns the struct-of-arrays columns
+ * (out_cols[0..8] in vlr_obs_columns order, rows out_obs_off[r] .. out_obs_off[r+1] of record r).
+ * out_cols == NULL and out_cat == NULL: only out_obs_off is filled (size query, no device work).
+ * A malformed vector (bad variant index, length mismatch, trailing bytes) -> VLR_ERR_INVALID. */
+int vlr_obs_decode_batch(vlr_ctx *ctx, int64_t n_records, const vlr_obs_wire *wire, int64_t capacity,
+                         int64_t *out_obs_off, double *const *out_cols, uint16_t *out_cat);
+/* Host-side write_observations for a batch (the counterpart a `preprocess` binding calls on the columns
+ * part 1 produced): appends record r's field f at out_words[f] + out_word_off[f][r]; every out_words[f]
+ * holds `capacity_words` u16 (sum over records of vlr_obs_encoded_bound(n_obs) suffices). */
+int vlr_obs_encode_batch(int64_t n_records, const double *const *cols, const uint16_t *cat, const int64_t *obs_off,
+                         uint16_t *const *out_words, int64_t *const *out_word_off, int64_t capacity_words);
+/* Whole part 2 straight from stored records: upload (chunked, H2D of chunk c+1 under the kernels of
+ * chunk c), device decode, vlr_posterior_batch_dev.  n_records = n_sites * model->n_samples. */
+int vlr_posterior_batch_wire(vlr_ctx *ctx, int64_t n_sites, const vlr_model *model, const vlr_obs_wire *wire,
+                             double *out_event_ln, double *out_marginal, double *out_map_af,
+                             int32_t *out_map_bias);
+
 #ifdef __cplusplus
 }
 #endif

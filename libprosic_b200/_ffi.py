@@ -92,8 +92,13 @@ EXPORTS = [
     "vlr_ctx_synchronize", "vlr_ctx_launch_count", "vlr_ref_math", "vlr_pairhmm_batch",
     "vlr_pairhmm_workspace_bytes", "vlr_pairhmm_batch_dev", "vlr_measure_fp64_peak",
     "vlr_besthit_batch", "vlr_pathhmm_batch", "vlr_allele_support_batch", "vlr_likelihood_batch", "vlr_call_records",
-    "vlr_obs_codes", "vlr_obs_cigar", "vlr_bias_chars", "vlr_model_leaves", "vlr_obs_decode", "vlr_obs_encode", "vlr_obs_encoded_bound", "vlr_posterior_batch", "vlr_posterior_batch_f32", "vlr_posterior_batch_dev",
+    "vlr_obs_codes", "vlr_obs_cigar", "vlr_bias_chars", "vlr_model_leaves", "vlr_obs_decode", "vlr_obs_encode", "vlr_obs_encoded_bound", "vlr_obs_decode_batch", "vlr_obs_encode_batch", "vlr_posterior_batch_wire", "vlr_posterior_batch", "vlr_posterior_batch_f32", "vlr_posterior_batch_dev",
 ]
+
+class ObsWire(C.Structure):
+    """vlr_obs_wire: per field the u16 words of all records and their offsets."""
+    _fields_ = [("words", C.c_void_p * 13), ("word_off", C.c_void_p * 13)]
+
 
 _lib = None
 
@@ -148,6 +153,9 @@ def load():
     L.vlr_obs_encode.argtypes = [i64, vp, vp, vp, i64, vp]
     L.vlr_obs_encoded_bound.argtypes = [i64]
     L.vlr_obs_encoded_bound.restype = i64
+    L.vlr_obs_decode_batch.argtypes = [vp, i64, C.POINTER(ObsWire), i64, vp, vp, vp]
+    L.vlr_obs_encode_batch.argtypes = [i64, vp, vp, vp, vp, vp, i64]
+    L.vlr_posterior_batch_wire.argtypes = [vp, i64, vp, C.POINTER(ObsWire), vp, vp, vp, vp]
     L.vlr_model_leaves.argtypes = [vp, C.POINTER(Model), i64, vp, vp, vp]
     L.vlr_posterior_batch.argtypes = [vp, i64, C.POINTER(Model), C.POINTER(ObsColumns), vp, vp, vp,
                                       vp, vp]

@@ -395,6 +395,21 @@ class Context:
                                                      _ptr(obs_off), _ptr(ev), _ptr(marg), _ptr(maf), _ptr(mb)))
         return dict(event_ln=ev, marginal=marg, map_af=maf, map_bias=mb)
 
+    def posterior_batch_wire(self, scn, wire, out=None):
+        """Part 2 straight from stored observation records (obs_codec.WireBatch): upload, device
+        decode, posterior.  Same outputs as posterior_batch.  `out`: optional dict of preallocated
+        (pinned) arrays event_ln / marginal / map_af / map_bias."""
+        model = self._cached_model(scn)
+        ns, ne = scn["n_samples"], len(scn["events"])
+        n_sites = wire.n_records // ns
+        if out is None:
+            out = dict(event_ln=np.empty((n_sites, ne), np.float64), marginal=np.empty(n_sites, np.float64),
+                       map_af=np.empty((n_sites, ns), np.float64), map_bias=np.empty((n_sites, ns), np.int32))
+        ws = wire.c_struct()
+        self._check(self.lib.vlr_posterior_batch_wire(self.h, n_sites, C.byref(model), C.byref(ws), _ptr(out["event_ln"]),
+                                                      _ptr(out["marginal"]), _ptr(out["map_af"]), _ptr(out["map_bias"])))
+        return out
+
     def _cached_model(self, scn):
         """vlr_model of a scenario dict, rebuilt when the dict changed.  The cache belongs to this
         context, holds the dict itself (its id cannot be reused while cached) and compares a

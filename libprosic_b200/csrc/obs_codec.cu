@@ -244,4 +244,36 @@ int vlr_obs_encode(int64_t n_obs, const double *const *cols, const uint16_t *cat
     return VLR_OK;
 }
 
+int vlr_obs_encode_batch(int64_t n_records, const double *const *cols, const uint16_t *cat, const int64_t *obs_off,
+                         uint16_t *const *out_words, int64_t *const *out_word_off, int64_t capacity_words) {
+    if (n_records < 0 || !cols || !cat || !obs_off || !out_words || !out_word_off) return VLR_ERR_INVALID;
+    for (int f = 0; f < VLR_OBS_N_FIELDS; ++f) {
+        if (!out_words[f] || !out_word_off[f]) return VLR_ERR_INVALID;
+        out_word_off[f][0] = 0;
+    }
+    std::vector<int32_t> tmp[VLR_OBS_N_FIELDS];
+    for (int64_t r = 0; r < n_records; ++r) {
+        const int64_t r0 = obs_off[r], n = obs_off[r + 1] - r0;
+        if (n < 0) return VLR_ERR_INVALID;
+        const int64_t cap = vlr_obs_encoded_bound(n);
+        const double *rc[9];
+        int32_t *fp[VLR_OBS_N_FIELDS];
+        int32_t nv[VLR_OBS_N_FIELDS];
+        for (int c = 0; c < 9; ++c) rc[c] = cols[c] ? cols[c] + r0 : nullptr;
+        for (int f = 0; f < VLR_OBS_N_FIELDS; ++f) {
+            if ((int64_t)tmp[f].size() < cap) tmp[f].resize((size_t)cap);
+            fp[f] = tmp[f].data();
+        }
+        const int st = vlr_obs_encode(n, rc, cat + r0, fp, cap, nv);
+        if (st != VLR_OK) return st;
+        for (int f = 0; f < VLR_OBS_N_FIELDS; ++f) {
+            const int64_t w0 = out_word_off[f][r];
+            if (w0 + nv[f] > capacity_words) return VLR_ERR_INVALID;
+            for (int32_t k = 0; k < nv[f]; ++k) out_words[f][w0 + k] = (uint16_t)fp[f][k];
+            out_word_off[f][r + 1] = w0 + nv[f];
+        }
+    }
+    return VLR_OK;
+}
+
 }  // extern "C"

@@ -333,6 +333,33 @@ def test_chunked_pipeline_and_f32_entry(ctx, oracle):
     assert np.array_equal(got32["map_bias"], got["map_bias"])
 
 
+def test_wire_entry_decodes_on_the_device(ctx, oracle):
+    """vlr_posterior_batch_wire: the records as `preprocess` stores them (bincode words per field)
+    are uploaded in chunks and decoded by a kernel; the posteriors are those of the f64 entry on the
+    host-decoded columns, bit for bit, for ragged two-sample pileups spanning several chunks."""
+    from libprosic_b200 import obs_codec as lc
+    scn = scenario.tumor_normal(purity=0.75, indel=True)
+    cols, cat, off, _ = synth.make_pileups(9000, [40, 100], seed=77, kind="indel", ragged=True,
+                                           af_sets=[[(0, .6), (.5, .3), (1, .1)], [(0, .4), (.3, .4), (.05, .2)]],
+                                           purity=[1.0, 0.75], artifact_frac=0.05)
+    wire = lc.encode_batch(cols, cat, off)
+    assert wire.nbytes > 2 * 32 * 2 ** 20  # at least three chunks
+    got = ctx.posterior_batch_wire(scn, wire)
+    dcols, dcat, doff = lc.decode_batch(ctx, wire)
+    assert np.array_equal(doff, off) and np.array_equal(dcat, cat)
+    for k in lc.COLUMNS:
+        if k not in ("prob_mismapping", "prob_single_overlap"):
+            assert np.array_equal(dcols[k], cols[k], equal_nan=True), k   # synth pileups are MiniLogProb-quantised
+    want = ctx.posterior_batch(scn, dcols, dcat, doff)
+    assert np.array_equal(got["event_ln"], want["event_ln"], equal_nan=True)
+    assert np.array_equal(got["marginal"], want["marginal"], equal_nan=True)
+    assert np.array_equal(got["map_af"], want["map_af"], equal_nan=True)
+    assert np.array_equal(got["map_bias"], want["map_bias"])
+    sites = [0, 4500, 8999]
+    for s, w in zip(sites, _oracle_run(oracle, scn, cols, cat, off, sites)):
+        _close(got["event_ln"][s], w["event_ln"])
+
+
 def _random_scenario(rng, n_samples):
     """Random event universe: 2-6 events, each 1-3 tree roots; a root is a chain over the samples in
     random order whose nodes are random Sets / Ranges (some chains end in a fan-out of two children,
