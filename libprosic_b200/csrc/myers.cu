@@ -8,14 +8,24 @@
 //   dist == 0 ? certainty_est : banded pair-HMM on the window shrunk to the hit (pairhmm.rs:38-44)
 //   -> max over haplotypes -> normalisation / 0.5 fallbacks.
 //
-// One thread per (read, haplotype) pair: the pattern is the read window (<= 248 rows = 4 words of
-// 64 bits), the text the haplotype window.  Each thread keeps the vertical-delta bit-vectors
-// (Pv, Mv) of every column in a private global scratch slot so that the traceback can evaluate
-// any D[j][i] with two masked popcounts per word -- the same information bio's lazy matcher
-// records.  Integer work only; results are bit-exact against the oracle.
+// One thread per (read, haplotype) pair: the pattern is the read window (KW words of 64 bits: 256
+// rows in the common instantiation, 1024 in the one for long windows -- bio's Myers::Long,
+// edit_distance.rs:42-46), the text the haplotype window.  Two scans:
+//   1. the whole text without storing anything: best distance d*, number and range of the best end
+//      positions.  Exact occurrences (d* = 0) are finished here (start = end - m, no operations).
+//   2. only the columns a traceback can look at, c0 = first_best - m - 2 d* - 1 .. last_best, this time
+//      keeping the vertical-delta bit-vectors (Pv, Mv) of every column in a private global scratch
+//      slot, so that the traceback can evaluate any D[j][i] with two masked popcounts per word.
+//      Starting at c0 instead of 0 is exact: a traceback from (m, e) stays on the diagonals
+//      e - m +- d* and consults their neighbours; a consulted cell only matters if its D is at most
+//      d*, and an alignment of cost <= d* ending there starts at or after c0 (the truncated scan's D'
+//      is never below D, so every "predecessor + cost == current" test has the same outcome).
+// This cut the scratch traffic of the C3 read set from 18 GB to under 6 GB per launch (the kernel was
+// bound by it).  Integer work only; results are bit-exact against the oracle.
 #include <math.h>
 #include <string.h>
 
+#include <type_traits>
 #include <vector>
 
 #include <stdlib.h>
@@ -27,7 +37,6 @@
 
 namespace vlr {
 
-constexpr int kMyW = 4;               // 64-bit words per column (pattern <= 256 rows)
 constexpr int kMaxIndelOps = VLR_MAX_INDEL_OPS;   // bytes per output record: one byte per run
 constexpr int kMaxRuns = kMaxIndelOps;
 constexpr int kMaxRunLen = 127;
@@ -44,7 +53,9 @@ struct MyersArgs {
     const int32_t *pair_hap, *pair_read;
     int64_t n_pairs;
     int32_t *cursor;
-    uint64_t *scratch;        // per worker: (max_lx + 1) * 2 * kMyW words
+    uint64_t *scratch;        // per worker: (max_lx + 1) * 4 * KW words
+    int32_t m_lo, m_hi;       // this launch takes the pairs with m_lo < rows <= m_hi
+    int32_t exp_skip;         // experiments (VLR_K2_EXP): 1 = no traceback, 2 = no second scan either
     int32_t *scratch_dm;      // per worker: (max_lx + 1) bottom distances
     int64_t scratch_stride;   // columns per worker
     HitOut *out;
@@ -58,13 +69,16 @@ struct MyersArgs {
 };
 
 __device__ __forceinline__ int up_char(int c) { return (unsigned)(c - 'a') < 26u ? c - 32 : c; }
-__device__ __forceinline__ int sym_of(int c) {  // A C G T N -> 0..4, anything else 5
-    return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : c == 'N' ? 4 : 5;
+__device__ __forceinline__ int sym_of(int c) {  // A C G T -> a code in 0..3, N -> 4, anything else 5
+    const unsigned t = (unsigned)(c - 'A');
+    const bool acgt = t < 20u && ((0x80045u >> t) & 1u);   // bits 0 (A), 2 (C), 6 (G), 19 (T)
+    return acgt ? (c >> 1) & 3 : (c == 'N' ? 4 : 5);       // A 0, C 1, T 2, G 3
 }
 
 // D[j][i] from the stored column state (i >= 1): bottom distance minus the vertical deltas of
 // rows j+1..m
 // D[j][i] from a column record (W words of Pv, then W words of Mv) and the bottom distance
+template <int kMyW>
 __device__ __forceinline__ int dist_from(const uint64_t *rec, int dm, int j, int m, int W) {
     int d = dm;
 #pragma unroll
@@ -79,30 +93,50 @@ __device__ __forceinline__ int dist_from(const uint64_t *rec, int dm, int j, int
     return d;
 }
 
+struct WalkRes {   // result of one traceback, handed from the executing lane to the owner of the pair
+    int32_t start, nindel, nruns, e;
+    double path;
+    uint8_t runs[kMaxRuns];
+};
+
+template <int kMyW>
 __global__ void __launch_bounds__(128) besthit_kernel(MyersArgs g) {
+    __shared__ int2 s_task[4][32];
+    __shared__ WalkRes s_res[4][32];
     const int64_t worker = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    // Scratch is interleaved across the lanes of a warp: word pair w of column c of lane l sits at
-    // ((c * kMyW + w) * 32 + l) * 16 bytes, the bottom distance at (c * 32 + l) * 4.  The lanes of
-    // a warp walk the columns in lock step, so a column's stores are whole 512-byte rows instead
-    // of 32 scattered 48-byte pieces.
+    // Scratch is interleaved across the lanes of a warp: word w of column c of lane l is one 32-byte
+    // sector (Pv, Mv, Ph, Mh) at ((c * kMyW + w) * 32 + l) * 32 bytes, the bottom distance sits at
+    // (c * 32 + l) * 4.  The lanes of a warp walk the columns in lock step, so a column's stores are whole
+    // 1 KB rows, and a traceback step fetches exactly one sector.
     const int64_t warp_id = worker >> 5;
     const int lane_id = (int)(worker & 31);
-    ulonglong2 *cols = reinterpret_cast<ulonglong2 *>(g.scratch) + warp_id * g.scratch_stride * (kMyW * 32) + lane_id;
+    ulonglong2 *cols = reinterpret_cast<ulonglong2 *>(g.scratch) + warp_id * g.scratch_stride * (2 * kMyW * 32) + lane_id * 2;
     int32_t *dms_base = g.scratch_dm + warp_id * g.scratch_stride * 32 + lane_id;
     auto dms = [&](int c) -> int32_t & { return dms_base[(int64_t)c * 32]; };
+    const bool want_path = g.out_path != nullptr;
+    // A warp takes 32 consecutive pairs at a time and stays converged: every loop below that nests
+    // data-dependent work (the tracebacks of several best end positions) runs warp-uniformly with
+    // the lanes' own state predicated -- as a plain "for e { while (j > 0) }" per thread the lanes
+    // drifted apart and the traceback ran with 5 of 32 lanes active.
     for (;;) {
-        const int64_t k = (int64_t)atomicAdd(g.cursor, 1);
-        if (k >= g.n_pairs) break;
-        const int64_t h = g.pair_hap ? g.pair_hap[k] : k;
-        const int64_t rd = g.pair_read ? g.pair_read[k] : k;
+        int base = 0;
+        if (lane_id == 0) base = atomicAdd(g.cursor, 32);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if ((int64_t)base >= g.n_pairs) break;
+        const int64_t k = (int64_t)base + lane_id;
+        const bool valid = k < g.n_pairs;
+        const int64_t h = !valid ? 0 : (g.pair_hap ? g.pair_hap[k] : k);
+        const int64_t rd = !valid ? 0 : (g.pair_read ? g.pair_read[k] : k);
         const int64_t ho = g.hap_off[h], ro = g.read_off[rd];
         const int n = (int)(g.hap_off[h + 1] - ho), m = (int)(g.read_off[rd + 1] - ro);
         HitOut res = {0, 0, 0, 0, 0};
-        if (n <= 0 || m <= 0 || m > 64 * kMyW) {
+        // this instantiation's pair?  (rows in (m_lo, m_hi]; degenerate pairs belong to the first launch)
+        const bool mine = valid && m <= g.m_hi && !(m <= g.m_lo && m > 0 && n > 0);
+        const bool work = mine && n > 0 && m > 0;
+        if (mine && !work) {
             res.dist = -1;  // no hit (calc_best_hit returns None for an empty text)
             g.out[k] = res;
             if (g.out_path) g.out_path[k] = NAN;
-            continue;
         }
         const uint8_t *pat = g.rbase + ro, *txt = g.hap + ho;
         // pattern masks for A C G T N
@@ -111,84 +145,149 @@ __global__ void __launch_bounds__(128) besthit_kernel(MyersArgs g) {
         for (int s = 0; s < 5; ++s)
 #pragma unroll
             for (int w = 0; w < kMyW; ++w) peq[s][w] = 0;
-        for (int j = 0; j < m; ++j) {
-            const int s = sym_of(pat[j]);
-            if (s < 5) peq[s][j >> 6] |= 1ull << (j & 63);
-        }
-        uint64_t Pv[kMyW], Mv[kMyW];
-#pragma unroll
-        for (int w = 0; w < kMyW; ++w) { Pv[w] = ~0ull; Mv[w] = 0; }
+        if (work)
+            for (int j = 0; j < m; ++j) {
+                const int s = sym_of(pat[j]);
+                if (s < 5) peq[s][j >> 6] |= 1ull << (j & 63);
+            }
         const int W = (m + 63) >> 6, lastbit = (m - 1) & 63;
-        int score = m, best = 1 << 30, n_best = 0, first_best = 0, last_best = 0;
-        // text characters arrive in aligned 8-byte chunks, one chunk ahead of their use (the
-        // staged haplotype buffer carries slack on both sides of every window)
+        int best = 1 << 30, n_best = 0, first_best = 0, last_best = 0;
         const int toff = (int)(reinterpret_cast<uintptr_t>(txt) & 7);
         const uint64_t *t8 = reinterpret_cast<const uint64_t *>(txt - toff);
-        uint64_t tw = t8[0], tw_next = t8[1];
-        for (int i = 0; i < n; ++i) {
-            const int tq = i + toff;
-            if ((tq & 7) == 0 && i > 0) { tw = tw_next; tw_next = t8[(tq >> 3) + 1]; }
-            const int c = up_char((int)((tw >> ((tq & 7) * 8)) & 0xffu));
-            const int s = sym_of(c);
-            int hin = 0;
+        // One scan of the text columns [i0, i1) as if the text began at i0.  STORE: keep the column
+        // records (second scan); else track the best bottom distance (first scan).
+        auto scan = [&](int i0, int i1, auto store_tag) {
+            constexpr bool STORE = decltype(store_tag)::value;
+            uint64_t Pv[kMyW], Mv[kMyW];
 #pragma unroll
-            for (int w = 0; w < kMyW; ++w) {
-                if (w >= W) break;
-                uint64_t Eq;
-                if (s < 5) Eq = peq[s][w];
-                else {  // rare symbol: build the mask on the fly
-                    Eq = 0;
-                    for (int j = w * 64; j < min(m, w * 64 + 64); ++j)
-                        if (pat[j] == c) Eq |= 1ull << (j & 63);
+            for (int w = 0; w < kMyW; ++w) { Pv[w] = ~0ull; Mv[w] = 0; }
+            int score = m;
+            // text characters arrive in aligned 8-byte chunks, one chunk ahead of their use (the
+            // staged haplotype buffer carries slack on both sides of every window)
+            uint64_t tw = 0, tw_next = 0;
+            if (i0 < i1) { tw = t8[(i0 + toff) >> 3]; tw_next = t8[((i0 + toff) >> 3) + 1]; }
+            for (int i = i0; i < i1; ++i) {
+                const int tq = i + toff;
+                if ((tq & 7) == 0 && i > i0) { tw = tw_next; tw_next = t8[(tq >> 3) + 1]; }
+                const int c = up_char((int)((tw >> ((tq & 7) * 8)) & 0xffu));
+                const int s = sym_of(c);
+                int hin = 0;
+                uint64_t PhS[STORE ? kMyW : 1], MhS[STORE ? kMyW : 1];
+#pragma unroll
+                for (int w = 0; w < kMyW; ++w) {
+                    if (w >= W) break;
+                    uint64_t Eq;
+                    if (s < 5) Eq = peq[s][w];
+                    else {  // rare symbol: build the mask on the fly
+                        Eq = 0;
+                        for (int j = w * 64; j < min(m, w * 64 + 64); ++j)
+                            if (pat[j] == c) Eq |= 1ull << (j & 63);
+                    }
+                    const uint64_t pv = Pv[w], mv = Mv[w];
+                    const uint64_t Xv = Eq | mv;
+                    if (hin < 0) Eq |= 1ull;
+                    const uint64_t Xh = (((Eq & pv) + pv) ^ pv) | Eq;
+                    uint64_t Ph = mv | ~(Xh | pv);
+                    uint64_t Mh = pv & Xh;
+                    const int top = (w == W - 1) ? lastbit : 63;
+                    const int hout = (int)((Ph >> top) & 1ull) - (int)((Mh >> top) & 1ull);
+                    if (STORE) { PhS[w] = Ph; MhS[w] = Mh; }  // horizontal deltas of this column's rows
+                    Ph <<= 1; Mh <<= 1;
+                    if (hin < 0) Mh |= 1ull; else if (hin > 0) Ph |= 1ull;
+                    Pv[w] = Mh | ~(Xv | Ph);
+                    Mv[w] = Ph & Xv;
+                    hin = hout;
                 }
-                const uint64_t pv = Pv[w], mv = Mv[w];
-                const uint64_t Xv = Eq | mv;
-                if (hin < 0) Eq |= 1ull;
-                const uint64_t Xh = (((Eq & pv) + pv) ^ pv) | Eq;
-                uint64_t Ph = mv | ~(Xh | pv);
-                uint64_t Mh = pv & Xh;
-                const int top = (w == W - 1) ? lastbit : 63;
-                const int hout = (int)((Ph >> top) & 1ull) - (int)((Mh >> top) & 1ull);
-                Ph <<= 1; Mh <<= 1;
-                if (hin < 0) Mh |= 1ull; else if (hin > 0) Ph |= 1ull;
-                Pv[w] = Mh | ~(Xv | Ph);
-                Mv[w] = Ph & Xv;
-                hin = hout;
-            }
-            score += hin;
-            // column record: (Pv, Mv) of the words the pattern uses
-            ulonglong2 *col = cols + (int64_t)(i + 1) * (kMyW * 32);
+                score += hin;
+                if (STORE) {
+                    // column record: the words the pattern uses, at the column's index RELATIVE to the scan
+                    // start -- the lanes of a warp then write the same scratch row in the same iteration
+                    // although their windows start at different columns
+                    ulonglong2 *col = cols + (int64_t)(i + 1 - i0) * (2 * kMyW * 32);
 #pragma unroll
-            for (int w = 0; w < kMyW; ++w)
-                if (w < W) col[w * 32] = make_ulonglong2(Pv[w], Mv[w]);
-            dms(i + 1) = score | (c << 16);  // bottom distance and the column's (upper-cased) text character
-            if (score < best) { best = score; n_best = 1; first_best = i + 1; last_best = i + 1; }
-            else if (score == best) { n_best++; last_best = i + 1; }
-        }
+                    for (int w = 0; w < kMyW; ++w)
+                        if (w < W) {
+                            col[w * 64] = make_ulonglong2(Pv[w], Mv[w]);          // vertical deltas
+                            col[w * 64 + 1] = make_ulonglong2(PhS[w], MhS[w]);    // horizontal deltas
+                        }
+                    dms(i + 1 - i0) = score;  // bottom distance
+                } else {
+                    if (score < best) { best = score; n_best = 1; first_best = i + 1; last_best = i + 1; }
+                    else if (score == best) { n_best++; last_best = i + 1; }
+                }
+            }
+        };
+        scan(0, work ? n : 0, std::false_type());
+        // the columns a traceback can consult (see the header); exact occurrences need none
+        const int c0 = work ? max(0, first_best - m - 2 * best - 1) : 0;
+        const bool walks = work && (best > 0 || want_path) && g.exp_skip == 0;
+        scan(c0, (work && (best > 0 || want_path) && g.exp_skip < 2) ? last_best : c0, std::true_type());
         // tracebacks of every best end position (edit_distance.rs:88-97), in increasing position
         int start_first = 0, start_last = 0, best_nindel = 1 << 30, best_nops = 0;
         uint8_t best_runs[kMaxRuns];  // best_indel_operations, run-length encoded (Ins << 7 | length), forward order
-        const bool want_path = g.out_path != nullptr;
         double best_path = -INFINITY;
         bool have_path = false;
-        for (int e = first_best; e <= last_best; ++e) {
-            if ((dms(e) & 0xffff) != best) continue;
-            if (best == 0 && !want_path) {
-                // an exact occurrence: D[m][e] = 0 forces the diagonal at every step, so the alignment
-                // starts at e - m and has no indel operation -- no walk through the column records
-                // (41 % of the pairs of the C3 read set)
-                if (e == first_best) start_first = e - m;
-                start_last = e - m;
-                if (best_nindel > 0) { best_nindel = 0; best_nops = 0; }
-                continue;
+        if (work && best == 0 && !want_path) {
+            // exact occurrences: D[m][e] = 0 forces the diagonal at every step, so the alignments start
+            // at e - m and have no indel operation -- no second scan, no walk (41 % of the pairs of the
+            // C3 read set)
+            start_first = first_best - m;
+            start_last = last_best - m;
+            best_nindel = 0;
+            best_nops = 0;
+        }
+        // ---- tracebacks, balanced over the lanes of the warp.  A lane OWNS a pair (its scratch
+        // records, its result), but any lane can EXECUTE the walk from one of its best end positions:
+        // pairs differ in the number of walks they need (none for exact occurrences, several for ends
+        // that tie), and with one lane walking all of its own pair's alignments the warp waited for the
+        // worst lane (6 of 32 lanes active on the C3 read set).  Per round the owners offer their next
+        // best end positions, a prefix sum packs up to 32 of them into a task list in shared memory,
+        // lane t walks task t with the owner's context fetched by shuffles, and the owners then fold
+        // the results of their tasks in increasing end position.
+        const int wib = (int)(threadIdx.x >> 5);
+        int remaining = walks ? n_best : 0;
+        int e_cursor = first_best - 1;
+        for (;;) {
+            const int offer = min(remaining, 8);
+            int incl = offer;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane_id >= o) incl += v;
             }
-            int j = m, i = e, nindel = 0;
+            const int excl = incl - offer;
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            if (total == 0) break;  // warp-uniform
+            const int acc = max(0, min(offer, 32 - excl));
+            for (int t = 0; t < acc; ++t) {
+                ++e_cursor;
+                while (dms(e_cursor - c0) != best) ++e_cursor;
+                s_task[wib][excl + t] = make_int2(lane_id, e_cursor);
+            }
+            remaining -= acc;
+            const int n_tasks = min(total, 32);
+            __syncwarp();
+            // ---- executor side: the owner's context
+            const bool has = lane_id < n_tasks;
+            const int2 tk = has ? s_task[wib][lane_id] : make_int2(lane_id, 0);
+            const int owner = tk.x, e = tk.y;
+            const int t_m = __shfl_sync(0xffffffffu, m, owner);
+            const int t_c0 = __shfl_sync(0xffffffffu, c0, owner);
+            const int t_best = __shfl_sync(0xffffffffu, best, owner);
+            const long long t_ro = __shfl_sync(0xffffffffu, (long long)ro, owner);
+            const long long t_ho = __shfl_sync(0xffffffffu, (long long)ho, owner);
+            const ulonglong2 *t_cols = cols + (owner - lane_id) * 2;
+            const uint8_t *t_pat = g.rbase + t_ro, *t_txt = g.hap + t_ho;
+            const int t_toff = (int)(reinterpret_cast<uintptr_t>(t_txt) & 7);
+            const uint64_t *t_t8 = reinterpret_cast<const uint64_t *>(t_txt - t_toff);
+            const int poff = (int)(reinterpret_cast<uintptr_t>(t_pat) & 7);
+            const uint64_t *p8 = reinterpret_cast<const uint64_t *>(t_pat - poff);
             // indel ops in traceback (reverse) order, run-length encoded in one byte per run: bit 7 = Ins
             // (else Del), bits 0-6 = length (<= 127, longer runs continue in the next byte).  An
             // alignment has a handful of indel runs however long they are (a 40-base insertion is one);
             // more than kMaxRuns runs leave the tail uncounted, which the host can tell from the count.
             uint8_t runs[kMaxRuns];
-            int nruns = 0;
+            int nruns = 0, nindel = 0;
             auto push_op = [&](int o) {
                 const int tag = o == 3 ? 0x80 : 0;
                 if (nruns > 0 && (runs[nruns - 1] & 0x80) == tag && (runs[nruns - 1] & 0x7f) < kMaxRunLen) runs[nruns - 1]++;
@@ -203,109 +302,136 @@ __global__ void __launch_bounds__(128) besthit_kernel(MyersArgs g) {
                 if (cur == 2) return prev == 2 ? g.reopen_y : (prev == 3 ? g.close_x + g.gap_y : g.gap_y);
                 return prev == 3 ? g.reopen_x : (prev == 2 ? g.close_y + g.gap_x : g.gap_x);
             };
-            // D[j][i] of the current cell is carried along; predecessors are evaluated on demand.
+            // D[j][i] of the current cell is carried along; its three predecessors follow from single
+            // bits of the column's record: the vertical delta of row j (Pv / Mv, bit j-1) gives
+            // D[j-1][i], the horizontal delta of row j (Ph / Mh) gives D[j][i-1], the horizontal delta of
+            // row j-1 then D[j-1][i-1] -- no popcounts, one 64-bit word of each vector per step.
             // Tie-breaking among equally good predecessors (bio's Myers traceback, recollected and
             // confirmed by the reference's integration tests): a substitution
-            // first, then Ins, then Del, a match last
-            // The records of columns i, i-1 live in registers and column i-2 is prefetched while
-            // the current step is evaluated: the walk moves left by at most one column per step,
-            // so the scratch latency stays off the dependent chain.
-            // Only the words at or above the current row are ever looked at (dist_from counts the
-            // deltas of rows j+1..m), and every 16-byte word pair costs a 32-byte sector: skip the
-            // words below.  A record survives at most two column moves in registers, each taking j
-            // down by at most one; an insertion takes j down without moving, so it reloads.
-            auto load_rec = [&](uint64_t *rec, int c) {
-                const int wmin = max(j - 4, 0) >> 6;
-#pragma unroll
-                for (int w = 0; w < kMyW; ++w)
-                    if (w < W && w >= wmin) {
-                        const ulonglong2 v = cols[((int64_t)max(c, 1) * kMyW + w) * 32];
-                        rec[w] = v.x;
-                        rec[kMyW + w] = v.y;
-                    }
+            // first, then Ins, then Del, a match last.
+            // The words of column i (the one holding row j) are in registers, those of column i-1 are
+            // loaded one step ahead, and the sectors of the columns further left are pulled into L1
+            // four steps ahead (a prefetch has no destination register, so nothing waits for it): the
+            // walk moves left by at most one column per step, so the scratch latency stays off the
+            // dependent chain.
+            struct Rec { uint64_t pv, mv, ph, mh; };
+            auto load_rec = [&](int c, int w) {
+                Rec r;
+                const int64_t at = ((int64_t)max(c - t_c0, 1) * kMyW + w) * 64;
+                const ulonglong2 v = t_cols[at], hh = t_cols[at + 1];
+                r.pv = v.x; r.mv = v.y; r.ph = hh.x; r.mh = hh.y;
+                return r;
             };
-            uint64_t r_cur[2 * kMyW], r_left[2 * kMyW], r_pre[2 * kMyW];
-            load_rec(r_cur, i);
-            load_rec(r_left, i - 1);
-            int dm_cur = dms(i), dm_left = dms(max(i - 1, 0));
-            int d = dm_cur & 0xffff;
-            const int poff = (int)(reinterpret_cast<uintptr_t>(pat) & 7);
-            const uint64_t *p8 = reinterpret_cast<const uint64_t *>(pat - poff);
-            int pchunk = -1;
-            uint64_t pw = 0;
-            while (j > 0) {
-                load_rec(r_pre, i - 2);                       // prefetch
-                const int dm_pre = dms(max(i - 2, 0));
-                int op;
-                bool match = false;
-                if (i > 0) {
-                    const int ddiag = i > 1 ? dist_from(r_left, dm_left & 0xffff, j - 1, m, W) : j - 1;
-                    const int pq = j - 1 + poff;  // pattern bytes in aligned 8-byte chunks, reloaded every 8 rows
-                    if ((pq >> 3) != pchunk) { pchunk = pq >> 3; pw = p8[pchunk]; }
-                    match = (int)((pw >> ((pq & 7) * 8)) & 0xffu) == (dm_cur >> 16);  // pat[j-1] == T[i-1]
-                    if (!match && ddiag + 1 == d) {   // substitution
-                        op = 0;
-                        d = ddiag;
+            auto prefetch_rec = [&](int c, int w) {
+                const ulonglong2 *ptr = &t_cols[((int64_t)max(c - t_c0, 1) * kMyW + w) * 64];
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
+            };
+            int pchunk = -1, tchunk = -(1 << 28);   // pattern / text bytes in aligned 8-byte chunks
+            uint64_t pw = 0, twd = 0;
+            Rec cur = {0, 0, 0, 0}, left = {0, 0, 0, 0};
+            int j = 0, i = 0, d = 0, wcur = 0;
+            bool walking = has;
+            if (has) {
+                j = t_m; i = e; d = t_best;
+                wcur = (j - 1) >> 6;
+                prefetch_rec(i - 2, wcur); prefetch_rec(i - 3, wcur); prefetch_rec(i - 4, wcur);
+                cur = load_rec(i, wcur);
+                left = load_rec(i - 1, wcur);
+            }
+            while (__any_sync(0xffffffffu, walking)) {
+                if (walking) {
+                    const int rbit = j - 1;
+                    if ((rbit >> 6) != wcur) {  // the row left the word in registers (once per 64 rows)
+                        wcur = rbit >> 6;
+                        cur = load_rec(i, wcur);
+                        left = load_rec(i - 1, wcur);
+                    }
+                    prefetch_rec(i - 5, wcur);
+                    const int bb = rbit & 63;
+                    int op;
+                    bool match = false;
+                    if (i > 0) {
+                        const int vd = (int)((cur.pv >> bb) & 1ull) - (int)((cur.mv >> bb) & 1ull);
+                        const int hd = (int)((cur.ph >> bb) & 1ull) - (int)((cur.mh >> bb) & 1ull);
+                        int hd1 = 0;  // horizontal delta of row j-1 (row 0: D[0][.] = 0)
+                        if (bb > 0) hd1 = (int)((cur.ph >> (bb - 1)) & 1ull) - (int)((cur.mh >> (bb - 1)) & 1ull);
+                        else if (rbit > 0) {
+                            const ulonglong2 hh = t_cols[((int64_t)max(i - t_c0, 1) * kMyW + (wcur - 1)) * 64 + 1];
+                            hd1 = (int)((hh.x >> 63) & 1ull) - (int)((hh.y >> 63) & 1ull);
+                        }
+                        const int dup = d - vd, dleft = d - hd, ddiag = dup - hd1;
+                        const int pq = j - 1 + poff;
+                        if ((pq >> 3) != pchunk) { pchunk = pq >> 3; pw = p8[pchunk]; }
+                        const int tq = i - 1 + t_toff;
+                        if ((tq >> 3) != tchunk) { tchunk = tq >> 3; twd = t_t8[tchunk]; }
+                        match = (int)((pw >> ((pq & 7) * 8)) & 0xffu) ==
+                                up_char((int)((twd >> ((tq & 7) * 8)) & 0xffu));  // pat[j-1] == T[i-1]
+                        if (!match && ddiag + 1 == d) { op = 0; d = ddiag; }    // substitution
+                        else if (d == dup + 1) { op = 3; d = dup; }             // Ins: vertical delta +1
+                        else if (dleft + 1 == d) { op = 2; d = dleft; }         // Del
+                        else { op = 0; d = ddiag; }                             // match
                     } else {
-                        const int dup = dist_from(r_cur, dm_cur & 0xffff, j - 1, m, W);
-                        if (d == dup + 1) { op = 3; d = dup; }   // Ins: vertical delta +1
-                        else {
-                            const int dleft = i > 1 ? dist_from(r_left, dm_left & 0xffff, j, m, W) : j;  // D[j][i-1]
-                            if (dleft + 1 == d) { op = 2; d = dleft; }   // Del
-                            else { op = 0; d = ddiag; }                    // match
+                        op = 3;  // text exhausted: D[j][0] = j
+                        d -= 1;
+                    }
+                    if (op != 3) {  // moved one column to the left: the prefetched record becomes current
+                        cur = left;
+                        left = load_rec(i - 2, wcur);
+                    }
+                    if (op == 3) {
+                        push_op(3);
+                        nindel++; j--;
+                        if (want_path) path += (double)g.rqual[t_ro + j] * -0.23025850929940456;  // prob_emit_y
+                    } else if (op == 2) {  // Del (prob_emit_x = ln 1)
+                        push_op(2);
+                        nindel++; i--;
+                    } else {               // Match / Subst
+                        j--; i--;
+                        if (want_path) {
+                            const int q = g.rqual[t_ro + j];
+                            path += match ? g.qlut[q * kQlutStride + 3]
+                                          : (double)q * -0.23025850929940456 + -1.098712293668443;
                         }
                     }
-                } else {
-                    op = 3;  // text exhausted: D[j][0] = j
-                    d -= 1;
-                }
-                if (op != 3) {  // moved one column to the left
-#pragma unroll
-                    for (int w = 0; w < 2 * kMyW; ++w) { r_cur[w] = r_left[w]; r_left[w] = r_pre[w]; }
-                    dm_cur = dm_left;
-                    dm_left = dm_pre;
-                }
-                if (op == 3) {
-                    push_op(3);
-                    nindel++; j--;
-                    load_rec(r_cur, i);  // the rows in reach may now start one word lower
-                    load_rec(r_left, i - 1);
-                    if (want_path) path += (double)g.rqual[ro + j] * -0.23025850929940456;  // prob_emit_y
-                } else if (op == 2) {  // Del (prob_emit_x = ln 1)
-                    push_op(2);
-                    nindel++; i--;
-                } else {               // Match / Subst
-                    j--; i--;
-                    if (want_path) {
-                        const int q = g.rqual[ro + j];
-                        path += match ? g.qlut[q * kQlutStride + 3]
-                                                          : (double)q * -0.23025850929940456 + -1.098712293668443;
+                    if (want_path && next >= 0) path += trans(op, next);
+                    next = op;
+                    if (j == 0) {  // this alignment is complete
+                        if (want_path && next >= 0) path += trans(-1, next);
+                        walking = false;
                     }
                 }
-                if (want_path && next >= 0) path += trans(op, next);
-                next = op;
             }
-            if (want_path) {
-                if (next >= 0) path += trans(-1, next);
-                if (!have_path || path > best_path) { best_path = path; have_path = true; }
+            if (has) {
+                WalkRes &r = s_res[wib][lane_id];
+                r.start = i; r.nindel = nindel; r.nruns = nruns; r.e = e; r.path = path;
+                for (int t = 0; t < nruns; ++t) r.runs[t] = runs[nruns - 1 - t];  // forward order
             }
-            if (e == first_best) start_first = i;
-            start_last = i;
-            if (nindel < best_nindel) {  // fewest indel ops, first on ties (min_by_key)
-                best_nindel = nindel;
-                best_nops = nruns;
-                for (int t = 0; t < nruns; ++t) best_runs[t] = runs[nruns - 1 - t];  // forward order
+            __syncwarp();
+            // ---- owner side: fold the results of my tasks, in increasing end position
+            for (int t = 0; t < acc; ++t) {
+                const WalkRes &r = s_res[wib][excl + t];
+                if (want_path && (!have_path || r.path > best_path)) { best_path = r.path; have_path = true; }
+                if (r.e == first_best) start_first = r.start;
+                start_last = r.start;
+                if (r.nindel < best_nindel) {  // fewest indel ops, first on ties (min_by_key)
+                    best_nindel = r.nindel;
+                    best_nops = r.nruns;
+                    for (int q = 0; q < r.nruns; ++q) best_runs[q] = r.runs[q];
+                }
             }
+            __syncwarp();
         }
-        res.dist = best;
-        res.start = start_first;
-        res.end = min(start_last + m + best, n);
-        res.n_best = n_best;
-        res.n_indel = best_nindel;
-        g.out[k] = res;
-        if (want_path) g.out_path[k] = best_path;
-        if (g.out_ops)
-            for (int t = 0; t < best_nops; ++t) g.out_ops[k * kMaxIndelOps + t] = best_runs[t];
+        if (work) {
+            res.dist = best;
+            res.start = start_first;
+            res.end = min(start_last + m + best, n);
+            res.n_best = n_best;
+            res.n_indel = best_nindel;
+            g.out[k] = res;
+            if (want_path) g.out_path[k] = best_path;
+            if (g.out_ops)
+                for (int t = 0; t < best_nops; ++t) g.out_ops[k * kMaxIndelOps + t] = best_runs[t];
+        }
     }
 }
 
@@ -488,19 +614,22 @@ static void set_path_consts(MyersArgs &a, const vlr_gap_params *gp) {
     a.reopen_y = lae(gp->prob_gap_y_extend, a.close_y + gp->prob_gap_y);
 }
 
-// launches K2 over device-resident pairs; returns workers used
-static int launch_besthit(vlr_ctx *ctx, MyersArgs &a, int64_t max_lx, int slot_base) {
+// launches K2 over device-resident pairs: the 4-word instantiation (read windows up to 256 rows) and,
+// if the batch holds longer windows, the 16-word one (up to 1024 rows; bio's Myers::Long)
+constexpr int kMyWShort = 4, kMyWLong = 16;
+template <int KW>
+static int launch_besthit_w(vlr_ctx *ctx, MyersArgs &a, int64_t max_lx, int slot_base, int m_lo, int m_hi) {
     cudaStream_t st = ctx->stream;
-    const size_t per_worker = (size_t)(max_lx + 1) * (2 * kMyW * 8 + 4);
+    const size_t per_worker = (size_t)(max_lx + 1) * (4 * KW * 8 + 4);
     // one thread per pair, latency bound (scratch stores, local-memory masks): many resident warps
     const char *wenv = getenv("VLR_K2_THREADS_PER_SM");
-    int64_t workers = (int64_t)ctx->sm_count * (wenv && atoi(wenv) > 0 ? atoi(wenv) : 512);
+    int64_t workers = (int64_t)ctx->sm_count * (wenv && atoi(wenv) > 0 ? atoi(wenv) : (KW > 4 ? 128 : 512));
     const size_t budget = (size_t)6 << 30;
     if ((size_t)workers * per_worker > budget) workers = (int64_t)(budget / per_worker);
     workers = workers / 128 * 128;
     if (workers < 128) return set_err(ctx, VLR_ERR_UNSUPPORTED, "haplotype window of %lld bytes is too long for the Myers scratch", (long long)max_lx);
     if (workers > a.n_pairs) workers = (a.n_pairs + 127) / 128 * 128;
-    uint64_t *scratch = (uint64_t *)dev_scratch(ctx, slot_base, (size_t)workers * (max_lx + 1) * (2 * kMyW * 8));
+    uint64_t *scratch = (uint64_t *)dev_scratch(ctx, slot_base, (size_t)workers * (max_lx + 1) * (4 * KW * 8));
     int32_t *dm = (int32_t *)dev_scratch(ctx, slot_base + 1, (size_t)workers * (max_lx + 1) * 4);
     int32_t *cnt = (int32_t *)dev_scratch(ctx, slot_base + 2, 64);
     if (!scratch || !dm || !cnt) return set_err(ctx, VLR_ERR_NOMEM, "scratch allocation failed");
@@ -509,9 +638,18 @@ static int launch_besthit(vlr_ctx *ctx, MyersArgs &a, int64_t max_lx, int slot_b
     a.scratch_dm = dm;
     a.scratch_stride = max_lx + 1;
     a.cursor = cnt;
-    besthit_kernel<<<(int)(workers / 128), 128, 0, st>>>(a);
+    a.m_lo = m_lo;
+    { const char *e = getenv("VLR_K2_EXP"); a.exp_skip = e ? atoi(e) : 0; }
+    a.m_hi = m_hi;
+    besthit_kernel<KW><<<(int)(workers / 128), 128, 0, st>>>(a);
     VLR_LAUNCH_CHECK(ctx);
     return VLR_OK;
+}
+static int launch_besthit(vlr_ctx *ctx, MyersArgs &a, int64_t max_lx, int64_t max_ly, int slot_base) {
+    int rc = launch_besthit_w<kMyWShort>(ctx, a, max_lx, slot_base, 0, 64 * kMyWShort);
+    if (rc == VLR_OK && max_ly > 64 * kMyWShort)
+        rc = launch_besthit_w<kMyWLong>(ctx, a, max_lx, slot_base, 64 * kMyWShort, 64 * kMyWLong);
+    return rc;
 }
 
 }  // namespace vlr
@@ -525,7 +663,7 @@ static int besthit_host(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *hap_bytes,
                         int32_t *out_start, int32_t *out_end, int32_t *out_n_best,
                         int32_t *out_n_indel_ops, uint8_t *out_indel_ops, double *out_path) {
     if (!ctx) return VLR_ERR_INVALID;
-    if (n_pairs < 0 || n_pairs > 0x7fffffff) return set_err(ctx, VLR_ERR_INVALID, "n_pairs out of range");
+    if (n_pairs < 0 || n_pairs > 0x7ff00000) return set_err(ctx, VLR_ERR_INVALID, "n_pairs out of range");
     if (n_pairs == 0) return VLR_OK;
     if (!hap_bytes || !hap_off || !read_bases || !read_off || n_haps <= 0 || n_reads <= 0 ||
         (out_path ? (!read_quals || !gap) : (!out_dist || !out_start || !out_end || !out_n_best)))
@@ -543,7 +681,7 @@ static int besthit_host(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *hap_bytes,
         if (read_off[r + 1] < read_off[r]) return set_err(ctx, VLR_ERR_INVALID, "read_off not monotone");
         max_ly = std::max(max_ly, read_off[r + 1] - read_off[r]);
     }
-    if (max_ly > 64 * kMyW) return set_err(ctx, VLR_ERR_UNSUPPORTED, "read window of %lld rows exceeds %d", (long long)max_ly, 64 * kMyW);
+    if (max_ly > 64 * kMyWLong) return set_err(ctx, VLR_ERR_UNSUPPORTED, "read window of %lld rows exceeds %d", (long long)max_ly, 64 * kMyWLong);
     if (pair_hap || pair_read)
         for (int64_t k = 0; k < n_pairs; ++k) {
             if (pair_hap && (pair_hap[k] < 0 || pair_hap[k] >= n_haps)) return set_err(ctx, VLR_ERR_INVALID, "pair_hap out of range");
@@ -582,7 +720,7 @@ static int besthit_host(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *hap_bytes,
         a.rqual = d_rq - rd_lo; a.qlut = ctx->d_qlut; a.out_path = d_path;
         set_path_consts(a, gap);
     }
-    int rc = launch_besthit(ctx, a, max_lx, S_SCR);
+    int rc = launch_besthit(ctx, a, max_lx, max_ly, S_SCR);
     if (rc != VLR_OK) return rc;
     if (out_path)
         VLR_CUDA(ctx, cudaMemcpyAsync(out_path, d_path, (size_t)n_pairs * 8, cudaMemcpyDeviceToHost, st));
@@ -654,7 +792,7 @@ int vlr_allele_support_batch(vlr_ctx *ctx, int64_t n_regions, const int32_t *reg
     VLR_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const int64_t n_slots = region_hap_off[n_regions];
-    if (n_slots <= 0 || n_slots > 0x7fffffff) return set_err(ctx, VLR_ERR_INVALID, "bad region_hap_off");
+    if (n_slots <= 0 || n_slots > 0x7ff00000) return set_err(ctx, VLR_ERR_INVALID, "bad region_hap_off");
     enum { S_HAP = 40, S_HOFF, S_RB, S_ROFF, S_PH, S_PR, S_OUT, S_OPS, S_SCR, S_SCR2, S_SCR3,
            S_RQ, S_RR, S_RHO, S_RNR, S_SE, S_WS0, S_WL, S_MED, S_SP, S_SM, S_O1, S_O2, S_O3, S_O4, S_O5,
            S_O6, S_O7, S_O8, S_PWS, S_LIT, S_PATH = 75 };
@@ -730,12 +868,15 @@ int vlr_allele_support_batch(vlr_ctx *ctx, int64_t n_regions, const int32_t *reg
     }
     for (int64_t k = 0; k < n_slots && !bad; ++k)
         if (region_haps[k] < 0 || region_haps[k] >= n_haps) bad = "region_haps out of range";
-    if (bad || max_ly > 248) {
+    // Myers takes read windows of up to 1024 rows; the banded pair-HMM behind it 248 (the fast mode,
+    // which needs no pair-HMM, goes all the way)
+    const int64_t ly_limit = (flags & VLR_REALIGN_FAST) ? 64 * kMyWLong : 248;
+    if (bad || max_ly > ly_limit) {
         // the copies read caller memory: let them finish before the buffers go back to the caller
         cudaStreamSynchronize(st);
         cudaStreamSynchronize(cp);
         if (bad) return set_err(ctx, VLR_ERR_INVALID, "%s", bad);
-        return set_err(ctx, VLR_ERR_UNSUPPORTED, "read window of %lld rows exceeds 248", (long long)max_ly);
+        return set_err(ctx, VLR_ERR_UNSUPPORTED, "read window of %lld rows exceeds %lld", (long long)max_ly, (long long)ly_limit);
     }
     // slot -> read index (the Myers pairs), on the device
     {
@@ -758,7 +899,7 @@ int vlr_allele_support_batch(vlr_ctx *ctx, int64_t n_regions, const int32_t *reg
         ma.rqual = d_rq - rd_lo; ma.qlut = ctx->d_qlut; ma.out_path = d_path;
         set_path_consts(ma, gap);
     }
-    rc = launch_besthit(ctx, ma, max_lx, S_SCR);
+    rc = launch_besthit(ctx, ma, max_lx, max_ly, S_SCR);
     if (rc != VLR_OK) return rc;
     lap("myers", true);
     // 2. minimal-distance selection, certainty short-circuit, HMM windows (from here on the base

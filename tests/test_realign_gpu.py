@@ -25,6 +25,29 @@ def test_besthit_ragged(ctx, oracle):
         assert np.array_equal(got["indel_ops"][k][:n], want["indel_ops"][:n]), k
 
 
+def test_besthit_long_windows(ctx, oracle):
+    """Read windows beyond 256 rows (bio's Myers::Long, edit_distance.rs:42-46): the 16-word
+    instantiation takes 257..1024 rows; a batch mixing short and long windows runs both kernels.
+    Related pairs (a few edits), unrelated ones (distances of hundreds) and the truncated second
+    scan must all agree with the oracle's explicit matrix, operations included."""
+    w = synth.make_ragged_pairs(160, seed=77, min_ly=200, max_ly=640, min_lx=300, max_lx=1100)
+    lens = np.diff(w["read_off"])
+    assert (lens > 256).sum() > 60 and (lens <= 256).sum() > 10
+    got = ctx.besthit_batch(w["hap_bytes"], w["hap_off"], w["read_bases"], w["read_off"])
+    for k in range(160):
+        want = oracle.best_hit(w["hap_bytes"][w["hap_off"][k]:w["hap_off"][k + 1]],
+                               w["read_bases"][w["read_off"][k]:w["read_off"][k + 1]])
+        assert [got["dist"][k], got["start"][k], got["end"][k], got["n_best"][k]] == \
+               [want["dist"], want["start"], want["end"], want["n_best"]], k
+        assert got["n_indel_ops"][k] == len(want["indel_ops"]), k
+        if not got["indel_overflow"][k]:
+            n = len(want["indel_ops"])
+            assert np.array_equal(got["indel_ops"][k][:n], want["indel_ops"][:n]), k
+    with pytest.raises(P.VlrError):   # beyond 1024 rows: refused, not truncated
+        big = synth.make_ragged_pairs(2, seed=3, min_ly=1100, max_ly=1200, min_lx=1300, max_lx=1400)
+        ctx.besthit_batch(big["hap_bytes"], big["hap_off"], big["read_bases"], big["read_off"])
+
+
 def test_besthit_repeats_and_ties(ctx, oracle):
     """Homopolymers / tandem repeats: many equally good end positions and indel placements."""
     rng = np.random.default_rng(4)
