@@ -10,6 +10,7 @@
 #include "pairhmm_host.cuh"
 #include "pairhmm_kernel.cuh"
 #include "pairhmm_band.cuh"
+#include "pairhmm_litband.cuh"
 
 namespace vlr {
 
@@ -362,6 +363,27 @@ int pairhmm_literal_dev(vlr_ctx *ctx, int64_t n_pairs_cap, const uint8_t *d_hap_
     a.out = d_out; a.qlut = ctx->d_qlut;
     a.lit_ws = ws; a.lit_stride = stride;
     make_consts(gap, flags, &a.lin, &a.ln);
+    // Banded pairs go through the row-sweep kernel (pairhmm_litband.cuh); what it does not take (no band,
+    // gap extension on the haplotype side, very long windows) is left on `rest` for the wavefront kernel
+    const char *lbenv = getenv("VLR_LIT_BAND");
+    if (d_med && !(lbenv && atoi(lbenv) == 0)) {
+        enum { S_LITREST = 94 };
+        int32_t *rest = (int32_t *)dev_scratch(ctx, S_LITREST, (size_t)n_pairs_cap * 4 + 64);
+        if (!rest) return set_err(ctx, VLR_ERR_NOMEM, "scratch allocation failed");
+        int32_t *rest_count = cnt + 2;  // cnt[0]: cursor of this launch, cnt[3]: cursor of the next
+        const int n_ctas = (int)std::min<size_t>(warps, (size_t)ctx->sm_count * 6);
+        cudaError_t e = cudaSuccess;
+        switch (approx_of(flags)) {
+        case 0: e = launch_pairhmm_litband<0>(a, rest, rest_count, n_ctas, st); break;
+        case 1: e = launch_pairhmm_litband<1>(a, rest, rest_count, n_ctas, st); break;
+        default: e = launch_pairhmm_litband<2>(a, rest, rest_count, n_ctas, st); break;
+        }
+        if (e != cudaSuccess) return set_err(ctx, VLR_ERR_CUDA, "pairhmm launch failed: %s", cudaGetErrorString(e));
+        ctx->launches++;
+        a.list = rest; a.list_off = nullptr;
+        a.count = rest_count;
+        a.cursor = cnt + 3;
+    }
     cudaError_t e = launch_literal(approx_of(flags), a, ctx->sm_count, st);
     if (e != cudaSuccess) return set_err(ctx, VLR_ERR_CUDA, "pairhmm launch failed: %s", cudaGetErrorString(e));
     ctx->launches++;
