@@ -11,7 +11,8 @@ OUT = os.path.join(HERE, "libvlr_b200.so")
 OBJ = os.path.join(HERE, "_build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "--expt-relaxed-constexpr"]
+         "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "--expt-relaxed-constexpr"] + \
+    os.environ.get("VLR_NVCC_DEFS", "").split()   # experiments only (e.g. -DVLR_OCC5=5); part of the build stamp
 
 
 def _sources():

@@ -93,7 +93,7 @@ __global__ void call_records_kernel(CallArgs g) {
 
 using namespace vlr;
 
-extern "C" int vlr_call_records(vlr_ctx *ctx, int64_t n_sites, int32_t n_events, int32_t n_samples,
+static int vlr_call_records_impl(vlr_ctx *ctx, int64_t n_sites, int32_t n_events, int32_t n_samples,
                                 const uint8_t *event_is_artifact, const double *event_ln,
                                 const double *marginal, const double *map_af,
                                 const double *prob_mapping, const int64_t *obs_off, float *out_prob,
@@ -144,6 +144,15 @@ extern "C" int vlr_call_records(vlr_ctx *ctx, int64_t n_sites, int32_t n_events,
     VLR_CUDA(ctx, cudaStreamSynchronize(st));
     return VLR_OK;
 }
+
+extern "C" int vlr_call_records(vlr_ctx *ctx, int64_t n_sites, int32_t n_events, int32_t n_samples,
+                                const uint8_t *event_is_artifact, const double *event_ln,
+                                const double *marginal, const double *map_af,
+                                const double *prob_mapping, const int64_t *obs_off, float *out_prob,
+                                float *out_af, int32_t *out_dp) {
+    return vlr::drain_on_error(ctx, vlr_call_records_impl(ctx, n_sites, n_events, n_samples, event_is_artifact, event_ln, marginal, map_af, prob_mapping, obs_off, out_prob, out_af, out_dp));
+}
+
 
 // ---------------------------------------------------------------- OBS / SOBS strings, bias flags
 // The per-sample OBS and SOBS FORMAT strings of the call record (src/calling/variants/mod.rs:186-260)

@@ -61,6 +61,17 @@ int ensure_copy_stream(vlr_ctx *ctx);
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Host-buffer entry points enqueue asynchronous copies FROM / TO caller memory before they can fail
+// (validation, allocation, a launch error).  Every error exit goes through this: the caller may free
+// or reuse its buffers as soon as the call returns, so both streams are drained first.
+static inline int drain_on_error(vlr_ctx *ctx, int rc) {
+    if (rc != VLR_OK && ctx) {
+        if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+        if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    }
+    return rc;
+}
+
 // qlut layout: [256][4] doubles: eps, 1-eps, eps*0.3333, ln(1-eps)
 constexpr int kQlutStride = 4;
 

@@ -741,7 +741,7 @@ static int besthit_host(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *hap_bytes,
 
 extern "C" {
 
-int vlr_besthit_batch(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *hap_bytes, const int64_t *hap_off,
+static int vlr_besthit_batch_impl(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *hap_bytes, const int64_t *hap_off,
                       int64_t n_haps, const uint8_t *read_bases, const int64_t *read_off,
                       int64_t n_reads, const int32_t *pair_hap, const int32_t *pair_read,
                       int32_t *out_dist, int32_t *out_start, int32_t *out_end, int32_t *out_n_best,
@@ -751,7 +751,16 @@ int vlr_besthit_batch(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *hap_bytes, c
                         out_n_indel_ops, out_indel_ops, nullptr);
 }
 
-int vlr_pathhmm_batch(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *hap_bytes, const int64_t *hap_off,
+int vlr_besthit_batch(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *hap_bytes, const int64_t *hap_off,
+                      int64_t n_haps, const uint8_t *read_bases, const int64_t *read_off,
+                      int64_t n_reads, const int32_t *pair_hap, const int32_t *pair_read,
+                      int32_t *out_dist, int32_t *out_start, int32_t *out_end, int32_t *out_n_best,
+                      int32_t *out_n_indel_ops, uint8_t *out_indel_ops) {
+    return vlr::drain_on_error(ctx, vlr_besthit_batch_impl(ctx, n_pairs, hap_bytes, hap_off, n_haps, read_bases, read_off, n_reads, pair_hap, pair_read, out_dist, out_start, out_end, out_n_best, out_n_indel_ops, out_indel_ops));
+}
+
+
+static int vlr_pathhmm_batch_impl(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *hap_bytes, const int64_t *hap_off,
                       int64_t n_haps, const uint8_t *read_bases, const uint8_t *read_quals,
                       const int64_t *read_off, int64_t n_reads, const int32_t *pair_hap,
                       const int32_t *pair_read, const vlr_gap_params *gap, double *out_lnprob,
@@ -763,7 +772,16 @@ int vlr_pathhmm_batch(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *hap_bytes, c
                         nullptr, out_lnprob);
 }
 
-int vlr_allele_support_batch(vlr_ctx *ctx, int64_t n_regions, const int32_t *region_read,
+int vlr_pathhmm_batch(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *hap_bytes, const int64_t *hap_off,
+                      int64_t n_haps, const uint8_t *read_bases, const uint8_t *read_quals,
+                      const int64_t *read_off, int64_t n_reads, const int32_t *pair_hap,
+                      const int32_t *pair_read, const vlr_gap_params *gap, double *out_lnprob,
+                      int32_t *out_dist) {
+    return vlr::drain_on_error(ctx, vlr_pathhmm_batch_impl(ctx, n_pairs, hap_bytes, hap_off, n_haps, read_bases, read_quals, read_off, n_reads, pair_hap, pair_read, gap, out_lnprob, out_dist));
+}
+
+
+static int vlr_allele_support_batch_impl(vlr_ctx *ctx, int64_t n_regions, const int32_t *region_read,
                              const int32_t *region_hap_off, const int32_t *region_haps,
                              const int32_t *region_n_ref, const uint8_t *hap_bytes,
                              const int64_t *hap_off, int64_t n_haps, const int32_t *shrink_extra,
@@ -961,5 +979,18 @@ int vlr_allele_support_batch(vlr_ctx *ctx, int64_t n_regions, const int32_t *reg
     }
     return VLR_OK;
 }
+
+int vlr_allele_support_batch(vlr_ctx *ctx, int64_t n_regions, const int32_t *region_read,
+                             const int32_t *region_hap_off, const int32_t *region_haps,
+                             const int32_t *region_n_ref, const uint8_t *hap_bytes,
+                             const int64_t *hap_off, int64_t n_haps, const int32_t *shrink_extra,
+                             const uint8_t *read_bases, const uint8_t *read_quals,
+                             const int64_t *read_off, int64_t n_reads, const vlr_gap_params *gap,
+                             uint32_t flags, double *out_prob_ref, double *out_prob_alt,
+                             double *out_raw_ref, double *out_raw_alt, int32_t *out_ref_dist,
+                             int32_t *out_alt_dist, int32_t *out_n_indel_ops, uint8_t *out_indel_ops) {
+    return vlr::drain_on_error(ctx, vlr_allele_support_batch_impl(ctx, n_regions, region_read, region_hap_off, region_haps, region_n_ref, hap_bytes, hap_off, n_haps, shrink_extra, read_bases, read_quals, read_off, n_reads, gap, flags, out_prob_ref, out_prob_alt, out_raw_ref, out_raw_alt, out_ref_dist, out_alt_dist, out_n_indel_ops, out_indel_ops));
+}
+
 
 }  // extern "C"

@@ -424,7 +424,7 @@ int vlr_pairhmm_batch_dev(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *d_hap_by
                             nullptr, nullptr, gap, flags, d_workspace, workspace_bytes, d_out_lnprob);
 }
 
-int vlr_pairhmm_batch(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *hap_bytes,
+static int vlr_pairhmm_batch_impl(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *hap_bytes,
                       const int64_t *hap_off, int64_t n_haps, const uint8_t *read_bases,
                       const uint8_t *read_quals, const int64_t *read_off, int64_t n_reads,
                       const int32_t *pair_hap, const int32_t *pair_read,
@@ -574,5 +574,15 @@ int vlr_pairhmm_batch(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *hap_bytes,
     }
     return VLR_OK;
 }
+
+int vlr_pairhmm_batch(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *hap_bytes,
+                      const int64_t *hap_off, int64_t n_haps, const uint8_t *read_bases,
+                      const uint8_t *read_quals, const int64_t *read_off, int64_t n_reads,
+                      const int32_t *pair_hap, const int32_t *pair_read,
+                      const int32_t *max_edit_dist, const vlr_gap_params *gap, uint32_t flags,
+                      double *out_lnprob) {
+    return vlr::drain_on_error(ctx, vlr_pairhmm_batch_impl(ctx, n_pairs, hap_bytes, hap_off, n_haps, read_bases, read_quals, read_off, n_reads, pair_hap, pair_read, max_edit_dist, gap, flags, out_lnprob));
+}
+
 
 }  // extern "C"

@@ -319,9 +319,12 @@ struct LogLit {
 };
 
 // ---------------------------------------------------------------- the kernel
+#ifndef VLR_OCC5
+#define VLR_OCC5 4
+#endif
 template <int R>
 struct Occ {
-    static constexpr int kMinBlocks = R <= 3 ? 5 : (R <= 5 ? 4 : (R <= 6 ? 3 : 2));
+    static constexpr int kMinBlocks = R <= 3 ? 5 : (R <= 4 ? 4 : (R <= 5 ? VLR_OCC5 : (R <= 6 ? 3 : 2)));
 };
 
 // Per-pair state that lives in registers across the sweep.

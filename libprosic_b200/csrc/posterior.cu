@@ -613,7 +613,7 @@ static int posterior_pipeline(vlr_ctx *ctx, int64_t n_sites, const vlr_model *mo
 
 extern "C" {
 
-int vlr_posterior_batch(vlr_ctx *ctx, int64_t n_sites, const vlr_model *model,
+static int vlr_posterior_batch_impl(vlr_ctx *ctx, int64_t n_sites, const vlr_model *model,
                         const vlr_obs_columns *obs, const int64_t *obs_off, double *out_event_ln,
                         double *out_marginal, double *out_map_af, int32_t *out_map_bias) {
     if (!ctx) return VLR_ERR_INVALID;
@@ -625,7 +625,14 @@ int vlr_posterior_batch(vlr_ctx *ctx, int64_t n_sites, const vlr_model *model,
                                       out_map_af, out_map_bias);
 }
 
-int vlr_posterior_batch_f32(vlr_ctx *ctx, int64_t n_sites, const vlr_model *model,
+int vlr_posterior_batch(vlr_ctx *ctx, int64_t n_sites, const vlr_model *model,
+                        const vlr_obs_columns *obs, const int64_t *obs_off, double *out_event_ln,
+                        double *out_marginal, double *out_map_af, int32_t *out_map_bias) {
+    return vlr::drain_on_error(ctx, vlr_posterior_batch_impl(ctx, n_sites, model, obs, obs_off, out_event_ln, out_marginal, out_map_af, out_map_bias));
+}
+
+
+static int vlr_posterior_batch_f32_impl(vlr_ctx *ctx, int64_t n_sites, const vlr_model *model,
                             const vlr_obs_columns_f32 *obs, const int64_t *obs_off, double *out_event_ln,
                             double *out_marginal, double *out_map_af, int32_t *out_map_bias) {
     if (!ctx) return VLR_ERR_INVALID;
@@ -635,6 +642,13 @@ int vlr_posterior_batch_f32(vlr_ctx *ctx, int64_t n_sites, const vlr_model *mode
     return posterior_pipeline<float>(ctx, n_sites, model, cols, 7, obs->cat, obs_off, out_event_ln, out_marginal,
                                      out_map_af, out_map_bias);
 }
+
+int vlr_posterior_batch_f32(vlr_ctx *ctx, int64_t n_sites, const vlr_model *model,
+                            const vlr_obs_columns_f32 *obs, const int64_t *obs_off, double *out_event_ln,
+                            double *out_marginal, double *out_map_af, int32_t *out_map_bias) {
+    return vlr::drain_on_error(ctx, vlr_posterior_batch_f32_impl(ctx, n_sites, model, obs, obs_off, out_event_ln, out_marginal, out_map_af, out_map_bias));
+}
+
 
 }  // extern "C"
 
@@ -664,7 +678,7 @@ __global__ void likelihood_items_kernel(vlr_obs_columns obs, const int64_t *obs_
 }
 }  // namespace vlr
 
-extern "C" int vlr_likelihood_batch(vlr_ctx *ctx, int64_t n_sites, int32_t n_samples,
+static int vlr_likelihood_batch_impl(vlr_ctx *ctx, int64_t n_sites, int32_t n_samples,
                                     const vlr_obs_columns *obs, const int64_t *obs_off,
                                     const vlr_biases *biases, int32_t n_biases,
                                     const vlr_lh_item *items, int64_t n_items, double *out_ln_lh) {
@@ -689,6 +703,9 @@ extern "C" int vlr_likelihood_batch(vlr_ctx *ctx, int64_t n_sites, int32_t n_sam
     const double *cols[9] = {obs->prob_mapping, obs->prob_mismapping, obs->prob_alt, obs->prob_ref,
                              obs->prob_missed_allele, obs->prob_sample_alt, obs->prob_double_overlap,
                              obs->prob_single_overlap, obs->prob_hit_base};
+    if (n_rows < 0) return set_err(ctx, VLR_ERR_INVALID, "obs_off not monotone");
+    for (int c = 0; c < 9; ++c)
+        if (n_rows > 0 && (!cols[c] || !obs->cat)) return set_err(ctx, VLR_ERR_INVALID, "null observation column");
     double *d_cols[9];
     for (int c = 0; c < 9; ++c) {
         d_cols[c] = (double *)dev_scratch(ctx, S_COL0 + c, (size_t)(n_rows + 1) * 8);
@@ -720,3 +737,11 @@ extern "C" int vlr_likelihood_batch(vlr_ctx *ctx, int64_t n_sites, int32_t n_sam
     VLR_CUDA(ctx, cudaStreamSynchronize(st));
     return VLR_OK;
 }
+
+extern "C" int vlr_likelihood_batch(vlr_ctx *ctx, int64_t n_sites, int32_t n_samples,
+                                    const vlr_obs_columns *obs, const int64_t *obs_off,
+                                    const vlr_biases *biases, int32_t n_biases,
+                                    const vlr_lh_item *items, int64_t n_items, double *out_ln_lh) {
+    return vlr::drain_on_error(ctx, vlr_likelihood_batch_impl(ctx, n_sites, n_samples, obs, obs_off, biases, n_biases, items, n_items, out_ln_lh));
+}
+
