@@ -218,6 +218,27 @@ def oracle_part2(wl, cols, cat, off, n_sample, threads=1):
     return res, n_sample / dt, dt
 
 
+def executed_utilisation(name):
+    """What the kernel EXECUTES next to the survey's flop convention (which prices a software log per
+    evaluation the kernel does not take): fp64-pipe and issue-slot utilisation of K3/K4 on this
+    workload from the committed ncu summary (profiles/, a separate capture of the same kernel on
+    65 536 sites -- never measured under this timed run)."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles",
+                        "r2_ncu_k3_posterior_%s_summary.txt" % name)
+    out = {"executed_fp64_pipe_pct": None, "issue_pct": None, "executed_source": None}
+    try:
+        for line in open(path):
+            f = line.split()
+            if len(f) >= 2 and f[0] == "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active":
+                out["executed_fp64_pipe_pct"] = float(f[1])
+            if len(f) >= 2 and f[0] == "sm__inst_issued.avg.pct_of_peak_sustained_active":
+                out["issue_pct"] = float(f[1])
+        out["executed_source"] = "profiles/" + os.path.basename(path)
+    except OSError:
+        pass
+    return out
+
+
 def bench_part2(args, ctx, torch, dist, dev, stream, rank, world, name, wl, timed):
     """sites/s of AF-grid likelihood + event integration (K3/K4) on one synthetic shard per rank."""
     from libprosic_b200 import synth
@@ -352,6 +373,7 @@ def bench_part2(args, ctx, torch, dist, dev, stream, rank, world, name, wl, time
                            "note": "survey convention (a software fp64 log = 24 flops per evaluation); the "
                                    "kernel takes one log per key instead of one per observation",
                            "hbm": {"achieved": sps_gpu * n_obs_site * BYTES_PER_OBS / 1e9, "unit": "GB/s"}}
+        res["roofline"].update(executed_utilisation(name))
         res["cpu_baseline"] = {"value": cpu_sps, "unit": "sites/s", "cores": 1, "kind": "port",
                                "sample": "%d sites of this workload, 1 thread, %.1f s" % (n_cpu, cpu_dt)}
         cores = os.cpu_count() or 1

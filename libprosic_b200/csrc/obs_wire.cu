@@ -8,7 +8,8 @@
 // A MiniLogProb element is 6 bytes (u32 variant 0 + f16) or 8 bytes (u32 variant 1 + f32), so element k
 // of a vector can only be found by walking elements 0..k-1: one thread per (record, field) walks its
 // vector (a pileup has tens to hundreds of observations; hundreds of thousands of records per batch
-// keep the device busy), one more thread per record assembles the packed categoricals from the four
+// keep the device busy; a warp takes the same field of 32 consecutive records), one more thread per
+// record assembles the packed categoricals from the four
 // enum vectors (fixed 4-byte elements) and the two BitVec<u8>.
 #include <cuda_fp16.h>
 #include <math.h>
@@ -51,9 +52,11 @@ __device__ __forceinline__ void wire_fail(int32_t *err, int64_t r, int f) {
 
 __global__ void __launch_bounds__(256) obs_wire_decode_kernel(WireDev W, int64_t n_records, const int64_t *obs_off,
                                                               int64_t row_base, ColsDev out, int32_t *err) {
-    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int64_t r = tid >> 3;
-    const int task = (int)(tid & 7);
+    // a CTA of 256 threads takes 32 records; warp w of the CTA handles task w of all of them, so the
+    // lanes of a warp run the same code (the transcendentals of the two derived columns fill whole
+    // warps instead of 2 lanes in 8)
+    const int64_t r = blockIdx.x * (int64_t)32 + (threadIdx.x & 31);
+    const int task = (int)(threadIdx.x >> 5);
     if (r >= n_records) return;
     const int64_t row0 = obs_off[r] - row_base, n = obs_off[r + 1] - obs_off[r];
     if (task < 7) {
@@ -246,9 +249,8 @@ static int wire_alloc(vlr_ctx *ctx, int b, const vlr_obs_wire *wire, const std::
 
 static int wire_launch_decode(vlr_ctx *ctx, cudaStream_t st, const WireDev &W, int64_t n_records, const int64_t *d_obs_off,
                               int64_t row_base, const ColsDev &C, int32_t *d_err) {
-    const int64_t threads = n_records * 8;
-    if (threads <= 0) return VLR_OK;
-    obs_wire_decode_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(W, n_records, d_obs_off, row_base, C, d_err);
+    if (n_records <= 0) return VLR_OK;
+    obs_wire_decode_kernel<<<(unsigned)((n_records + 31) / 32), 256, 0, st>>>(W, n_records, d_obs_off, row_base, C, d_err);
     VLR_LAUNCH_CHECK(ctx);
     return VLR_OK;
 }
