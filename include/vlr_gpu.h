@@ -114,8 +114,8 @@ int vlr_pairhmm_batch(vlr_ctx *ctx, int64_t n_pairs,
  * accepted (the kernel aligns its TMA bulk copies down to 16 bytes); the hap buffer must be
  * readable for 32 bytes past hap_off[n_haps] and 16 bytes before hap_off[0].  `workspace` must
  * hold vlr_pairhmm_workspace_bytes(n_pairs, max_len_x, max_len_y) bytes.  Read windows longer
- * than 248 rows take the strip-wise long-read variant (unbanded only; NaN if banded or if the
- * workspace was sized without max_len_x / max_len_y).
+ * than 248 rows take the strip-wise long-read variant when unbanded and the anti-diagonal
+ * log-space variant when banded (NaN if the workspace was sized without max_len_x / max_len_y).
  */
 size_t vlr_pairhmm_workspace_bytes(int64_t n_pairs, int64_t max_len_x, int64_t max_len_y);
 int vlr_pairhmm_batch_dev(vlr_ctx *ctx, int64_t n_pairs,
@@ -140,7 +140,7 @@ int vlr_measure_fp64_peak(vlr_ctx *ctx, double *out_tflops);
  * forward order, bit 7 = Ins (else Del), bits 0-6 = run length (1..127; a longer run continues in the next
  * byte), zero padded -- 32 runs per alignment, however long the runs (a 60-base insertion is one byte).
  * An alignment with more runs (an unrelated read) has its tail uncounted: the sum of the run lengths is
- * then below out_n_indel_ops.  Read windows up to 256 rows. ------ */
+ * then below out_n_indel_ops.  Read windows up to 1024 rows (Myers::Long). ------ */
 #define VLR_MAX_INDEL_OPS 32
 int vlr_besthit_batch(vlr_ctx *ctx, int64_t n_pairs,
                       const uint8_t *hap_bytes, const int64_t *hap_off, int64_t n_haps,

@@ -838,11 +838,9 @@ static int vlr_allele_support_batch_impl(vlr_ctx *ctx, int64_t n_regions, const 
     int32_t *d_rd = (int32_t *)D(S_O5, (size_t)n_regions * 4), *d_ad = (int32_t *)D(S_O6, (size_t)n_regions * 4);
     int32_t *d_ni = (int32_t *)D(S_O7, (size_t)n_regions * 4);
     uint8_t *d_io = (uint8_t *)D(S_O8, (size_t)n_regions * kMaxIndelOps);
-    const size_t pws_bytes = vlr_pairhmm_workspace_bytes(n_slots, 0, 0);
-    void *d_pws = D(S_PWS, pws_bytes);
     if (!d_hap || !d_hoff || !d_rb || !d_rq || !d_roff || !d_rr || !d_rho || !d_rh || !d_rnr ||
         (shrink_extra && !d_se) || !d_slot_read || !d_hits || !d_ops || !d_ws || !d_wl || !d_med ||
-        !d_sp || !d_sm || !d_pref || !d_palt || !d_rref || !d_ralt || !d_rd || !d_ad || !d_ni || !d_io || !d_pws)
+        !d_sp || !d_sm || !d_pref || !d_palt || !d_rref || !d_ralt || !d_rd || !d_ad || !d_ni || !d_io)
         return set_err(ctx, VLR_ERR_NOMEM, "scratch allocation failed");
     lap("scratch", false);
     // Copies first, checks while they fly: everything the Myers kernel needs goes on the main stream,
@@ -886,15 +884,23 @@ static int vlr_allele_support_batch_impl(vlr_ctx *ctx, int64_t n_regions, const 
     }
     for (int64_t k = 0; k < n_slots && !bad; ++k)
         if (region_haps[k] < 0 || region_haps[k] >= n_haps) bad = "region_haps out of range";
-    // Myers takes read windows of up to 1024 rows; the banded pair-HMM behind it 248 (the fast mode,
-    // which needs no pair-HMM, goes all the way)
-    const int64_t ly_limit = (flags & VLR_REALIGN_FAST) ? 64 * kMyWLong : 248;
+    // Myers takes read windows of up to 1024 rows (bio's Myers::Long); the banded pair-HMM behind it takes
+    // windows above 248 rows through the anti-diagonal kernel (pairhmm_diag.cuh)
+    const int64_t ly_limit = 64 * kMyWLong;
     if (bad || max_ly > ly_limit) {
         // the copies read caller memory: let them finish before the buffers go back to the caller
         cudaStreamSynchronize(st);
         cudaStreamSynchronize(cp);
         if (bad) return set_err(ctx, VLR_ERR_INVALID, "%s", bad);
         return set_err(ctx, VLR_ERR_UNSUPPORTED, "read window of %lld rows exceeds %lld", (long long)max_ly, (long long)ly_limit);
+    }
+    // workspace of the pair-HMM stage (sized now that the window lengths are known)
+    const size_t pws_bytes = vlr_pairhmm_workspace_bytes(n_slots, max_lx, max_ly);
+    void *d_pws = D(S_PWS, pws_bytes);
+    if (!d_pws) {
+        cudaStreamSynchronize(st);
+        cudaStreamSynchronize(cp);
+        return set_err(ctx, VLR_ERR_NOMEM, "scratch allocation failed");
     }
     // slot -> read index (the Myers pairs), on the device
     {
@@ -955,7 +961,7 @@ static int vlr_allele_support_batch_impl(vlr_ctx *ctx, int64_t n_regions, const 
         support_epilogue_kernel<true><<<grid, 128, 0, st>>>(sa);
         VLR_LAUNCH_CHECK(ctx);
         rc = pairhmm_literal_dev(ctx, n_slots, d_hap - hap_lo, nullptr, d_ws, d_wl, d_rb - rd_lo, d_rq - rd_lo, d_roff,
-                                 nullptr, d_slot_read, d_med, sa.lit_list, sa.lit_count, gap, flags, max_lx, d_sp);
+                                 nullptr, d_slot_read, d_med, sa.lit_list, sa.lit_count, gap, flags, max_lx, max_ly, d_sp);
         if (rc != VLR_OK) return rc;
         lap("near ties", true);
     }

@@ -11,6 +11,7 @@
 #include "pairhmm_kernel.cuh"
 #include "pairhmm_band.cuh"
 #include "pairhmm_litband.cuh"
+#include "pairhmm_diag.cuh"
 
 namespace vlr {
 
@@ -139,6 +140,15 @@ static cudaError_t launch_literal(int approx, const HmmArgs &a, int sm_count, cu
     VLR_APPROX_SWITCH(approx, VLR_CALL)
 #undef VLR_CALL
 }
+static cudaError_t launch_diag(int approx, bool literal, const HmmArgs &a, const DiagArgs &da, int n_ctas,
+                               cudaStream_t st) {
+#define VLR_CALL(A) launch_pairhmm_diag<A>(literal, a, da, n_ctas, st)
+    VLR_APPROX_SWITCH(approx, VLR_CALL)
+#undef VLR_CALL
+}
+// per-warp scratch of the anti-diagonal kernel: three diagonals of (M, X, Y, distance) per read row
+constexpr int kDiagBlocksPerSm = 2;
+static size_t diag_warp_bytes(int64_t max_ly) { return align_up((size_t)(max_ly + 1) * 84 + 64, 256); }
 static int approx_of(uint32_t flags) {
     return (flags & VLR_HMM_SUM3_APPROX3) ? 2 : ((flags & VLR_HMM_SUM3_APPROX) ? 1 : 0);
 }
@@ -224,6 +234,9 @@ static int pairhmm_core_dev(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *d_hap_
     // whatever the caller allocated beyond the bookkeeping is boundary-row space for long reads
     const int64_t long_stride =
         (int64_t)((workspace_bytes - pair_ws_bytes(n_pairs)) / (size_t)(kLongWarpsCap * 6 * sizeof(double)));
+    // the same space, cut per warp, is the scratch of the anti-diagonal kernel (banded long windows)
+    const int64_t diag_bytes =
+        (int64_t)((workspace_bytes - pair_ws_bytes(n_pairs)) / (size_t)kLongWarpsCap) & ~(int64_t)255;
     VLR_CUDA(ctx, cudaMemsetAsync(w.counters, 0, kCntTotal * sizeof(int32_t), st));
     const int64_t want = (n_pairs + 255) / 256, cap = (int64_t)ctx->sm_count * 8;
     const int cgrid = (int)(want < cap ? want : cap);
@@ -322,6 +335,18 @@ static int pairhmm_core_dev(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *d_hap_
         e = launch_long(approx, ext, true, al, ctx->sm_count, st);
         if (e != cudaSuccess) return set_err(ctx, VLR_ERR_CUDA, "pairhmm launch failed: %s", cudaGetErrorString(e));
         ctx->launches++;
+    } else if (diag_bytes >= (int64_t)diag_warp_bytes(249) && ctx->sm_count <= 160) {
+        // banded pairs / explicit windows with read windows above 248 rows: anti-diagonal log-space sweep
+        HmmArgs ad = a;
+        ad.list = w.list;
+        ad.list_off = w.counters + kCntOff + 7;
+        ad.count = w.counters + kCntCount + 7;
+        ad.cursor = w.counters + kCntWork + 7;
+        DiagArgs da;
+        da.ws = (uint8_t *)w.long_ws; da.ws_bytes = diag_bytes; da.min_rows = 0;
+        cudaError_t e = launch_diag(approx, false, ad, da, ctx->sm_count * kDiagBlocksPerSm, st);
+        if (e != cudaSuccess) return set_err(ctx, VLR_ERR_CUDA, "pairhmm launch failed: %s", cudaGetErrorString(e));
+        ctx->launches++;
     } else {
         mark_unsupported_kernel<<<32, 256, 0, st>>>(w.list, w.counters, d_out_lnprob);
         VLR_LAUNCH_CHECK(ctx);
@@ -338,8 +363,8 @@ int pairhmm_literal_dev(vlr_ctx *ctx, int64_t n_pairs_cap, const uint8_t *d_hap_
                         const uint8_t *d_read_quals, const int64_t *d_read_off, const int32_t *d_pair_hap,
                         const int32_t *d_pair_read, const int32_t *d_med, const int32_t *d_list,
                         const int32_t *d_count, const vlr_gap_params *gap, uint32_t flags, int64_t max_lx,
-                        double *d_out) {
-    enum { S_LIT = 90, S_LITCNT = 91 };
+                        int64_t max_ly, double *d_out) {
+    enum { S_LIT = 90, S_LITCNT = 91, S_LITDIAG = 95 };
     cudaStream_t st = ctx->stream;
     const int64_t stride = (max_lx + 31) / 32 * 32;
     const size_t warps = (size_t)ctx->sm_count * kLitBlocksPerSm * kWarps;
@@ -387,6 +412,20 @@ int pairhmm_literal_dev(vlr_ctx *ctx, int64_t n_pairs_cap, const uint8_t *d_hap_
     cudaError_t e = launch_literal(approx_of(flags), a, ctx->sm_count, st);
     if (e != cudaSuccess) return set_err(ctx, VLR_ERR_CUDA, "pairhmm launch failed: %s", cudaGetErrorString(e));
     ctx->launches++;
+    if (max_ly > 248) {
+        // read windows above the wavefront kernel's 248 rows (it skips them): anti-diagonal sweep over the
+        // same list, same arithmetic.  kLitBlocksPerSm == kDiagBlocksPerSm: the prob_cols slots match.
+        static_assert(kLitBlocksPerSm == kDiagBlocksPerSm, "per-warp prob_cols are indexed by the same warp id");
+        DiagArgs da;
+        da.ws_bytes = (int64_t)diag_warp_bytes(max_ly);
+        da.ws = (uint8_t *)dev_scratch(ctx, S_LITDIAG, warps * (size_t)da.ws_bytes);
+        da.min_rows = 249;
+        if (!da.ws) return set_err(ctx, VLR_ERR_NOMEM, "scratch allocation failed");
+        a.cursor = cnt + 4;
+        e = launch_diag(approx_of(flags), true, a, da, ctx->sm_count * kDiagBlocksPerSm, st);
+        if (e != cudaSuccess) return set_err(ctx, VLR_ERR_CUDA, "pairhmm launch failed: %s", cudaGetErrorString(e));
+        ctx->launches++;
+    }
     return VLR_OK;
 }
 
@@ -406,8 +445,10 @@ extern "C" {
 
 size_t vlr_pairhmm_workspace_bytes(int64_t n_pairs, int64_t max_len_x, int64_t max_len_y) {
     size_t b = pair_ws_bytes(n_pairs < 1 ? 1 : n_pairs);
-    if (max_len_y > 248 && max_len_x > 0)  // boundary rows of the strip-wise long-read variant
-        b += (size_t)kLongWarpsCap * 6 * sizeof(double) * (size_t)(max_len_x + 32);
+    if (max_len_y > 248 && max_len_x > 0)  // boundary rows of the strip-wise long-read variant or the
+                                           // three anti-diagonals of the banded one, whichever is larger
+        b += (size_t)kLongWarpsCap * std::max<size_t>(6 * sizeof(double) * (size_t)(max_len_x + 32),
+                                                      diag_warp_bytes(max_len_y));
     return b;
 }
 
@@ -447,9 +488,6 @@ static int vlr_pairhmm_batch_impl(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *
         if (l < 0) return set_err(ctx, VLR_ERR_INVALID, "read_off not monotone");
         if (l > max_ly) max_ly = l;
     }
-    if (max_ly > 248 && max_edit_dist)
-        return set_err(ctx, VLR_ERR_UNSUPPORTED, "banded read window of %lld rows exceeds 248",
-                       (long long)max_ly);
     bool reads_in_pair_order = pair_hap && pair_read;  // pair_read non-decreasing: reads can stream in chunks
     if (pair_hap || pair_read)
         for (int64_t k = 0; k < n_pairs; ++k) {
@@ -489,12 +527,7 @@ static int vlr_pairhmm_batch_impl(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *
     const double stream_bytes = 2.0 * (double)rd_bytes_n + 12.0 * (double)n_pairs;
     int n_chunks = reads_in_pair_order ? (int)std::min<double>(32.0, floor(stream_bytes / (32.0 * 1048576.0))) : 1;
     const bool literal = (flags & VLR_HMM_LITERAL) != 0;
-    if (literal) {
-        if (max_ly > 248)
-            return set_err(ctx, VLR_ERR_UNSUPPORTED, "literal evaluation of a read window of %lld rows (limit 248)",
-                           (long long)max_ly);
-        n_chunks = 1;
-    }
+    if (literal) n_chunks = 1;
     if (n_chunks > 1 && ensure_copy_stream(ctx) != VLR_OK) n_chunks = 1;
     if (n_chunks <= 1) {
         VLR_CUDA(ctx, cudaMemcpyAsync(d_rb, read_bases + rd_lo, rd_bytes_n, cudaMemcpyHostToDevice, st));
@@ -507,7 +540,7 @@ static int vlr_pairhmm_batch_impl(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *
         int rc = literal
                      ? pairhmm_literal_dev(ctx, n_pairs, d_hap - hap_lo, d_hoff, nullptr, nullptr, d_rb - rd_lo,
                                            d_rq - rd_lo, d_roff, d_ph, d_pr, d_med, nullptr, nullptr, gap, flags,
-                                           max_lx, d_out)
+                                           max_lx, max_ly, d_out)
                      : vlr_pairhmm_batch_dev(ctx, n_pairs, d_hap - hap_lo, d_hoff, n_haps, d_rb - rd_lo,
                                              d_rq - rd_lo, d_roff, n_reads, d_ph, d_pr, d_med, gap, flags, d_ws,
                                              ws_bytes, d_out);

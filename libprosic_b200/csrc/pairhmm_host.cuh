@@ -15,11 +15,12 @@ int pairhmm_windows_dev(vlr_ctx *ctx, int64_t n_slots, const uint8_t *d_hap_base
                         void *d_workspace, size_t workspace_bytes, double *d_out);
 // Literal log-space evaluation (policy LogLit of pairhmm_kernel.cuh: the reference's operation order
 // with the library's deterministic libm) of the listed pairs; d_list == nullptr: all n_pairs_cap
-// pairs; d_count: device count of list entries.  Context scratch holds the per-warp prob_cols.
+// pairs; d_count: device count of list entries.  Context scratch holds the per-warp prob_cols (sized by
+// max_lx) and, for read windows above 248 rows, the anti-diagonals of pairhmm_diag.cuh (sized by max_ly).
 int pairhmm_literal_dev(vlr_ctx *ctx, int64_t n_pairs_cap, const uint8_t *d_hap_bytes, const int64_t *d_hap_off,
                         const int64_t *d_win_start, const int32_t *d_win_len, const uint8_t *d_read_bases,
                         const uint8_t *d_read_quals, const int64_t *d_read_off, const int32_t *d_pair_hap,
                         const int32_t *d_pair_read, const int32_t *d_med, const int32_t *d_list,
                         const int32_t *d_count, const vlr_gap_params *gap, uint32_t flags, int64_t max_lx,
-                        double *d_out);
+                        int64_t max_ly, double *d_out);
 }  // namespace vlr

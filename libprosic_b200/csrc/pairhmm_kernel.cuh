@@ -598,6 +598,7 @@ __global__ void __launch_bounds__(kWarps * 32, Occ<R>::kMinBlocks) pairhmm_kerne
             if (lane == 0) g.out[pair] = -INFINITY;
             continue;
         }
+        if (A::kLit && ly > 31 * R) continue;  // taken by the anti-diagonal kernel (pairhmm_diag.cuh)
 
         // ---- per-row constants (ReadEmission, pairhmm.rs:160-200)
         PairState<R> s;

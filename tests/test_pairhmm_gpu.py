@@ -109,7 +109,7 @@ def test_errors_are_loud(ctx):
     read = np.frombuffer(b"A" * 300, dtype=np.uint8)
     with pytest.raises(P.VlrError):
         ctx.pairhmm_batch(hap, np.array([0, 400]), read, np.full(300, 30, np.uint8),
-                          np.array([0, 300]), gap, max_edit_dist=np.array([5], np.int32))  # banded + long
+                          np.array([300, 0]), gap, max_edit_dist=np.array([5], np.int32))  # offsets not monotone
     with pytest.raises(P.VlrError):
         ctx.pairhmm_batch(hap, np.array([0, 400]), read[:10], np.full(10, 30, np.uint8),
                           np.array([0, 10]), gap, pair_hap=np.array([3], np.int32),
@@ -260,6 +260,47 @@ def test_literal_kernel_is_bit_identical_to_the_oracle(ctx, oracle, gi, flags):
         hit = oracle.best_hit(w["hap_bytes"][w["hap_off"][k]:w["hap_off"][k + 1]],
                               w["read_bases"][w["read_off"][k]:w["read_off"][k + 1]])
         med[k] = hit["dist"] + 2
+    got = ctx.pairhmm_batch(w["hap_bytes"], w["hap_off"], w["read_bases"], w["read_quals"],
+                            w["read_off"], gap, max_edit_dist=med, flags=flags | P.HMM_LITERAL)
+    want = oracle.pairhmm_batch(w["hap_bytes"], w["hap_off"], w["read_bases"], w["read_quals"],
+                                w["read_off"], gap.as_ln_array(), med, flags)
+    assert np.array_equal(got.view(np.int64), want.view(np.int64)), \
+        "first difference at %d: %r vs %r" % (int(np.argmax(got != want)), got[np.argmax(got != want)],
+                                              want[np.argmax(got != want)])
+
+
+def _long_banded(oracle, n, seed, unbanded_every):
+    w = synth.make_ragged_pairs(n, seed=seed, min_ly=249, max_ly=700, min_lx=200, max_lx=900,
+                                related_frac=0.85)
+    med = np.empty(n, dtype=np.int32)
+    for k in range(n):
+        hit = oracle.best_hit(w["hap_bytes"][w["hap_off"][k]:w["hap_off"][k + 1]],
+                              w["read_bases"][w["read_off"][k]:w["read_off"][k + 1]])
+        med[k] = hit["dist"] + 2
+    med[::unbanded_every] = -1
+    return w, med
+
+
+@pytest.mark.parametrize("gi,flags", [(0, P.HMM_DEFAULT), (1, P.HMM_DEFAULT), (2, 0), (0, P.HMM_SUM3_APPROX)])
+def test_long_banded_windows(ctx, oracle, gi, flags):
+    """Banded read windows of 249-700 rows (reachable through merged multi-locus regions and breakend
+    alleles, bio's Myers::Long): the anti-diagonal log-space kernel (pairhmm_diag.cuh) with the
+    reference's cell set; the unbanded entries of the same batch take the strip-wise kernel."""
+    gap = _gap_sets()[gi]
+    w, med = _long_banded(oracle, 40, 900 + gi, 9)
+    got = ctx.pairhmm_batch(w["hap_bytes"], w["hap_off"], w["read_bases"], w["read_quals"],
+                            w["read_off"], gap, max_edit_dist=med, flags=flags)
+    want = oracle.pairhmm_batch(w["hap_bytes"], w["hap_off"], w["read_bases"], w["read_quals"],
+                                w["read_off"], gap.as_ln_array(), med, flags)
+    _compare(got, want)
+    assert np.isfinite(want).sum() > 20
+
+
+@pytest.mark.parametrize("gi,flags", [(0, P.HMM_SUM3_APPROX3), (1, P.HMM_SUM3_APPROX3), (2, 0)])
+def test_literal_long_windows_are_bit_identical_to_the_oracle(ctx, oracle, gi, flags):
+    """VLR_HMM_LITERAL above 248 rows: the literal instantiation of the anti-diagonal kernel."""
+    gap = _gap_sets()[gi]
+    w, med = _long_banded(oracle, 14, 950 + gi, 7)
     got = ctx.pairhmm_batch(w["hap_bytes"], w["hap_off"], w["read_bases"], w["read_quals"],
                             w["read_off"], gap, max_edit_dist=med, flags=flags | P.HMM_LITERAL)
     want = oracle.pairhmm_batch(w["hap_bytes"], w["hap_off"], w["read_bases"], w["read_quals"],

@@ -70,26 +70,27 @@ def test_besthit_repeats_and_ties(ctx, oracle):
         assert np.array_equal(got["indel_ops"][k][:len(want["indel_ops"])], want["indel_ops"]), k
 
 
-def _make_regions(rng, n_sites, reads_per_site, multi_alt=False):
+def _make_regions(rng, n_sites, reads_per_site, multi_alt=False, rl=100):
     """Indel candidates with reference-like windows: ref window 192 bp around the locus, alt
     window with the variant spliced in (insertions grow by ins_len: shrink_extra), read windows
-    of <= 128 bases."""
+    of <= 128 bases (rl = read length before trimming; the windows scale with it)."""
     haps, extra, reads, quals = [], [], [], []
     region_read, region_haps, region_hap_off, region_n_ref = [], [], [0], []
+    W = rl - 4
     for _ in range(n_sites):
-        contig = ACGT[rng.integers(0, 4, 500)]
-        locus = 250
+        contig = ACGT[rng.integers(0, 4, 5 * rl)]
+        locus = 5 * rl // 2
         L = int(rng.integers(1, 25))
         is_ins = rng.random() < 0.5
-        ref = contig[locus - 96:locus + 96]
+        ref = contig[locus - W:locus + W]
         if is_ins:
             ins = ACGT[rng.integers(0, 4, L)]
             full_alt = np.concatenate([contig[:locus + 1], ins, contig[locus + 1:]])
-            alt = full_alt[locus - 96:locus + 96 + L]
+            alt = full_alt[locus - W:locus + W + L]
             alt_extra = L
         else:
             full_alt = np.concatenate([contig[:locus + 1], contig[locus + 1 + L:]])
-            alt = full_alt[locus - 96:locus + 96]
+            alt = full_alt[locus - W:locus + W]
             alt_extra = 0
         h0 = len(haps)
         haps += [ref, alt]
@@ -101,15 +102,15 @@ def _make_regions(rng, n_sites, reads_per_site, multi_alt=False):
             alt_ids.append(h0 + 2)
         for _r in range(reads_per_site):
             src = full_alt if rng.random() < 0.5 else contig
-            start = locus - int(rng.integers(20, 100))
-            read = src[start:start + 100].copy()
-            q = np.clip(np.rint(rng.normal(30, 8, 100)), 0, 41).astype(np.uint8)
-            err = rng.random(100) < np.power(10.0, -q / 10.0)
+            start = locus - int(rng.integers(20, rl))
+            read = src[start:start + rl].copy()
+            q = np.clip(np.rint(rng.normal(30, 8, rl)), 0, 41).astype(np.uint8)
+            err = rng.random(rl) < np.power(10.0, -q / 10.0)
             read[err] = ACGT[rng.integers(0, 4, int(err.sum()))]
             if rng.random() < 0.05:
                 q[:] = 0
             lo = int(rng.integers(0, 10))
-            hi = 100 - int(rng.integers(0, 10))
+            hi = rl - int(rng.integers(0, 10))
             region_read.append(len(reads))
             reads.append(read[lo:hi])
             quals.append(q[lo:hi])
@@ -151,6 +152,33 @@ def test_allele_support_regions(ctx, oracle, multi_alt, flags):
         assert np.array_equal(got["indel_ops"][r][:len(want["indel_ops"])], want["indel_ops"]), r
         n_inf += want["informative"]
     assert n_inf > 20  # most reads must discriminate the alleles for the test to mean anything
+
+
+@pytest.mark.parametrize("rl", [300, 620])
+def test_allele_support_long_read_windows(ctx, oracle, rl):
+    """Read windows of 280-620 rows in the exact mode (Myers::Long hits, then the banded pair-HMM
+    through the anti-diagonal kernel, near ties through its literal instantiation): same values,
+    distances and indel operations as the oracle."""
+    rng = np.random.default_rng(4100 + rl)
+    R = _make_regions(rng, 4, 6, multi_alt=(rl == 300), rl=rl)
+    gap = P.GapParams()
+    got = ctx.allele_support_batch(R["region_read"], R["region_hap_off"], R["region_haps"],
+                                   R["region_n_ref"], R["hap_bytes"], R["hap_off"], R["read_bases"],
+                                   R["read_quals"], R["read_off"], gap, shrink_extra=R["extra"])
+    n_inf = 0
+    for r in range(len(R["region_read"])):
+        ids = R["region_haps"][R["region_hap_off"][r]:R["region_hap_off"][r + 1]]
+        rd = R["region_read"][r]
+        want = oracle.allele_support_region(
+            [R["haps"][ids[0]]], [R["haps"][h] for h in ids[1:]], R["reads"][rd], R["quals"][rd],
+            gap.as_ln_array(), shrink_extra=[int(R["extra"][h]) for h in ids], flags=P.HMM_DEFAULT)
+        for key in ("prob_ref", "prob_alt", "raw_ref", "raw_alt"):
+            g, w = got[key][r], want[key]
+            assert (np.isneginf(g) and np.isneginf(w)) or abs(g - w) <= 1e-6, (r, key, g, w)
+        assert got["ref_dist"][r] == want["ref_dist"] and got["alt_dist"][r] == want["alt_dist"], r
+        assert got["n_indel_ops"][r] == len(want["indel_ops"]), r
+        n_inf += want["informative"]
+    assert n_inf > 10
 
 
 def test_pathhmm_fast_mode(ctx, oracle):
