@@ -577,7 +577,15 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    host_binding = None
     if world > 1:
+        # one process per GPU: run on (and first-touch the pinned buffers on) the GPU's own NUMA node.
+        # The CPU legs only run at N=1, where the process keeps all host cores.
+        from libprosic_b200.sharding import bind_host_to_device
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = ("%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+               if hasattr(pr, "pci_bus_id") else None)
+        host_binding = bind_host_to_device(local_rank, bus)
         dist.init_process_group("nccl", device_id=dev)
     ctx = P.Context(local_rank)
     # a real (non-default) stream: the context enqueues on it and the CUDA events are recorded on it
@@ -726,6 +734,7 @@ def main():
                        "pairs_per_gpu": n_pairs, "cells_per_step_per_gpu": cells,
                        "m_state_sum": "exact" if args.exact_sum else "ln_sum3_exp_approx (reference)",
                        "gap_params": "cli defaults 2.8e-6/5.1e-6/0/0", "parallelism": "region-sharded x%d" % world,
+                       "host_binding": host_binding,
                        "l2": "inputs %.0f MB per step > 126 MB L2, no flush" % (in_bytes / 1e6)},
             "e2e": {"value": gcups_e2e, "unit": "GCUPS", "h2d_bytes_per_step": in_bytes,
                     "d2h_bytes_per_step": n_pairs * 8, "ms_per_step": ms_e2e / args.steps,

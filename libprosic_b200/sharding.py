@@ -50,3 +50,33 @@ def gather_in_record_order(local, bounds, rank, world, dist=None, dst=0):
     if rank != dst:
         return None
     return np.concatenate(parts, axis=0)
+
+
+def bind_host_to_device(device_index, pci_bus_id=None):
+    """Pin this process to the CPU cores NVML reports as local to GPU `device_index` (its NUMA node),
+    so that the pinned host buffers allocated afterwards are first-touched on that node: with one
+    process per GPU, eight ranks streaming host buffers no longer pull them all through one socket's
+    memory controller and inter-socket link.  Returns a short description, or None when NVML or the
+    affinity call is unavailable (nothing is changed then).  `pci_bus_id` ("domain:bus:device.fn") selects
+    the NVML device when CUDA_VISIBLE_DEVICES renumbers the CUDA indices."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            h = (pynvml.nvmlDeviceGetHandleByPciBusId(pci_bus_id.encode() if isinstance(pci_bus_id, str) else pci_bus_id)
+                 if pci_bus_id else pynvml.nvmlDeviceGetHandleByIndex(int(device_index)))
+            n_cpu = os.cpu_count() or 1
+            words = (n_cpu + 63) // 64
+            mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        finally:
+            pynvml.nvmlShutdown()
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus or cpus == allowed:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return "%d of %d cores (NVML affinity of GPU %d)" % (len(cpus), len(allowed), int(device_index))
+    except Exception:  # no NVML, no sched_setaffinity, containerised cpuset: leave the process alone
+        return None

@@ -71,3 +71,16 @@ def test_gather_in_record_order_world2_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert ok
+
+
+def test_bind_host_to_device_is_harmless_without_a_gpu():
+    """No NVML / no device: the helper reports None and leaves the affinity mask alone."""
+    import os
+    from libprosic_b200.sharding import bind_host_to_device
+    before = os.sched_getaffinity(0)
+    got = bind_host_to_device(0)
+    if got is None:
+        assert os.sched_getaffinity(0) == before
+    else:  # a GPU box: the mask shrank to the device's cores; restore it
+        assert os.sched_getaffinity(0) <= before
+        os.sched_setaffinity(0, before)
