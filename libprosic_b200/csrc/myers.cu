@@ -204,9 +204,19 @@ __global__ void __launch_bounds__(128) besthit_kernel(MyersArgs g) {
                     // start -- the lanes of a warp then write the same scratch row in the same iteration
                     // although their windows start at different columns
                     ulonglong2 *col = cols + (int64_t)(i + 1 - i0) * (2 * kMyW * 32);
+                    // Only the words a traceback can consult are written.  A walk from (m, e) stays on the
+                    // diagonals (e - m) +- d*; at column c it reads the rows j and j - 1 of that band, and
+                    // (one and two columns ahead of its position) row j of the columns c - 1 and c - 2:
+                    // rows [c - (last_best - m) - d* - 1, c - (first_best - m) + d* + 2], one more on
+                    // either side for good measure.  With a unique best end and a few edits that is one
+                    // word of the three a 150-row read has (5.6 -> 2 GB of scratch writes per launch on the
+                    // C3 read set).
+                    const int cdp = i + 1;
+                    const int w_lo = max(0, (cdp - (last_best - m) - best - 3) >> 6);
+                    const int w_hi = (cdp - (first_best - m) + best + 2) >> 6;
 #pragma unroll
                     for (int w = 0; w < kMyW; ++w)
-                        if (w < W) {
+                        if (w < W && w >= w_lo && w <= w_hi) {
                             col[w * 64] = make_ulonglong2(Pv[w], Mv[w]);          // vertical deltas
                             col[w * 64 + 1] = make_ulonglong2(PhS[w], MhS[w]);    // horizontal deltas
                         }
