@@ -3,7 +3,8 @@
 through K3/K4 and 18 000 more banded windows (random, homopolymer, tandem repeat) through the
 band-only pair-HMM, each against the oracle.  Last run of round 1: no mismatch; worst |delta ln| of
 the band kernel 6.1e-13; three random models hit the documented limit of 48 distinct VAF spectra
-and were rejected with an error.
+and were rejected with an error.  Round 2 adds 288 banded windows of 249-700 rows through the
+anti-diagonal kernel (Log against the oracle within 1e-6, literal bit for bit).
 
     python tools/fuzz_more.py
 """
@@ -43,3 +44,24 @@ for seed in range(100,130):
         if np.isnan(d).any(): print('band',seed,kind,'NaN/inf mismatch'); bad+=1
         else: worst=max(worst,float(d.max()))
 print('band fuzz worst |d|',worst,'bad',bad)
+# ---- banded read windows above 248 rows: the anti-diagonal kernel (Log) and its literal instantiation
+worst_long=0.0
+n_long=0
+lit_bad=0
+for seed in range(300,312):
+    gi=seed%3
+    gap=th._gap_sets()[gi]
+    flags=(P.HMM_SUM3_APPROX3,P.HMM_SUM3_APPROX,0)[(seed//3)%3]
+    w,med=th._long_banded(O,24,seed,5)
+    args=(w["hap_bytes"],w["hap_off"],w["read_bases"],w["read_quals"],w["read_off"])
+    want=O.pairhmm_batch(*args,gap.as_ln_array(),med,flags)
+    got=ctx.pairhmm_batch(*args,gap,max_edit_dist=med,flags=flags)
+    both=np.isneginf(got)&np.isneginf(want)
+    d=np.abs(np.where(both,0.0,got-want))
+    if np.isnan(d).any(): print('long band',seed,'NaN/inf mismatch'); bad+=1
+    else: worst_long=max(worst_long,float(d.max()))
+    lit=ctx.pairhmm_batch(*args,gap,max_edit_dist=med,flags=flags|P.HMM_LITERAL)
+    if not np.array_equal(lit.view(np.int64),want.view(np.int64)):
+        lit_bad+=1; print('long band',seed,'literal result differs from the oracle')
+    n_long+=len(med)
+print('long banded windows:',n_long,'pairs, worst |d|',worst_long,'literal mismatches',lit_bad,'bad',bad)
