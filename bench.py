@@ -267,8 +267,15 @@ def bench_part2(args, ctx, torch, dist, dev, stream, rank, world, name, wl, time
     np_cols = {n: h_cols[n].numpy() for n in names}
     np_cat = h_cat.numpy().view(np.uint16)
 
+    def pinned_out():
+        return dict(event_ln=torch.empty((n_sites, ne), dtype=torch.float64).pin_memory().numpy(),
+                    marginal=torch.empty(n_sites, dtype=torch.float64).pin_memory().numpy(),
+                    map_af=torch.empty((n_sites, ns), dtype=torch.float64).pin_memory().numpy(),
+                    map_bias=torch.empty((n_sites, ns), dtype=torch.int32).pin_memory().numpy())
+    e2e_out, f32_out = pinned_out(), pinned_out()
+
     def step_e2e():
-        return ctx.posterior_batch(scn, np_cols, np_cat, h_off.numpy())
+        return ctx.posterior_batch(scn, np_cols, np_cat, h_off.numpy(), out=e2e_out)
 
     # compact entry: the seven stored fields as f32 (lossless for MiniLogProb-quantised values)
     stored = ("prob_mapping", "prob_alt", "prob_ref", "prob_missed_allele", "prob_sample_alt",
@@ -277,7 +284,7 @@ def bench_part2(args, ctx, torch, dist, dev, stream, rank, world, name, wl, time
     np_cols32 = {n: h_cols32[n].numpy() for n in stored}
 
     def step_e2e_f32():
-        return ctx.posterior_batch_f32(scn, np_cols32, np_cat, h_off.numpy())
+        return ctx.posterior_batch_f32(scn, np_cols32, np_cat, h_off.numpy(), out=f32_out)
 
     for _ in range(max(args.warmup, 3)):
         step_dev()
@@ -303,10 +310,7 @@ def bench_part2(args, ctx, torch, dist, dev, stream, rank, world, name, wl, time
     # the records as `preprocess` stores them (bincode words per field), decoded on the device
     from libprosic_b200 import obs_codec as lc
     wire = lc.encode_batch(cols, cat, off, pin=True)
-    wire_out = dict(event_ln=torch.empty((n_sites, ne), dtype=torch.float64).pin_memory().numpy(),
-                    marginal=torch.empty(n_sites, dtype=torch.float64).pin_memory().numpy(),
-                    map_af=torch.empty((n_sites, ns), dtype=torch.float64).pin_memory().numpy(),
-                    map_bias=torch.empty((n_sites, ns), dtype=torch.int32).pin_memory().numpy())
+    wire_out = pinned_out()
 
     def step_e2e_wire():
         return ctx.posterior_batch_wire(scn, wire, wire_out)
@@ -327,10 +331,12 @@ def bench_part2(args, ctx, torch, dist, dev, stream, rank, world, name, wl, time
            "unit": "sites/s", "ms_per_step": ms / args.steps, "gpu_launches": int(launches),
            "e2e": {"value": n_sites * world * args.steps / (ms_e2e * 1e-3), "unit": "sites/s",
                    "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
-                   "ms_per_step": ms_e2e / args.steps},
+                   "ms_per_step": ms_e2e / args.steps,
+                   "host_gb_per_s": float(in_bytes + out_bytes) / (ms_e2e / args.steps * 1e-3) / 1e9},
            "e2e_f32": {"value": n_sites * world * args.steps / (ms_e2e32 * 1e-3), "unit": "sites/s",
                        "h2d_bytes_per_step": in_bytes32, "d2h_bytes_per_step": out_bytes,
                        "ms_per_step": ms_e2e32 / args.steps,
+                       "host_gb_per_s": float(in_bytes32 + out_bytes) / (ms_e2e32 / args.steps * 1e-3) / 1e9,
                        "note": "vlr_posterior_batch_f32: stored fields as f32, derived columns on the device"},
            "e2e_wire": {"value": n_sites * world * args.steps / (ms_e2ew * 1e-3), "unit": "sites/s",
                         "h2d_bytes_per_step": int(wire.nbytes), "d2h_bytes_per_step": out_bytes,
@@ -645,6 +651,27 @@ def main():
     gap = P.GapParams()
     flags = 0 if args.exact_sum else P.HMM_DEFAULT
 
+    # ---- host <-> device copy rate of this box (pinned memory, one 256 MB copy, best of 5): the roof of
+    # every host-buffer ("e2e") leg whose kernels are faster than its copies
+    def copy_rate(h2d):
+        nbytes = 256 << 20
+        hbuf = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        dbuf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        best = 0.0
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            if h2d:
+                dbuf.copy_(hbuf, non_blocking=True)
+            else:
+                hbuf.copy_(dbuf, non_blocking=True)
+            e1.record(stream)
+            e1.synchronize()
+            best = max(best, nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+        return best
+    pcie = {"h2d_gb_per_s": copy_rate(True), "d2h_gb_per_s": copy_rate(False),
+            "how": "one 256 MB pinned copy on the bench stream, best of 5, CUDA events"}
+
     # ---- synthetic shard of this rank (config C3 shape), pinned on the host for the e2e path
     w = gen_workload(args, rank)
     n_pairs = len(w["pair_hap"])
@@ -815,6 +842,7 @@ def main():
             "c1_testcases": c1,
             "c4_long_reads": c4,
             "sites_per_sec": part2,
+            "host_copy_peak": pcie,
             "clocks": clocks,
         }
         for v in part2.values():

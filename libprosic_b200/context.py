@@ -355,30 +355,39 @@ class Context:
         self._check(self.lib.vlr_model_leaves(self.h, C.byref(model), n.value, C.byref(n), _ptr(ev), _ptr(afs)))
         return ev, afs
 
-    def posterior_batch(self, scn, cols, cat, obs_off):
+    @staticmethod
+    def _posterior_out(out, n_sites, ne, ns):
+        """Output arrays of the posterior entries: the caller's (pinned) buffers or fresh ones."""
+        if out is None:
+            out = dict(event_ln=np.empty((n_sites, ne), np.float64), marginal=np.empty(n_sites, np.float64),
+                       map_af=np.empty((n_sites, ns), np.float64), map_bias=np.empty((n_sites, ns), np.int32))
+        for k, shape, dt in (("event_ln", (n_sites, ne), np.float64), ("marginal", (n_sites,), np.float64),
+                             ("map_af", (n_sites, ns), np.float64), ("map_bias", (n_sites, ns), np.int32)):
+            a = out[k]
+            if a.dtype != dt or a.size != int(np.prod(shape)) or not a.flags["C_CONTIGUOUS"]:
+                raise ValueError("out[%r] must be a C-contiguous %s array of %d elements" % (k, np.dtype(dt).name, int(np.prod(shape))))
+        return out
+
+    def posterior_batch(self, scn, cols, cat, obs_off, out=None):
         """Model::compute for every site: returns dict(event_ln[n_sites, n_events], marginal,
-        map_af[n_sites, n_samples], map_bias)."""
+        map_af[n_sites, n_samples], map_bias).  `out`: optional dict of preallocated (pinned) arrays."""
         keep = []
-        model = self.build_model(scn, keep)
+        model = self._cached_model(scn)
         oc = self._obs_columns(cols, cat, keep)
         obs_off = np.ascontiguousarray(obs_off, dtype=np.int64)
         ns, ne = scn["n_samples"], len(scn["events"])
         n_sites = (len(obs_off) - 1) // ns
-        ev = np.empty((n_sites, ne), np.float64)
-        marg = np.empty(n_sites, np.float64)
-        maf = np.empty((n_sites, ns), np.float64)
-        mb = np.empty((n_sites, ns), np.int32)
+        out = self._posterior_out(out, n_sites, ne, ns)
         self._check(self.lib.vlr_posterior_batch(self.h, n_sites, C.byref(model), C.byref(oc),
-                                                 _ptr(obs_off), _ptr(ev), _ptr(marg), _ptr(maf),
-                                                 _ptr(mb)))
-        return dict(event_ln=ev, marginal=marg, map_af=maf, map_bias=mb)
+                                                 _ptr(obs_off), _ptr(out["event_ln"]), _ptr(out["marginal"]),
+                                                 _ptr(out["map_af"]), _ptr(out["map_bias"])))
+        return out
 
-    def posterior_batch_f32(self, scn, cols32, cat, obs_off):
+    def posterior_batch_f32(self, scn, cols32, cat, obs_off, out=None):
         """Compact variant: the seven stored fields as float32 arrays (dict), derived columns on the
         device.  Same outputs as posterior_batch."""
         from ._ffi import ObsColumnsF32
-        keep = []
-        model = self.build_model(scn, keep)
+        model = self._cached_model(scn)
         names = ("prob_mapping", "prob_alt", "prob_ref", "prob_missed_allele", "prob_sample_alt",
                  "prob_double_overlap", "prob_hit_base")
         arrs = [np.ascontiguousarray(cols32[n], dtype=np.float32) for n in names]
@@ -387,13 +396,11 @@ class Context:
         obs_off = np.ascontiguousarray(obs_off, dtype=np.int64)
         ns, ne = scn["n_samples"], len(scn["events"])
         n_sites = (len(obs_off) - 1) // ns
-        ev = np.empty((n_sites, ne), np.float64)
-        marg = np.empty(n_sites, np.float64)
-        maf = np.empty((n_sites, ns), np.float64)
-        mb = np.empty((n_sites, ns), np.int32)
+        out = self._posterior_out(out, n_sites, ne, ns)
         self._check(self.lib.vlr_posterior_batch_f32(self.h, n_sites, C.byref(model), C.byref(oc),
-                                                     _ptr(obs_off), _ptr(ev), _ptr(marg), _ptr(maf), _ptr(mb)))
-        return dict(event_ln=ev, marginal=marg, map_af=maf, map_bias=mb)
+                                                     _ptr(obs_off), _ptr(out["event_ln"]), _ptr(out["marginal"]),
+                                                     _ptr(out["map_af"]), _ptr(out["map_bias"])))
+        return out
 
     def posterior_batch_wire(self, scn, wire, out=None):
         """Part 2 straight from stored observation records (obs_codec.WireBatch): upload, device
@@ -402,9 +409,7 @@ class Context:
         model = self._cached_model(scn)
         ns, ne = scn["n_samples"], len(scn["events"])
         n_sites = wire.n_records // ns
-        if out is None:
-            out = dict(event_ln=np.empty((n_sites, ne), np.float64), marginal=np.empty(n_sites, np.float64),
-                       map_af=np.empty((n_sites, ns), np.float64), map_bias=np.empty((n_sites, ns), np.int32))
+        out = self._posterior_out(out, n_sites, ne, ns)
         ws = wire.c_struct()
         self._check(self.lib.vlr_posterior_batch_wire(self.h, n_sites, C.byref(model), C.byref(ws), _ptr(out["event_ln"]),
                                                       _ptr(out["marginal"]), _ptr(out["map_af"]), _ptr(out["map_bias"])))
