@@ -3,7 +3,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/vlr_gpu.h"
@@ -70,6 +72,25 @@ static inline int drain_on_error(vlr_ctx *ctx, int rc) {
         if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     }
     return rc;
+}
+
+// Host-side validation of large index / offset arrays runs at the memory bandwidth of ONE core (a few
+// GB/s: 5 ms for the 2 M pairs of the C3 batch, serial in front of the first copy).  f(t, begin, end)
+// is called for `n_threads` contiguous ranges of [0, n), range 0 on the calling thread.
+template <class F>
+static inline void parallel_ranges(int64_t n, int n_threads, F f) {
+    if (n_threads < 1) n_threads = 1;
+    if ((int64_t)n_threads > n) n_threads = n > 0 ? (int)n : 1;
+    std::vector<std::thread> th;
+    th.reserve((size_t)n_threads);
+    for (int t = 1; t < n_threads; ++t) th.emplace_back(f, t, n * t / n_threads, n * (t + 1) / n_threads);
+    f(0, (int64_t)0, n / n_threads);
+    for (std::thread &x : th) x.join();
+}
+static inline int validation_threads(int64_t items) {
+    if (items < 262144) return 1;
+    const unsigned hw = std::thread::hardware_concurrency();
+    return (int)std::min<unsigned>(8u, std::max<unsigned>(1u, hw / 4));
 }
 
 // qlut layout: [256][4] doubles: eps, 1-eps, eps*0.3333, ln(1-eps)

@@ -481,22 +481,39 @@ static int vlr_pairhmm_batch_impl(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *
         return set_err(ctx, VLR_ERR_INVALID, "identity pair mapping needs n_haps/n_reads >= n_pairs");
     VLR_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    // validate indices and lengths on the host (cheap, and errors must not reach the kernels)
-    int64_t max_ly = 0;
-    for (int64_t r = 0; r < n_reads; ++r) {
-        int64_t l = read_off[r + 1] - read_off[r];
-        if (l < 0) return set_err(ctx, VLR_ERR_INVALID, "read_off not monotone");
-        if (l > max_ly) max_ly = l;
-    }
-    bool reads_in_pair_order = pair_hap && pair_read;  // pair_read non-decreasing: reads can stream in chunks
-    if (pair_hap || pair_read)
-        for (int64_t k = 0; k < n_pairs; ++k) {
-            if (pair_hap && (pair_hap[k] < 0 || pair_hap[k] >= n_haps))
-                return set_err(ctx, VLR_ERR_INVALID, "pair_hap[%lld] out of range", (long long)k);
-            if (pair_read && (pair_read[k] < 0 || pair_read[k] >= n_reads))
-                return set_err(ctx, VLR_ERR_INVALID, "pair_read[%lld] out of range", (long long)k);
-            if (reads_in_pair_order && k > 0 && pair_read[k] < pair_read[k - 1]) reads_in_pair_order = false;
+    // validate indices and lengths on the host (errors must not reach the kernels); a few threads, each
+    // on a contiguous range: one core's memory bandwidth made this 5 ms of a 144 ms call at 2 M pairs
+    struct Part { int64_t max_ly = 0, bad_hap = -1, bad_read = -1; bool bad_off = false, unordered = false; };
+    const int vt = validation_threads(n_pairs + n_reads);
+    std::vector<Part> parts((size_t)vt);
+    parallel_ranges(n_reads, vt, [&](int t, int64_t r0, int64_t r1) {
+        Part &q = parts[(size_t)t];
+        for (int64_t r = r0; r < r1; ++r) {
+            const int64_t l = read_off[r + 1] - read_off[r];
+            if (l < 0) q.bad_off = true;
+            if (l > q.max_ly) q.max_ly = l;
         }
+    });
+    if (pair_hap || pair_read)
+        parallel_ranges(n_pairs, vt, [&](int t, int64_t k0, int64_t k1) {
+            Part &q = parts[(size_t)t];
+            for (int64_t k = k0; k < k1; ++k) {
+                if (pair_hap && (pair_hap[k] < 0 || pair_hap[k] >= n_haps) && q.bad_hap < 0) q.bad_hap = k;
+                if (pair_read) {
+                    if ((pair_read[k] < 0 || pair_read[k] >= n_reads) && q.bad_read < 0) q.bad_read = k;
+                    if (k > 0 && pair_read[k] < pair_read[k - 1]) q.unordered = true;
+                }
+            }
+        });
+    int64_t max_ly = 0;
+    bool reads_in_pair_order = pair_hap && pair_read;  // pair_read non-decreasing: reads can stream in chunks
+    for (const Part &q : parts) {
+        if (q.bad_off) return set_err(ctx, VLR_ERR_INVALID, "read_off not monotone");
+        if (q.bad_hap >= 0) return set_err(ctx, VLR_ERR_INVALID, "pair_hap[%lld] out of range", (long long)q.bad_hap);
+        if (q.bad_read >= 0) return set_err(ctx, VLR_ERR_INVALID, "pair_read[%lld] out of range", (long long)q.bad_read);
+        if (q.unordered) reads_in_pair_order = false;
+        max_ly = std::max(max_ly, q.max_ly);
+    }
     const int64_t hap_lo = hap_off[0], hap_hi = hap_off[n_haps];
     const int64_t rd_lo = read_off[0], rd_hi = read_off[n_reads];
     int64_t max_lx = 0;
@@ -525,7 +542,23 @@ static int vlr_pairhmm_batch_impl(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *
     VLR_CUDA(ctx, cudaMemcpyAsync(d_hoff, hap_off, (size_t)(n_haps + 1) * 8, cudaMemcpyHostToDevice, st));
     VLR_CUDA(ctx, cudaMemcpyAsync(d_roff, read_off, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
     const double stream_bytes = 2.0 * (double)rd_bytes_n + 12.0 * (double)n_pairs;
-    int n_chunks = reads_in_pair_order ? (int)std::min<double>(32.0, floor(stream_bytes / (32.0 * 1048576.0))) : 1;
+    // Chunk sizes grow geometrically (x3 from ~8 MB): the first copy, which nothing hides, is short, the
+    // copy of chunk c+1 still hides under the kernels of chunk c as long as they take a third of its
+    // transfer time per byte (the C3 shape computes 20x longer than it copies), and the batch needs 4-5
+    // kernel chains instead of the 10 of equal 32 MB chunks -- each chain ends in the tails of its
+    // persistent kernels and of the small re-evaluation launches (~0.4 ms per chunk on the C3 shape).
+    std::vector<int64_t> chunk_end;   // pair index where each chunk ends
+    if (reads_in_pair_order && stream_bytes >= 64.0 * 1048576.0) {
+        const char *ce = getenv("VLR_K1_CHUNK_MB");   // tuning aid: size of the first chunk
+        double want = (ce && atof(ce) > 0 ? atof(ce) : 8.0) * 1048576.0, done = 0.0;
+        while (done + want * 1.34 < stream_bytes && chunk_end.size() < 31) {  // no sliver at the end
+            done += want;
+            chunk_end.push_back((int64_t)((double)n_pairs * (done / stream_bytes)));
+            want *= 3.0;
+        }
+    }
+    chunk_end.push_back(n_pairs);
+    int n_chunks = (int)chunk_end.size();
     const bool literal = (flags & VLR_HMM_LITERAL) != 0;
     if (literal) n_chunks = 1;
     if (n_chunks > 1 && ensure_copy_stream(ctx) != VLR_OK) n_chunks = 1;
@@ -565,7 +598,7 @@ static int vlr_pairhmm_batch_impl(vlr_ctx *ctx, int64_t n_pairs, const uint8_t *
         int64_t p0 = 0;
         int rc = VLR_OK;
         for (int c = 0; c < n_chunks && rc == VLR_OK; ++c) {
-            const int64_t p1 = c + 1 == n_chunks ? n_pairs : n_pairs * (c + 1) / n_chunks;
+            const int64_t p1 = chunk_end[(size_t)c];
             if (p1 <= p0) continue;
             // reads [ra, rb) are first needed by this chunk (earlier chunks brought everything below ra)
             const int64_t ra = c == 0 ? 0 : (int64_t)pair_read[p0 - 1] + 1;
