@@ -310,6 +310,46 @@ def test_literal_long_windows_are_bit_identical_to_the_oracle(ctx, oracle, gi, f
                                               want[np.argmax(got != want)])
 
 
+@pytest.mark.parametrize("literal", [False, True])
+def test_long_banded_edge_cases(ctx, oracle, literal):
+    """Corners of the anti-diagonal kernel: the Myers limit (1024 rows) and beyond it, a haplotype
+    shorter than the read, a five-base haplotype, band 0 on an exact copy, a read of N's whose band dies
+    after a few rows (ln 0), lower-case haplotype, Q0 bases."""
+    rng = np.random.default_rng(5150)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+    def related(ly, lx, n_sub):
+        hap = acgt[rng.integers(0, 4, lx)]
+        start = int(rng.integers(0, max(1, lx - ly + 1)))
+        read = hap[start:start + ly].copy()
+        if len(read) < ly:
+            read = np.concatenate([read, acgt[rng.integers(0, 4, ly - len(read))]])
+        pos = rng.choice(ly, n_sub, replace=False)
+        read[pos] = acgt[rng.integers(0, 4, n_sub)]
+        return hap, read
+    cases = [related(1024, 1100, 6), related(1500, 1490, 12), related(300, 5, 0), related(260, 260, 0),
+             (acgt[rng.integers(0, 4, 500)], np.full(400, ord("N"), np.uint8)), related(700, 760, 3)]
+    cases[5] = (np.where(cases[5][0] < 96, cases[5][0] + 32, cases[5][0]).astype(np.uint8), cases[5][1])
+    haps, reads = [c[0] for c in cases], [c[1] for c in cases]
+    quals = [rng.integers(0, 42, len(r)).astype(np.uint8) for r in reads]
+    quals[3][:] = 30
+    hap_off = np.concatenate([[0], np.cumsum([len(h) for h in haps])]).astype(np.int64)
+    read_off = np.concatenate([[0], np.cumsum([len(r) for r in reads])]).astype(np.int64)
+    med = np.array([oracle.best_hit(h, r)["dist"] + 2 for h, r in zip(haps, reads)], dtype=np.int32)
+    med[3] = 0
+    med[4] = 3
+    args = (np.concatenate(haps), hap_off, np.concatenate(reads), np.concatenate(quals), read_off)
+    gap = P.GapParams()
+    flags = P.HMM_DEFAULT | (P.HMM_LITERAL if literal else 0)
+    got = ctx.pairhmm_batch(*args, gap, max_edit_dist=med, flags=flags)
+    want = oracle.pairhmm_batch(*args, gap.as_ln_array(), med, P.HMM_DEFAULT)
+    assert np.isneginf(want[4]) and np.isfinite(want[3]) and np.isfinite(want[0])
+    if literal:
+        assert np.array_equal(got.view(np.int64), want.view(np.int64)), (got, want)
+    else:
+        _compare(got, want)
+
+
 def test_three_way_and_two_way_rules_differ_where_expected(ctx, oracle):
     """The two recollections of ln_sum3_exp_approx: results differ by at most ~e^-10 per cell
     (<= 1e-3 in ln on these reads) and both match their oracle variants."""
