@@ -83,8 +83,14 @@ static inline void parallel_ranges(int64_t n, int n_threads, F f) {
     if ((int64_t)n_threads > n) n_threads = n > 0 ? (int)n : 1;
     std::vector<std::thread> th;
     th.reserve((size_t)n_threads);
-    for (int t = 1; t < n_threads; ++t) th.emplace_back(f, t, n * t / n_threads, n * (t + 1) / n_threads);
+    int started = 1;  // ranges [1, started) run on their own threads
+    try {
+        for (; started < n_threads; ++started)
+            th.emplace_back(f, started, n * started / n_threads, n * (started + 1) / n_threads);
+    } catch (...) {  // no more threads to be had: the remaining ranges run here (nothing crosses the C ABI)
+    }
     f(0, (int64_t)0, n / n_threads);
+    for (int t = started; t < n_threads; ++t) f(t, n * t / n_threads, n * (t + 1) / n_threads);
     for (std::thread &x : th) x.join();
 }
 static inline int validation_threads(int64_t items) {
