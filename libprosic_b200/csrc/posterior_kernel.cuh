@@ -464,7 +464,10 @@ __device__ __forceinline__ double s_eff(double af, double sigma) {
 // unroll and their small index arrays stay in registers instead of local memory; CONT = false
 // leaves out the contaminated-sample paths (scenarios without contamination) -- the kernel is
 // instruction-fetch sensitive, less code is measurably faster.
-template <int TEAM, int MINB, int NSC, bool CONT>
+// PROG = false leaves out the prior program (set-only universes with a prior table, flat priors): the
+// call sits in the innermost loop of the integration and costs 3-8 % on the small-site workloads even
+// when it is never taken (registers of the allele-frequency vector, code size).
+template <int TEAM, int MINB, int NSC, bool CONT, bool PROG>
 __global__ void __launch_bounds__(kTeamThreadsMax, MINB) posterior_kernel(PostArgs g) {
     constexpr int NSA = NSC > 0 ? NSC : kMaxSamples;   // capacity of per-sample register arrays
     constexpr int NSU = NSC > 0 ? NSC : 1;              // unroll factor of per-sample loops
@@ -1059,7 +1062,7 @@ __global__ void __launch_bounds__(kTeamThreadsMax, MINB) posterior_kernel(PostAr
                     lw += S.lnw[S.sample_voff[smp] + vidx[smp]];
                 }
                 double J = prior ? prior[combo] : 0.0;  // Prior::compute (prior.rs:788-805) via the host's table
-                if (!prior && m.prog) {                  // ... or evaluated here (universes with Ranges)
+                if (PROG && !prior && m.prog) {          // ... or evaluated here (universes with Ranges)
                     double afv[NSA];
                     #pragma unroll NSU
                     for (int smp = 0; smp < NS; ++smp) afv[smp] = S.val[S.sample_voff[smp] + vidx[smp]];
@@ -1231,11 +1234,19 @@ __global__ void __launch_bounds__(kTeamThreadsMax, MINB) posterior_kernel(PostAr
 #define VLR_POSTERIOR_INSTANTIATE(TEAM, MINB, NSC, CONT)                                          \
     cudaError_t VLR_POSTERIOR_LAUNCHER(TEAM, MINB, NSC, CONT)(int grid, size_t dyn_smem,          \
                                                               cudaStream_t st, const PostArgs &a) { \
-        cudaError_t e = cudaFuncSetAttribute(posterior_kernel<TEAM, MINB, NSC, CONT != 0>,        \
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize,         \
-                                             (int)dyn_smem);                                      \
-        if (e != cudaSuccess) return e;                                                           \
-        posterior_kernel<TEAM, MINB, NSC, CONT != 0><<<grid, kTeamThreadsMax, dyn_smem, st>>>(a); \
+        if (a.m.prog) {                                                                           \
+            cudaError_t e = cudaFuncSetAttribute(posterior_kernel<TEAM, MINB, NSC, CONT != 0, true>, \
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                                 (int)dyn_smem);                                  \
+            if (e != cudaSuccess) return e;                                                       \
+            posterior_kernel<TEAM, MINB, NSC, CONT != 0, true><<<grid, kTeamThreadsMax, dyn_smem, st>>>(a); \
+        } else {                                                                                  \
+            cudaError_t e = cudaFuncSetAttribute(posterior_kernel<TEAM, MINB, NSC, CONT != 0, false>, \
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                                 (int)dyn_smem);                                  \
+            if (e != cudaSuccess) return e;                                                       \
+            posterior_kernel<TEAM, MINB, NSC, CONT != 0, false><<<grid, kTeamThreadsMax, dyn_smem, st>>>(a); \
+        }                                                                                         \
         return cudaGetLastError();                                                                \
     }
 // every (team, CTAs per SM, compile-time sample count, contamination) combination that is built
