@@ -55,3 +55,17 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "vlr_oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_pairhmm_workspace_accounts_for_long_windows():
+    """vlr_pairhmm_workspace_bytes is a pure function (no context): bookkeeping grows with the pairs,
+    read windows above 248 rows add the per-warp scratch of the strip-wise and the anti-diagonal
+    kernels (84 bytes per read row and warp for the latter), shorter windows add nothing."""
+    from libprosic_b200 import _ffi
+    lib = _ffi.load()
+    w = lib.vlr_pairhmm_workspace_bytes
+    assert w(1000, 0, 0) < w(100000, 0, 0)
+    assert w(1000, 500, 248) == w(1000, 0, 0)
+    base, long_rows = w(1000, 300, 0), w(1000, 300, 1024)
+    assert long_rows - base >= 1184 * 84 * 1024            # 148 SMs x 2 CTAs x 4 warps at least
+    assert w(1000, 20000, 15000) - base >= 1184 * 6 * 8 * 20000   # boundary rows of the strip-wise variant
