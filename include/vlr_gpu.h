@@ -172,7 +172,9 @@ int vlr_pathhmm_batch(vlr_ctx *ctx, int64_t n_pairs,
  *      : banded pair-HMM (band dist+2; with VLR_REALIGN_FAST in flags: best-path probability
  *      of PathHMMRealigner instead) -> max over haplotypes -> normalisation / 0.5 fallbacks.
  *      Outputs per region: normalised prob_ref / prob_alt, raw (unnormalised) values (nullable),
- *      edit distances of the chosen hits, and the alt hit's best_indel_operations. ------ */
+ *      edit distances of the chosen hits, and the alt hit's best_indel_operations.
+ *      Read windows up to 1024 rows in both modes (VLR_ERR_UNSUPPORTED beyond).  Contexts are
+ *      independent: calls on different contexts of one device overlap (one per worker thread). -- */
 int vlr_allele_support_batch(vlr_ctx *ctx, int64_t n_regions, const int32_t *region_read,
                              const int32_t *region_hap_off, const int32_t *region_haps,
                              const int32_t *region_n_ref,
