@@ -239,11 +239,16 @@ int vlr_posterior_batch_dev(vlr_ctx *ctx, int64_t n_sites, const vlr_model *mode
                        "%d observations x %d bias configurations do not fit the shared-memory staging",
                        max_obs_per_pileup, (int)H.cfg.size());
     // static shared memory: TeamShared per team + event partials (4 KB) + per-CTA reserve (1 KB).
-    // One-warp teams are latency bound (serial per-site sections): up to 5 CTAs per SM (measured
-    // best of 3..6 on the C2 / C5 workloads); the
-    // register cap of the instantiation follows the number of CTAs that fit.
+    // One-warp teams are latency bound (serial per-site sections): up to 7 CTAs per SM = 28 warps at
+    // 72 registers with 48-96 bytes of spills (measured best of 3..8 on the C2 / C5 workloads once the
+    // prior program was out of the program-free instantiations: germline 157 -> 167 M sites/s, trio
+    // 48 -> 56 M against 5 CTAs at 96 registers; 8 CTAs at 64 registers lose again); the register cap
+    // of the instantiation follows the number of CTAs that fit.
     const size_t cta_smem = dyn_smem + (size_t)teams_per_cta * sizeof(TeamShared) + 4096 + 1024 + 1024;
-    int minb = (int)std::max<size_t>(1, std::min<size_t>(big ? 3 : 5, (size_t)(224 * 1024) / cta_smem));
+    bool cont_or_generic = model->n_samples > 3;   // the instantiations with the contaminated paths / run-time
+    for (int k = 0; k < model->n_samples; ++k)     // sample count spill heavily below 96 registers: 5 CTAs
+        cont_or_generic |= model->contaminated[k] != 0;
+    int minb = (int)std::max<size_t>(1, std::min<size_t>(big ? 3 : (cont_or_generic ? 5 : 7), (size_t)(224 * 1024) / cta_smem));
     if (!big) {
         if (const char *e = getenv("VLR_POST_MINB")) minb = std::max(1, std::min(minb, atoi(e)));
     }
@@ -392,7 +397,7 @@ int vlr_posterior_batch_dev(vlr_ctx *ctx, int64_t n_sites, const vlr_model *mode
     {
         const int NS = model->n_samples;
         const int team = big ? 4 : 1;
-        const int mb = big ? 3 : (minb >= 5 ? 5 : 3);
+        const int mb = big ? 3 : (minb >= 7 ? 7 : (minb >= 6 ? 6 : (minb >= 5 ? 5 : 3)));
         bool any_cont = false;
         for (int k = 0; k < NS; ++k) any_cont |= model->contaminated[k] != 0;
         // instantiations: without contamination 1..3 samples; with contamination 2 samples or generic

@@ -1,0 +1,5 @@
+// explicit instantiation of posterior_kernel<TEAM=1, MINB=7, NSC=3, CONT=0> (see posterior_kernel.cuh)
+#include "posterior_kernel.cuh"
+namespace vlr {
+VLR_POSTERIOR_INSTANTIATE(1, 7, 3, 0)
+}

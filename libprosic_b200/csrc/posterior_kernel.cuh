@@ -1251,6 +1251,8 @@ __global__ void __launch_bounds__(kTeamThreadsMax, MINB) posterior_kernel(PostAr
     }
 // every (team, CTAs per SM, compile-time sample count, contamination) combination that is built
 #define VLR_POSTERIOR_FOR_ALL(X)                                                                  \
+    X(1, 7, 1, 0) X(1, 7, 2, 0) X(1, 7, 3, 0)                                                     \
+    X(1, 6, 1, 0) X(1, 6, 2, 0) X(1, 6, 3, 0)                                                     \
     X(1, 5, 1, 0) X(1, 5, 2, 0) X(1, 5, 3, 0) X(1, 5, 2, 1) X(1, 5, 0, 1)                         \
     X(1, 3, 1, 0) X(1, 3, 2, 0) X(1, 3, 3, 0) X(1, 3, 2, 1) X(1, 3, 0, 1)                         \
     X(4, 3, 2, 1) X(4, 3, 0, 1)
