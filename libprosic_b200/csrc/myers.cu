@@ -100,7 +100,13 @@ struct WalkRes {   // result of one traceback, handed from the executing lane to
 };
 
 template <int kMyW>
-__global__ void __launch_bounds__(128) besthit_kernel(MyersArgs g) {
+// CTAs per SM the register allocation must allow.  More resident threads do NOT help this kernel (5 or 6
+// CTAs at 96 / 80 registers: 4.2 / 4.1 ms against 3.7 ms on the C3 read set -- the scratch working set
+// grows with them); no cap at all (125 registers, nothing spilled) is the fastest.
+#ifndef VLR_K2_MINB
+#define VLR_K2_MINB 1
+#endif
+__global__ void __launch_bounds__(128, VLR_K2_MINB) besthit_kernel(MyersArgs g) {
     __shared__ int2 s_task[4][32];
     __shared__ WalkRes s_res[4][32];
     const int64_t worker = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
